@@ -1,0 +1,32 @@
+// ccx_gemm.h — internal descriptor for the tcgen05 GEMM launcher (not part of the public C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ccx {
+
+struct GemmDesc {
+  // C[M,N] = epi(A[M,K] . B[N,K]^T); A,B row-major with leading dims lda/ldb (elements)
+  const void* A = nullptr;      // bf16, or fp32 (tf32 "hi" part when A_lo is given)
+  const void* A_lo = nullptr;   // fp32 residual part for 3xTF32, or nullptr
+  const void* B = nullptr;
+  const void* B_lo = nullptr;
+  void* C = nullptr;            // bf16 or fp32
+  float* C_lo = nullptr;        // if split: C <- tf32_hi(y), C_lo <- y - hi
+  const float* bias = nullptr;      // [N]
+  const float* colscale = nullptr;  // [N]
+  const float* rowscale = nullptr;  // [ceil(M / rows_per_group)]
+  const void* residual = nullptr;   // [M, ldr], dtype of C
+  long long lda = 0, ldb = 0, ldc = 0, ldr = 0;
+  int M = 0, N = 0, K = 0;
+  int rows_per_group = 1;
+  int act = 0;        // 0 none, 1 gelu(erf), 2 relu
+  int in_dtype = 1;   // CCX_F32 (tf32 path) / CCX_BF16
+  int out_dtype = 1;  // CCX_F32 / CCX_BF16
+  int split = 0;
+  int force_bn = 0;   // 0 = auto, else 64/128/256
+};
+
+int gemm_tn(const GemmDesc& g, cudaStream_t stream);
+int num_sms();
+
+}  // namespace ccx

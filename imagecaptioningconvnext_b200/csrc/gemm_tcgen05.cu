@@ -1,0 +1,449 @@
+// gemm_tcgen05.cu — the one dense-contraction kernel of libccx (sm_100a only).
+//
+//   C[M,N] = epilogue( A[M,K] · B[N,K]^T )          (both operands K-major, "TN")
+//
+// * operands are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
+//   multi-stage shared-memory ring by one producer thread,
+// * one thread issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16 for bf16 inputs;
+//   UMMA 128 x BN x 8, kind::tf32 for the fp32 path) with fp32 accumulators in TMEM,
+// * four epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue
+//   (bias, exact-erf GELU / ReLU, layer-scale x stochastic-depth row scale, residual)
+//   while the MMA thread already works on the next tile (2 TMEM accumulator stages),
+// * persistent CTAs, one per SM, static round-robin tile schedule.
+//
+// fp32 mode ("3xTF32"): A and B are each given as a (hi, lo) pair of fp32 arrays whose
+// hi part is exactly representable in tf32; the K loop runs three segments
+// (Alo·Bhi, Ahi·Blo, Ahi·Bhi) into the same accumulator, which restores ~2^-21 relative
+// accuracy per product (needed for the fp32 parity bar: 1e-3 on features, exact argmax).
+//
+// Replaces, on the reference's hot path, every nn.Linear / 1x1-equivalent conv call:
+//   torchvision/models/convnext.py:55-57 (CNBlock MLP), :146-151 (downsample conv),
+//   models/decoder.py:19-21,50-54 (attention / init / f_beta / fc Linear layers),
+//   models/transformerDecoder.py:84-85 + torch/nn/modules/transformer.py (QKV/FFN/out-proj).
+#include "ccx_common.cuh"
+#include "ccx_gemm.h"
+
+namespace ccx {
+
+static constexpr int BM = 128;          // UMMA M (one TMEM lane per row)
+static constexpr int ROW_BYTES = 128;   // one swizzle row = 64 bf16 or 32 tf32 elements
+static constexpr int NUM_THREADS = 256; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * ROW_BYTES;
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+struct EpiArgs {
+  void* out;            // [M, ldc] bf16 or fp32
+  float* out_lo;        // fp32 split output (lo part) or nullptr
+  const float* bias;    // [N] or nullptr
+  const float* colscale;  // [N] or nullptr   (layer_scale)
+  const float* rowscale;  // [M / rows_per_group] or nullptr (stochastic-depth noise/(1-p))
+  const void* residual;   // [M, ldr] same dtype as out, or nullptr
+  long long ldc, ldr;
+  int rows_per_group;
+  int act;              // 0 none, 1 gelu(erf), 2 relu
+  int out_dtype;        // CCX_F32 / CCX_BF16
+  int split;            // 1: write tf32 hi to out, residual lo to out_lo
+};
+
+template <typename T>
+__device__ __forceinline__ float ld_as_float(const T* p);
+template <>
+__device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+
+// IS_TF32: fp32 words in smem, kind::tf32, UMMA_K = 8; else bf16, kind::f16, UMMA_K = 16
+template <int BN, bool IS_TF32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmB_hi,
+               const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
+               int M, int N, int K, int nseg, EpiArgs ep) {
+  using S = GemmSmem<BN>;
+  constexpr int STAGES = S::STAGES;
+  constexpr int BK = IS_TF32 ? 32 : 64;  // elements per 128-byte row
+  constexpr uint32_t IDESC = umma_idesc(IS_TF32 ? 2u : 1u, BM, BN);
+  constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * S::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+  const int k_iters = num_kb * nseg;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (nseg > 1) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      for (int it = 0; it < k_iters; ++it) {
+        const int seg = it / num_kb, kb = it - seg * num_kb;
+        // segment order: (Alo,Bhi), (Ahi,Blo), (Ahi,Bhi); single-segment runs use (hi,hi)
+        const CUtensorMap* ta = (nseg > 1 && seg == 0) ? &tmA_lo : &tmA_hi;
+        const CUtensorMap* tb = (nseg > 1 && seg == 1) ? &tmB_lo : &tmB_hi;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+        tma_load_2d(smem_a + stage * S::A_BYTES, ta, &full_bar[stage], kb * BK, m_blk * BM);
+        tma_load_2d(smem_b + stage * S::B_BYTES, tb, &full_bar[stage], kb * BK, n_blk * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * S::A_BYTES));
+        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * S::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte row
+          if constexpr (IS_TF32)
+            mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) ? 1u : 0u);
+          else
+            mma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int row = m_blk * BM + ew * 32 + lane;
+      const bool row_ok = row < M;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      float rs = 1.0f;
+      if (ep.rowscale != nullptr && row_ok) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const bool full = (n0 + 32 <= N);
+        if (ep.bias != nullptr) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < N) f[j] += __ldg(ep.bias + n0 + j);
+          }
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        } else if (ep.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (ep.colscale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < N) f[j] *= __ldg(ep.colscale + n0 + j) * rs;
+        } else if (ep.rowscale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] *= rs;
+        }
+        if (row_ok) {
+        if (ep.out_dtype == CCX_BF16) {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldc + n0;
+          const __nv_bfloat16* rrow =
+              ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + n0
+                          : nullptr;
+          const bool vec = full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
+                           (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+          if (vec) {
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(rrow + j));
+                float2 t;
+                t = unpack_bf16x2(r.x); f[j] += t.x; f[j + 1] += t.y;
+                t = unpack_bf16x2(r.y); f[j + 2] += t.x; f[j + 3] += t.y;
+                t = unpack_bf16x2(r.z); f[j + 4] += t.x; f[j + 5] += t.y;
+                t = unpack_bf16x2(r.w); f[j + 6] += t.x; f[j + 7] += t.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = pack_bf16x2(f[j], f[j + 1]);
+              o.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              o.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              o.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(orow + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + j < N) {
+                float y = f[j];
+                if (rrow) y += __bfloat162float(rrow[j]);
+                orow[j] = __float2bfloat16_rn(y);
+              }
+            }
+          }
+        } else {
+          float* orow = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n0;
+          float* lrow = ep.split ? ep.out_lo + (long long)row * ep.ldc + n0 : nullptr;
+          const float* rrow =
+              ep.residual ? reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0 : nullptr;
+          const bool vec = full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
+                           (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
+          if (vec) {
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
+                f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+              }
+            }
+            if (ep.split) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 h, l;
+                h.x = tf32_hi(f[j]);     l.x = f[j] - h.x;
+                h.y = tf32_hi(f[j + 1]); l.y = f[j + 1] - h.y;
+                h.z = tf32_hi(f[j + 2]); l.z = f[j + 2] - h.z;
+                h.w = tf32_hi(f[j + 3]); l.w = f[j + 3] - h.w;
+                *reinterpret_cast<float4*>(orow + j) = h;
+                *reinterpret_cast<float4*>(lrow + j) = l;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n0 + j < N) {
+                float y = f[j];
+                if (rrow) y += __ldg(rrow + j);
+                if (ep.split) {
+                  const float h = tf32_hi(y);
+                  orow[j] = h;
+                  lrow[j] = y - h;
+                } else {
+                  orow[j] = y;
+                }
+              }
+            }
+          }
+        }
+        }  // row_ok
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major [rows, cols] tensor, box = [box_rows, 128 bytes], 128-byte swizzle
+static int make_map_2d(CUtensorMap* map, const void* ptr, int is_f32, long long rows, long long cols,
+                       long long ld_elems, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return CCX_ERR_TMA;
+  const int es = is_f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld_elems * es) & 15)) return CCX_ERR_SHAPE;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * es)};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CCX_OK : CCX_ERR_TMA;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN, bool IS_TF32>
+static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo,
+                  const CUtensorMap& b_lo, int M, int N, int K, int nseg, const EpiArgs& ep,
+                  cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  auto kfn = gemm_tn_kernel<BN, IS_TF32>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
+      return CCX_ERR_CUDA;
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid < 1) return CCX_OK;
+  kfn<<<grid, NUM_THREADS, S::TOTAL, stream>>>(a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return g.M == 0 ? CCX_OK : CCX_ERR_SHAPE;
+  const bool tf32 = (g.in_dtype == CCX_F32);
+  const int BK = tf32 ? 32 : 64;
+  if (g.K % 8) return CCX_ERR_SHAPE;
+  if (!tf32 && g.out_dtype == CCX_F32 && g.split) return CCX_ERR_DTYPE;
+  if (tf32 && g.out_dtype != CCX_F32) return CCX_ERR_DTYPE;
+  (void)BK;
+  // tile-N choice: widest tile that still gives every SM work
+  int bn = g.force_bn;
+  if (bn == 0) {
+    const long long mt = (g.M + BM - 1) / BM;
+    if (g.N % 256 == 0 && mt * (g.N / 256) >= num_sms()) bn = 256;
+    else if (mt * ((g.N + 127) / 128) >= num_sms() / 2 || g.N <= 64) bn = 128;
+    else bn = 64;
+    if (g.N <= 64) bn = 64;
+  }
+  CUtensorMap a_hi, b_hi, a_lo, b_lo;
+  int rc;
+  if ((rc = make_map_2d(&a_hi, g.A, tf32, g.M, g.K, g.lda, BM))) return rc;
+  if ((rc = make_map_2d(&b_hi, g.B, tf32, g.N, g.K, g.ldb, bn))) return rc;
+  int nseg = 1;
+  if (tf32 && g.A_lo != nullptr && g.B_lo != nullptr) {
+    nseg = 3;
+    if ((rc = make_map_2d(&a_lo, g.A_lo, tf32, g.M, g.K, g.lda, BM))) return rc;
+    if ((rc = make_map_2d(&b_lo, g.B_lo, tf32, g.N, g.K, g.ldb, bn))) return rc;
+  } else {
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+  EpiArgs ep;
+  ep.out = g.C;
+  ep.out_lo = g.C_lo;
+  ep.bias = g.bias;
+  ep.colscale = g.colscale;
+  ep.rowscale = g.rowscale;
+  ep.residual = g.residual;
+  ep.ldc = g.ldc;
+  ep.ldr = g.ldr;
+  ep.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
+  ep.act = g.act;
+  ep.out_dtype = g.out_dtype;
+  ep.split = (g.split && g.C_lo != nullptr) ? 1 : 0;
+  if (tf32) {
+    if (bn == 256) return launch<256, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+    if (bn == 128) return launch<128, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+    return launch<64, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+  } else {
+    if (bn == 256) return launch<256, false>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+    if (bn == 128) return launch<128, false>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+    return launch<64, false>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+  }
+}
+
+}  // namespace ccx
