@@ -1,0 +1,9 @@
+"""B200-native (sm_100a) captioning hot path: drop-in modules for sa06840/ImageCaptioningConvNeXt.
+
+``Encoder``, ``DecoderWithAttention`` and ``TransformerDecoder`` keep the reference's nn.Module API
+(models/encoder.py, models/decoder.py, models/transformerDecoder.py) and run on hand-written CUDA kernels in
+``libccx.so`` (C ABI: include/ccx.h).  No eager / CPU fallback exists.
+"""
+from .encoder import Encoder  # noqa: F401
+
+__all__ = ["Encoder"]

@@ -1,0 +1,182 @@
+"""ctypes binding of libccx.so (the C ABI declared in include/ccx.h).
+
+There is NO fallback: if the shared library is missing or a kernel rejects a shape, this raises.  The library is
+built in-tree by ``make`` / ``__graft_entry__.build()`` for sm_100a only.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libccx.so")
+
+CCX_F32, CCX_BF16 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+MAX_BLOCKS = 64
+
+_vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [("A", _vp), ("A_lo", _vp), ("W", _vp), ("W_lo", _vp), ("C", _vp), ("C_lo", _vp),
+                ("bias", _vp), ("colscale", _vp), ("rowscale", _vp), ("residual", _vp),
+                ("lda", _i64), ("ldw", _i64), ("ldc", _i64), ("ldr", _i64),
+                ("M", _i32), ("N", _i32), ("K", _i32), ("rows_per_group", _i32),
+                ("act", _i32), ("in_dtype", _i32), ("out_dtype", _i32), ("split", _i32)]
+
+
+class CNBlockWeights(C.Structure):
+    _fields_ = [("dw_w", _vp), ("dw_b", _vp), ("ln_g", _vp), ("ln_b", _vp),
+                ("w1", _vp), ("w1_lo", _vp), ("b1", _vp),
+                ("w2", _vp), ("w2_lo", _vp), ("b2", _vp), ("layer_scale", _vp)]
+
+
+class DownsampleWeights(C.Structure):
+    _fields_ = [("ln_g", _vp), ("ln_b", _vp), ("w", _vp), ("w_lo", _vp), ("b", _vp)]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [("stem_w", _vp), ("stem_b", _vp), ("stem_ln_g", _vp), ("stem_ln_b", _vp),
+                ("blocks", CNBlockWeights * MAX_BLOCKS), ("down", DownsampleWeights * 3),
+                ("depths", _i32 * 4), ("dims", _i32 * 4), ("compute_dtype", _i32)]
+
+
+# name -> (restype, argtypes); must list every symbol include/ccx.h declares (tests/test_abi.py checks it)
+SIGNATURES = {
+    "ccx_version": (C.c_int, []),
+    "ccx_status_string": (C.c_char_p, [C.c_int]),
+    "ccx_num_sms": (C.c_int, []),
+    "ccx_linear": (C.c_int, [C.POINTER(LinearDesc), _vp]),
+    "ccx_split_tf32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "ccx_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "ccx_stem_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+    "ccx_dwconv7_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "ccx_ln_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_avgpool_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "ccx_encoder_run": (C.c_int, [C.POINTER(EncoderWeights), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
+                                  _sz, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built — there is no Python/CPU substitute."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()). "
+                "imagecaptioningconvnext_b200 has no CPU / eager fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().ccx_status_string(rc).decode()
+        raise RuntimeError(f"libccx {what} failed: {msg} (status {rc})")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt_code(dtype):
+    if dtype == torch.float32:
+        return CCX_F32
+    if dtype == torch.bfloat16:
+        return CCX_BF16
+    raise ValueError(f"unsupported compute dtype {dtype}; libccx computes in float32 (3xTF32) or bfloat16")
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor: imagecaptioningconvnext_b200 has no CPU path")
+
+
+# ------------------------------------------------------------------------------------------------
+# thin op wrappers (allocate outputs with torch, launch on the current stream)
+# ------------------------------------------------------------------------------------------------
+def split_tf32(x):
+    """fp32 tensor -> (hi, lo) fp32 tensors, hi exactly tf32-representable."""
+    x = x.contiguous()
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    check(lib().ccx_split_tf32(ptr(x), ptr(hi), ptr(lo), x.numel(), stream_ptr()), "split_tf32")
+    return hi, lo
+
+
+def cast_bf16(x):
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().ccx_cast_bf16(ptr(x), ptr(y), x.numel(), stream_ptr()), "cast_bf16")
+    return y
+
+
+class Operand:
+    """A GEMM operand prepared for the chosen compute dtype: bf16 tensor, or (hi, lo) fp32 pair."""
+    __slots__ = ("hi", "lo", "dtype")
+
+    def __init__(self, hi, lo, dtype):
+        self.hi, self.lo, self.dtype = hi, lo, dtype
+
+    @staticmethod
+    def prepare(x_fp32, compute_dtype):
+        if compute_dtype == torch.bfloat16:
+            return Operand(cast_bf16(x_fp32), None, torch.bfloat16)
+        hi, lo = split_tf32(x_fp32)
+        return Operand(hi, lo, torch.float32)
+
+    @staticmethod
+    def empty(shape, compute_dtype, device):
+        if compute_dtype == torch.bfloat16:
+            return Operand(torch.empty(shape, dtype=torch.bfloat16, device=device), None, torch.bfloat16)
+        return Operand(torch.empty(shape, dtype=torch.float32, device=device),
+                       torch.empty(shape, dtype=torch.float32, device=device), torch.float32)
+
+
+def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per_group=1, residual=None,
+           out=None, out_dtype=torch.float32, split=False):
+    """C = epilogue(A . W^T).  a, w: Operand (2-D, row-major, unit inner stride).  Returns a tensor, or an
+    Operand when split=True (fp32 compute only)."""
+    M, K = a.hi.shape
+    N, K2 = w.hi.shape
+    if K != K2 or a.dtype != w.dtype:
+        raise ValueError(f"linear: operand mismatch A{tuple(a.hi.shape)} {a.dtype} W{tuple(w.hi.shape)} {w.dtype}")
+    dev = a.hi.device
+    d = LinearDesc()
+    d.A, d.A_lo, d.W, d.W_lo = ptr(a.hi), ptr(a.lo), ptr(w.hi), ptr(w.lo)
+    res = None
+    if split:
+        res = Operand.empty((M, N), torch.float32, dev) if out is None else out
+        d.C, d.C_lo, d.ldc = ptr(res.hi), ptr(res.lo), res.hi.stride(0)
+        out_dtype = torch.float32
+    else:
+        res = torch.empty((M, N), dtype=out_dtype, device=dev) if out is None else out
+        d.C, d.C_lo, d.ldc = ptr(res), None, res.stride(0)
+        out_dtype = res.dtype
+    d.bias, d.colscale, d.rowscale = ptr(bias), ptr(colscale), ptr(rowscale)
+    d.residual = ptr(residual)
+    d.lda, d.ldw = a.hi.stride(0), w.hi.stride(0)
+    d.ldr = residual.stride(0) if residual is not None else 0
+    d.M, d.N, d.K = M, N, K
+    d.rows_per_group = rows_per_group
+    d.act = act
+    d.in_dtype, d.out_dtype = dt_code(a.dtype), dt_code(out_dtype)
+    d.split = 1 if split else 0
+    check(lib().ccx_linear(C.byref(d), stream_ptr()), f"linear M={M} N={N} K={K}")
+    return res

@@ -1,0 +1,202 @@
+// ccx_api.cu — extern "C" surface of libccx.so (declared in include/ccx.h) and the whole-encoder runner.
+#include "../../include/ccx.h"
+
+#include "ccx_common.cuh"
+#include "ccx_gemm.h"
+#include "ccx_ops.h"
+
+using namespace ccx;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int ccx_version(void) { return 100; }
+
+const char* ccx_status_string(int status) {
+  switch (status) {
+    case CCX_OK: return "ok";
+    case CCX_ERR_SHAPE: return "unsupported shape / alignment (no fallback path exists)";
+    case CCX_ERR_DTYPE: return "unsupported dtype combination";
+    case CCX_ERR_CUDA: {
+      cudaError_t e = cudaGetLastError();
+      return e == cudaSuccess ? "CUDA launch/config error" : cudaGetErrorString(e);
+    }
+    case CCX_ERR_TMA: return "cuTensorMapEncodeTiled failed";
+    case CCX_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown ccx status";
+  }
+}
+
+int ccx_num_sms(void) { return num_sms(); }
+
+int ccx_linear(const ccx_linear_desc* d, void* stream) {
+  if (d == nullptr) return CCX_ERR_SHAPE;
+  GemmDesc g;
+  g.A = d->A; g.A_lo = d->A_lo; g.B = d->W; g.B_lo = d->W_lo;
+  g.C = d->C; g.C_lo = d->C_lo;
+  g.bias = d->bias; g.colscale = d->colscale; g.rowscale = d->rowscale; g.residual = d->residual;
+  g.lda = d->lda; g.ldb = d->ldw; g.ldc = d->ldc; g.ldr = d->ldr;
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.rows_per_group = d->rows_per_group;
+  g.act = d->act; g.in_dtype = d->in_dtype; g.out_dtype = d->out_dtype; g.split = d->split;
+  return gemm_tn(g, as_stream(stream));
+}
+
+int ccx_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  return split_tf32(x, hi, lo, n, as_stream(stream));
+}
+int ccx_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
+  return cast_bf16(x, y, n, as_stream(stream));
+}
+
+int ccx_stem_ln(const float* images, const float* w_k, const float* bias, const float* ln_g, const float* ln_b,
+                float* out, int32_t B, int32_t Hin, int32_t Win, float eps, void* stream) {
+  return stem_ln(images, w_k, bias, ln_g, ln_b, out, B, Hin, Win, eps, as_stream(stream));
+}
+
+int ccx_dwconv7_ln(const float* x, const float* w_tap_major, const float* bias, const float* ln_g,
+                   const float* ln_b, void* out, float* out_lo, int32_t B, int32_t H, int32_t W, int32_t C,
+                   float eps, int32_t out_dtype, void* stream) {
+  return dwconv7_ln(x, w_tap_major, bias, ln_g, ln_b, out, out_lo, B, H, W, C, eps, out_dtype, as_stream(stream));
+}
+
+int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo, int64_t M,
+                int32_t C, float eps, int32_t out_dtype, int32_t merge, int32_t H, int32_t W, void* stream) {
+  return ln_rows(x, ln_g, ln_b, out, out_lo, M, C, eps, out_dtype, merge, H, W, as_stream(stream));
+}
+
+int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
+                     void* stream) {
+  return avgpool_nhwc(x, out, B, H, W, C, S, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// whole-encoder runner
+// ------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v) { return (v + 1023) & ~size_t(1023); }
+
+struct EncoderScratch {
+  size_t x_bytes, y_bytes, h_bytes;
+  size_t total;
+};
+static EncoderScratch encoder_scratch(int B, int Hin, int Win, int compute_dtype) {
+  EncoderScratch s;
+  const size_t px = static_cast<size_t>(B) * (Hin / 4) * (Win / 4);
+  const size_t es = (compute_dtype == CCX_BF16) ? 2 : 8;  // bf16, or fp32 hi + fp32 lo
+  s.x_bytes = align_up(px * 128 * 4);
+  s.y_bytes = align_up(px * 128 * es);
+  s.h_bytes = align_up(px * 512 * es);
+  s.total = 2 * s.x_bytes + s.y_bytes + s.h_bytes + 1024;
+  return s;
+}
+
+size_t ccx_encoder_workspace_bytes(int32_t B, int32_t Hin, int32_t Win, int32_t compute_dtype) {
+  if (B <= 0 || Hin < 32 || Win < 32) return 0;
+  return encoder_scratch(B, Hin, Win, compute_dtype).total;
+}
+
+int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float* out, int32_t B, int32_t Hin,
+                    int32_t Win, int32_t child_begin, int32_t child_end, const float* sd_rowscale,
+                    void* workspace, size_t workspace_bytes, void* stream_) {
+  if (w == nullptr || in == nullptr || out == nullptr) return CCX_ERR_SHAPE;
+  if (child_begin < 0 || child_end > 8 || child_begin >= child_end) return CCX_ERR_SHAPE;
+  if (B <= 0 || Hin < 32 || Win < 32 || (Hin % 32) != 0 || (Win % 32) != 0) return CCX_ERR_SHAPE;
+  const int cd = w->compute_dtype;
+  if (cd != CCX_F32 && cd != CCX_BF16) return CCX_ERR_DTYPE;
+  cudaStream_t stream = as_stream(stream_);
+  const EncoderScratch sc = encoder_scratch(B, Hin, Win, cd);
+  if (workspace == nullptr || workspace_bytes < sc.total) return CCX_ERR_WORKSPACE;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+  float* X0 = reinterpret_cast<float*>(base);
+  float* X1 = reinterpret_cast<float*>(base + sc.x_bytes);
+  uint8_t* Y = base + 2 * sc.x_bytes;
+  uint8_t* Hb = Y + sc.y_bytes;
+
+  const bool f32 = (cd == CCX_F32);
+  const float* cur = in;
+  int rc;
+  int blk_base[4];
+  {
+    int acc = 0;
+    for (int s = 0; s < 4; ++s) { blk_base[s] = acc; acc += w->depths[s]; }
+    if (acc > CCX_MAX_BLOCKS) return CCX_ERR_SHAPE;
+  }
+
+  for (int child = child_begin; child < child_end; ++child) {
+    const bool last_child = (child == child_end - 1);
+    if (child == 0) {
+      float* dst = last_child ? out : X0;
+      if ((rc = stem_ln(cur, w->stem_w, w->stem_b, w->stem_ln_g, w->stem_ln_b, dst, B, Hin, Win, 1e-6f, stream)))
+        return rc;
+      cur = dst;
+      continue;
+    }
+    const int stage = (child - 1) / 2;  // children 1,3,5,7 are stages 0..3 ; 2,4,6 downsample into stage 1..3
+    if (child & 1) {
+      const int C = w->dims[stage];
+      const int H = Hin >> (2 + stage), W = Win >> (2 + stage);
+      const long long M = static_cast<long long>(B) * H * W;
+      if (M > 0x7fffffffLL) return CCX_ERR_SHAPE;
+      float* y_hi = reinterpret_cast<float*>(Y);
+      float* y_lo = f32 ? y_hi + M * C : nullptr;
+      float* h_hi = reinterpret_cast<float*>(Hb);
+      float* h_lo = f32 ? h_hi + M * 4 * C : nullptr;
+      const int nblk = w->depths[stage];
+      for (int i = 0; i < nblk; ++i) {
+        const ccx_cnblock_weights& bw = w->blocks[blk_base[stage] + i];
+        const bool last = last_child && (i == nblk - 1);
+        float* dst;
+        if (last) dst = out;
+        else if (cur == X0 || cur == X1) dst = const_cast<float*>(cur);
+        else dst = X0;
+        if ((rc = dwconv7_ln(cur, bw.dw_w, bw.dw_b, bw.ln_g, bw.ln_b, Y, y_lo, B, H, W, C, 1e-6f, cd, stream)))
+          return rc;
+        GemmDesc g1;
+        g1.A = Y; g1.A_lo = y_lo; g1.B = bw.w1; g1.B_lo = f32 ? bw.w1_lo : nullptr;
+        g1.C = Hb; g1.C_lo = h_lo;
+        g1.bias = bw.b1;
+        g1.lda = C; g1.ldb = C; g1.ldc = 4 * C;
+        g1.M = static_cast<int>(M); g1.N = 4 * C; g1.K = C;
+        g1.act = CCX_ACT_GELU;
+        g1.in_dtype = cd; g1.out_dtype = cd; g1.split = f32 ? 1 : 0;
+        if ((rc = gemm_tn(g1, stream))) return rc;
+        GemmDesc g2;
+        g2.A = Hb; g2.A_lo = h_lo; g2.B = bw.w2; g2.B_lo = f32 ? bw.w2_lo : nullptr;
+        g2.C = dst;
+        g2.bias = bw.b2; g2.colscale = bw.layer_scale;
+        g2.rowscale = sd_rowscale ? sd_rowscale + static_cast<size_t>(blk_base[stage] + i) * B : nullptr;
+        g2.rows_per_group = H * W;
+        g2.residual = cur;
+        g2.lda = 4 * C; g2.ldb = 4 * C; g2.ldc = C; g2.ldr = C;
+        g2.M = static_cast<int>(M); g2.N = C; g2.K = 4 * C;
+        g2.in_dtype = cd; g2.out_dtype = CCX_F32;
+        if ((rc = gemm_tn(g2, stream))) return rc;
+        cur = dst;
+      }
+    } else {
+      // downsample child 2/4/6: LN2d over Cin + 2x2/s2 conv as patch-merge GEMM, into stage (child/2)
+      const int sin = child / 2 - 1;
+      const int Cin = w->dims[sin], Cout = w->dims[sin + 1];
+      const int H = Hin >> (2 + sin), W = Win >> (2 + sin);
+      const long long M = static_cast<long long>(B) * H * W;
+      const ccx_downsample_weights& dw = w->down[sin];
+      float* y_hi = reinterpret_cast<float*>(Y);
+      float* y_lo = f32 ? y_hi + M * Cin : nullptr;
+      if ((rc = ln_rows(cur, dw.ln_g, dw.ln_b, Y, y_lo, M, Cin, 1e-6f, cd, 1, H, W, stream))) return rc;
+      float* dst = last_child ? out : ((cur == X0) ? X1 : X0);
+      GemmDesc g;
+      g.A = Y; g.A_lo = y_lo; g.B = dw.w; g.B_lo = f32 ? dw.w_lo : nullptr;
+      g.C = dst;
+      g.bias = dw.b;
+      g.lda = 4 * Cin; g.ldb = 4 * Cin; g.ldc = Cout;
+      g.M = static_cast<int>(M / 4); g.N = Cout; g.K = 4 * Cin;
+      g.in_dtype = cd; g.out_dtype = CCX_F32;
+      if ((rc = gemm_tn(g, stream))) return rc;
+      cur = dst;
+    }
+  }
+  return CCX_OK;
+}
+
+}  // extern "C"

@@ -9,21 +9,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "../../include/ccx.h"
+
 namespace ccx {
 
-// ----------------------------------------------------------------------------
-// status codes returned by every extern "C" entry point (see include/ccx.h)
-// ----------------------------------------------------------------------------
-enum : int {
-  CCX_OK = 0,
-  CCX_ERR_SHAPE = -1,
-  CCX_ERR_DTYPE = -2,
-  CCX_ERR_CUDA = -3,
-  CCX_ERR_TMA = -4,
-  CCX_ERR_WORKSPACE = -5,
-};
-
-enum : int { CCX_F32 = 0, CCX_BF16 = 1 };
+// status codes (CCX_OK, CCX_ERR_*) and dtype codes (CCX_F32, CCX_BF16) come from the public header
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

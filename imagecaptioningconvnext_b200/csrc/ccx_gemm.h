@@ -1,5 +1,6 @@
 // ccx_gemm.h — internal descriptor for the tcgen05 GEMM launcher (not part of the public C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace ccx {
@@ -27,6 +28,13 @@ struct GemmDesc {
 };
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream);
+
+// driver entry point for building TMA descriptors (resolved through the runtime; no -lcuda needed)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn();
 int num_sms();
 
 }  // namespace ccx

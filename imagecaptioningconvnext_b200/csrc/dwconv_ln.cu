@@ -1,0 +1,244 @@
+// dwconv_ln.cu — channels-last depthwise 7x7 convolution fused with the LayerNorm that follows it.
+//
+// Replaces, per CNBlock, torchvision/models/convnext.py:52-54
+//     Conv2d(C, C, kernel_size=7, padding=3, groups=C, bias=True) -> Permute -> LayerNorm(C, eps=1e-6)
+// (called from the reference through models/encoder.py:24).
+//
+// Layout: x is the fp32 NHWC residual stream [B, H, W, C]; the output is the row-major [B*H*W, C]
+// A-operand of the following pointwise GEMM, written either as bf16 or as a (tf32-hi, fp32-lo) pair.
+//
+// Work decomposition
+//   * one CTA = an 8x8 pixel tile x 128 channels; the (8+6)x(8+6)x128 fp32 halo tile is brought in by ONE
+//     4-D TMA bulk-tensor copy (out-of-bounds = zero fill gives the conv padding for free),
+//   * a thread-block cluster of C/128 CTAs covers all channels of the same pixel tile, and the LayerNorm
+//     statistics (sum, sum of squares per pixel) are exchanged through distributed shared memory,
+//   * inside a CTA: warp = (pixel half p, channel group g): a 4x8 output patch for 32 channels; every lane
+//     owns ONE channel, keeps its 49 filter taps in registers and 32 fp32 accumulators, so each halo value is
+//     read from shared memory exactly once per thread (140 conflict-free LDS.32 for 1568 FFMA).
+#include <cooperative_groups.h>
+
+#include "ccx_common.cuh"
+#include "ccx_gemm.h"
+
+namespace cg = cooperative_groups;
+
+namespace ccx {
+
+static constexpr int DW_TILE = 8;
+static constexpr int DW_HALO = DW_TILE + 6;  // 14
+static constexpr int DW_CH = 128;            // channels per CTA
+static constexpr int DW_THREADS = 256;
+static constexpr int DW_TILE_BYTES = DW_HALO * DW_HALO * DW_CH * 4;  // 100,352
+static constexpr int DW_SMEM = DW_TILE_BYTES + 128 /*align*/ + 6144 /*stats*/;
+
+struct DwArgs {
+  const float* w;      // [49][C]  tap-major depthwise filter
+  const float* bias;   // [C]
+  const float* gamma;  // [C]
+  const float* beta;   // [C]
+  void* out;           // [B*H*W, C] bf16 or fp32 (hi)
+  float* out_lo;       // fp32 lo part or nullptr
+  int B, H, W, C;
+  int tiles_w, tiles_h;
+  float eps;
+  int out_dtype;       // CCX_F32 / CCX_BF16
+};
+
+// sum the 32 per-lane arrays v[0..31] across the warp; lane L ends up with the total of element L in v[0]
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DW_THREADS, 2)
+dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
+  extern __shared__ uint8_t dw_smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+  float* tile = reinterpret_cast<float*>(sm);                        // [14][14][128]
+  float* part = reinterpret_cast<float*>(sm + DW_TILE_BYTES);        // [2 stat][2 p][4 g][32 px] = 512 f
+  float* clpart = part + 512;                                        // [8 rank][2 stat][64 px]   = 1024 f (max)
+  __shared__ uint64_t bar;
+  __shared__ float s_mean[64], s_rstd[64];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nc = a.C / DW_CH;                 // cluster size (gridDim.x)
+  const int crank = blockIdx.x;               // cluster spans gridDim.x exactly
+  const int b = blockIdx.z;
+  const int th = blockIdx.y / a.tiles_w, tw = blockIdx.y - th * a.tiles_w;
+  const int h0 = th * DW_TILE, w0 = tw * DW_TILE;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = warp >> 2;   // pixel half: output rows p*4 .. p*4+3 of the tile
+  const int g = warp & 3;    // channel group of 32 inside the CTA's 128
+  const int ch_local = g * 32 + lane;
+  const int ch = crank * DW_CH + ch_local;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, DW_TILE_BYTES);
+    tma_load_4d(tile, &tmX, &bar, crank * DW_CH, w0 - 3, h0 - 3, b);
+  }
+
+  // filter taps and affine parameters while the tile is in flight
+  float wt[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wt[t] = __ldg(a.w + t * a.C + ch);
+  const float bias = __ldg(a.bias + ch);
+  const float gam = __ldg(a.gamma + ch);
+  const float bet = __ldg(a.beta + ch);
+
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = bias;
+
+  mbar_wait(&bar, 0);
+
+  const float* tp = tile + (p * 4) * DW_HALO * DW_CH + ch_local;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int c = 0; c < DW_HALO; ++c) {
+      const float v = tp[(r * DW_HALO + c) * DW_CH];
+#pragma unroll
+      for (int oh = 0; oh < 4; ++oh) {
+        const int kr = r - oh;
+        if (kr < 0 || kr > 6) continue;
+#pragma unroll
+        for (int ow = 0; ow < 8; ++ow) {
+          const int kc = c - ow;
+          if (kc < 0 || kc > 6) continue;
+          acc[oh * 8 + ow] = fmaf(v, wt[kr * 7 + kc], acc[oh * 8 + ow]);
+        }
+      }
+    }
+  }
+
+  // ---- LayerNorm statistics: per pixel over all C channels (this warp: 32 of them) ----
+  {
+    float s1[32], s2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s1[i] = acc[i]; s2[i] = acc[i] * acc[i]; }
+    warp_transpose_reduce32(s1, lane);
+    warp_transpose_reduce32(s2, lane);
+    part[((0 * 2 + p) * 4 + g) * 32 + lane] = s1[0];
+    part[((1 * 2 + p) * 4 + g) * 32 + lane] = s2[0];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    // thread -> (stat, p, px): sum the 4 channel-group partials, publish to every CTA of the cluster
+    const int stat = threadIdx.x >> 6, pp = (threadIdx.x >> 5) & 1, px = threadIdx.x & 31;
+    const float* src = part + ((stat * 2 + pp) * 4) * 32 + px;
+    const float tot = src[0] + src[32] + src[64] + src[96];
+    for (int r = 0; r < nc; ++r) {
+      float* dst = cluster.map_shared_rank(clpart, r);
+      dst[(crank * 2 + stat) * 64 + pp * 32 + px] = tot;
+    }
+  }
+  cluster.sync();
+  if (threadIdx.x < 64) {
+    float s = 0.f, q = 0.f;
+    for (int r = 0; r < nc; ++r) {
+      s += clpart[(r * 2 + 0) * 64 + threadIdx.x];
+      q += clpart[(r * 2 + 1) * 64 + threadIdx.x];
+    }
+    const float inv = 1.0f / static_cast<float>(a.C);
+    const float mean = s * inv;
+    const float var = fmaxf(q * inv - mean * mean, 0.0f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+  }
+  __syncthreads();
+
+  // ---- normalise + write ----
+#pragma unroll
+  for (int oh = 0; oh < 4; ++oh) {
+    const int h = h0 + p * 4 + oh;
+#pragma unroll
+    for (int ow = 0; ow < 8; ++ow) {
+      const int w = w0 + ow;
+      const int px = p * 32 + oh * 8 + ow;
+      const float y = (acc[oh * 8 + ow] - s_mean[px]) * s_rstd[px] * gam + bet;
+      if (h < a.H && w < a.W) {
+        const long long m = (static_cast<long long>(b) * a.H + h) * a.W + w;
+        if (a.out_dtype == CCX_BF16) {
+          reinterpret_cast<__nv_bfloat16*>(a.out)[m * a.C + ch] = __float2bfloat16_rn(y);
+        } else if (a.out_lo != nullptr) {
+          const float hi = tf32_hi(y);
+          reinterpret_cast<float*>(a.out)[m * a.C + ch] = hi;
+          a.out_lo[m * a.C + ch] = y - hi;
+        } else {
+          reinterpret_cast<float*>(a.out)[m * a.C + ch] = y;
+        }
+      }
+    }
+  }
+  // no trailing cluster barrier: every remote store into a CTA's clpart happened before the barrier above
+}
+
+int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float* gamma, const float* beta,
+               void* out, float* out_lo, int B, int H, int W, int C, float eps, int out_dtype,
+               cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || B > 65535) return CCX_ERR_SHAPE;
+  if (C % DW_CH != 0 || C / DW_CH > 8 || C < DW_CH) return CCX_ERR_SHAPE;
+  if (out_dtype != CCX_F32 && out_dtype != CCX_BF16) return CCX_ERR_DTYPE;
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return CCX_ERR_TMA;
+  if (reinterpret_cast<uintptr_t>(x) & 15) return CCX_ERR_SHAPE;
+
+  CUtensorMap tm;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {DW_CH, DW_HALO, DW_HALO, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return CCX_ERR_TMA;
+
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
+        cudaSuccess)
+      return CCX_ERR_CUDA;
+    configured = true;
+  }
+  DwArgs a;
+  a.w = w49c; a.bias = bias; a.gamma = gamma; a.beta = beta;
+  a.out = out; a.out_lo = out_lo;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.tiles_w = (W + DW_TILE - 1) / DW_TILE;
+  a.tiles_h = (H + DW_TILE - 1) / DW_TILE;
+  a.eps = eps;
+  a.out_dtype = out_dtype;
+
+  const int nc = C / DW_CH;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nc, a.tiles_w * a.tiles_h, B);
+  cfg.blockDim = dim3(DW_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = DW_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = nc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+  return CCX_OK;
+}
+
+}  // namespace ccx

@@ -328,12 +328,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
+PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
   if (fn == nullptr) {
     void* p = nullptr;

@@ -1,0 +1,164 @@
+/* ccx.h — public C ABI of libccx.so, the sm_100a kernel library behind the captioning hot path.
+ *
+ * The reference (sa06840/ImageCaptioningConvNeXt) has no FFI of its own: its hot path is three nn.Modules
+ * (models/encoder.py:14-34, models/decoder.py:34-172, models/transformerDecoder.py:53-168) that call
+ * torch / torchvision library ops.  Each entry point below replaces one group of those library calls; the
+ * reference call site it stands in for is cited next to it.  The Python host side
+ * (imagecaptioningconvnext_b200/*.py) binds these with ctypes and keeps the reference's nn.Module API.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the library never allocates, never
+ *     synchronises and keeps no global state besides one-time kernel attribute setup;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - every function returns CCX_OK (0) or a negative CCX_ERR_* code; ccx_status_string() names it;
+ *   - matrices are row-major; "linear" weights are [out_features, in_features] like torch.nn.Linear;
+ *   - dtype codes: CCX_F32 = 0, CCX_BF16 = 1.  "fp32 compute" means 3xTF32 on the tensor cores: operands are
+ *     passed as a (hi, lo) pair of fp32 arrays with hi exactly representable in tf32 (ccx_split_tf32 makes one).
+ *   - no CPU fallback exists anywhere: a shape the kernels do not support returns CCX_ERR_SHAPE.
+ */
+#ifndef CCX_H_
+#define CCX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CCX_API __attribute__((visibility("default")))
+#else
+#define CCX_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCX_OK 0
+#define CCX_ERR_SHAPE (-1)
+#define CCX_ERR_DTYPE (-2)
+#define CCX_ERR_CUDA (-3)
+#define CCX_ERR_TMA (-4)
+#define CCX_ERR_WORKSPACE (-5)
+
+#define CCX_F32 0
+#define CCX_BF16 1
+
+#define CCX_ACT_NONE 0
+#define CCX_ACT_GELU 1 /* exact erf GELU (nn.GELU default) */
+#define CCX_ACT_RELU 2
+
+CCX_API int ccx_version(void);
+CCX_API const char* ccx_status_string(int status);
+CCX_API int ccx_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction  C[M,N] = epilogue(A[M,K] . W[N,K]^T)  on tcgen05 / TMEM, operands by TMA.
+ * Replaces every nn.Linear / 1x1-equivalent conv on the path:
+ *   torchvision/models/convnext.py:55-57 (CNBlock MLP), :146-151 (downsample conv as patch-merge GEMM),
+ *   models/decoder.py:19-21,50-54, models/transformerDecoder.py:84-85, torch/nn/modules/transformer.py.
+ * epilogue(y) = act(y + bias[n]) * colscale[n] * rowscale[m / rows_per_group] + residual[m,n]
+ * in_dtype CCX_BF16: A, W bf16; A_lo/W_lo ignored.  in_dtype CCX_F32: A/W are tf32-hi parts, A_lo/W_lo
+ * the fp32 remainders (3xTF32); if both *_lo are NULL a single TF32 pass is run.
+ * split != 0 (fp32 out only): C receives tf32-hi(y), C_lo the remainder (ready to be the next A operand).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ccx_linear_desc {
+  const void* A;
+  const void* A_lo;
+  const void* W;
+  const void* W_lo;
+  void* C;
+  float* C_lo;
+  const float* bias;     /* [N] or NULL */
+  const float* colscale; /* [N] or NULL (layer_scale) */
+  const float* rowscale; /* [ceil(M/rows_per_group)] or NULL (stochastic-depth noise/(1-p)) */
+  const void* residual;  /* [M, ldr] dtype of C, or NULL */
+  int64_t lda, ldw, ldc, ldr; /* leading dimensions in elements */
+  int32_t M, N, K;
+  int32_t rows_per_group;
+  int32_t act;
+  int32_t in_dtype;
+  int32_t out_dtype;
+  int32_t split;
+} ccx_linear_desc;
+CCX_API int ccx_linear(const ccx_linear_desc* d, void* stream);
+
+/* fp32 -> (tf32 hi, fp32 lo) and fp32 -> bf16 operand preparation (weights once, activations in epilogues) */
+CCX_API int ccx_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+CCX_API int ccx_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ConvNeXt pieces (channels-last fp32 residual stream [B,H,W,C]).
+ * ------------------------------------------------------------------------------------------------ */
+/* Conv2d(3,128,4,4)+bias -> LayerNorm2d: torchvision/models/convnext.py:120-131.
+ * images NCHW fp32 [B,3,Hin,Win]; w_k [48][128] with k = c*16+kh*4+kw; out NHWC fp32 [B,Hin/4,Win/4,128]. */
+CCX_API int ccx_stem_ln(const float* images, const float* w_k, const float* bias, const float* ln_g, const float* ln_b,
+                float* out, int32_t B, int32_t Hin, int32_t Win, float eps, void* stream);
+
+/* Depthwise Conv2d(C,C,7,padding=3,groups=C)+bias -> LayerNorm(C): torchvision/models/convnext.py:52-54.
+ * x NHWC fp32; w_tap_major [49][C]; out [B*H*W, C] as bf16 (out_lo NULL) or tf32 (hi, lo) fp32 pair, or plain
+ * fp32 when out_dtype == CCX_F32 and out_lo == NULL.  C must be a multiple of 128, at most 1024. */
+CCX_API int ccx_dwconv7_ln(const float* x, const float* w_tap_major, const float* bias, const float* ln_g,
+                   const float* ln_b, void* out, float* out_lo, int32_t B, int32_t H, int32_t W, int32_t C,
+                   float eps, int32_t out_dtype, void* stream);
+
+/* Row LayerNorm over C of x[M,C] fp32 (torchvision LayerNorm2d, convnext.py:31-36).  merge != 0 additionally
+ * scatters row (b,h,w) to row (b,h/2,w/2), column block (h%2)*2+(w%2) of a [M/4, 4C] matrix — the im2col of the
+ * k=2,s=2 downsample conv (convnext.py:146-151), whose weight the host re-orders to [Cout][(kh,kw,c)]. */
+CCX_API int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo, int64_t M,
+                int32_t C, float eps, int32_t out_dtype, int32_t merge, int32_t H, int32_t W, void* stream);
+
+/* AdaptiveAvgPool2d((S,S)) + permute(0,2,3,1): models/encoder.py:25-26.  x NHWC fp32 -> out [B,S,S,C] fp32. */
+CCX_API int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
+                     void* stream);
+
+/* Whole-encoder runner: children [child_begin, child_end) of convnext_base().features
+ * (0 stem, 1 stage1, 2 down, 3 stage2, 4 down, 5 stage3, 6 down, 7 stage4) = models/encoder.py:24.
+ * One call = the full launch sequence on `stream` (no host sync), so the Python side pays one FFI call. */
+typedef struct ccx_cnblock_weights {
+  const float* dw_w; /* [49][C] */
+  const float* dw_b;
+  const float* ln_g;
+  const float* ln_b;
+  const void* w1; /* [4C][C] bf16, or tf32 hi */
+  const void* w1_lo;
+  const float* b1;
+  const void* w2; /* [C][4C] */
+  const void* w2_lo;
+  const float* b2;
+  const float* layer_scale; /* [C] */
+} ccx_cnblock_weights;
+
+typedef struct ccx_downsample_weights {
+  const float* ln_g;
+  const float* ln_b;
+  const void* w; /* [2C][4C], columns ordered (kh,kw,c) */
+  const void* w_lo;
+  const float* b;
+} ccx_downsample_weights;
+
+#define CCX_MAX_BLOCKS 64
+typedef struct ccx_encoder_weights {
+  const float* stem_w; /* [48][128] */
+  const float* stem_b;
+  const float* stem_ln_g;
+  const float* stem_ln_b;
+  ccx_cnblock_weights blocks[CCX_MAX_BLOCKS]; /* stage-major */
+  ccx_downsample_weights down[3];
+  int32_t depths[4]; /* 3,3,27,3 */
+  int32_t dims[4];   /* 128,256,512,1024 */
+  int32_t compute_dtype;
+} ccx_encoder_weights;
+
+/* bytes of scratch needed by ccx_encoder_run for a batch of B images of Hin x Win */
+CCX_API size_t ccx_encoder_workspace_bytes(int32_t B, int32_t Hin, int32_t Win, int32_t compute_dtype);
+
+/* in: NCHW fp32 images when child_begin == 0, else the NHWC fp32 stream entering child_begin.
+ * out: NHWC fp32 stream leaving child_end-1 (may alias `in` only when no stem/downsample is in range).
+ * sd_rowscale: [total_blocks][B] stochastic-depth row factors (train mode, tv:ops/stochastic_depth.py:8-44) or NULL. */
+CCX_API int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float* out, int32_t B, int32_t Hin,
+                    int32_t Win, int32_t child_begin, int32_t child_end, const float* sd_rowscale,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCX_H_ */

@@ -1,0 +1,72 @@
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference modules.
+
+Run in the build container only (needs /root/reference; the GPU box never runs this):
+    python tests/golden/make_golden.py
+The reference ships no tests or known-answer vectors, so the oracle (oracle/*.py) is pinned against
+outputs of the reference itself: reference nn.Modules imported from /root/reference with three shims
+(no-download convnext_base, gensim stub, matplotlib/skimage stubs), random-init weights under fixed seeds,
+synthetic inputs.  Only (seed, small inputs, outputs) are stored — weights are regenerated from the seed.
+"""
+import os
+import sys
+import types
+
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+
+def install_shims():
+    import torchvision
+
+    real = torchvision.models.convnext_base
+
+    def convnext_base_no_download(*a, **k):  # models/encoder.py:18 asks for IMAGENET1K_V1 (network)
+        k["weights"] = None
+        return real(*a[:0], **k)
+
+    torchvision.models.convnext_base = convnext_base_no_download
+    for name in ("gensim", "gensim.downloader", "gensim.models", "matplotlib", "matplotlib.pyplot",
+                 "matplotlib.cm", "skimage", "skimage.transform"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["gensim.models"].KeyedVectors = type("KeyedVectors", (), {})
+    sys.modules["gensim"].downloader = sys.modules["gensim.downloader"]
+    sys.modules["gensim"].models = sys.modules["gensim.models"]
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].cm = sys.modules["matplotlib.cm"]
+    sys.modules["skimage"].transform = sys.modules["skimage.transform"]
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def golden_encoder():
+    """Reference Encoder (models/encoder.py) on 1 synthetic 256x256 image and 2 synthetic 64x64 images."""
+    from models.encoder import Encoder
+    from oracle.encoder_oracle import random_encoder_state
+
+    out = {}
+    for name, seed, shape, s in (("img256_s7", 0, (1, 3, 256, 256), 7), ("img64_s7", 1, (2, 3, 64, 64), 7),
+                                 ("img256_s14", 0, (1, 3, 256, 256), 14)):
+        torch.manual_seed(seed)
+        enc = Encoder(encoded_image_size=s).eval()
+        sd = random_encoder_state(seed=seed, layer_scale=1.0)
+        enc.load_state_dict(sd)
+        g = torch.Generator().manual_seed(1234 + seed)
+        x = torch.randn(*shape, generator=g)
+        with torch.no_grad():
+            y = enc(x).contiguous()
+        out[name] = {"weight_seed": seed, "input_seed": 1234 + seed, "shape": shape, "enc_size": s, "out": y}
+        print(name, tuple(y.shape), float(y.abs().max()), float(y.std()))
+    torch.save(out, os.path.join(HERE, "encoder.pt"))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    torch.set_flush_denormal(True)
+    install_shims()
+    which = sys.argv[1:] or ["encoder"]
+    for w in which:
+        globals()["golden_" + w]()

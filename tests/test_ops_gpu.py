@@ -1,0 +1,133 @@
+"""GPU parity of the individual C-ABI entry points against plain torch fp32 ops on the same inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(seed=0):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("C,H,W,B", [(128, 64, 64, 2), (256, 32, 32, 2), (512, 16, 16, 3), (1024, 8, 8, 3),
+                                     (128, 13, 21, 1), (384, 5, 9, 2)])
+@pytest.mark.parametrize("mode", ["bf16", "split", "plain"])
+def test_dwconv7_ln(C, H, W, B, mode):
+    from imagecaptioningconvnext_b200 import _lib
+    g = _g(C + H)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(C, 1, 7, 7, generator=g) * 0.2
+    b = torch.randn(C, generator=g)
+    gam = 1 + 0.3 * torch.randn(C, generator=g)
+    bet = 0.3 * torch.randn(C, generator=g)
+    ref = F.layer_norm(F.conv2d(x, w, b, padding=3, groups=C).permute(0, 2, 3, 1), (C,), gam, bet, 1e-6)
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wd = w.reshape(C, 49).t().contiguous().cuda()
+    M = B * H * W
+    if mode == "bf16":
+        out = torch.empty(M, C, dtype=torch.bfloat16, device="cuda")
+        lo = None
+        dt = _lib.CCX_BF16
+    else:
+        out = torch.empty(M, C, dtype=torch.float32, device="cuda")
+        lo = torch.empty_like(out) if mode == "split" else None
+        dt = _lib.CCX_F32
+    rc = _lib.lib().ccx_dwconv7_ln(xd.data_ptr(), wd.data_ptr(), b.cuda().data_ptr(), gam.cuda().data_ptr(),
+                                   bet.cuda().data_ptr(), out.data_ptr(), _lib.ptr(lo), B, H, W, C, 1e-6, dt,
+                                   _lib.stream_ptr())
+    _lib.check(rc)
+    y = out.float() + (lo if lo is not None else 0)
+    tol = 1e-2 if mode == "bf16" else 2e-5
+    assert rel_err(y.view(B, H, W, C), ref) < tol
+    if mode == "split":  # hi must be exactly tf32-representable
+        assert int((out.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 256, 256), (1, 64, 96), (3, 32, 32)])
+def test_stem_ln(B, H, W):
+    from imagecaptioningconvnext_b200 import _lib
+    g = _g(B)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(128, 3, 4, 4, generator=g) * 0.1
+    b = torch.randn(128, generator=g)
+    gam, bet = 1 + 0.2 * torch.randn(128, generator=g), 0.2 * torch.randn(128, generator=g)
+    ref = F.layer_norm(F.conv2d(x, w, b, stride=4).permute(0, 2, 3, 1), (128,), gam, bet, 1e-6)
+    out = torch.empty(B, H // 4, W // 4, 128, device="cuda")
+    wk = w.reshape(128, 48).t().contiguous().cuda()
+    _lib.check(_lib.lib().ccx_stem_ln(x.cuda().data_ptr(), wk.data_ptr(), b.cuda().data_ptr(), gam.cuda().data_ptr(),
+                                      bet.cuda().data_ptr(), out.data_ptr(), B, H, W, 1e-6, _lib.stream_ptr()))
+    assert rel_err(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("C", [128, 256, 512])
+def test_ln_rows_patchmerge_equals_ln2d_plus_conv_im2col(C):
+    from imagecaptioningconvnext_b200 import _lib
+    g = _g(C)
+    B, H, W = 2, 8, 12
+    x = torch.randn(B, H, W, C, generator=g)
+    gam, bet = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    wc = torch.randn(2 * C, C, 2, 2, generator=g) * 0.05
+    ln = F.layer_norm(x, (C,), gam, bet, 1e-6)
+    ref = F.conv2d(ln.permute(0, 3, 1, 2), wc, None, stride=2).permute(0, 2, 3, 1)
+    out = torch.empty(B * H * W // 4, 4 * C, device="cuda")
+    _lib.check(_lib.lib().ccx_ln_rows(x.cuda().data_ptr(), gam.cuda().data_ptr(), bet.cuda().data_ptr(),
+                                      out.data_ptr(), None, B * H * W, C, 1e-6, _lib.CCX_F32, 1, H, W,
+                                      _lib.stream_ptr()))
+    wm = wc.permute(0, 2, 3, 1).reshape(2 * C, 4 * C)
+    got = (out.cpu() @ wm.t()).view(B, H // 2, W // 2, 2 * C)
+    assert rel_err(got, ref) < 1e-4
+    # plain (no merge) bf16 output
+    o2 = torch.empty(B * H * W, C, dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().ccx_ln_rows(x.cuda().data_ptr(), gam.cuda().data_ptr(), bet.cuda().data_ptr(),
+                                      o2.data_ptr(), None, B * H * W, C, 1e-6, _lib.CCX_BF16, 0, H, W,
+                                      _lib.stream_ptr()))
+    assert rel_err(o2.float().view(B, H, W, C), ln) < 1e-2
+
+
+@pytest.mark.parametrize("H,S", [(8, 7), (8, 14), (8, 1), (2, 7), (16, 7)])
+def test_avgpool_nhwc(H, S):
+    from imagecaptioningconvnext_b200 import _lib
+    x = torch.randn(3, 1024, H, H, generator=_g(H))
+    ref = F.adaptive_avg_pool2d(x, (S, S)).permute(0, 2, 3, 1)
+    out = torch.empty(3, S, S, 1024, device="cuda")
+    xd = x.permute(0, 2, 3, 1).contiguous().cuda()
+    _lib.check(_lib.lib().ccx_avgpool_nhwc(xd.data_ptr(), out.data_ptr(), 3, H, H, 1024, S, _lib.stream_ptr()))
+    assert rel_err(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 192), (77, 9490, 512), (4096, 512, 128),
+                                   (1000, 512, 2048), (5, 1536, 512), (1, 512, 1024)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_epilogues(M, N, K, dtype):
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import Operand
+    g = _g(M + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    cs = torch.rand(N, generator=g) + 0.5
+    res = torch.randn(M, N, generator=g)
+    rpg = 7
+    rs = torch.rand((M + rpg - 1) // rpg, generator=g) + 0.5
+    A, Wt = Operand.prepare(a.cuda(), dtype), Operand.prepare(w.cuda(), dtype)
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    # bias only
+    y = _lib.linear(A, Wt, bias=bias.cuda())
+    assert rel_err(y, a @ w.t() + bias) < tol
+    # GELU
+    y = _lib.linear(A, Wt, bias=bias.cuda(), act=_lib.ACT_GELU)
+    assert rel_err(y, F.gelu(a @ w.t() + bias)) < tol
+    # ReLU + layer-scale + row-scale + residual
+    y = _lib.linear(A, Wt, bias=bias.cuda(), act=_lib.ACT_RELU, colscale=cs.cuda(), rowscale=rs.cuda(),
+                    rows_per_group=rpg, residual=res.cuda())
+    ref = F.relu(a @ w.t() + bias) * cs * rs.repeat_interleave(rpg)[:M, None] + res
+    assert rel_err(y, ref) < tol
+    if dtype == torch.float32:
+        op = _lib.linear(A, Wt, bias=bias.cuda(), split=True)
+        assert rel_err(op.hi + op.lo, a @ w.t() + bias) < tol
+    else:
+        y = _lib.linear(A, Wt, bias=bias.cuda(), out_dtype=torch.bfloat16)
+        assert y.dtype == torch.bfloat16 and rel_err(y.float(), a @ w.t() + bias) < tol
