@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the captioning hot path (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32] [--batch B]
+
+Workload (BASELINE.json configs[1]): ``Encoder.forward`` on a batch of 64 synthetic 256x256 images per GPU.
+One "step" = one Encoder.forward over one batch.  N > 1 (launched by torchrun, one rank per GPU): every rank runs
+its own batch (weak scaling, no data-path collective — inference shards by sample).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, live, vs MEASURED_PEAKS.json
+  kernels       per-kernel-kind breakdown from the same instrumented pass (ms share, achieved TFLOP/s or GB/s)
+  cpu_baseline  the oracle (CPU restatement of the reference's torchvision/torch arithmetic) on the host cores
+  e2e           same metric through the public nn.Module call with pinned HOST input and a D2H read of the result
+``--impl reference`` times the reference's CPU implementation of the same path (the oracle port: the reference
+itself is pure Python on torchvision and /root/reference does not exist on the GPU box) with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENCODER_GFLOP_PER_IMAGE = 40.11   # 20.054 GMAC per 256x256 image
+L2_BYTES = 126 * 2 ** 20
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_images(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, 256, 256, generator=g)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_encoder_throughput(sample_images, steps, warmup):
+    """images/s of the oracle's Encoder.forward restatement (fp32, all host threads)."""
+    from oracle.encoder_oracle import encoder_forward, random_encoder_state
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_flush_denormal(True)   # exact-GELU tails make denormals: 14x slowdown otherwise
+    sd = random_encoder_state(seed=0, layer_scale=1.0)
+    x = synthetic_images(sample_images, 1234)
+    with torch.no_grad():
+        for _ in range(warmup):
+            encoder_forward(sd, x, 7)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            encoder_forward(sd, x, 7)
+        dt = time.perf_counter() - t0
+    return sample_images * steps / dt, cores, dt / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 4
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    ips, cores, spstep = cpu_encoder_throughput(sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "encoder_forward_images_per_sec", "value": ips, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spstep * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args, sample_note=f"CPU arm: each step = {sample} of the 64 images"),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} synthetic 256x256 images per step, {steps} steps, fp32, "
+                                   f"torch {torch.__version__} CPU ops, flush-denormal on"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_note=None):
+    c = {"workload": f"Encoder.forward (ConvNeXt-Base features + AdaptiveAvgPool 7x7), batch {args.batch} per GPU, "
+                     f"256x256 synthetic images (BASELINE.json configs[1])",
+         "batch_per_gpu": args.batch, "image": "3x256x256", "encoded_image_size": 7,
+         "weights": "random init (torchvision initialiser, seed 0), layer_scale=1.0",
+         "l2_policy": "4 input batches rotated (201 MB > 126 MB L2); activations per step (>2 GB) exceed L2"}
+    if sample_note:
+        c["note"] = sample_note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from imagecaptioningconvnext_b200 import Encoder, _lib
+    from oracle.encoder_oracle import random_encoder_state
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    enc = Encoder(encoded_image_size=7, compute_dtype=dtype)
+    enc.load_state_dict(random_encoder_state(seed=0, layer_scale=1.0))
+    enc = enc.to(dev).eval()
+
+    B = args.batch
+    nbuf = 4
+    host = [synthetic_images(B, 1234 + rank * 16 + i).pin_memory() for i in range(nbuf)]
+    devbuf = [h.to(dev) for h in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    with torch.no_grad():
+        for i in range(args.warmup):
+            enc(devbuf[i % nbuf])
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            out = enc(devbuf[i % nbuf])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public call, host buffers ----------------------------------------
+    with torch.no_grad():
+        stage = torch.empty_like(devbuf[0])
+        res_host = torch.empty((B, 7, 7, 1024), dtype=torch.float32).pin_memory()
+        for i in range(2):
+            stage.copy_(host[i % nbuf], non_blocking=True)
+            res_host.copy_(enc(stage), non_blocking=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            stage.copy_(host[i % nbuf], non_blocking=True)        # H2D of this step's images (pinned)
+            res_host.copy_(enc(stage), non_blocking=True)         # D2H of this step's features
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    # ---- instrumented pass: per-kernel CUDA events (same steps, same data) -------------------------
+    with torch.no_grad():
+        torch.cuda.synchronize()
+        _lib.prof_begin()
+        for i in range(args.steps):
+            enc(devbuf[i % nbuf])
+        prof = _lib.prof_end()
+    if world > 1:
+        dist.barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    kernels = {}
+    for k, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        rate = v["work"] / (v["ms"] * 1e-3) if v["ms"] > 0 else 0.0
+        kernels[k] = {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+                      "share": v["ms"] / tot_ms,
+                      ("tflops" if k == "gemm" else "gbs"): rate / (1e12 if k == "gemm" else 1e9)}
+    g = prof["gemm"]
+    achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"] if dtype == torch.bfloat16 else peaks["bf16_tflops_sustained"] / 6.0
+    roofline = {"kernel": "gemm_tn_kernel (tcgen05, all encoder pointwise/downsample GEMMs)", "bound": "tensor",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peaks["source"] + (" bf16 sustained" if dtype == torch.bfloat16
+                                                                     else " bf16 sustained / 6 (3xTF32 at half rate)"),
+                "flops_per_launch": g["work"] / max(g["launches"], 1),
+                "us_per_launch": g["ms"] * 1e3 / max(g["launches"], 1)}
+    launches = sum(v["launches"] for v in prof.values()) // args.steps
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample, csteps = 4, 3
+        ips, cores, _ = cpu_encoder_throughput(sample, csteps, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"oracle Encoder.forward on {sample} of the {B} images x {csteps} steps, fp32, all host threads"}
+
+    line = {
+        "metric": "encoder_forward_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if dtype == torch.bfloat16 else "fp32(3xTF32)", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
+                "d2h_bytes_per_step": B * 49 * 1024 * 4},
+        "gpu_launches": int(launches * args.steps),
+        "gpu_launches_per_step": int(launches),
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+        "model_tflops": value / world * ENCODER_GFLOP_PER_IMAGE / 1e3,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,7 +57,10 @@ SIGNATURES = {
     "ccx_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ccx_encoder_run": (C.c_int, [C.POINTER(EncoderWeights), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                   _sz, _vp]),
+    "ccx_prof_begin": (C.c_int, []),
+    "ccx_prof_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
 }
+PROF_KINDS = ("gemm", "dwconv_ln", "stem", "ln_rows", "pool", "elementwise", "attention", "lstm", "loss", "optimizer")
 
 _lib = None
 
@@ -83,6 +86,18 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib().ccx_status_string(rc).decode()
         raise RuntimeError(f"libccx {what} failed: {msg} (status {rc})")
+
+
+def prof_begin():
+    check(lib().ccx_prof_begin(), "prof_begin")
+
+
+def prof_end():
+    """-> {kind: {"ms": total ms, "work": FLOPs (gemm) or bytes, "launches": n}}; synchronises the device."""
+    n = len(PROF_KINDS)
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (_i64 * n)()
+    check(lib().ccx_prof_end(ms, work, cnt, n), "prof_end")
+    return {k: {"ms": ms[i], "work": work[i], "launches": int(cnt[i])} for i, k in enumerate(PROF_KINDS)}
 
 
 def ptr(t):

@@ -19,6 +19,7 @@
 
 #include "ccx_common.cuh"
 #include "ccx_gemm.h"
+#include "ccx_prof.h"
 
 namespace cg = cooperative_groups;
 
@@ -237,6 +238,8 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  const double bytes = (double)B * H * W * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0)));
+  ProfScope prof(PROF_DWCONV_LN, stream, bytes);
   if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
   return CCX_OK;
 }

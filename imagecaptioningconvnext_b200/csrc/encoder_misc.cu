@@ -9,6 +9,7 @@
 //   cast_bf16         helper: fp32 -> bf16
 #include "ccx_common.cuh"
 #include "ccx_ops.h"
+#include "ccx_prof.h"
 
 namespace ccx {
 
@@ -95,6 +96,7 @@ int stem_ln(const float* img, const float* wk, const float* bias, const float* g
   const int segs = (Wout + STEM_PX - 1) / STEM_PX;
   const long long grid = static_cast<long long>(B) * Hout * segs;
   if (grid > 0x7fffffffLL) return CCX_ERR_SHAPE;
+  ProfScope prof(PROF_STEM, stream, (double)B * (3.0 * Hin * Win + (double)Hout * Wout * STEM_C) * 4.0);
   stem_ln_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(img, wk, bias, gamma, beta, out, B, Hin, Win,
                                                                    Hout, Wout, eps);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
@@ -175,6 +177,7 @@ int ln_rows(const float* x, const float* gamma, const float* beta, void* out, fl
   if (merge && ((H & 1) || (W & 1) || H <= 0 || W <= 0 || (M % (static_cast<long long>(H) * W)) != 0))
     return CCX_ERR_SHAPE;
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  ProfScope prof(PROF_LN_ROWS, stream, (double)M * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0))));
 #define CCX_LN_CASE(V)                                                                                      \
   case V:                                                                                                   \
     ln_rows_kernel<V><<<grid, 256, 0, stream>>>(x, gamma, beta, out, out_lo, M, C, eps, out_dtype, merge, H, \
@@ -220,6 +223,7 @@ int avgpool_nhwc(const float* x, float* out, int B, int H, int W, int C, int S, 
   if (B <= 0 || H <= 0 || W <= 0 || S <= 0 || (C % 4) != 0) return CCX_ERR_SHAPE;
   const long long total = static_cast<long long>(B) * S * S * (C / 4);
   const unsigned grid = static_cast<unsigned>(total / 256 + 1 > 148 * 16 ? 148 * 16 : total / 256 + 1);
+  ProfScope prof(PROF_POOL, stream, ((double)B * H * W * C + (double)total * 4) * 4.0);
   avgpool_nhwc_kernel<<<grid, 256, 0, stream>>>(x, out, B, H, W, C, S);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
@@ -240,6 +244,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
 int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t stream) {
   if (n <= 0) return n == 0 ? CCX_OK : CCX_ERR_SHAPE;
   const unsigned grid = static_cast<unsigned>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)n * 12.0);
   split_tf32_kernel<<<grid, 256, 0, stream>>>(x, hi, lo, n);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
@@ -252,6 +257,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 int cast_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
   if (n <= 0) return n == 0 ? CCX_OK : CCX_ERR_SHAPE;
   const unsigned grid = static_cast<unsigned>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)n * 6.0);
   cast_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }

@@ -22,6 +22,7 @@
 //   models/transformerDecoder.py:84-85 + torch/nn/modules/transformer.py (QKV/FFN/out-proj).
 #include "ccx_common.cuh"
 #include "ccx_gemm.h"
+#include "ccx_prof.h"
 
 namespace ccx {
 
@@ -417,6 +418,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
     a_lo = a_hi;
     b_lo = b_hi;
   }
+  ProfScope prof(PROF_GEMM, stream, 2.0 * g.M * (double)g.N * g.K);
   EpiArgs ep;
   ep.out = g.C;
   ep.out_lo = g.C_lo;

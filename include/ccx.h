@@ -158,6 +158,17 @@ CCX_API int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float
                     int32_t Win, int32_t child_begin, int32_t child_end, const float* sd_rowscale,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the
+ * library is bracketed by two events on its stream; end() synchronises the device and returns, per kernel kind
+ * (0 gemm, 1 dwconv+ln, 2 stem, 3 ln_rows, 4 pool, 5 elementwise, 6 attention, 7 lstm, 8 loss, 9 optimizer),
+ * the summed milliseconds, the summed algorithmic work (FLOPs for kind 0, bytes otherwise) and the launch count.
+ * ------------------------------------------------------------------------------------------------ */
+#define CCX_PROF_KINDS 10
+CCX_API int ccx_prof_begin(void);
+CCX_API int ccx_prof_end(double* ms_per_kind_host, double* work_per_kind_host, int64_t* launches_per_kind_host,
+                         int32_t n_kinds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,8 +35,9 @@ def test_dwconv7_ln(C, H, W, B, mode):
         out = torch.empty(M, C, dtype=torch.float32, device="cuda")
         lo = torch.empty_like(out) if mode == "split" else None
         dt = _lib.CCX_F32
-    rc = _lib.lib().ccx_dwconv7_ln(xd.data_ptr(), wd.data_ptr(), b.cuda().data_ptr(), gam.cuda().data_ptr(),
-                                   bet.cuda().data_ptr(), out.data_ptr(), _lib.ptr(lo), B, H, W, C, 1e-6, dt,
+    bd, gd, ed = b.cuda(), gam.cuda(), bet.cuda()  # keep alive: data_ptr() of a temporary dangles
+    rc = _lib.lib().ccx_dwconv7_ln(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), gd.data_ptr(),
+                                   ed.data_ptr(), out.data_ptr(), _lib.ptr(lo), B, H, W, C, 1e-6, dt,
                                    _lib.stream_ptr())
     _lib.check(rc)
     y = out.float() + (lo if lo is not None else 0)
@@ -57,8 +58,9 @@ def test_stem_ln(B, H, W):
     ref = F.layer_norm(F.conv2d(x, w, b, stride=4).permute(0, 2, 3, 1), (128,), gam, bet, 1e-6)
     out = torch.empty(B, H // 4, W // 4, 128, device="cuda")
     wk = w.reshape(128, 48).t().contiguous().cuda()
-    _lib.check(_lib.lib().ccx_stem_ln(x.cuda().data_ptr(), wk.data_ptr(), b.cuda().data_ptr(), gam.cuda().data_ptr(),
-                                      bet.cuda().data_ptr(), out.data_ptr(), B, H, W, 1e-6, _lib.stream_ptr()))
+    xd, bd, gd, ed = x.cuda(), b.cuda(), gam.cuda(), bet.cuda()
+    _lib.check(_lib.lib().ccx_stem_ln(xd.data_ptr(), wk.data_ptr(), bd.data_ptr(), gd.data_ptr(),
+                                      ed.data_ptr(), out.data_ptr(), B, H, W, 1e-6, _lib.stream_ptr()))
     assert rel_err(out, ref) < 2e-5
 
 
@@ -73,7 +75,8 @@ def test_ln_rows_patchmerge_equals_ln2d_plus_conv_im2col(C):
     ln = F.layer_norm(x, (C,), gam, bet, 1e-6)
     ref = F.conv2d(ln.permute(0, 3, 1, 2), wc, None, stride=2).permute(0, 2, 3, 1)
     out = torch.empty(B * H * W // 4, 4 * C, device="cuda")
-    _lib.check(_lib.lib().ccx_ln_rows(x.cuda().data_ptr(), gam.cuda().data_ptr(), bet.cuda().data_ptr(),
+    xd, gd, ed = x.cuda(), gam.cuda(), bet.cuda()
+    _lib.check(_lib.lib().ccx_ln_rows(xd.data_ptr(), gd.data_ptr(), ed.data_ptr(),
                                       out.data_ptr(), None, B * H * W, C, 1e-6, _lib.CCX_F32, 1, H, W,
                                       _lib.stream_ptr()))
     wm = wc.permute(0, 2, 3, 1).reshape(2 * C, 4 * C)
@@ -81,7 +84,7 @@ def test_ln_rows_patchmerge_equals_ln2d_plus_conv_im2col(C):
     assert rel_err(got, ref) < 1e-4
     # plain (no merge) bf16 output
     o2 = torch.empty(B * H * W, C, dtype=torch.bfloat16, device="cuda")
-    _lib.check(_lib.lib().ccx_ln_rows(x.cuda().data_ptr(), gam.cuda().data_ptr(), bet.cuda().data_ptr(),
+    _lib.check(_lib.lib().ccx_ln_rows(xd.data_ptr(), gd.data_ptr(), ed.data_ptr(),
                                       o2.data_ptr(), None, B * H * W, C, 1e-6, _lib.CCX_BF16, 0, H, W,
                                       _lib.stream_ptr()))
     assert rel_err(o2.float().view(B, H, W, C), ln) < 1e-2
