@@ -230,7 +230,18 @@ def run_ours(args):
         _lib.prof_begin()
         for i in range(args.steps):
             enc(devbuf[i % nbuf])
+        spans = _lib.prof_spans() if args.spans else None
         prof = _lib.prof_end()
+    if spans is not None and rank == 0:
+        per = len(spans) // args.steps
+        with open(args.spans, "w") as f:
+            f.write("# launch index within one step, kind, mean ms over steps, work (FLOPs for gemm, bytes otherwise), rate\n")
+            for i in range(per):
+                ms_i = sum(spans[s * per + i][1] for s in range(args.steps)) / args.steps
+                k, _, wk = spans[i]
+                rate = wk / (ms_i * 1e-3) if ms_i > 0 else 0
+                f.write(f"{i:4d} {k:12s} {ms_i * 1e3:9.1f} us  work={wk:.4g}  "
+                        f"{rate / 1e12:8.1f} {'TFLOP/s' if k == 'gemm' else 'TB/s'}\n")
     if world > 1:
         dist.barrier()
 
@@ -294,6 +305,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spans", default=None, help="write the per-launch timing table of the instrumented pass here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -52,12 +52,23 @@ SIGNATURES = {
     "ccx_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ccx_stem_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "ccx_dwconv7_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
-    "ccx_ln_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_ln_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_embed_rows": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _i64,
+                                 _i64, _i32, _i32, _vp]),
+    "ccx_mean_pixels": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i64, _vp]),
+    "ccx_bahdanau_attention": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i64, _i32,
+                                         _i32, _i32, _i32, _vp]),
+    "ccx_lstm_pointwise": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _vp,
+                                     _i64, _i32, _i32, _vp]),
+    "ccx_greedy_next": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "ccx_mha_small": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _vp,
+                                _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
     "ccx_avgpool_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ccx_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ccx_encoder_run": (C.c_int, [C.POINTER(EncoderWeights), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                   _sz, _vp]),
     "ccx_prof_begin": (C.c_int, []),
+    "ccx_prof_spans": (C.c_int, [C.POINTER(_i32), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "ccx_prof_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
 }
 PROF_KINDS = ("gemm", "dwconv_ln", "stem", "ln_rows", "pool", "elementwise", "attention", "lstm", "loss", "optimizer")
@@ -90,6 +101,15 @@ def check(rc, what=""):
 
 def prof_begin():
     check(lib().ccx_prof_begin(), "prof_begin")
+
+
+def prof_spans(max_spans=100000):
+    """Per-launch [(kind, ms, work)] since prof_begin (synchronises); call before prof_end."""
+    kind, ms, work = (_i32 * max_spans)(), (C.c_double * max_spans)(), (C.c_double * max_spans)()
+    n = lib().ccx_prof_spans(kind, ms, work, max_spans)
+    if n < 0:
+        check(n, "prof_spans")
+    return [(PROF_KINDS[kind[i]], ms[i], work[i]) for i in range(min(n, max_spans))]
 
 
 def prof_end():

@@ -61,9 +61,55 @@ int ccx_dwconv7_ln(const float* x, const float* w_tap_major, const float* bias, 
   return dwconv7_ln(x, w_tap_major, bias, ln_g, ln_b, out, out_lo, B, H, W, C, eps, out_dtype, as_stream(stream));
 }
 
-int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo, int64_t M,
-                int32_t C, float eps, int32_t out_dtype, int32_t merge, int32_t H, int32_t W, void* stream) {
-  return ln_rows(x, ln_g, ln_b, out, out_lo, M, C, eps, out_dtype, merge, H, W, as_stream(stream));
+int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo, float* out_plain,
+                int64_t M, int32_t C, float eps, int32_t out_dtype, int32_t merge, int32_t H, int32_t W,
+                void* stream) {
+  return ln_rows(x, ln_g, ln_b, out, out_lo, out_plain, M, C, eps, out_dtype, merge, H, W, as_stream(stream));
+}
+
+int ccx_embed_rows(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* table, int32_t V, int32_t D,
+                   const float* pe, const float* dropmask, float* out_plain, int64_t sb_p, int64_t st_p,
+                   void* op_hi, float* op_lo, int32_t op_dtype, int64_t sb_o, int64_t st_o, int32_t nb, int32_t nt,
+                   void* stream) {
+  return embed_rows(reinterpret_cast<const long long*>(tokens), tok_ld, t0, table, V, D, pe, dropmask, out_plain,
+                    sb_p, st_p, op_hi, op_lo, op_dtype, sb_o, st_o, nb, nt, as_stream(stream));
+}
+
+int ccx_mean_pixels(const float* enc, int32_t B, int32_t P, int32_t E, void* op_hi, float* op_lo, int32_t op_dtype,
+                    int64_t ldo, void* stream) {
+  return mean_pixels(enc, B, P, E, op_hi, op_lo, op_dtype, ldo, as_stream(stream));
+}
+
+int ccx_bahdanau_attention(const float* att1, const float* hg, int64_t ldhg, const float* w_f, const float* b_f,
+                           const float* enc, const float* active, float* alpha_out, int64_t alpha_ld,
+                           void* awe_hi, float* awe_lo, int32_t awe_dtype, int64_t ld_awe, int32_t bt, int32_t P,
+                           int32_t A, int32_t E, void* stream) {
+  return bahdanau_attention(att1, hg, ldhg, w_f, b_f, enc, active, alpha_out, alpha_ld, awe_hi, awe_lo, awe_dtype,
+                            ld_awe, bt, P, A, E, as_stream(stream));
+}
+
+int ccx_lstm_pointwise(const float* gates, int64_t ldg, const float* c_prev, float* c_new, void* hn_hi,
+                       float* hn_lo, int64_t ld_hn, void* ha_hi, float* ha_lo, int64_t ld_ha, int32_t op_dtype,
+                       const float* dropmask, int64_t ld_dm, float* h_plain, int64_t ld_hp, int32_t bt, int32_t D,
+                       void* stream) {
+  return lstm_pointwise(gates, ldg, c_prev, c_new, hn_hi, hn_lo, ld_hn, ha_hi, ha_lo, ld_ha, op_dtype, dropmask,
+                        ld_dm, h_plain, ld_hp, bt, D, as_stream(stream));
+}
+
+int ccx_greedy_next(const float* preds, int64_t ld_preds, int32_t B, int32_t V, int32_t t, int32_t T,
+                    int64_t* sequences, float* active, int64_t* next_tok, int64_t ld_next, int64_t end_token,
+                    void* stream) {
+  return greedy_next(preds, ld_preds, B, V, t, T, reinterpret_cast<long long*>(sequences), active,
+                     reinterpret_cast<long long*>(next_tok), ld_next, end_token, as_stream(stream));
+}
+
+int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
+                  const float* v, int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo, int32_t ctx_dtype,
+                  int64_t c_sb, int64_t c_st, const uint8_t* key_pad, const float* prob_mask, float* probs_out,
+                  int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t hd, int32_t causal, int32_t q_pos0,
+                  float scale, void* stream) {
+  return mha_small(q, q_sb, q_st, k, k_sb, k_st, v, v_sb, v_st, ctx_hi, ctx_lo, ctx_dtype, c_sb, c_st, key_pad,
+                   prob_mask, probs_out, B, H, Tq, Tk, hd, causal, q_pos0, scale, as_stream(stream));
 }
 
 int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
@@ -183,7 +229,7 @@ int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float* out, i
       const ccx_downsample_weights& dw = w->down[sin];
       float* y_hi = reinterpret_cast<float*>(Y);
       float* y_lo = f32 ? y_hi + M * Cin : nullptr;
-      if ((rc = ln_rows(cur, dw.ln_g, dw.ln_b, Y, y_lo, M, Cin, 1e-6f, cd, 1, H, W, stream))) return rc;
+      if ((rc = ln_rows(cur, dw.ln_g, dw.ln_b, Y, y_lo, nullptr, M, Cin, 1e-6f, cd, 1, H, W, stream))) return rc;
       float* dst = last_child ? out : ((cur == X0) ? X1 : X0);
       GemmDesc g;
       g.A = Y; g.A_lo = y_lo; g.B = dw.w; g.B_lo = f32 ? dw.w_lo : nullptr;

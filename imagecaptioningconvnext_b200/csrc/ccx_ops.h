@@ -12,10 +12,32 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
 // encoder_misc.cu
 int stem_ln(const float* img, const float* wk, const float* bias, const float* gamma, const float* beta,
             float* out, int B, int Hin, int Win, float eps, cudaStream_t stream);
-int ln_rows(const float* x, const float* gamma, const float* beta, void* out, float* out_lo, long long M, int C,
-            float eps, int out_dtype, int merge, int H, int W, cudaStream_t stream);
+int ln_rows(const float* x, const float* gamma, const float* beta, void* out, float* out_lo, float* out_plain,
+            long long M, int C, float eps, int out_dtype, int merge, int H, int W, cudaStream_t stream);
 int avgpool_nhwc(const float* x, float* out, int B, int H, int W, int C, int S, cudaStream_t stream);
 int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t stream);
 int cast_bf16(const float* x, void* y, long long n, cudaStream_t stream);
+
+// decoder_kernels.cu
+int embed_rows(const long long* tokens, long long tok_ld, int t0, const float* table, int V, int D,
+               const float* pe, const float* dropmask, float* out_plain, long long sb_p, long long st_p,
+               void* op_hi, float* op_lo, int op_dtype, long long sb_o, long long st_o, int nb, int nt,
+               cudaStream_t stream);
+int mean_pixels(const float* enc, int B, int P, int E, void* op_hi, float* op_lo, int op_dtype, long long ldo,
+                cudaStream_t stream);
+int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* b_f,
+                       const float* enc, const float* active, float* alpha_out, long long alpha_ld, void* awe_hi,
+                       float* awe_lo, int awe_dtype, long long ld_awe, int bt, int P, int A, int E,
+                       cudaStream_t stream);
+int lstm_pointwise(const float* gates, long long ldg, const float* c_prev, float* c_new, void* hn_hi, float* hn_lo,
+                   long long ld_hn, void* ha_hi, float* ha_lo, long long ld_ha, int op_dtype, const float* dropmask,
+                   long long ld_dm, float* h_plain, long long ld_hp, int bt, int D, cudaStream_t stream);
+int greedy_next(const float* preds, long long ld_preds, int B, int V, int t, int T, long long* sequences,
+                float* active, long long* next_tok, long long ld_next, long long end_token, cudaStream_t stream);
+int mha_small(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
+              const float* v, long long v_sb, long long v_st, void* ctx_hi, float* ctx_lo, int ctx_dtype,
+              long long c_sb, long long c_st, const unsigned char* key_pad, const float* prob_mask,
+              float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
+              cudaStream_t stream);
 
 }  // namespace ccx

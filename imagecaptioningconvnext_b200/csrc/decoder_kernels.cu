@@ -1,0 +1,411 @@
+// decoder_kernels.cu — the non-GEMM kernels of the two caption decoders (forward / inference side).
+//
+//   embed_rows          nn.Embedding (+ dropout mask + positional encoding)   models/decoder.py:84, models/transformerDecoder.py:97-98,25-26
+//   mean_pixels         encoder_out.mean(dim=1)                               models/decoder.py:64
+//   bahdanau_attention  relu(att1+att2) . w_f -> softmax over pixels -> weighted sum -> * sigmoid(f_beta h)
+//                                                                             models/decoder.py:25-31,104-105
+//   lstm_pointwise      nn.LSTMCell gate math (i,f,g,o)                        torch/nn/modules/rnn.py:1755-1778
+//   greedy_next         argmax over the vocabulary + finished bookkeeping     models/decoder.py:156-159, transformerDecoder.py:146-148
+//   mha_small           scaled-dot-product attention for T<=~200 keys          torch/nn/functional.py multi_head_attention_forward
+//
+// "Operand" outputs feed the next tcgen05 GEMM: bf16, or an fp32 (tf32-hi, lo) pair for the 3xTF32 path.
+#include "ccx_common.cuh"
+#include "ccx_ops.h"
+#include "ccx_prof.h"
+
+namespace ccx {
+
+struct OpOut {
+  void* hi;   // bf16* or float*
+  float* lo;  // fp32 remainder, or nullptr (plain fp32 / bf16)
+  int dtype;  // CCX_F32 / CCX_BF16
+};
+
+__device__ __forceinline__ void store_op(const OpOut& o, long long idx, float v) {
+  if (o.dtype == CCX_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(o.hi)[idx] = __float2bfloat16_rn(v);
+  } else if (o.lo != nullptr) {
+    const float h = tf32_hi(v);
+    reinterpret_cast<float*>(o.hi)[idx] = h;
+    o.lo[idx] = v - h;
+  } else {
+    reinterpret_cast<float*>(o.hi)[idx] = v;
+  }
+}
+__device__ __forceinline__ void store_op4(const OpOut& o, long long idx, float4 v) {
+  if (o.dtype == CCX_BF16) {
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(o.hi) + idx) = pk;
+  } else if (o.lo != nullptr) {
+    float4 h, l;
+    h.x = tf32_hi(v.x); l.x = v.x - h.x;
+    h.y = tf32_hi(v.y); l.y = v.y - h.y;
+    h.z = tf32_hi(v.z); l.z = v.z - h.z;
+    h.w = tf32_hi(v.w); l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.hi) + idx) = h;
+    *reinterpret_cast<float4*>(o.lo + idx) = l;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(o.hi) + idx) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// embedding gather (+ dropout multiplier, + positional encoding); one warp per (b, t) row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_rows_kernel(const long long* __restrict__ tokens, long long tok_ld, int t0, const float* __restrict__ table,
+                  int V, int D, const float* __restrict__ pe, const float* __restrict__ dropmask,
+                  float* __restrict__ out_plain, long long sb_p, long long st_p, OpOut op, long long sb_o,
+                  long long st_o, int nb, int nt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (r >= static_cast<long long>(nb) * nt) return;
+  const int b = static_cast<int>(r / nt), t = static_cast<int>(r % nt);
+  long long tok = tokens[b * tok_ld + t0 + t];
+  if (tok < 0) tok = 0;
+  if (tok >= V) tok = V - 1;
+  const float4* src = reinterpret_cast<const float4*>(table + tok * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    float4 v = __ldg(src + i);
+    if (dropmask != nullptr) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(dropmask + r * D) + i);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    }
+    if (pe != nullptr) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(t0 + t) * D) + i);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    if (out_plain != nullptr) *reinterpret_cast<float4*>(out_plain + b * sb_p + t * st_p + i * 4) = v;
+    if (op.hi != nullptr) store_op4(op, b * sb_o + t * st_o + i * 4, v);
+  }
+}
+
+int embed_rows(const long long* tokens, long long tok_ld, int t0, const float* table, int V, int D,
+               const float* pe, const float* dropmask, float* out_plain, long long sb_p, long long st_p,
+               void* op_hi, float* op_lo, int op_dtype, long long sb_o, long long st_o, int nb, int nt,
+               cudaStream_t stream) {
+  if (nb <= 0 || nt <= 0) return CCX_OK;
+  if (D % 4 != 0 || V <= 0) return CCX_ERR_SHAPE;
+  OpOut op{op_hi, op_lo, op_dtype};
+  const long long rows = static_cast<long long>(nb) * nt;
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)rows * D * 8.0);
+  embed_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      tokens, tok_ld, t0, table, V, D, pe, dropmask, out_plain, sb_p, st_p, op, sb_o, st_o, nb, nt);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean over pixels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mean_pixels_kernel(const float* __restrict__ enc, int P, int E, OpOut op, long long ldo, int B) {
+  const int e4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (e4 >= E / 4) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* src = reinterpret_cast<const float4*>(enc + static_cast<long long>(b) * P * E) + e4;
+  for (int p = 0; p < P; ++p) {
+    const float4 v = __ldg(src + static_cast<long long>(p) * (E / 4));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float inv = 1.0f / static_cast<float>(P);
+  acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+  store_op4(op, static_cast<long long>(b) * ldo + e4 * 4, acc);
+}
+
+int mean_pixels(const float* enc, int B, int P, int E, void* op_hi, float* op_lo, int op_dtype, long long ldo,
+                cudaStream_t stream) {
+  if (B <= 0) return CCX_OK;
+  if (E % 4 != 0 || P <= 0 || B > 65535) return CCX_ERR_SHAPE;
+  OpOut op{op_hi, op_lo, op_dtype};
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)B * P * E * 4.0);
+  dim3 grid((E / 4 + 255) / 256, B);
+  mean_pixels_kernel<<<grid, 256, 0, stream>>>(enc, P, E, op, ldo, B);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bahdanau attention step: one CTA per sample
+// ---------------------------------------------------------------------------------------------
+static constexpr int ATT_MAX_P = 256;
+
+__global__ void __launch_bounds__(256)
+bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
+                          const float* __restrict__ hg, long long ldhg,  // [bt, >= A+E]: att2 | gate pre-activation
+                          const float* __restrict__ w_f, const float* __restrict__ b_f,
+                          const float* __restrict__ enc,   // [B, P, E]
+                          const float* __restrict__ active,  // [bt] 1/0 or nullptr
+                          float* __restrict__ alpha_out, long long alpha_ld,  // row b at alpha_out + b*alpha_ld
+                          OpOut awe, long long ld_awe,     // row b at b*ld_awe (column offset folded into pointers)
+                          int P, int A, int E) {
+  extern __shared__ float att_sm[];
+  float* s_att2 = att_sm;        // [A]
+  float* s_wf = att_sm + A;      // [A]
+  __shared__ float s_e[ATT_MAX_P];
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < A; i += 256) {
+    s_att2[i] = hg[b * ldhg + i];
+    s_wf[i] = __ldg(w_f + i);
+  }
+  __syncthreads();
+  const float bf = b_f ? __ldg(b_f) : 0.f;
+  for (int p = warp; p < P; p += 8) {
+    const float4* a1 = reinterpret_cast<const float4*>(att1 + (static_cast<long long>(b) * P + p) * A);
+    float acc = 0.f;
+    for (int i = lane; i < A / 4; i += 32) {
+      const float4 v = __ldg(a1 + i);
+      const float4 h = *reinterpret_cast<const float4*>(s_att2 + i * 4);
+      const float4 w = *reinterpret_cast<const float4*>(s_wf + i * 4);
+      acc = fmaf(fmaxf(v.x + h.x, 0.f), w.x, acc);
+      acc = fmaf(fmaxf(v.y + h.y, 0.f), w.y, acc);
+      acc = fmaf(fmaxf(v.z + h.z, 0.f), w.z, acc);
+      acc = fmaf(fmaxf(v.w + h.w, 0.f), w.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_e[p] = acc + bf;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int p = lane; p < P; p += 32) mx = fmaxf(mx, s_e[p]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int p = lane; p < P; p += 32) {
+      const float ex = expf(s_e[p] - mx);
+      s_e[p] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    const bool wr = (alpha_out != nullptr) && (active == nullptr || active[b] != 0.f);
+    for (int p = lane; p < P; p += 32) {
+      const float a = s_e[p] * inv;
+      s_e[p] = a;
+      if (wr) alpha_out[b * alpha_ld + p] = a;
+    }
+  }
+  __syncthreads();
+  for (int e4 = threadIdx.x; e4 < E / 4; e4 += 256) {
+    const float4* src = reinterpret_cast<const float4*>(enc + static_cast<long long>(b) * P * E) + e4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < P; ++p) {
+      const float4 v = __ldg(src + static_cast<long long>(p) * (E / 4));
+      const float a = s_e[p];
+      acc.x = fmaf(v.x, a, acc.x); acc.y = fmaf(v.y, a, acc.y);
+      acc.z = fmaf(v.z, a, acc.z); acc.w = fmaf(v.w, a, acc.w);
+    }
+    const float4 gp = *reinterpret_cast<const float4*>(hg + b * ldhg + A + e4 * 4);
+    acc.x *= 1.0f / (1.0f + expf(-gp.x));
+    acc.y *= 1.0f / (1.0f + expf(-gp.y));
+    acc.z *= 1.0f / (1.0f + expf(-gp.z));
+    acc.w *= 1.0f / (1.0f + expf(-gp.w));
+    store_op4(awe, b * ld_awe + e4 * 4, acc);
+  }
+}
+
+int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* b_f,
+                       const float* enc, const float* active, float* alpha_out, long long alpha_ld, void* awe_hi,
+                       float* awe_lo, int awe_dtype, long long ld_awe, int bt, int P, int A, int E,
+                       cudaStream_t stream) {
+  if (bt <= 0) return CCX_OK;
+  if (P <= 0 || P > ATT_MAX_P || A % 4 != 0 || E % 4 != 0 || (ldhg % 4) != 0) return CCX_ERR_SHAPE;
+  OpOut awe{awe_hi, awe_lo, awe_dtype};
+  ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (A + E) * 4.0);
+  bahdanau_attention_kernel<<<bt, 256, 2 * A * sizeof(float), stream>>>(att1, hg, ldhg, w_f, b_f, enc, active,
+                                                                        alpha_out, alpha_ld, awe, ld_awe, P, A, E);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSTM cell point-wise part (gate order i, f, g, o as torch)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lstm_pointwise_kernel(const float* __restrict__ gates, long long ldg, const float* __restrict__ c_prev,
+                      float* __restrict__ c_new, OpOut h_next, long long ld_hn, OpOut h_all, long long ld_ha,
+                      const float* __restrict__ dropmask, long long ld_dm, float* __restrict__ h_plain,
+                      long long ld_hp, int bt, int D) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(bt) * D) return;
+  const int b = static_cast<int>(i / D), j = static_cast<int>(i % D);
+  const float* g = gates + b * ldg;
+  const float ig = 1.0f / (1.0f + expf(-g[j]));
+  const float fg = 1.0f / (1.0f + expf(-g[D + j]));
+  const float gg = tanhf(g[2 * D + j]);
+  const float og = 1.0f / (1.0f + expf(-g[3 * D + j]));
+  const float c = fg * c_prev[static_cast<long long>(b) * D + j] + ig * gg;
+  const float h = og * tanhf(c);
+  c_new[static_cast<long long>(b) * D + j] = c;
+  if (h_next.hi != nullptr) store_op(h_next, b * ld_hn + j, h);
+  if (h_plain != nullptr) h_plain[b * ld_hp + j] = h;
+  if (h_all.hi != nullptr) {
+    const float m = dropmask ? dropmask[b * ld_dm + j] : 1.0f;
+    store_op(h_all, b * ld_ha + j, h * m);
+  }
+}
+
+int lstm_pointwise(const float* gates, long long ldg, const float* c_prev, float* c_new, void* hn_hi, float* hn_lo,
+                   long long ld_hn, void* ha_hi, float* ha_lo, long long ld_ha, int op_dtype, const float* dropmask,
+                   long long ld_dm, float* h_plain, long long ld_hp, int bt, int D, cudaStream_t stream) {
+  if (bt <= 0) return CCX_OK;
+  OpOut hn{hn_hi, hn_lo, op_dtype}, ha{ha_hi, ha_lo, op_dtype};
+  const long long n = static_cast<long long>(bt) * D;
+  ProfScope prof(PROF_LSTM, stream, (double)n * 36.0);
+  lstm_pointwise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      gates, ldg, c_prev, c_new, hn, ld_hn, ha, ld_ha, dropmask, ld_dm, h_plain, ld_hp, bt, D);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// greedy step: argmax over V (first index on ties), sequences / finished / active / next-token bookkeeping
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+greedy_next_kernel(const float* __restrict__ preds, long long ld_preds, int V, int t, int T,
+                   long long* __restrict__ sequences,  // [B, T]
+                   float* __restrict__ active,         // [B] in/out (1 = still decoding)
+                   long long* __restrict__ next_tok, long long ld_next,  // next_tok[b*ld_next] <- argmax (if active)
+                   long long end_token) {
+  const int b = blockIdx.x;
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const float* row = preds + b * ld_preds;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float x = row[v];
+    if (x > best || (x == best && v < bi)) { best = x; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_v[warp] = best; s_i[warp] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (s_v[w] > best || (s_v[w] == best && s_i[w] < bi)) { best = s_v[w]; bi = s_i[w]; }
+    if (active[b] != 0.f) {
+      sequences[static_cast<long long>(b) * T + t] = bi;
+      if (next_tok != nullptr) next_tok[b * ld_next] = bi;
+      if (bi == end_token) active[b] = 0.f;
+    }
+  }
+}
+
+int greedy_next(const float* preds, long long ld_preds, int B, int V, int t, int T, long long* sequences,
+                float* active, long long* next_tok, long long ld_next, long long end_token, cudaStream_t stream) {
+  if (B <= 0) return CCX_OK;
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)B * V * 4.0);
+  greedy_next_kernel<<<B, 256, 0, stream>>>(preds, ld_preds, V, t, T, sequences, active, next_tok, ld_next,
+                                            end_token);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small-sequence multi-head attention: one CTA per (batch, head); K/V of the head staged in shared memory
+// ---------------------------------------------------------------------------------------------
+struct MhaArgs {
+  const float* q; long long q_sb, q_st;  // element (b, i, h*hd + d) at q[b*q_sb + i*q_st + h*hd + d]
+  const float* k; long long k_sb, k_st;
+  const float* v; long long v_sb, v_st;
+  OpOut ctx; long long c_sb, c_st;
+  const unsigned char* key_pad;  // [B, Tk] 1 = masked, or nullptr
+  const float* prob_mask;        // [B, H, Tq, Tk] dropout multiplier or nullptr
+  float* probs_out;              // [B, H, Tq, Tk] softmax output (before dropout) or nullptr
+  int B, H, Tq, Tk, hd;
+  int causal;                    // key j allowed iff j <= q_pos0 + i
+  int q_pos0;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128)
+mha_small_kernel(MhaArgs a) {
+  extern __shared__ float mha_sm[];
+  const int hd = a.hd, ldk = hd + 1;
+  float* s_k = mha_sm;                    // [Tk][hd+1]
+  float* s_v = s_k + a.Tk * ldk;          // [Tk][hd+1]
+  float* s_q = s_v + a.Tk * ldk;          // [4 warps][hd]
+  float* s_p = s_q + 4 * hd;              // [4 warps][Tk]
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int idx = threadIdx.x; idx < a.Tk * hd; idx += 128) {
+    const int j = idx / hd, d = idx - j * hd;
+    s_k[j * ldk + d] = a.k[b * a.k_sb + j * a.k_st + h * hd + d];
+    s_v[j * ldk + d] = a.v[b * a.v_sb + j * a.v_st + h * hd + d];
+  }
+  __syncthreads();
+  float* q = s_q + warp * hd;
+  float* p = s_p + warp * a.Tk;
+  for (int i = warp; i < a.Tq; i += 4) {
+    for (int d = lane; d < hd; d += 32) q[d] = a.q[b * a.q_sb + i * a.q_st + h * hd + d] * a.scale;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < a.Tk; j += 32) {
+      float s = 0.f;
+      for (int d = 0; d < hd; ++d) s = fmaf(q[d], s_k[j * ldk + d], s);
+      const bool masked = (a.causal && j > a.q_pos0 + i) || (a.key_pad && a.key_pad[b * a.Tk + j]);
+      s = masked ? -INFINITY : s;
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < a.Tk; j += 32) {
+      const float e = (p[j] == -INFINITY) ? 0.f : expf(p[j] - mx);
+      p[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    const long long prow = ((static_cast<long long>(b) * a.H + h) * a.Tq + i) * a.Tk;
+    for (int j = lane; j < a.Tk; j += 32) {
+      float pr = p[j] * inv;
+      if (a.probs_out) a.probs_out[prow + j] = pr;
+      if (a.prob_mask) pr *= a.prob_mask[prow + j];
+      p[j] = pr;
+    }
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < a.Tk; ++j) acc = fmaf(p[j], s_v[j * ldk + d], acc);
+      store_op(a.ctx, b * a.c_sb + i * a.c_st + h * hd + d, acc);
+    }
+    __syncwarp();
+  }
+}
+
+int mha_small(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
+              const float* v, long long v_sb, long long v_st, void* ctx_hi, float* ctx_lo, int ctx_dtype,
+              long long c_sb, long long c_st, const unsigned char* key_pad, const float* prob_mask,
+              float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
+              cudaStream_t stream) {
+  if (B <= 0 || Tq <= 0) return CCX_OK;
+  if (Tk <= 0 || hd <= 0 || H <= 0) return CCX_ERR_SHAPE;
+  const size_t smem = (static_cast<size_t>(2) * Tk * (hd + 1) + 4 * hd + 4 * Tk) * sizeof(float);
+  if (smem > 200 * 1024) return CCX_ERR_SHAPE;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    if (cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+        cudaSuccess)
+      return CCX_ERR_CUDA;
+    configured = 200 * 1024;
+  }
+  MhaArgs a;
+  a.q = q; a.q_sb = q_sb; a.q_st = q_st;
+  a.k = k; a.k_sb = k_sb; a.k_st = k_st;
+  a.v = v; a.v_sb = v_sb; a.v_st = v_st;
+  a.ctx = OpOut{ctx_hi, ctx_lo, ctx_dtype}; a.c_sb = c_sb; a.c_st = c_st;
+  a.key_pad = key_pad; a.prob_mask = prob_mask; a.probs_out = probs_out;
+  a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.hd = hd;
+  a.causal = causal; a.q_pos0 = q_pos0; a.scale = scale;
+  ProfScope prof(PROF_ATTENTION, stream, (double)B * H * (Tq + 2.0 * Tk) * hd * 4.0);
+  mha_small_kernel<<<B * H, 128, smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+}  // namespace ccx

@@ -108,8 +108,8 @@ int stem_ln(const float* img, const float* wk, const float* bias, const float* g
 template <int VPL>  // float4 vectors per lane: C = 128 * VPL
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-               void* __restrict__ out, float* __restrict__ out_lo, long long M, int C, float eps, int out_dtype,
-               int merge, int H, int W) {
+               void* __restrict__ out, float* __restrict__ out_lo, float* __restrict__ out_plain, long long M,
+               int C, float eps, int out_dtype, int merge, int H, int W) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (m >= M) return;
@@ -151,6 +151,8 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     y.z = v[i].z * rstd * g.z + bb.z;
     y.w = v[i].w * rstd * g.w + bb.w;
     const long long o = orow * ldo + ocol0 + c;
+    if (out_plain != nullptr) *reinterpret_cast<float4*>(out_plain + o) = y;
+    if (out == nullptr) continue;
     if (out_dtype == CCX_BF16) {
       uint2 pk;
       pk.x = pack_bf16x2(y.x, y.y);
@@ -170,8 +172,8 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
-int ln_rows(const float* x, const float* gamma, const float* beta, void* out, float* out_lo, long long M, int C,
-            float eps, int out_dtype, int merge, int H, int W, cudaStream_t stream) {
+int ln_rows(const float* x, const float* gamma, const float* beta, void* out, float* out_lo, float* out_plain,
+            long long M, int C, float eps, int out_dtype, int merge, int H, int W, cudaStream_t stream) {
   if (M <= 0) return M == 0 ? CCX_OK : CCX_ERR_SHAPE;
   if (C % 128 != 0 || C > 1024) return CCX_ERR_SHAPE;
   if (merge && ((H & 1) || (W & 1) || H <= 0 || W <= 0 || (M % (static_cast<long long>(H) * W)) != 0))
@@ -180,8 +182,8 @@ int ln_rows(const float* x, const float* gamma, const float* beta, void* out, fl
   ProfScope prof(PROF_LN_ROWS, stream, (double)M * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0))));
 #define CCX_LN_CASE(V)                                                                                      \
   case V:                                                                                                   \
-    ln_rows_kernel<V><<<grid, 256, 0, stream>>>(x, gamma, beta, out, out_lo, M, C, eps, out_dtype, merge, H, \
-                                                W);                                                         \
+    ln_rows_kernel<V><<<grid, 256, 0, stream>>>(x, gamma, beta, out, out_lo, out_plain, M, C, eps, out_dtype, \
+                                                merge, H, W);                                               \
     break;
   switch (C / 128) {
     CCX_LN_CASE(1) CCX_LN_CASE(2) CCX_LN_CASE(3) CCX_LN_CASE(4) CCX_LN_CASE(5) CCX_LN_CASE(6) CCX_LN_CASE(7)

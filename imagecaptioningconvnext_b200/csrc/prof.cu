@@ -56,6 +56,25 @@ int ccx_prof_begin(void) {
   return CCX_OK;
 }
 
+// Per-launch detail of the spans recorded since ccx_prof_begin (call BEFORE ccx_prof_end, after a device sync):
+// fills up to `max` entries, returns the number of spans recorded (or a negative status).
+int ccx_prof_spans(int32_t* kind, double* ms, double* work, int32_t max) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return CCX_ERR_CUDA;
+  int n = 0;
+  for (const auto& s : ccx::g_spans) {
+    if (s.b == nullptr) continue;
+    if (n < max) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, s.a, s.b) != cudaSuccess) return CCX_ERR_CUDA;
+      kind[n] = s.kind;
+      ms[n] = t;
+      work[n] = s.work;
+    }
+    ++n;
+  }
+  return n;
+}
+
 int ccx_prof_end(double* ms_per_kind, double* work_per_kind, int64_t* launches_per_kind, int32_t n_kinds) {
   ccx::g_prof_on = false;
   if (cudaDeviceSynchronize() != cudaSuccess) return CCX_ERR_CUDA;

@@ -100,11 +100,14 @@ CCX_API int ccx_dwconv7_ln(const float* x, const float* w_tap_major, const float
                    const float* ln_b, void* out, float* out_lo, int32_t B, int32_t H, int32_t W, int32_t C,
                    float eps, int32_t out_dtype, void* stream);
 
-/* Row LayerNorm over C of x[M,C] fp32 (torchvision LayerNorm2d, convnext.py:31-36).  merge != 0 additionally
+/* Row LayerNorm over C of x[M,C] fp32 (torchvision LayerNorm2d, convnext.py:31-36; also the post-norm
+ * LayerNorm(512, eps 1e-5) of nn.TransformerDecoderLayer, torch/nn/modules/transformer.py:1133-1135).
+ * Writes any of: `out` (GEMM operand: bf16, or tf32 hi + `out_lo`) and `out_plain` (fp32, for residual use).  merge != 0 additionally
  * scatters row (b,h,w) to row (b,h/2,w/2), column block (h%2)*2+(w%2) of a [M/4, 4C] matrix — the im2col of the
  * k=2,s=2 downsample conv (convnext.py:146-151), whose weight the host re-orders to [Cout][(kh,kw,c)]. */
-CCX_API int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo, int64_t M,
-                int32_t C, float eps, int32_t out_dtype, int32_t merge, int32_t H, int32_t W, void* stream);
+CCX_API int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo,
+                        float* out_plain, int64_t M, int32_t C, float eps, int32_t out_dtype, int32_t merge,
+                        int32_t H, int32_t W, void* stream);
 
 /* AdaptiveAvgPool2d((S,S)) + permute(0,2,3,1): models/encoder.py:25-26.  x NHWC fp32 -> out [B,S,S,C] fp32. */
 CCX_API int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
@@ -159,6 +162,59 @@ CCX_API int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Caption decoders.  "operand" outputs (op_hi/op_lo/op_dtype) feed the next ccx_linear: bf16 (op_lo NULL), or
+ * tf32 hi + fp32 lo for the 3xTF32 path, or plain fp32 (CCX_F32 with op_lo NULL).
+ * ------------------------------------------------------------------------------------------------ */
+/* nn.Embedding gather (+ dropout multiplier + sinusoidal PE): models/decoder.py:84,
+ * models/transformerDecoder.py:97-98 (pos_encoding(dropout(embedding(tokens)))).  Row (b,t), t in [0,nt):
+ * token = tokens[b*tok_ld + t0 + t];  value = table[token]*dropmask[(b*nt+t)] + pe[t0+t];
+ * written to out_plain[b*sb_p + t*st_p + :] and/or the operand at [b*sb_o + t*st_o + :]. */
+CCX_API int ccx_embed_rows(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* table, int32_t V,
+                           int32_t D, const float* pe, const float* dropmask, float* out_plain, int64_t sb_p,
+                           int64_t st_p, void* op_hi, float* op_lo, int32_t op_dtype, int64_t sb_o, int64_t st_o,
+                           int32_t nb, int32_t nt, void* stream);
+
+/* encoder_out.mean(dim=1): models/decoder.py:64.  enc [B,P,E] fp32 -> operand [B, ldo]. */
+CCX_API int ccx_mean_pixels(const float* enc, int32_t B, int32_t P, int32_t E, void* op_hi, float* op_lo,
+                            int32_t op_dtype, int64_t ldo, void* stream);
+
+/* One decode step of Attention.forward + the f_beta gate: models/decoder.py:25-31,104-105.
+ * att1 = encoder_att(enc) [B,P,A] is hoisted (time-invariant); hg[b] = [decoder_att(h) | f_beta(h)] (A+E cols).
+ * alpha = softmax_p(w_f . relu(att1 + att2) + b_f); awe = sigmoid(f_beta h) * sum_p alpha_p enc_p.
+ * alpha -> alpha_out[b*alpha_ld + p] (skipped for rows with active[b]==0); awe -> operand row b at b*ld_awe. */
+CCX_API int ccx_bahdanau_attention(const float* att1, const float* hg, int64_t ldhg, const float* w_f,
+                                   const float* b_f, const float* enc, const float* active, float* alpha_out,
+                                   int64_t alpha_ld, void* awe_hi, float* awe_lo, int32_t awe_dtype, int64_t ld_awe,
+                                   int32_t bt, int32_t P, int32_t A, int32_t E, void* stream);
+
+/* nn.LSTMCell point-wise half (torch/nn/modules/rnn.py:1755-1778; gates = [i|f|g|o] pre-activations incl. both
+ * biases): c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c').  h' goes to the next step's GEMM operand (hn_*), to
+ * the hoisted-fc operand (ha_*, times the dropout multiplier: models/decoder.py:109) and/or plain fp32. */
+CCX_API int ccx_lstm_pointwise(const float* gates, int64_t ldg, const float* c_prev, float* c_new, void* hn_hi,
+                               float* hn_lo, int64_t ld_hn, void* ha_hi, float* ha_lo, int64_t ld_ha,
+                               int32_t op_dtype, const float* dropmask, int64_t ld_dm, float* h_plain,
+                               int64_t ld_hp, int32_t bt, int32_t D, void* stream);
+
+/* Greedy bookkeeping of forwardWithoutTeacherForcing (models/decoder.py:156-159,
+ * models/transformerDecoder.py:146-148): argmax over V (lowest index on ties); for rows with active[b] != 0:
+ * sequences[b,t] = argmax, next_tok[b*ld_next] = argmax, active[b] = 0 once <end> is produced. */
+CCX_API int ccx_greedy_next(const float* preds, int64_t ld_preds, int32_t B, int32_t V, int32_t t, int32_t T,
+                            int64_t* sequences, float* active, int64_t* next_tok, int64_t ld_next,
+                            int64_t end_token, void* stream);
+
+/* Scaled-dot-product attention for short sequences (Tk <= ~380 at hd 64): one CTA per (batch, head).
+ * Replaces F.scaled_dot_product_attention inside nn.MultiheadAttention (torch/nn/functional.py
+ * multi_head_attention_forward) for self-attention (causal + key padding) and cross-attention over pixels.
+ * Element (b, i, h*hd+d) of q at q[b*q_sb + i*q_st + h*hd + d]; likewise k, v, ctx.  key_pad [B,Tk] 1 = masked.
+ * causal: key j allowed iff j <= q_pos0 + i (q_pos0 = cache length for KV-cache decoding).
+ * prob_mask [B,H,Tq,Tk]: attention-dropout multiplier (train); probs_out: softmax saved for backward. */
+CCX_API int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
+                          const float* v, int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo,
+                          int32_t ctx_dtype, int64_t c_sb, int64_t c_st, const uint8_t* key_pad,
+                          const float* prob_mask, float* probs_out, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
+                          int32_t hd, int32_t causal, int32_t q_pos0, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the
  * library is bracketed by two events on its stream; end() synchronises the device and returns, per kernel kind
  * (0 gemm, 1 dwconv+ln, 2 stem, 3 ln_rows, 4 pool, 5 elementwise, 6 attention, 7 lstm, 8 loss, 9 optimizer),
@@ -166,6 +222,7 @@ CCX_API int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float
  * ------------------------------------------------------------------------------------------------ */
 #define CCX_PROF_KINDS 10
 CCX_API int ccx_prof_begin(void);
+CCX_API int ccx_prof_spans(int32_t* kind_host, double* ms_host, double* work_host, int32_t max);
 CCX_API int ccx_prof_end(double* ms_per_kind_host, double* work_per_kind_host, int64_t* launches_per_kind_host,
                          int32_t n_kinds);
 

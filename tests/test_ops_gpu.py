@@ -77,7 +77,7 @@ def test_ln_rows_patchmerge_equals_ln2d_plus_conv_im2col(C):
     out = torch.empty(B * H * W // 4, 4 * C, device="cuda")
     xd, gd, ed = x.cuda(), gam.cuda(), bet.cuda()
     _lib.check(_lib.lib().ccx_ln_rows(xd.data_ptr(), gd.data_ptr(), ed.data_ptr(),
-                                      out.data_ptr(), None, B * H * W, C, 1e-6, _lib.CCX_F32, 1, H, W,
+                                      out.data_ptr(), None, None, B * H * W, C, 1e-6, _lib.CCX_F32, 1, H, W,
                                       _lib.stream_ptr()))
     wm = wc.permute(0, 2, 3, 1).reshape(2 * C, 4 * C)
     got = (out.cpu() @ wm.t()).view(B, H // 2, W // 2, 2 * C)
@@ -85,7 +85,7 @@ def test_ln_rows_patchmerge_equals_ln2d_plus_conv_im2col(C):
     # plain (no merge) bf16 output
     o2 = torch.empty(B * H * W, C, dtype=torch.bfloat16, device="cuda")
     _lib.check(_lib.lib().ccx_ln_rows(xd.data_ptr(), gd.data_ptr(), ed.data_ptr(),
-                                      o2.data_ptr(), None, B * H * W, C, 1e-6, _lib.CCX_BF16, 0, H, W,
+                                      o2.data_ptr(), None, None, B * H * W, C, 1e-6, _lib.CCX_BF16, 0, H, W,
                                       _lib.stream_ptr()))
     assert rel_err(o2.float().view(B, H, W, C), ln) < 1e-2
 
