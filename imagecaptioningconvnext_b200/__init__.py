@@ -4,6 +4,8 @@
 (models/encoder.py, models/decoder.py, models/transformerDecoder.py) and run on hand-written CUDA kernels in
 ``libccx.so`` (C ABI: include/ccx.h).  No eager / CPU fallback exists.
 """
+from .decoder import Attention, DecoderWithAttention  # noqa: F401
 from .encoder import Encoder  # noqa: F401
+from .transformerDecoder import PositionalEncoding, TransformerDecoder  # noqa: F401
 
-__all__ = ["Encoder"]
+__all__ = ["Encoder", "Attention", "DecoderWithAttention", "PositionalEncoding", "TransformerDecoder"]

@@ -1,0 +1,66 @@
+"""Host-side helpers shared by the decoder modules: parameter holders whose ``forward`` runs on libccx, and the
+prepared-weight cache (bf16 / tf32-split copies of the fp32 master weights, rebuilt when a parameter changes)."""
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import Operand, ptr
+
+
+class CcxLinear(nn.Linear):
+    """nn.Linear's parameters / init / state_dict keys; ``forward`` is the tcgen05 GEMM (no autograd: modules
+    that train call the autograd Functions in *_train.py instead)."""
+
+    def __init__(self, in_features, out_features, bias=True, compute_dtype=torch.float32):
+        super().__init__(in_features, out_features, bias=bias)
+        self.compute_dtype = compute_dtype
+        self._key, self._w = None, None
+
+    def operand(self):
+        key = (self.weight.data_ptr(), self.weight._version, self.compute_dtype)
+        if key != self._key:
+            self._w, self._key = Operand.prepare(self.weight.detach(), self.compute_dtype), key
+        return self._w
+
+    def forward(self, x):
+        _lib.require_cuda(x, "input")
+        shp = x.shape
+        a = Operand.prepare(x.reshape(-1, shp[-1]).float().contiguous(), self.compute_dtype)
+        y = _lib.linear(a, self.operand(), bias=None if self.bias is None else self.bias.detach())
+        return y.view(*shp[:-1], self.out_features)
+
+
+class CcxEmbedding(nn.Embedding):
+    """nn.Embedding's parameters / init; ``forward`` is the gather kernel."""
+
+    def forward(self, tokens):
+        _lib.require_cuda(tokens, "tokens")
+        tok = tokens.reshape(-1, 1).contiguous().long()
+        n, D = tok.shape[0], self.embedding_dim
+        out = torch.empty((n, D), dtype=torch.float32, device=tokens.device)
+        _lib.check(_lib.lib().ccx_embed_rows(ptr(tok), 1, 0, ptr(self.weight.detach()), self.num_embeddings, D, None,
+                                             None, ptr(out), D, 0, None, None, _lib.CCX_F32, 0, 0, n, 1,
+                                             _lib.stream_ptr()), "embed_rows")
+        return out.view(*tokens.shape, D)
+
+
+class PreparedCache:
+    """Caches ``owner._prepare()`` (dict of kernel-side weight tensors) until any parameter changes."""
+
+    def __init__(self, owner):
+        self._owner = [owner]   # list: keep the module out of nn.Module's attribute registration
+        self._key, self._val = None, None
+
+    def get(self):
+        owner = self._owner[0]
+        params = list(owner.parameters())
+        key = (owner.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(), sum(p._version for p in params))
+        if key != self._key:
+            for p in params:
+                if not p.is_cuda or p.dtype != torch.float32:
+                    raise ValueError("parameters must be float32 CUDA tensors (call .cuda()); there is no CPU path")
+            self._val, self._key = owner._prepare(), key
+        return self._val
+
+    def invalidate(self):
+        self._key = None

@@ -57,12 +57,12 @@ SIGNATURES = {
                                  _i64, _i32, _i32, _vp]),
     "ccx_mean_pixels": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i64, _vp]),
     "ccx_bahdanau_attention": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i64, _i32,
-                                         _i32, _i32, _i32, _vp]),
+                                         _i32, _i32, _i32, _i32, _i32, _vp]),
     "ccx_lstm_pointwise": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _vp, _i64, _vp,
                                      _i64, _i32, _i32, _vp]),
     "ccx_greedy_next": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp]),
     "ccx_mha_small": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i32, _i64, _i64, _vp,
-                                _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp]),
+                                _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "ccx_avgpool_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ccx_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ccx_encoder_run": (C.c_int, [C.POINTER(EncoderWeights), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
@@ -168,6 +168,22 @@ class Operand:
 
     def __init__(self, hi, lo, dtype):
         self.hi, self.lo, self.dtype = hi, lo, dtype
+
+    def map(self, fn):
+        """Apply a view-producing function (slice / reshape) to both halves."""
+        return Operand(fn(self.hi), None if self.lo is None else fn(self.lo), self.dtype)
+
+    @property
+    def lo_ptr(self):
+        return None if self.lo is None else self.lo.data_ptr()
+
+    @staticmethod
+    def zeros(shape, compute_dtype, device):
+        op = Operand.empty(shape, compute_dtype, device)
+        op.hi.zero_()
+        if op.lo is not None:
+            op.lo.zero_()
+        return op
 
     @staticmethod
     def prepare(x_fp32, compute_dtype):

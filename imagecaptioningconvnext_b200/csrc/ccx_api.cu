@@ -83,9 +83,9 @@ int ccx_mean_pixels(const float* enc, int32_t B, int32_t P, int32_t E, void* op_
 int ccx_bahdanau_attention(const float* att1, const float* hg, int64_t ldhg, const float* w_f, const float* b_f,
                            const float* enc, const float* active, float* alpha_out, int64_t alpha_ld,
                            void* awe_hi, float* awe_lo, int32_t awe_dtype, int64_t ld_awe, int32_t bt, int32_t P,
-                           int32_t A, int32_t E, void* stream) {
+                           int32_t A, int32_t E, int32_t apply_gate, int32_t enc_group, void* stream) {
   return bahdanau_attention(att1, hg, ldhg, w_f, b_f, enc, active, alpha_out, alpha_ld, awe_hi, awe_lo, awe_dtype,
-                            ld_awe, bt, P, A, E, as_stream(stream));
+                            ld_awe, bt, P, A, E, apply_gate, enc_group, as_stream(stream));
 }
 
 int ccx_lstm_pointwise(const float* gates, int64_t ldg, const float* c_prev, float* c_new, void* hn_hi,
@@ -107,9 +107,9 @@ int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const float* k, in
                   const float* v, int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo, int32_t ctx_dtype,
                   int64_t c_sb, int64_t c_st, const uint8_t* key_pad, const float* prob_mask, float* probs_out,
                   int32_t B, int32_t H, int32_t Tq, int32_t Tk, int32_t hd, int32_t causal, int32_t q_pos0,
-                  float scale, void* stream) {
+                  float scale, int32_t kv_group, void* stream) {
   return mha_small(q, q_sb, q_st, k, k_sb, k_st, v, v_sb, v_st, ctx_hi, ctx_lo, ctx_dtype, c_sb, c_st, key_pad,
-                   prob_mask, probs_out, B, H, Tq, Tk, hd, causal, q_pos0, scale, as_stream(stream));
+                   prob_mask, probs_out, B, H, Tq, Tk, hd, causal, q_pos0, scale, kv_group, as_stream(stream));
 }
 
 int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,

@@ -28,7 +28,7 @@ int mean_pixels(const float* enc, int B, int P, int E, void* op_hi, float* op_lo
 int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* b_f,
                        const float* enc, const float* active, float* alpha_out, long long alpha_ld, void* awe_hi,
                        float* awe_lo, int awe_dtype, long long ld_awe, int bt, int P, int A, int E,
-                       cudaStream_t stream);
+                       int apply_gate, int enc_group, cudaStream_t stream);
 int lstm_pointwise(const float* gates, long long ldg, const float* c_prev, float* c_new, void* hn_hi, float* hn_lo,
                    long long ld_hn, void* ha_hi, float* ha_lo, long long ld_ha, int op_dtype, const float* dropmask,
                    long long ld_dm, float* h_plain, long long ld_hp, int bt, int D, cudaStream_t stream);
@@ -38,6 +38,6 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               const float* v, long long v_sb, long long v_st, void* ctx_hi, float* ctx_lo, int ctx_dtype,
               long long c_sb, long long c_st, const unsigned char* key_pad, const float* prob_mask,
               float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
-              cudaStream_t stream);
+              int kv_group, cudaStream_t stream);
 
 }  // namespace ccx

@@ -139,12 +139,13 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
                           const float* __restrict__ active,  // [bt] 1/0 or nullptr
                           float* __restrict__ alpha_out, long long alpha_ld,  // row b at alpha_out + b*alpha_ld
                           OpOut awe, long long ld_awe,     // row b at b*ld_awe (column offset folded into pointers)
-                          int P, int A, int E) {
+                          int P, int A, int E, int apply_gate, int enc_group) {
   extern __shared__ float att_sm[];
   float* s_att2 = att_sm;        // [A]
   float* s_wf = att_sm + A;      // [A]
   __shared__ float s_e[ATT_MAX_P];
   const int b = blockIdx.x;
+  const int be = b / enc_group;  // row of att1 / enc this decode row reads (beam search: beams share the image)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < A; i += 256) {
     s_att2[i] = hg[b * ldhg + i];
@@ -153,7 +154,7 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
   __syncthreads();
   const float bf = b_f ? __ldg(b_f) : 0.f;
   for (int p = warp; p < P; p += 8) {
-    const float4* a1 = reinterpret_cast<const float4*>(att1 + (static_cast<long long>(b) * P + p) * A);
+    const float4* a1 = reinterpret_cast<const float4*>(att1 + (static_cast<long long>(be) * P + p) * A);
     float acc = 0.f;
     for (int i = lane; i < A / 4; i += 32) {
       const float4 v = __ldg(a1 + i);
@@ -189,7 +190,7 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
   }
   __syncthreads();
   for (int e4 = threadIdx.x; e4 < E / 4; e4 += 256) {
-    const float4* src = reinterpret_cast<const float4*>(enc + static_cast<long long>(b) * P * E) + e4;
+    const float4* src = reinterpret_cast<const float4*>(enc + static_cast<long long>(be) * P * E) + e4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = 0; p < P; ++p) {
       const float4 v = __ldg(src + static_cast<long long>(p) * (E / 4));
@@ -197,11 +198,13 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
       acc.x = fmaf(v.x, a, acc.x); acc.y = fmaf(v.y, a, acc.y);
       acc.z = fmaf(v.z, a, acc.z); acc.w = fmaf(v.w, a, acc.w);
     }
-    const float4 gp = *reinterpret_cast<const float4*>(hg + b * ldhg + A + e4 * 4);
-    acc.x *= 1.0f / (1.0f + expf(-gp.x));
-    acc.y *= 1.0f / (1.0f + expf(-gp.y));
-    acc.z *= 1.0f / (1.0f + expf(-gp.z));
-    acc.w *= 1.0f / (1.0f + expf(-gp.w));
+    if (apply_gate) {
+      const float4 gp = *reinterpret_cast<const float4*>(hg + b * ldhg + A + e4 * 4);
+      acc.x *= 1.0f / (1.0f + expf(-gp.x));
+      acc.y *= 1.0f / (1.0f + expf(-gp.y));
+      acc.z *= 1.0f / (1.0f + expf(-gp.z));
+      acc.w *= 1.0f / (1.0f + expf(-gp.w));
+    }
     store_op4(awe, b * ld_awe + e4 * 4, acc);
   }
 }
@@ -209,13 +212,14 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
 int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* b_f,
                        const float* enc, const float* active, float* alpha_out, long long alpha_ld, void* awe_hi,
                        float* awe_lo, int awe_dtype, long long ld_awe, int bt, int P, int A, int E,
-                       cudaStream_t stream) {
+                       int apply_gate, int enc_group, cudaStream_t stream) {
   if (bt <= 0) return CCX_OK;
   if (P <= 0 || P > ATT_MAX_P || A % 4 != 0 || E % 4 != 0 || (ldhg % 4) != 0) return CCX_ERR_SHAPE;
   OpOut awe{awe_hi, awe_lo, awe_dtype};
   ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (A + E) * 4.0);
   bahdanau_attention_kernel<<<bt, 256, 2 * A * sizeof(float), stream>>>(att1, hg, ldhg, w_f, b_f, enc, active,
-                                                                        alpha_out, alpha_ld, awe, ld_awe, P, A, E);
+                                                                        alpha_out, alpha_ld, awe, ld_awe, P, A, E,
+                                                                        apply_gate, enc_group > 0 ? enc_group : 1);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
@@ -318,6 +322,7 @@ struct MhaArgs {
   const float* prob_mask;        // [B, H, Tq, Tk] dropout multiplier or nullptr
   float* probs_out;              // [B, H, Tq, Tk] softmax output (before dropout) or nullptr
   int B, H, Tq, Tk, hd;
+  int kv_group;                  // k/v batch row = b / kv_group (beam search: beams share the image memory)
   int causal;                    // key j allowed iff j <= q_pos0 + i
   int q_pos0;
   float scale;
@@ -332,11 +337,12 @@ mha_small_kernel(MhaArgs a) {
   float* s_q = s_v + a.Tk * ldk;          // [4 warps][hd]
   float* s_p = s_q + 4 * hd;              // [4 warps][Tk]
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const long long bk = b / a.kv_group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int idx = threadIdx.x; idx < a.Tk * hd; idx += 128) {
     const int j = idx / hd, d = idx - j * hd;
-    s_k[j * ldk + d] = a.k[b * a.k_sb + j * a.k_st + h * hd + d];
-    s_v[j * ldk + d] = a.v[b * a.v_sb + j * a.v_st + h * hd + d];
+    s_k[j * ldk + d] = a.k[bk * a.k_sb + j * a.k_st + h * hd + d];
+    s_v[j * ldk + d] = a.v[bk * a.v_sb + j * a.v_st + h * hd + d];
   }
   __syncthreads();
   float* q = s_q + warp * hd;
@@ -383,7 +389,7 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               const float* v, long long v_sb, long long v_st, void* ctx_hi, float* ctx_lo, int ctx_dtype,
               long long c_sb, long long c_st, const unsigned char* key_pad, const float* prob_mask,
               float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
-              cudaStream_t stream) {
+              int kv_group, cudaStream_t stream) {
   if (B <= 0 || Tq <= 0) return CCX_OK;
   if (Tk <= 0 || hd <= 0 || H <= 0) return CCX_ERR_SHAPE;
   const size_t smem = (static_cast<size_t>(2) * Tk * (hd + 1) + 4 * hd + 4 * Tk) * sizeof(float);
@@ -403,6 +409,7 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
   a.key_pad = key_pad; a.prob_mask = prob_mask; a.probs_out = probs_out;
   a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.hd = hd;
   a.causal = causal; a.q_pos0 = q_pos0; a.scale = scale;
+  a.kv_group = kv_group > 0 ? kv_group : 1;
   ProfScope prof(PROF_ATTENTION, stream, (double)B * H * (Tq + 2.0 * Tk) * hd * 4.0);
   mha_small_kernel<<<B * H, 128, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;

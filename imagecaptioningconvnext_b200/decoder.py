@@ -1,0 +1,291 @@
+"""``Attention`` / ``DecoderWithAttention`` — drop-in for the reference's ``models/decoder.py:16-172``.
+
+Same constructor signature, attribute names and ``state_dict`` keys (``attention.{encoder_att,decoder_att,full_att}``,
+``embedding``, ``decode_step.{weight_ih,weight_hh,bias_ih,bias_hh}``, ``init_h``, ``init_c``, ``f_beta``, ``fc``); same
+``forward(teacherForcing, encoder_out, encoded_captions, caption_lengths, wordMap, maxDecodeLen)`` return tuples.
+
+What runs underneath (all libccx kernels, no torch compute on the path):
+  * ``encoder_att`` is time-invariant and is hoisted out of the step loop (the reference recomputes it 51x);
+  * per step: ONE tcgen05 GEMM for [decoder_att | f_beta](h), one fused attention kernel
+    (add+ReLU+dot+softmax-over-pixels+weighted-sum+sigmoid gate), ONE tcgen05 GEMM for the LSTM gates over the
+    concatenated operand [emb_t | awe | h] x [W_ih | W_hh]^T (no torch.cat), one point-wise LSTM kernel;
+  * teacher forcing: the vocabulary projection ``fc`` is hoisted into ONE GEMM over all (b, t) rows whose epilogue
+    zeroes the rows past each caption's length (the reference allocates zeros on the host and scatters);
+  * greedy: per-step fc GEMM with finished-row masking in the epilogue + an argmax/bookkeeping kernel; no
+    ``nonzero()`` host sync per step.
+Extra ctor kwarg: ``compute_dtype`` (float32 = 3xTF32, bfloat16).  There is no CPU path.
+"""
+import torch
+from torch import nn
+
+from . import _lib
+from ._host import CcxEmbedding, CcxLinear, PreparedCache
+from ._lib import Operand, ptr
+
+
+class Attention(nn.Module):
+    """models/decoder.py:16-31."""
+
+    def __init__(self, encoder_dim, decoder_dim, attention_dim, compute_dtype=torch.float32):
+        super().__init__()
+        self.encoder_att = CcxLinear(encoder_dim, attention_dim, compute_dtype=compute_dtype)
+        self.decoder_att = CcxLinear(decoder_dim, attention_dim, compute_dtype=compute_dtype)
+        self.full_att = CcxLinear(attention_dim, 1, compute_dtype=compute_dtype)
+        self.relu = nn.ReLU()
+        self.softmax = nn.Softmax(dim=1)
+
+    def forward(self, encoder_out, decoder_hidden):
+        """(b,P,E), (b,D) -> (awe (b,E), alpha (b,P)); un-hoisted form for external callers (caption.py:98)."""
+        b, P, E = encoder_out.shape
+        enc = encoder_out.contiguous().float()
+        att1 = self.encoder_att(enc.view(b * P, E))
+        att2 = self.decoder_att(decoder_hidden)
+        A = att2.shape[1]
+        alpha = torch.empty((b, P), dtype=torch.float32, device=enc.device)
+        awe = torch.empty((b, E), dtype=torch.float32, device=enc.device)
+        w_f = self.full_att.weight.detach().view(-1)
+        _lib.check(_lib.lib().ccx_bahdanau_attention(
+            ptr(att1), ptr(att2), A, ptr(w_f), ptr(self.full_att.bias.detach()), ptr(enc), None, ptr(alpha), P,
+            ptr(awe), None, _lib.CCX_F32, E, b, P, A, E, 0, 1, _lib.stream_ptr()), "attention")
+        return awe, alpha
+
+
+class _LSTMCellParams(nn.Module):
+    """Parameter holder with nn.LSTMCell's names/shapes/init (uniform +-1/sqrt(hidden)); forward on libccx."""
+
+    def __init__(self, input_size, hidden_size, compute_dtype):
+        super().__init__()
+        self.input_size, self.hidden_size, self.compute_dtype = input_size, hidden_size, compute_dtype
+        k = 1.0 / hidden_size ** 0.5
+        self.weight_ih = nn.Parameter(torch.empty(4 * hidden_size, input_size).uniform_(-k, k))
+        self.weight_hh = nn.Parameter(torch.empty(4 * hidden_size, hidden_size).uniform_(-k, k))
+        self.bias_ih = nn.Parameter(torch.empty(4 * hidden_size).uniform_(-k, k))
+        self.bias_hh = nn.Parameter(torch.empty(4 * hidden_size).uniform_(-k, k))
+
+    def forward(self, x, state):
+        """(x (b,In), (h, c)) -> (h', c'), as nn.LSTMCell (external callers: caption.py:102)."""
+        h, c = state
+        cd = self.compute_dtype
+        w = Operand.prepare(torch.cat([self.weight_ih.detach(), self.weight_hh.detach()], dim=1), cd)
+        a = Operand.prepare(torch.cat([x.float(), h.float()], dim=1), cd)
+        gates = _lib.linear(a, w, bias=(self.bias_ih + self.bias_hh).detach())
+        b, D = h.shape
+        c2 = torch.empty_like(c, dtype=torch.float32)
+        h2 = torch.empty_like(c2)
+        _lib.check(_lib.lib().ccx_lstm_pointwise(ptr(gates), 4 * D, ptr(c.float().contiguous()), ptr(c2), None, None, 0,
+                                                 None, None, 0, _lib.CCX_F32, None, 0, ptr(h2), D, b, D,
+                                                 _lib.stream_ptr()), "lstm_pointwise")
+        return h2, c2
+
+
+class DecoderWithAttention(nn.Module):
+    def __init__(self, attention_dim, embed_dim, decoder_dim, vocab_size, device, encoder_dim=1024, dropout=0.5,
+                 compute_dtype=torch.float32):
+        super().__init__()
+        _lib.dt_code(compute_dtype)
+        self.encoder_dim = encoder_dim
+        self.attention_dim = attention_dim
+        self.embed_dim = embed_dim
+        self.decoder_dim = decoder_dim
+        self.vocab_size = vocab_size
+        self.compute_dtype = compute_dtype
+        self.dropout_p = dropout
+        cd = compute_dtype
+        self.attention = Attention(encoder_dim, decoder_dim, attention_dim, cd)
+        self.embedding = CcxEmbedding(vocab_size, embed_dim)
+        self.dropout = nn.Dropout(p=dropout)                      # mask source only (see _dropout_mask)
+        self.decode_step = _LSTMCellParams(embed_dim + encoder_dim, decoder_dim, cd)
+        self.init_h = CcxLinear(encoder_dim, decoder_dim, compute_dtype=cd)
+        self.init_c = CcxLinear(encoder_dim, decoder_dim, compute_dtype=cd)
+        self.f_beta = CcxLinear(decoder_dim, encoder_dim, compute_dtype=cd)
+        self.sigmoid = nn.Sigmoid()
+        self.fc = CcxLinear(decoder_dim, vocab_size, compute_dtype=cd)
+        self.init_weights()
+        self.device = device
+        self._cache = PreparedCache(self)
+        self.inject_dropmask = None   # tests: (B, T, decoder_dim) multiplier used instead of a fresh Bernoulli draw
+
+    def init_weights(self):
+        """models/decoder.py:58-61."""
+        self.embedding.weight.data.uniform_(-0.1, 0.1)
+        self.fc.bias.data.fill_(0)
+        self.fc.weight.data.uniform_(-0.1, 0.1)
+
+    # ---- prepared (kernel-side) weights ------------------------------------------------------------------------
+    def _prepare(self):
+        cd = self.compute_dtype
+        d = lambda p: p.detach()
+        att = self.attention
+        P = {}
+        P["w_enc_att"] = Operand.prepare(d(att.encoder_att.weight), cd)
+        P["b_enc_att"] = d(att.encoder_att.bias).contiguous()
+        P["w_h"] = Operand.prepare(torch.cat([d(att.decoder_att.weight), d(self.f_beta.weight)], dim=0), cd)
+        P["b_h"] = torch.cat([d(att.decoder_att.bias), d(self.f_beta.bias)]).contiguous()
+        P["w_f"] = d(att.full_att.weight).reshape(-1).contiguous()
+        P["b_f"] = d(att.full_att.bias).contiguous()
+        P["w_init_h"] = Operand.prepare(d(self.init_h.weight), cd)
+        P["w_init_c"] = Operand.prepare(d(self.init_c.weight), cd)
+        ds = self.decode_step
+        P["w_lstm"] = Operand.prepare(torch.cat([d(ds.weight_ih), d(ds.weight_hh)], dim=1), cd)
+        P["b_lstm"] = (d(ds.bias_ih) + d(ds.bias_hh)).contiguous()
+        P["w_fc"] = Operand.prepare(d(self.fc.weight), cd)
+        return P
+
+    def init_hidden_state(self, encoder_out):
+        """models/decoder.py:63-67 (external callers: caption.py:94)."""
+        b, Pn, E = encoder_out.shape
+        Pw = self._cache.get()
+        m = Operand.empty((b, E), self.compute_dtype, encoder_out.device)
+        _lib.check(_lib.lib().ccx_mean_pixels(ptr(encoder_out.contiguous()), b, Pn, E, ptr(m.hi), m.lo_ptr,
+                                              _lib.dt_code(m.dtype), E, _lib.stream_ptr()), "mean_pixels")
+        return (_lib.linear(m, Pw["w_init_h"], bias=self.init_h.bias.detach()),
+                _lib.linear(m, Pw["w_init_c"], bias=self.init_c.bias.detach()))
+
+    # ---- shared set-up -----------------------------------------------------------------------------------------
+    def _setup(self, enc, T):
+        """Hoisted work: att1 = encoder_att(enc), h0/c0, and the per-step operand buffer XH[t] = [emb | awe | h]."""
+        B, Pn, E = enc.shape
+        cd, dev = self.compute_dtype, enc.device
+        Pw = self._cache.get()
+        L = _lib.lib()
+        st = _lib.stream_ptr()
+        enc_op = Operand.prepare(enc.view(B * Pn, E), cd)
+        att1 = _lib.linear(enc_op, Pw["w_enc_att"], bias=Pw["b_enc_att"])            # (B*P, A) fp32
+        K = self.embed_dim + E + self.decoder_dim
+        XH = Operand.zeros((T + 1, B, K), cd, dev)
+        C_all = torch.empty((T + 1, B, self.decoder_dim), dtype=torch.float32, device=dev)
+        m = Operand.empty((B, E), cd, dev)
+        _lib.check(L.ccx_mean_pixels(ptr(enc), B, Pn, E, ptr(m.hi), m.lo_ptr, _lib.dt_code(cd), E, st), "mean_pixels")
+        hoff = self.embed_dim + E
+        h0 = XH.map(lambda t: t[0, :, hoff:])
+        if cd == torch.bfloat16:
+            _lib.linear(m, Pw["w_init_h"], bias=self.init_h.bias.detach(), out=h0.hi)
+        else:
+            _lib.linear(m, Pw["w_init_h"], bias=self.init_h.bias.detach(), out=h0, split=True)
+        _lib.linear(m, Pw["w_init_c"], bias=self.init_c.bias.detach(), out=C_all[0])
+        return Pw, att1, XH, C_all
+
+    def _step(self, Pw, enc, att1, XH, C_all, HG, G, t, bt, alphas_t, alpha_ld, active, h_all, ha_ld, dm, dm_ld,
+              enc_group=1):
+        """One decode step for rows [0, bt): models/decoder.py:102-108."""
+        L, st = _lib.lib(), _lib.stream_ptr()
+        Pn, E, A, D = enc.shape[1], enc.shape[2], self.attention_dim, self.decoder_dim
+        hoff = self.embed_dim + E
+        code = _lib.dt_code(self.compute_dtype)
+        xh_t = XH.map(lambda x: x[t, :bt])
+        h_prev = XH.map(lambda x: x[t, :bt, hoff:])
+        hg = _lib.linear(h_prev, Pw["w_h"], bias=Pw["b_h"], out=HG[t, :bt])                  # [att2 | gate pre-act]
+        awe = XH.map(lambda x: x[t, :bt, self.embed_dim:hoff])
+        _lib.check(L.ccx_bahdanau_attention(ptr(att1), ptr(hg), hg.stride(0), ptr(Pw["w_f"]), ptr(Pw["b_f"]),
+                                            ptr(enc), ptr(active), ptr(alphas_t), alpha_ld, ptr(awe.hi), awe.lo_ptr,
+                                            code, awe.hi.stride(0), bt, Pn, A, E, 1, enc_group, st), "attention")
+        gates = _lib.linear(xh_t, Pw["w_lstm"], bias=Pw["b_lstm"], out=G[t, :bt])
+        h_next = XH.map(lambda x: x[t + 1, :bt, hoff:])
+        _lib.check(L.ccx_lstm_pointwise(ptr(gates), gates.stride(0), ptr(C_all[t]), ptr(C_all[t + 1]),
+                                        ptr(h_next.hi), h_next.lo_ptr, h_next.hi.stride(0),
+                                        ptr(h_all.hi), h_all.lo_ptr, ha_ld, code, ptr(dm), dm_ld, None, 0, bt, D,
+                                        st), "lstm_pointwise")
+
+    def _dropout_mask(self, B, T, dev):
+        """nn.Dropout(p) of models/decoder.py:109 as a multiplier tensor (None in eval mode)."""
+        if not self.training or self.dropout_p == 0:
+            return None
+        if self.inject_dropmask is not None:
+            return self.inject_dropmask.to(device=dev, dtype=torch.float32).contiguous()
+        keep = 1.0 - self.dropout_p
+        return (torch.bernoulli(torch.full((B, T, self.decoder_dim), keep, device=dev)) / keep).contiguous()
+
+    # ---- reference API -----------------------------------------------------------------------------------------
+    def forwardWithTeacherForcing(self, encoder_out, encoded_captions, caption_lengths):
+        """models/decoder.py:69-113."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .decoder_train import lstm_teacher_forcing_with_grad
+            return lstm_teacher_forcing_with_grad(self, encoder_out, encoded_captions, caption_lengths)
+        return self._tf_forward(encoder_out, encoded_captions, caption_lengths)[:5]
+
+    def _tf_forward(self, encoder_out, encoded_captions, caption_lengths):
+        _lib.require_cuda(encoder_out, "encoder_out")
+        B, E = encoder_out.size(0), encoder_out.size(-1)
+        V, D = self.vocab_size, self.decoder_dim
+        dev = encoder_out.device
+        enc = encoder_out.reshape(B, -1, E)
+        Pn = enc.size(1)
+        caption_lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)
+        enc = enc[sort_ind].float().contiguous()
+        encoded_captions = encoded_captions[sort_ind].contiguous()
+        decode_lengths = (caption_lengths - 1).tolist()
+        T = max(decode_lengths)
+        L, st, cd = _lib.lib(), _lib.stream_ptr(), self.compute_dtype
+        code = _lib.dt_code(cd)
+
+        Pw, att1, XH, C_all = self._setup(enc, T)
+        HG = torch.empty((T, B, self.attention_dim + E), dtype=torch.float32, device=dev)
+        G = torch.empty((T, B, 4 * D), dtype=torch.float32, device=dev)
+        alphas = torch.zeros((B, T, Pn), dtype=torch.float32, device=dev)
+        H_all = Operand.zeros((B, T, D), cd, dev)
+        dm = self._dropout_mask(B, T, dev)
+        # all embeddings at once: XH[t, b, 0:embed] = embedding[caps[b, t]]
+        K = XH.hi.shape[2]
+        _lib.check(L.ccx_embed_rows(ptr(encoded_captions), encoded_captions.stride(0), 0, ptr(self.embedding.weight),
+                                    V, self.embed_dim, None, None, None, 0, 0, ptr(XH.hi), XH.lo_ptr, code,
+                                    K, B * K, B, T, st), "embed_rows")
+        bts = [sum(l > t for l in decode_lengths) for t in range(T)]
+        for t in range(T):
+            bt = bts[t]
+            h_all_t = H_all.map(lambda x: x[:, t])
+            dm_t = None if dm is None else dm[:, t]
+            self._step(Pw, enc, att1, XH, C_all, HG, G, t, bt, alphas[:, t], T * Pn, None, h_all_t, T * D,
+                       dm_t, T * D)
+        valid = (torch.arange(T, device=dev).unsqueeze(0) <
+                 torch.tensor(decode_lengths, device=dev).unsqueeze(1)).to(torch.float32).reshape(-1).contiguous()
+        predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)
+        _lib.linear(H_all.map(lambda x: x.view(B * T, D)), Pw["w_fc"], bias=self.fc.bias.detach(), rowscale=valid,
+                    rows_per_group=1, out=predictions.view(B * T, V))
+        saved = dict(enc=enc, att1=att1, XH=XH, C_all=C_all, HG=HG, G=G, H_all=H_all, dm=dm, valid=valid, bts=bts,
+                     sort_ind=sort_ind, caps=encoded_captions, Pw=Pw)
+        return predictions, encoded_captions, decode_lengths, alphas, sort_ind, saved
+
+    @torch.no_grad()
+    def forwardWithoutTeacherForcing(self, encoder_out, wordMap, maxDecodeLen):
+        """models/decoder.py:119-163 (greedy).  Finished rows are masked on the device instead of being compacted
+        with nonzero(): their predictions/alphas/sequences stay zero exactly as in the reference."""
+        _lib.require_cuda(encoder_out, "encoder_out")
+        B, E = encoder_out.size(0), encoder_out.size(-1)
+        V, D, T = self.vocab_size, self.decoder_dim, int(maxDecodeLen)
+        dev = encoder_out.device
+        enc = encoder_out.reshape(B, -1, E).float().contiguous()
+        Pn = enc.size(1)
+        L, st, cd = _lib.lib(), _lib.stream_ptr(), self.compute_dtype
+        code = _lib.dt_code(cd)
+        Pw, att1, XH, C_all = self._setup(enc, T)
+        HG = torch.empty((T, B, self.attention_dim + E), dtype=torch.float32, device=dev)
+        G = torch.empty((T, B, 4 * D), dtype=torch.float32, device=dev)
+        predictions = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
+        alphas = torch.zeros((B, T, Pn), dtype=torch.float32, device=dev)
+        sequences = torch.zeros((B, T), dtype=torch.long, device=dev)
+        tokens = torch.zeros((B, T + 1), dtype=torch.long, device=dev)
+        tokens[:, 0] = wordMap['<start>']
+        active = torch.ones(B, dtype=torch.float32, device=dev)
+        h_cur = Operand.empty((B, D), cd, dev)
+        dm = self._dropout_mask(B, T, dev)
+        K = XH.hi.shape[2]
+        for t in range(T):
+            _lib.check(L.ccx_embed_rows(ptr(tokens), T + 1, t, ptr(self.embedding.weight), V, self.embed_dim, None,
+                                        None, None, 0, 0, ptr(XH.hi[t]), None if XH.lo is None else ptr(XH.lo[t]),
+                                        code, K, 0, B, 1, st), "embed_rows")
+            dm_t = None if dm is None else dm[:, t]
+            self._step(Pw, enc, att1, XH, C_all, HG, G, t, B, alphas[:, t], T * Pn, active, h_cur, D, dm_t, T * D)
+            p_t = predictions[:, t]
+            _lib.linear(h_cur, Pw["w_fc"], bias=self.fc.bias.detach(), rowscale=active, rows_per_group=1, out=p_t)
+            _lib.check(L.ccx_greedy_next(ptr(p_t), T * V, B, V, t, T, ptr(sequences), ptr(active),
+                                         tokens.data_ptr() + 8 * (t + 1), T + 1, wordMap['<end>'], st), "greedy_next")
+            if t % 8 == 7 and not bool(active.any()):   # the reference breaks when every row has finished
+                break
+        return predictions, alphas, sequences
+
+    def forward(self, teacherForcing, encoder_out, encoded_captions=None, caption_lengths=None, wordMap=None,
+                maxDecodeLen=None):
+        """models/decoder.py:165-172."""
+        if teacherForcing is True:
+            return self.forwardWithTeacherForcing(encoder_out, encoded_captions, caption_lengths)
+        return self.forwardWithoutTeacherForcing(encoder_out, wordMap, maxDecodeLen)

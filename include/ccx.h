@@ -181,11 +181,14 @@ CCX_API int ccx_mean_pixels(const float* enc, int32_t B, int32_t P, int32_t E, v
 /* One decode step of Attention.forward + the f_beta gate: models/decoder.py:25-31,104-105.
  * att1 = encoder_att(enc) [B,P,A] is hoisted (time-invariant); hg[b] = [decoder_att(h) | f_beta(h)] (A+E cols).
  * alpha = softmax_p(w_f . relu(att1 + att2) + b_f); awe = sigmoid(f_beta h) * sum_p alpha_p enc_p.
- * alpha -> alpha_out[b*alpha_ld + p] (skipped for rows with active[b]==0); awe -> operand row b at b*ld_awe. */
+ * alpha -> alpha_out[b*alpha_ld + p] (skipped for rows with active[b]==0); awe -> operand row b at b*ld_awe.
+ * apply_gate = 0 gives plain Attention.forward; enc_group = g makes decode row b read att1/enc row b/g
+ * (beam search: the g beams of an image share its features, caption.py:77 expand()). */
 CCX_API int ccx_bahdanau_attention(const float* att1, const float* hg, int64_t ldhg, const float* w_f,
                                    const float* b_f, const float* enc, const float* active, float* alpha_out,
                                    int64_t alpha_ld, void* awe_hi, float* awe_lo, int32_t awe_dtype, int64_t ld_awe,
-                                   int32_t bt, int32_t P, int32_t A, int32_t E, void* stream);
+                                   int32_t bt, int32_t P, int32_t A, int32_t E, int32_t apply_gate,
+                                   int32_t enc_group, void* stream);
 
 /* nn.LSTMCell point-wise half (torch/nn/modules/rnn.py:1755-1778; gates = [i|f|g|o] pre-activations incl. both
  * biases): c' = s(f) c + s(i) tanh(g), h' = s(o) tanh(c').  h' goes to the next step's GEMM operand (hn_*), to
@@ -207,12 +210,14 @@ CCX_API int ccx_greedy_next(const float* preds, int64_t ld_preds, int32_t B, int
  * multi_head_attention_forward) for self-attention (causal + key padding) and cross-attention over pixels.
  * Element (b, i, h*hd+d) of q at q[b*q_sb + i*q_st + h*hd + d]; likewise k, v, ctx.  key_pad [B,Tk] 1 = masked.
  * causal: key j allowed iff j <= q_pos0 + i (q_pos0 = cache length for KV-cache decoding).
- * prob_mask [B,H,Tq,Tk]: attention-dropout multiplier (train); probs_out: softmax saved for backward. */
+ * prob_mask [B,H,Tq,Tk]: attention-dropout multiplier (train); probs_out: softmax saved for backward.
+ * kv_group = g: k/v batch row is b/g (beams of one image share its projected memory, caption.py:182). */
 CCX_API int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
                           const float* v, int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo,
                           int32_t ctx_dtype, int64_t c_sb, int64_t c_st, const uint8_t* key_pad,
                           const float* prob_mask, float* probs_out, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
-                          int32_t hd, int32_t causal, int32_t q_pos0, float scale, void* stream);
+                          int32_t hd, int32_t causal, int32_t q_pos0, float scale, int32_t kv_group,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the

@@ -1,0 +1,412 @@
+"""CPU oracle for the two caption decoders and the search loops.  Test infrastructure only (see oracle/__init__.py).
+
+Restates, in plain torch tensor ops on a reference-format ``state_dict``:
+  * models/decoder.py:25-31        Attention.forward                          -> ``attention``
+  * models/decoder.py:63-67        init_hidden_state                          -> ``init_hidden_state``
+  * models/decoder.py:69-113       forwardWithTeacherForcing                  -> ``lstm_teacher_forcing``
+  * models/decoder.py:119-163      forwardWithoutTeacherForcing (greedy)      -> ``lstm_greedy``
+  * caption.py:39-155              caption_image_beam_search (LSTM)           -> ``beam_search`` (step_fn = lstm)
+  * models/transformerDecoder.py:14-27,88-108   PositionalEncoding, TF forward -> ``transformer_teacher_forcing``
+  * models/transformerDecoder.py:110-160        greedy without KV cache        -> ``transformer_greedy``
+  * caption.py:160-255             caption_image_beam_search_transformer      -> ``beam_search`` (step_fn = transformer)
+  * trainMultiGPU.py:357-394       loss of the train step (packed CE + alpha regulariser) -> ``train_loss_*``
+The third-party arithmetic restated here is torch 2.11's nn.LSTMCell (torch/nn/modules/rnn.py:1755-1778),
+nn.TransformerDecoderLayer post-norm forward (torch/nn/modules/transformer.py:1089-1199) and
+F.multi_head_attention_forward (packed in-proj, 1/sqrt(hd) scaling, additive -inf masks).
+Every function works in the dtype of the tensors it is given (fp32 for parity, fp64 to label near-ties, H12).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic random-init weights in the reference's state_dict layout
+# ------------------------------------------------------------------------------------------------
+def _perturb(sd, seed, scale):
+    """Add small noise to every tensor so that zero-initialised biases / identical cloned layers do not hide
+    indexing bugs.  Deterministic in (seed, key order)."""
+    g = torch.Generator().manual_seed(seed + 7919)
+    for k in sd:
+        if sd[k].is_floating_point() and k != "pos_encoding.pe":
+            sd[k] = sd[k] + scale * sd[k].abs().mean().clamp_min(0.02) * torch.randn(sd[k].shape, generator=g)
+    return sd
+
+
+def random_lstm_decoder_state(seed=0, vocab=9490, attention_dim=512, embed_dim=512, decoder_dim=512,
+                              encoder_dim=1024, end_bias=None, perturb=0.5):
+    """Same module-construction order as models/decoder.py:35-61, so under the same seed the tensors equal
+    ``DecoderWithAttention(...).state_dict()`` bit for bit (checked by tests/golden/make_golden.py) before the
+    optional perturbation.  end_bias: value written to fc.bias[<end> = vocab-1]."""
+    from torch import nn
+    rng = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    mods = {}
+    mods["attention.encoder_att"] = nn.Linear(encoder_dim, attention_dim)
+    mods["attention.decoder_att"] = nn.Linear(decoder_dim, attention_dim)
+    mods["attention.full_att"] = nn.Linear(attention_dim, 1)
+    mods["embedding"] = nn.Embedding(vocab, embed_dim)
+    mods["decode_step"] = nn.LSTMCell(embed_dim + encoder_dim, decoder_dim, bias=True)
+    mods["init_h"] = nn.Linear(encoder_dim, decoder_dim)
+    mods["init_c"] = nn.Linear(encoder_dim, decoder_dim)
+    mods["f_beta"] = nn.Linear(decoder_dim, encoder_dim)
+    mods["fc"] = nn.Linear(decoder_dim, vocab)
+    mods["embedding"].weight.data.uniform_(-0.1, 0.1)
+    mods["fc"].bias.data.fill_(0)
+    mods["fc"].weight.data.uniform_(-0.1, 0.1)
+    torch.random.set_rng_state(rng)
+    sd = {}
+    for name, m in mods.items():
+        for k, v in m.state_dict().items():
+            sd[f"{name}.{k}"] = v.detach().clone()
+    if perturb:
+        _perturb(sd, seed, perturb)
+    if end_bias is not None:
+        sd["fc.bias"][vocab - 1] = end_bias
+    return sd
+
+
+def random_transformer_decoder_state(seed=0, vocab=9490, embed_dim=512, decoder_dim=512, max_len=52,
+                                     encoder_dim=1024, nheads=8, nlayers=6, end_bias=None, perturb=0.5):
+    """Same construction order as models/transformerDecoder.py:54-86 (random embeddings branch)."""
+    from torch import nn
+    rng = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    emb = nn.Embedding(vocab, embed_dim)
+    layer = nn.TransformerDecoderLayer(d_model=embed_dim, nhead=nheads, dim_feedforward=decoder_dim, dropout=0.5)
+    dec = nn.TransformerDecoder(layer, num_layers=nlayers)
+    fc_out = nn.Linear(embed_dim, vocab)
+    proj = nn.Linear(encoder_dim, embed_dim)
+    torch.random.set_rng_state(rng)
+    sd = {"embedding.weight": emb.weight.detach().clone(),
+          "pos_encoding.pe": positional_encoding(embed_dim, max_len).unsqueeze(0)}
+    for k, v in dec.state_dict().items():
+        sd["transformer_decoder." + k] = v.detach().clone()
+    for k, v in fc_out.state_dict().items():
+        sd["fc_out." + k] = v.detach().clone()
+    for k, v in proj.state_dict().items():
+        sd["encoder_proj." + k] = v.detach().clone()
+    if perturb:
+        _perturb(sd, seed, perturb)
+    if end_bias is not None:
+        sd["fc_out.bias"][vocab - 1] = end_bias
+    return sd
+
+
+def synthetic_features(B, seed, P=49, E=1024):
+    """Encoder-output-like features (B, 7, 7, E): non-negative-ish, O(1) scale."""
+    g = torch.Generator().manual_seed(seed)
+    s = int(round(P ** 0.5))
+    return torch.randn(B, s, s, E, generator=g) * 0.7
+
+
+def synthetic_captions(B, seed, vocab=9490, T=52, min_len=7):
+    """<start>, len-2 tokens in [1, V-4], <end>, then <pad>=0; lengths uniform in [min_len, T]."""
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(min_len, T + 1, (B, 1), generator=g)
+    caps = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        L = int(lens[b])
+        caps[b, 0] = vocab - 2
+        caps[b, 1:L - 1] = torch.randint(1, vocab - 3, (L - 2,), generator=g)
+        caps[b, L - 1] = vocab - 1
+    return caps, lens
+
+
+# ------------------------------------------------------------------------------------------------
+# LSTM + Bahdanau attention decoder
+# ------------------------------------------------------------------------------------------------
+def attention(sd, enc, h, att1=None):
+    """models/decoder.py:25-31.  enc (b,P,E), h (b,D) -> awe (b,E), alpha (b,P)."""
+    if att1 is None:
+        att1 = F.linear(enc, sd["attention.encoder_att.weight"], sd["attention.encoder_att.bias"])
+    att2 = F.linear(h, sd["attention.decoder_att.weight"], sd["attention.decoder_att.bias"])
+    att = F.linear(F.relu(att1 + att2.unsqueeze(1)), sd["attention.full_att.weight"],
+                   sd["attention.full_att.bias"]).squeeze(2)
+    alpha = F.softmax(att, dim=1)
+    awe = (enc * alpha.unsqueeze(2)).sum(dim=1)
+    return awe, alpha
+
+
+def init_hidden_state(sd, enc):
+    m = enc.mean(dim=1)
+    return F.linear(m, sd["init_h.weight"], sd["init_h.bias"]), F.linear(m, sd["init_c.weight"], sd["init_c.bias"])
+
+
+def lstm_cell(sd, x, h, c):
+    """torch nn.LSTMCell: gates = W_ih x + b_ih + W_hh h + b_hh, chunks (i, f, g, o)."""
+    g = F.linear(x, sd["decode_step.weight_ih"], sd["decode_step.bias_ih"]) + \
+        F.linear(h, sd["decode_step.weight_hh"], sd["decode_step.bias_hh"])
+    i, f, gg, o = g.chunk(4, dim=1)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+    h2 = torch.sigmoid(o) * torch.tanh(c2)
+    return h2, c2
+
+
+def lstm_step(sd, enc, emb, h, c):
+    """One decode step shared by TF / greedy / beam: models/decoder.py:102-108."""
+    awe, alpha = attention(sd, enc, h)
+    gate = torch.sigmoid(F.linear(h, sd["f_beta.weight"], sd["f_beta.bias"]))
+    h, c = lstm_cell(sd, torch.cat([emb, gate * awe], dim=1), h, c)
+    return h, c, alpha
+
+
+def lstm_teacher_forcing(sd, encoder_out, caps, caplens, dropmask=None):
+    """models/decoder.py:69-113.  dropmask: optional (B, max_dl, D) multiplier applied to h before fc (the
+    nn.Dropout of :109 with the mask injected, rows in SORTED order); None = eval mode."""
+    B, E = encoder_out.size(0), encoder_out.size(-1)
+    enc = encoder_out.reshape(B, -1, E)
+    lens, sort_ind = caplens.squeeze(1).sort(dim=0, descending=True)
+    enc, caps = enc[sort_ind], caps[sort_ind]
+    emb = sd["embedding.weight"][caps]
+    h, c = init_hidden_state(sd, enc)
+    dl = (lens - 1).tolist()
+    V = sd["fc.weight"].shape[0]
+    preds = torch.zeros(B, max(dl), V, dtype=enc.dtype)
+    alphas = torch.zeros(B, max(dl), enc.size(1), dtype=enc.dtype)
+    for t in range(max(dl)):
+        bt = sum(l > t for l in dl)
+        h, c, alpha = lstm_step(sd, enc[:bt], emb[:bt, t], h[:bt], c[:bt])
+        hd = h if dropmask is None else h * dropmask[:bt, t]
+        preds[:bt, t] = F.linear(hd, sd["fc.weight"], sd["fc.bias"])
+        alphas[:bt, t] = alpha
+    return preds, caps, dl, alphas, sort_ind
+
+
+def lstm_greedy(sd, encoder_out, start_tok, end_tok, max_len):
+    """models/decoder.py:119-163 (eval mode)."""
+    B, E = encoder_out.size(0), encoder_out.size(-1)
+    enc = encoder_out.reshape(B, -1, E)
+    h, c = init_hidden_state(sd, enc)
+    V = sd["fc.weight"].shape[0]
+    inputs = sd["embedding.weight"][torch.full((B,), start_tok, dtype=torch.long)].clone()
+    preds = torch.zeros(B, max_len, V, dtype=enc.dtype)
+    alphas = torch.zeros(B, max_len, enc.size(1), dtype=enc.dtype)
+    seqs = torch.zeros(B, max_len, dtype=torch.long)
+    finished = torch.zeros(B, dtype=torch.bool)
+    for t in range(max_len):
+        act = (~finished).nonzero(as_tuple=False).squeeze(1)
+        if len(act) == 0:
+            break
+        hn, cn, alpha = lstm_step(sd, enc[act], inputs[act], h[act], c[act])
+        p = F.linear(hn, sd["fc.weight"], sd["fc.bias"])
+        preds[act, t] = p
+        alphas[act, t] = alpha
+        ids = p.argmax(dim=1)
+        seqs[act, t] = ids
+        finished[act] |= ids == end_tok
+        inputs[act] = sd["embedding.weight"][ids]
+        h[act], c[act] = hn, cn
+    return preds, alphas, seqs
+
+
+# ------------------------------------------------------------------------------------------------
+# Transformer decoder
+# ------------------------------------------------------------------------------------------------
+def positional_encoding(embed_dim, max_len, dtype=torch.float32):
+    """models/transformerDecoder.py:14-27."""
+    pe = torch.zeros(max_len, embed_dim)
+    pos = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div = torch.exp(torch.arange(0, embed_dim, 2).float() * (-math.log(10000.0) / embed_dim))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe.to(dtype)
+
+
+def _mha(x_q, x_kv, w_in, b_in, w_out, b_out, nheads, add_mask=None, prob_mask=None):
+    """F.multi_head_attention_forward restated, batch-first: x_q (B,Tq,D), x_kv (B,Tk,D);
+    add_mask broadcastable to (B,H,Tq,Tk) with 0 / -inf entries; prob_mask = attention-dropout multiplier."""
+    B, Tq, D = x_q.shape
+    Tk = x_kv.shape[1]
+    hd = D // nheads
+    q = F.linear(x_q, w_in[:D], b_in[:D])
+    k = F.linear(x_kv, w_in[D:2 * D], b_in[D:2 * D])
+    v = F.linear(x_kv, w_in[2 * D:], b_in[2 * D:])
+    q = q.view(B, Tq, nheads, hd).transpose(1, 2)
+    k = k.view(B, Tk, nheads, hd).transpose(1, 2)
+    v = v.view(B, Tk, nheads, hd).transpose(1, 2)
+    s = (q / math.sqrt(hd)) @ k.transpose(-1, -2)
+    if add_mask is not None:
+        s = s + add_mask
+    p = F.softmax(s, dim=-1)
+    if prob_mask is not None:
+        p = p * prob_mask
+    ctx = (p @ v).transpose(1, 2).reshape(B, Tq, D)
+    return F.linear(ctx, w_out, b_out)
+
+
+def transformer_layers(sd, x, mem, nheads, nlayers, self_mask, drop=None):
+    """nn.TransformerDecoder of post-norm ReLU layers (torch/nn/modules/transformer.py:1089-1199), batch-first.
+    drop: optional dict of injected dropout multipliers keyed (layer, name), names: 'sa_p','ca_p' (attention
+    probabilities), 'd1','d2','d3' (residual dropouts), 'ff' (FFN hidden)."""
+    drop = drop or {}
+    for l in range(nlayers):
+        p = f"transformer_decoder.layers.{l}."
+        sa = _mha(x, x, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
+                  sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nheads, self_mask,
+                  drop.get((l, "sa_p")))
+        if (l, "d1") in drop:
+            sa = sa * drop[(l, "d1")]
+        x = F.layer_norm(x + sa, (x.shape[-1],), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+        ca = _mha(x, mem, sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"],
+                  sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"], nheads, None,
+                  drop.get((l, "ca_p")))
+        if (l, "d2") in drop:
+            ca = ca * drop[(l, "d2")]
+        x = F.layer_norm(x + ca, (x.shape[-1],), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+        hdn = F.relu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))
+        if (l, "ff") in drop:
+            hdn = hdn * drop[(l, "ff")]
+        ff = F.linear(hdn, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+        if (l, "d3") in drop:
+            ff = ff * drop[(l, "d3")]
+        x = F.layer_norm(x + ff, (x.shape[-1],), sd[p + "norm3.weight"], sd[p + "norm3.bias"], 1e-5)
+    return x
+
+
+def _num_layers(sd):
+    return 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer_decoder.layers."))
+
+
+def transformer_memory(sd, encoder_out):
+    B, E = encoder_out.size(0), encoder_out.size(-1)
+    enc = encoder_out.reshape(B, -1, E)
+    if "encoder_proj.weight" in sd:
+        return F.linear(enc, sd["encoder_proj.weight"], sd["encoder_proj.bias"])
+    return enc
+
+
+def transformer_teacher_forcing(sd, encoder_out, caps, caplens, key_padding_mask, nheads=8, drop=None):
+    """models/transformerDecoder.py:88-108.  key_padding_mask (B,T) bool, True = pad.
+    drop: injected dropout multipliers; additionally key 'emb' (B,T,D) for the embedding dropout of :98."""
+    drop = drop or {}
+    dl = (caplens.squeeze(1) - 1).tolist()
+    mem = transformer_memory(sd, encoder_out)
+    emb = sd["embedding.weight"][caps]
+    if "emb" in drop:
+        emb = emb * drop["emb"]
+    T = caps.shape[1]
+    x = emb + sd["pos_encoding.pe"][0, :T].to(emb.dtype)
+    causal = torch.full((T, T), float("-inf"), dtype=x.dtype).triu(1)
+    mask = causal.view(1, 1, T, T)
+    if key_padding_mask is not None:
+        kp = torch.zeros(key_padding_mask.shape, dtype=x.dtype).masked_fill(key_padding_mask, float("-inf"))
+        mask = mask + kp.view(-1, 1, 1, T)
+    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), mask, drop)
+    return F.linear(y, sd["fc_out.weight"], sd["fc_out.bias"]), caps, dl
+
+
+def transformer_last_logits(sd, mem, tokens, nheads=8):
+    """Re-run the whole prefix (no KV cache, as the reference does) and return fc_out of the last position."""
+    T = tokens.shape[1]
+    x = sd["embedding.weight"][tokens] + sd["pos_encoding.pe"][0, :T].to(mem.dtype)
+    causal = torch.full((T, T), float("-inf"), dtype=x.dtype).triu(1).view(1, 1, T, T)
+    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), causal)
+    return F.linear(y[:, -1], sd["fc_out.weight"], sd["fc_out.bias"])
+
+
+def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nheads=8):
+    """models/transformerDecoder.py:110-160 (eval mode)."""
+    B = encoder_out.size(0)
+    mem = transformer_memory(sd, encoder_out)
+    V = sd["fc_out.weight"].shape[0]
+    inputs = torch.full((B, 1), start_tok, dtype=torch.long)
+    preds = torch.zeros(B, max_len, V, dtype=mem.dtype)
+    seqs = torch.zeros(B, max_len, dtype=torch.long)
+    finished = torch.zeros(B, dtype=torch.bool)
+    for t in range(max_len):
+        act = (~finished).nonzero(as_tuple=False).squeeze(1)
+        if len(act) == 0:
+            break
+        p = transformer_last_logits(sd, mem[act], inputs[act], nheads)
+        preds[act, t] = p
+        ids = p.argmax(dim=-1)
+        seqs[act, t] = ids
+        finished[act] |= ids == end_tok
+        new = torch.full((B, t + 2), pad_tok, dtype=torch.long)
+        new[:, :t + 1] = inputs
+        new[act, t + 1] = ids
+        inputs = new
+    return preds, seqs
+
+
+# ------------------------------------------------------------------------------------------------
+# beam search (caption.py:39-155 and :160-255) — one image, beams as batch
+# ------------------------------------------------------------------------------------------------
+def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=50, nheads=8, trace=None):
+    """Returns (best_seq or None if nothing completed, complete_seqs, complete_scores).
+    ``trace`` (a list) receives per step: (top-k scores, prev beam indices, next words) — the per-step contract."""
+    E = encoder_out.size(-1)
+    enc1 = encoder_out.reshape(1, -1, E)
+    seqs = torch.full((k, 1), start_tok, dtype=torch.long)
+    top = torch.zeros(k, 1, dtype=enc1.dtype)
+    done_seqs, done_scores = [], []
+    if kind == "lstm":
+        enc = enc1.expand(k, -1, -1)
+        h, c = init_hidden_state(sd, enc)
+        prev_words = seqs[:, 0]
+    else:
+        mem = transformer_memory(sd, enc1).expand(k, -1, -1)
+    step = 1
+    while True:
+        if kind == "lstm":
+            h, c, _ = lstm_step(sd, enc, sd["embedding.weight"][prev_words], h, c)
+            logits = F.linear(h, sd["fc.weight"], sd["fc.bias"])
+        else:
+            logits = transformer_last_logits(sd, mem[:seqs.shape[0]], seqs, nheads)
+        scores = top.expand_as(logits) + F.log_softmax(logits, dim=1)
+        if step == 1:
+            top_s, top_w = scores[0].topk(k, 0, True, True)
+        else:
+            top_s, top_w = scores.view(-1).topk(k, 0, True, True)
+        prev = (top_w / vocab).long()       # caption.py:116,118 (true division then trunc)
+        nxt = top_w % vocab
+        if trace is not None:
+            trace.append((top_s.clone(), prev.clone(), nxt.clone()))
+        seqs = torch.cat([seqs[prev], nxt.unsqueeze(1)], dim=1)
+        inc = [i for i, w in enumerate(nxt.tolist()) if w != end_tok]
+        com = [i for i in range(len(nxt)) if i not in inc]
+        if com:
+            done_seqs.extend(seqs[com].tolist())
+            done_scores.extend(top_s[com].tolist())
+        k -= len(com)
+        if k == 0:
+            break
+        seqs = seqs[inc]
+        if kind == "lstm":
+            h, c, enc = h[prev[inc]], c[prev[inc]], enc[prev[inc]]
+            prev_words = nxt[inc]
+        top = top_s[inc].unsqueeze(1)
+        # caption.py:147 (`if step > 50`, step counted from 1) and caption.py:249 (`if step + 1 >= 51`, step counted
+        # from 0) are the same bound: at most max_steps + 1 = 51 decode steps.
+        if step > max_steps:
+            break
+        step += 1
+    if not done_scores:
+        return None, done_seqs, done_scores
+    return done_seqs[done_scores.index(max(done_scores))], done_seqs, done_scores
+
+
+# ------------------------------------------------------------------------------------------------
+# train-step loss (trainMultiGPU.py:357-378)
+# ------------------------------------------------------------------------------------------------
+def packed_cross_entropy(scores, targets, decode_lengths):
+    """pack_padded_sequence(...).data on both sides then CrossEntropyLoss (mean over packed rows).  The mean is
+    order-independent, so rows are simply gathered by (b, t < len)."""
+    rows, tg = [], []
+    for b, l in enumerate(decode_lengths):
+        rows.append(scores[b, :l])
+        tg.append(targets[b, :l])
+    return F.cross_entropy(torch.cat(rows), torch.cat(tg))
+
+
+def train_loss_lstm(preds, caps_sorted, decode_lengths, alphas, alpha_c=1.0):
+    """trainMultiGPU.py:364-369: CE over packed rows + alpha_c * ((1 - sum_t alpha)^2).mean()."""
+    loss = packed_cross_entropy(preds, caps_sorted[:, 1:], decode_lengths)
+    return loss + alpha_c * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+
+
+def train_loss_transformer(preds, caps, decode_lengths):
+    """trainMultiGPU.py:373-377."""
+    return packed_cross_entropy(preds, caps[:, 1:], decode_lengths)

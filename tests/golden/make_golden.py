@@ -63,6 +63,75 @@ def golden_encoder():
     torch.save(out, os.path.join(HERE, "encoder.pt"))
 
 
+V = 9490
+WORDMAP = {"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1}
+
+
+def _sub(preds):
+    """Keep the fixtures small: every 31st vocabulary column + per-row argmax and logsumexp."""
+    return {"sub": preds[..., ::31].contiguous(), "argmax": preds.argmax(-1), "lse": preds.logsumexp(-1)}
+
+
+def golden_lstm():
+    """Reference DecoderWithAttention (models/decoder.py): teacher forcing (eval) and greedy."""
+    from models.decoder import DecoderWithAttention
+    from oracle import decoder_oracle as do
+
+    out = {}
+    seed = 0
+    torch.manual_seed(seed)
+    ref = DecoderWithAttention(512, 512, 512, V, torch.device("cpu")).eval()
+    plain = do.random_lstm_decoder_state(seed, V, perturb=0)
+    for k, v in ref.state_dict().items():          # the oracle's generator reproduces the reference init bit for bit
+        assert torch.equal(v, plain[k]), k
+    sd = do.random_lstm_decoder_state(seed, V, end_bias=0.21)
+    ref.load_state_dict(sd)
+    B = 5
+    enc = do.synthetic_features(B, 100)
+    caps, lens = do.synthetic_captions(B, 101, V)
+    with torch.no_grad():
+        preds, caps_s, dl, alphas, sort_ind = ref(teacherForcing=True, encoder_out=enc, encoded_captions=caps,
+                                                  caption_lengths=lens)
+        loss = do.train_loss_lstm(preds, caps_s, dl, alphas)
+        gp, ga, gs = ref(teacherForcing=False, encoder_out=enc, wordMap=WORDMAP, maxDecodeLen=51)
+    out["tf"] = {"B": B, "feat_seed": 100, "cap_seed": 101, "weight_seed": seed, "end_bias": 0.21,
+                 "preds": _sub(preds), "alphas": alphas, "sort_ind": sort_ind, "decode_lengths": dl,
+                 "caps_sorted": caps_s, "loss": loss}
+    out["greedy"] = {"preds": _sub(gp), "alphas": ga, "sequences": gs}
+    print("lstm tf loss", float(loss), "greedy lengths", [(int((r == V - 1).nonzero()[0]) if (r == V - 1).any() else -1) for r in gs])
+    torch.save(out, os.path.join(HERE, "lstm_decoder.pt"))
+
+
+def golden_transformer():
+    """Reference TransformerDecoder (models/transformerDecoder.py): teacher forcing (eval) and greedy."""
+    from models.transformerDecoder import TransformerDecoder
+    from oracle import decoder_oracle as do
+
+    out = {}
+    seed = 0
+    torch.manual_seed(seed)
+    ref = TransformerDecoder(512, 512, V, 52, torch.device("cpu"), None, None, True).eval()
+    plain = do.random_transformer_decoder_state(seed, V, perturb=0)
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, plain[k]), k
+    sd = do.random_transformer_decoder_state(seed, V, end_bias=3.2)
+    ref.load_state_dict(sd)
+    B = 4
+    enc = do.synthetic_features(B, 200)
+    caps, lens = do.synthetic_captions(B, 201, V)
+    kpm = caps == 0
+    with torch.no_grad():
+        preds, caps_o, dl = ref(teacherForcing=True, encoder_out=enc, encoded_captions=caps, caption_lengths=lens,
+                                tgt_key_padding_mask=kpm)
+        loss = do.train_loss_transformer(preds, caps_o, dl)
+        gp, gs = ref(teacherForcing=False, encoder_out=enc, wordMap=WORDMAP, maxDecodeLen=51)
+    out["tf"] = {"B": B, "feat_seed": 200, "cap_seed": 201, "weight_seed": seed, "end_bias": 3.2,
+                 "preds": _sub(preds), "decode_lengths": dl, "loss": loss}
+    out["greedy"] = {"preds": _sub(gp), "sequences": gs}
+    print("transformer tf loss", float(loss), "greedy lengths", [(int((r == V - 1).nonzero()[0]) if (r == V - 1).any() else -1) for r in gs])
+    torch.save(out, os.path.join(HERE, "transformer_decoder.pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     torch.set_flush_denormal(True)

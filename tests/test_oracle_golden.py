@@ -23,3 +23,65 @@ def test_adaptive_pool_8_to_7_is_avgpool_2_1():
     import torch.nn.functional as F
     x = torch.randn(2, 16, 8, 8)
     assert torch.equal(F.adaptive_avg_pool2d(x, (7, 7)), F.avg_pool2d(x, 2, 1))
+
+
+V = 9490
+WORDMAP = {"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1}
+
+
+def _check_sub(preds, g, tol):
+    assert rel_err(preds[..., ::31], g["sub"]) < tol
+    assert rel_err(preds.logsumexp(-1), g["lse"]) < tol
+
+
+def test_lstm_oracle_matches_reference_golden(golden_dir):
+    from oracle import decoder_oracle as do
+    gold = torch.load(os.path.join(golden_dir, "lstm_decoder.pt"))
+    g = gold["tf"]
+    sd = do.random_lstm_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    enc = do.synthetic_features(g["B"], g["feat_seed"])
+    caps, lens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    preds, caps_s, dl, alphas, sort_ind = do.lstm_teacher_forcing(sd, enc, caps, lens)
+    assert dl == g["decode_lengths"] and torch.equal(sort_ind, g["sort_ind"]) and torch.equal(caps_s, g["caps_sorted"])
+    _check_sub(preds, g["preds"], 1e-5)
+    assert rel_err(alphas, g["alphas"]) < 1e-5
+    assert abs(float(do.train_loss_lstm(preds, caps_s, dl, alphas)) - float(g["loss"])) < 1e-5
+    # invariants (SURVEY.md §8c ii, iii): alpha rows sum to 1 inside, everything exactly 0 past each length
+    for b, l in enumerate(dl):
+        assert torch.allclose(alphas[b, :l].sum(-1), torch.ones(l), atol=1e-5)
+        assert float(preds[b, l:].abs().max() if l < preds.shape[1] else 0) == 0.0
+    gp, ga, gs = do.lstm_greedy(sd, enc, V - 2, V - 1, 51)
+    assert torch.equal(gs, gold["greedy"]["sequences"])
+    _check_sub(gp, gold["greedy"]["preds"], 1e-5)
+    assert rel_err(ga, gold["greedy"]["alphas"]) < 1e-5
+
+
+def test_transformer_oracle_matches_reference_golden(golden_dir):
+    from oracle import decoder_oracle as do
+    gold = torch.load(os.path.join(golden_dir, "transformer_decoder.pt"))
+    g = gold["tf"]
+    sd = do.random_transformer_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    enc = do.synthetic_features(g["B"], g["feat_seed"])
+    caps, lens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    preds, _, dl = do.transformer_teacher_forcing(sd, enc, caps, lens, caps == 0)
+    assert dl == g["decode_lengths"]
+    _check_sub(preds, g["preds"], 2e-5)
+    assert abs(float(do.train_loss_transformer(preds, caps, dl)) - float(g["loss"])) < 1e-5
+    gp, gs = do.transformer_greedy(sd, enc, V - 2, V - 1, 0, 51)
+    assert torch.equal(gs, gold["greedy"]["sequences"])
+    _check_sub(gp, gold["greedy"]["preds"], 2e-5)
+
+
+def test_beam_k1_equals_greedy():
+    # SURVEY.md §8c invariant (iv) / H4: caption.py's "greedy" is beam search with k=1
+    from oracle import decoder_oracle as do
+    sd = do.random_lstm_decoder_state(1, V, end_bias=0.21)
+    enc = do.synthetic_features(1, 5)
+    _, _, seqs = do.lstm_greedy(sd, enc, V - 2, V - 1, 51)
+    best, done, _ = do.beam_search(sd, enc, "lstm", 1, V - 2, V - 1, V)
+    row = seqs[0].tolist()
+    if V - 1 in row:
+        n = row.index(V - 1) + 1
+        assert best == [V - 2] + row[:n]
+    else:
+        assert best is None and done == []
