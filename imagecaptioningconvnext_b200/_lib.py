@@ -67,6 +67,10 @@ SIGNATURES = {
     "ccx_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ccx_encoder_run": (C.c_int, [C.POINTER(EncoderWeights), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                   _sz, _vp]),
+    "ccx_beam_topk": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "ccx_beam_update": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _i64, _vp]),
+    "ccx_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "ccx_prof_begin": (C.c_int, []),
     "ccx_prof_spans": (C.c_int, [C.POINTER(_i32), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "ccx_prof_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), _i32]),

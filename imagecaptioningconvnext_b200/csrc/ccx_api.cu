@@ -112,6 +112,28 @@ int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const float* k, in
                    prob_mask, probs_out, B, H, Tq, Tk, hd, causal, q_pos0, scale, kv_group, as_stream(stream));
 }
 
+int ccx_beam_topk(const float* logits, int64_t ld, int32_t NI, int32_t k, int32_t V, const float* top_scores,
+                  const int32_t* k_rem, int32_t first_step, float* cand_score, int32_t* cand_prev,
+                  int32_t* cand_word, void* stream) {
+  return beam_topk(logits, ld, NI, k, V, top_scores, k_rem, first_step, cand_score, cand_prev, cand_word,
+                   as_stream(stream));
+}
+
+int ccx_beam_update(int32_t NI, int32_t k, int32_t Tcap, int32_t step, int64_t end_token, const float* cand_score,
+                    const int32_t* cand_prev, const int32_t* cand_word, const int64_t* seqs_in, int64_t* seqs_out,
+                    float* top_scores, int32_t* k_rem, int64_t* done_seqs, float* done_scores, int32_t* done_len,
+                    int32_t* n_done, int32_t* src_row, int64_t* next_tok, int64_t ld_next, void* stream) {
+  return beam_update(NI, k, Tcap, step, end_token, cand_score, cand_prev, cand_word,
+                     reinterpret_cast<const long long*>(seqs_in), reinterpret_cast<long long*>(seqs_out), top_scores,
+                     k_rem, reinterpret_cast<long long*>(done_seqs), done_scores, done_len, n_done, src_row,
+                     reinterpret_cast<long long*>(next_tok), ld_next, as_stream(stream));
+}
+
+int ccx_gather_rows(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,
+                    const int32_t* src_row, int64_t row_bytes, int32_t rows, void* stream) {
+  return gather_rows(src, src_stride_bytes, dst, dst_stride_bytes, src_row, row_bytes, rows, as_stream(stream));
+}
+
 int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
                      void* stream) {
   return avgpool_nhwc(x, out, B, H, W, C, S, as_stream(stream));

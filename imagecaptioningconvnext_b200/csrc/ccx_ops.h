@@ -40,4 +40,14 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
               int kv_group, cudaStream_t stream);
 
+// beam_kernels.cu
+int beam_topk(const float* logits, long long ld, int NI, int k, int V, const float* top_scores, const int* k_rem,
+              int first_step, float* cand_score, int* cand_prev, int* cand_word, cudaStream_t stream);
+int beam_update(int NI, int k, int Tcap, int step, long long end_token, const float* cand_score,
+                const int* cand_prev, const int* cand_word, const long long* seqs_in, long long* seqs_out,
+                float* top_scores, int* k_rem, long long* done_seqs, float* done_scores, int* done_len, int* n_done,
+                int* src_row, long long* next_tok, long long ld_next, cudaStream_t stream);
+int gather_rows(const void* src, long long src_stride, void* dst, long long dst_stride, const int* src_row,
+                long long row_bytes, int rows, cudaStream_t stream);
+
 }  // namespace ccx

@@ -220,6 +220,32 @@ CCX_API int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const floa
                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched beam search (caption.py:96-155 LSTM, caption.py:197-251 Transformer), NI images x k beams (k <= 8) as
+ * NI*k decode rows; row img*k + j is beam j of image img, alive beams compacted to the front.
+ * ------------------------------------------------------------------------------------------------ */
+/* log_softmax over V per row, + top_scores[img, beam], flat top-k_rem[img] over (alive beams x V) sorted
+ * descending (ties: lowest flat index); first_step != 0 restricts to beam 0 (caption.py:110, all beams equal).
+ * cand_prev = idx / V, cand_word = idx % V (caption.py:116-117). */
+CCX_API int ccx_beam_topk(const float* logits, int64_t ld, int32_t NI, int32_t k, int32_t V,
+                          const float* top_scores, const int32_t* k_rem, int32_t first_step, float* cand_score,
+                          int32_t* cand_prev, int32_t* cand_word, void* stream);
+
+/* Bookkeeping of caption.py:121-145: seqs_out[slot] = seqs_in[prev] + word; candidates ending in <end> are moved
+ * to done_seqs/done_scores/done_len (in candidate order), k_rem shrinks; src_row[row] = parent row of each survivor
+ * (identity for dead slots) for ccx_gather_rows; next_tok[row*ld_next] = the survivor's new word.
+ * step = tokens per sequence before this step (1 at the first step: just <start>). */
+CCX_API int ccx_beam_update(int32_t NI, int32_t k, int32_t Tcap, int32_t step, int64_t end_token,
+                            const float* cand_score, const int32_t* cand_prev, const int32_t* cand_word,
+                            const int64_t* seqs_in, int64_t* seqs_out, float* top_scores, int32_t* k_rem,
+                            int64_t* done_seqs, float* done_scores, int32_t* done_len, int32_t* n_done,
+                            int32_t* src_row, int64_t* next_tok, int64_t ld_next, void* stream);
+
+/* dst[r, 0:row_bytes) = src[src_row[r], 0:row_bytes) — beam re-ordering of h/c (caption.py:140-141) and of the
+ * KV caches; src_row NULL = identity.  16-byte granules; strides in bytes. */
+CCX_API int ccx_gather_rows(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,
+                            const int32_t* src_row, int64_t row_bytes, int32_t rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the
  * library is bracketed by two events on its stream; end() synchronises the device and returns, per kernel kind
  * (0 gemm, 1 dwconv+ln, 2 stem, 3 ln_rows, 4 pool, 5 elementwise, 6 attention, 7 lstm, 8 loss, 9 optimizer),

@@ -65,6 +65,8 @@ def golden_encoder():
 
 V = 9490
 WORDMAP = {"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1}
+WORDMAP.update({f"w{i}": i for i in range(1, V - 3)})   # len(wordMap) == V, as caption.py:49,163 needs
+assert len(WORDMAP) == V
 
 
 def _sub(preds):
@@ -130,6 +132,43 @@ def golden_transformer():
     out["greedy"] = {"preds": _sub(gp), "sequences": gs}
     print("transformer tf loss", float(loss), "greedy lengths", [(int((r == V - 1).nonzero()[0]) if (r == V - 1).any() else -1) for r in gs])
     torch.save(out, os.path.join(HERE, "transformer_decoder.pt"))
+
+
+def golden_beam():
+    """Reference caption.py beam search (k=5), full pipeline image file -> Encoder -> decoder, both decoders."""
+    import numpy as np
+    from PIL import Image
+    import caption as cap                      # /root/reference/caption.py (matplotlib / skimage stubbed)
+    from models.decoder import DecoderWithAttention
+    from models.encoder import Encoder
+    from models.transformerDecoder import TransformerDecoder
+    from oracle import decoder_oracle as do
+    from oracle.encoder_oracle import random_encoder_state
+
+    cap.device = torch.device("cpu")
+    enc = Encoder().eval()
+    enc.load_state_dict(random_encoder_state(seed=0, layer_scale=1.0))
+    lstm = DecoderWithAttention(512, 512, 512, V, torch.device("cpu")).eval()
+    lstm.load_state_dict(do.random_lstm_decoder_state(0, V, end_bias=0.5))
+    tr = TransformerDecoder(512, 512, V, 52, torch.device("cpu"), None, None, True).eval()
+    tr.load_state_dict(do.random_transformer_decoder_state(0, V, end_bias=3.6))
+    out = {"image_seeds": [11, 12], "k": 5, "lstm_end_bias": 0.5, "transformer_end_bias": 3.6, "lstm": [], "transformer": [], "features": []}
+    for seed in out["image_seeds"]:
+        img = np.random.RandomState(seed).randint(0, 256, size=(256, 256, 3), dtype=np.uint8)
+        path = f"/tmp/golden_beam_{seed}.png"
+        Image.fromarray(img).save(path)
+        with torch.no_grad():
+            seq, _ = cap.caption_image_beam_search(enc, lstm, path, WORDMAP, 5)
+            seq_t, _ = cap.caption_image_beam_search_transformer(enc, tr, path, WORDMAP, 5)
+            x = torch.from_numpy(img.transpose(2, 0, 1) / 255.).float()
+            mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+            std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+            feats = enc(((x - mean) / std).unsqueeze(0)).contiguous()
+        out["lstm"].append(seq)
+        out["transformer"].append(seq_t)
+        out["features"].append(feats[0, ::3, ::3, ::64].clone())   # spot-check values of the encoder output
+        print("beam", seed, seq, seq_t)
+    torch.save(out, os.path.join(HERE, "beam.pt"))
 
 
 if __name__ == "__main__":

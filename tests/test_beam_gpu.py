@@ -1,0 +1,94 @@
+"""GPU parity of the batched beam search against the oracle's restatement of caption.py (per image)."""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+from test_decoders_gpu import V, WORDMAP, _lstm, _transformer
+from test_oracle_golden import _beam_inputs
+
+pytestmark = pytest.mark.gpu
+TAU = 1e-4
+
+
+def _compare(kind, sd, model, feats, k, fn):
+    from oracle import decoder_oracle as do
+    trace = []
+    best, done = fn(model, feats.cuda(), WORDMAP, beamSize=k, trace=trace, return_all=True)
+    agree = 0
+    for i in range(feats.shape[0]):
+        otrace = []
+        obest, odone, oscores = do.beam_search(sd, feats[i:i + 1], kind, k, V - 2, V - 1, V, trace=otrace)
+        # per-step contract: top-k scores within tolerance, (prev, word) exact unless a near-tie
+        diverged = False
+        for s, (ts, tp, tw) in enumerate(otrace):
+            kr = int(trace[s][0][i])
+            assert kr == len(ts), (i, s)
+            gs, gp, gw = trace[s][1][i, :kr].cpu(), trace[s][2][i, :kr].cpu(), trace[s][3][i, :kr].cpu()
+            same = torch.equal(gp.long(), tp) and torch.equal(gw.long(), tw)
+            if not same:
+                gaps = (ts[:-1] - ts[1:]).abs()
+                assert float(gaps.min()) <= TAU or s > 0, f"image {i} step {s}: beams differ without a near-tie"
+                diverged = True
+                break
+            assert torch.allclose(gs, ts, rtol=1e-4, atol=1e-4), (i, s)
+        if not diverged:
+            agree += 1
+            assert best[i] == obest
+            assert done[i][0] == odone
+            assert torch.allclose(torch.tensor(done[i][1]), torch.tensor(oscores), rtol=1e-4, atol=1e-4)
+    return agree
+
+
+def test_lstm_beam_vs_oracle():
+    from imagecaptioningconvnext_b200.beam import beam_search_lstm
+    from oracle import decoder_oracle as do
+    sd = do.random_lstm_decoder_state(0, V, end_bias=0.21)
+    feats = do.synthetic_features(4, 300)
+    assert _compare("lstm", sd, _lstm(sd, torch.float32), feats, 5, beam_search_lstm) >= 3
+
+
+def test_transformer_beam_vs_oracle():
+    from imagecaptioningconvnext_b200.beam import beam_search_transformer
+    from oracle import decoder_oracle as do
+    sd = do.random_transformer_decoder_state(0, V, end_bias=3.2)
+    feats = do.synthetic_features(3, 300)
+    assert _compare("transformer", sd, _transformer(sd, torch.float32), feats, 5, beam_search_transformer) >= 2
+
+
+def test_beam_k1_equals_greedy_tokens():
+    """caption.py hard-codes beamSize=1 (caption.py:484): k=1 beam == greedy argmax sequence."""
+    from imagecaptioningconvnext_b200.beam import beam_search_lstm
+    from oracle import decoder_oracle as do
+    sd = do.random_lstm_decoder_state(1, V, end_bias=0.21)
+    feats = do.synthetic_features(6, 5)
+    m = _lstm(sd, torch.float32)
+    _, _, seqs = m(teacherForcing=False, encoder_out=feats.cuda(), wordMap=WORDMAP, maxDecodeLen=51)
+    best = beam_search_lstm(m, feats.cuda(), WORDMAP, beamSize=1)
+    for i in range(6):
+        row = seqs[i].tolist()
+        if V - 1 in row:
+            assert best[i] == [V - 2] + row[:row.index(V - 1) + 1]
+        else:
+            assert best[i] is None
+
+
+def test_full_pipeline_matches_reference_caption_py_golden(golden_dir):
+    """image -> Encoder -> beam search k=5 on libccx equals caption.py's output (tests/golden/beam.pt)."""
+    from imagecaptioningconvnext_b200 import Encoder
+    from imagecaptioningconvnext_b200.beam import beam_search_lstm, beam_search_transformer
+    from oracle import decoder_oracle as do
+    from oracle.encoder_oracle import random_encoder_state
+    gold = torch.load(os.path.join(golden_dir, "beam.pt"))
+    imgs, feats = _beam_inputs(gold)
+    enc = Encoder()
+    enc.load_state_dict(random_encoder_state(seed=0, layer_scale=1.0))
+    enc = enc.cuda().eval()
+    with torch.no_grad():
+        f = enc(torch.cat(imgs).cuda())
+    assert rel_err(f, torch.cat(feats)) < 1e-3
+    lsd = do.random_lstm_decoder_state(0, V, end_bias=gold["lstm_end_bias"])
+    tsd = do.random_transformer_decoder_state(0, V, end_bias=gold["transformer_end_bias"])
+    assert beam_search_lstm(_lstm(lsd, torch.float32), f, WORDMAP, beamSize=gold["k"]) == gold["lstm"]
+    assert beam_search_transformer(_transformer(tsd, torch.float32), f, WORDMAP, beamSize=gold["k"]) == gold["transformer"]

@@ -85,3 +85,31 @@ def test_beam_k1_equals_greedy():
         assert best == [V - 2] + row[:n]
     else:
         assert best is None and done == []
+
+
+def _beam_inputs(gold):
+    import numpy as np
+    from oracle.encoder_oracle import encoder_forward, random_encoder_state
+    esd = random_encoder_state(seed=0, layer_scale=1.0)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    feats, imgs = [], []
+    for seed in gold["image_seeds"]:
+        img = np.random.RandomState(seed).randint(0, 256, size=(256, 256, 3), dtype=np.uint8)
+        x = ((torch.from_numpy(img.transpose(2, 0, 1) / 255.).float() - mean) / std).unsqueeze(0)
+        imgs.append(x)
+        feats.append(encoder_forward(esd, x, 7))
+    return imgs, feats
+
+
+def test_beam_oracle_matches_reference_caption_py_golden(golden_dir):
+    """Full pipeline image -> Encoder -> beam search (k=5) against caption.py's own output for both decoders."""
+    from oracle import decoder_oracle as do
+    gold = torch.load(os.path.join(golden_dir, "beam.pt"))
+    _, feats = _beam_inputs(gold)
+    lsd = do.random_lstm_decoder_state(0, V, end_bias=gold["lstm_end_bias"])
+    tsd = do.random_transformer_decoder_state(0, V, end_bias=gold["transformer_end_bias"])
+    for i, f in enumerate(feats):
+        assert rel_err(f[0, ::3, ::3, ::64], gold["features"][i]) < 1e-5
+        assert do.beam_search(lsd, f, "lstm", gold["k"], V - 2, V - 1, V)[0] == gold["lstm"][i]
+        assert do.beam_search(tsd, f, "transformer", gold["k"], V - 2, V - 1, V)[0] == gold["transformer"][i]
