@@ -20,8 +20,8 @@ _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_si
 
 class LinearDesc(C.Structure):
     _fields_ = [("A", _vp), ("A_lo", _vp), ("W", _vp), ("W_lo", _vp), ("C", _vp), ("C_lo", _vp),
-                ("bias", _vp), ("colscale", _vp), ("rowscale", _vp), ("residual", _vp),
-                ("lda", _i64), ("ldw", _i64), ("ldc", _i64), ("ldr", _i64),
+                ("bias", _vp), ("colscale", _vp), ("rowscale", _vp), ("residual", _vp), ("emask", _vp),
+                ("lda", _i64), ("ldw", _i64), ("ldc", _i64), ("ldr", _i64), ("ldm", _i64),
                 ("M", _i32), ("N", _i32), ("K", _i32), ("rows_per_group", _i32),
                 ("act", _i32), ("in_dtype", _i32), ("out_dtype", _i32), ("split", _i32)]
 
@@ -71,6 +71,17 @@ SIGNATURES = {
     "ccx_beam_update": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _i64, _vp]),
     "ccx_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "ccx_convert_operand": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i32, _i64, _i32, _i32,
+                                      _i32, _i32, _vp]),
+    "ccx_colsum_acc": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i32, _i32, _vp]),
+    "ccx_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "ccx_mha_bwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
+                              _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
+                              _f32, _vp]),
+    "ccx_softmax_ce": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
+    "ccx_embedding_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_adam_clamp": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_double,
+                                 _vp]),
     "ccx_prof_begin": (C.c_int, []),
     "ccx_prof_spans": (C.c_int, [C.POINTER(_i32), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "ccx_prof_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
@@ -205,11 +216,15 @@ class Operand:
 
 
 def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per_group=1, residual=None,
-           out=None, out_dtype=torch.float32, split=False):
+           out=None, out_dtype=torch.float32, split=False, emask=None, k=None, n=None):
     """C = epilogue(A . W^T).  a, w: Operand (2-D, row-major, unit inner stride).  Returns a tensor, or an
     Operand when split=True (fp32 compute only)."""
     M, K = a.hi.shape
     N, K2 = w.hi.shape
+    if k is not None:      # logical contraction length when the operands carry zero-padded columns
+        K = K2 = k
+    if n is not None:
+        N = n
     if K != K2 or a.dtype != w.dtype:
         raise ValueError(f"linear: operand mismatch A{tuple(a.hi.shape)} {a.dtype} W{tuple(w.hi.shape)} {w.dtype}")
     dev = a.hi.device
@@ -226,8 +241,10 @@ def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per
         out_dtype = res.dtype
     d.bias, d.colscale, d.rowscale = ptr(bias), ptr(colscale), ptr(rowscale)
     d.residual = ptr(residual)
+    d.emask = ptr(emask)
     d.lda, d.ldw = a.hi.stride(0), w.hi.stride(0)
     d.ldr = residual.stride(0) if residual is not None else 0
+    d.ldm = emask.stride(0) if emask is not None else 0
     d.M, d.N, d.K = M, N, K
     d.rows_per_group = rows_per_group
     d.act = act

@@ -36,6 +36,7 @@ int ccx_linear(const ccx_linear_desc* d, void* stream) {
   g.A = d->A; g.A_lo = d->A_lo; g.B = d->W; g.B_lo = d->W_lo;
   g.C = d->C; g.C_lo = d->C_lo;
   g.bias = d->bias; g.colscale = d->colscale; g.rowscale = d->rowscale; g.residual = d->residual;
+  g.emask = d->emask; g.ldm = d->ldm;
   g.lda = d->lda; g.ldb = d->ldw; g.ldc = d->ldc; g.ldr = d->ldr;
   g.M = d->M; g.N = d->N; g.K = d->K;
   g.rows_per_group = d->rows_per_group;
@@ -132,6 +133,46 @@ int ccx_beam_update(int32_t NI, int32_t k, int32_t Tcap, int32_t step, int64_t e
 int ccx_gather_rows(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,
                     const int32_t* src_row, int64_t row_bytes, int32_t rows, void* stream) {
   return gather_rows(src, src_stride_bytes, dst, dst_stride_bytes, src_row, row_bytes, rows, as_stream(stream));
+}
+
+int ccx_convert_operand(const void* x_hi, const float* x_lo, int32_t x_dtype, int64_t ldx, const float* mul,
+                        int64_t ldm, int32_t mul_mode, float mul_scale, void* o_hi, float* o_lo, int32_t o_dtype,
+                        int64_t ldo, int32_t R, int32_t C, int32_t transpose, int32_t Rpad, void* stream) {
+  return convert_operand(x_hi, x_lo, x_dtype, ldx, mul, ldm, mul_mode, mul_scale, o_hi, o_lo, o_dtype, ldo, R, C,
+                         transpose, Rpad, as_stream(stream));
+}
+int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode, float mul_scale,
+                   float* out, int32_t R, int32_t C, void* stream) {
+  return colsum_acc(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, as_stream(stream));
+}
+int ccx_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+               int64_t M, int32_t C, float eps, void* stream) {
+  return ln_bwd(dy, x, gamma, dx, dgamma, dbeta, M, C, eps, as_stream(stream));
+}
+int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
+                const float* v, int64_t v_sb, int64_t v_st, const float* dctx, int64_t d_sb, int64_t d_st,
+                const float* probs, const float* prob_mask, float* dq, int64_t dq_sb, int64_t dq_st, float* dk,
+                int64_t dk_sb, int64_t dk_st, float* dv, int64_t dv_sb, int64_t dv_st, int32_t B, int32_t H,
+                int32_t Tq, int32_t Tk, int32_t hd, float scale, void* stream) {
+  return mha_bwd(q, q_sb, q_st, k, k_sb, k_st, v, v_sb, v_st, dctx, d_sb, d_st, probs, prob_mask, dq, dq_sb, dq_st,
+                 dk, dk_sb, dk_st, dv, dv_sb, dv_st, B, H, Tq, Tk, hd, scale, as_stream(stream));
+}
+int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V, float inv_n,
+                   float* loss_sum, float* dlogits, int64_t ldd, float* correct_top1, void* stream) {
+  return softmax_ce(logits, ld, reinterpret_cast<const long long*>(targets), R, V, inv_n, loss_sum, dlogits, ldd,
+                    correct_top1, as_stream(stream));
+}
+int ccx_embedding_bwd(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* dx, int64_t sb, int64_t st,
+                      const float* dropmask, float* dtable, int32_t V, int32_t D, int32_t nb, int32_t nt,
+                      void* stream) {
+  return embedding_bwd(reinterpret_cast<const long long*>(tokens), tok_ld, t0, dx, sb, st, dropmask, dtable, V, D,
+                       nb, nt, as_stream(stream));
+}
+int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t* block_offset, int32_t n_blocks,
+                   float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip,
+                   int32_t chunk, double total_params, void* stream) {
+  return adam_clamp(table, block_entry, reinterpret_cast<const long long*>(block_offset), n_blocks, lr, beta1, beta2,
+                    eps, bc1, bc2_sqrt, clip, chunk, total_params, as_stream(stream));
 }
 
 int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,

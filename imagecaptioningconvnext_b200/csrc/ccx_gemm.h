@@ -17,7 +17,8 @@ struct GemmDesc {
   const float* colscale = nullptr;  // [N]
   const float* rowscale = nullptr;  // [ceil(M / rows_per_group)]
   const void* residual = nullptr;   // [M, ldr], dtype of C
-  long long lda = 0, ldb = 0, ldc = 0, ldr = 0;
+  const float* emask = nullptr;     // [M, ldm] element-wise multiplier after the activation
+  long long lda = 0, ldb = 0, ldc = 0, ldr = 0, ldm = 0;
   int M = 0, N = 0, K = 0;
   int rows_per_group = 1;
   int act = 0;        // 0 none, 1 gelu(erf), 2 relu

@@ -50,4 +50,25 @@ int beam_update(int NI, int k, int Tcap, int step, long long end_token, const fl
 int gather_rows(const void* src, long long src_stride, void* dst, long long dst_stride, const int* src_row,
                 long long row_bytes, int rows, cudaStream_t stream);
 
+// train_kernels.cu
+int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long ldx, const float* mul,
+                    long long ldm, int mul_mode, float mul_scale, void* o_hi, float* o_lo, int o_dtype, long long ldo,
+                    int R, int C, int transpose, int Rpad, cudaStream_t stream);
+int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
+               float* out, int R, int C, cudaStream_t stream);
+int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+           long long M, int C, float eps, cudaStream_t stream);
+int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
+            const float* v, long long v_sb, long long v_st, const float* dctx, long long d_sb, long long d_st,
+            const float* probs, const float* prob_mask, float* dq, long long dq_sb, long long dq_st, float* dk,
+            long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
+            int Tk, int hd, float scale, cudaStream_t stream);
+int softmax_ce(const float* logits, long long ld, const long long* targets, long long R, int V, float inv_n,
+               float* loss_sum, float* dlogits, long long ldd, float* correct_top1, cudaStream_t stream);
+int embedding_bwd(const long long* tokens, long long tok_ld, int t0, const float* dx, long long sb, long long st,
+                  const float* dropmask, float* dtable, int V, int D, int nb, int nt, cudaStream_t stream);
+int adam_clamp(const void* table, const int* block_entry, const long long* block_offset, int n_blocks, float lr,
+               float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip, int chunk,
+               double total_params, cudaStream_t stream);
+
 }  // namespace ccx

@@ -47,7 +47,8 @@ struct EpiArgs {
   const float* colscale;  // [N] or nullptr   (layer_scale)
   const float* rowscale;  // [M / rows_per_group] or nullptr (stochastic-depth noise/(1-p))
   const void* residual;   // [M, ldr] same dtype as out, or nullptr
-  long long ldc, ldr;
+  const float* emask;     // [M, ldm] element-wise multiplier applied after the activation (dropout), or nullptr
+  long long ldc, ldr, ldm;
   int rows_per_group;
   int act;              // 0 none, 1 gelu(erf), 2 relu
   int out_dtype;        // CCX_F32 / CCX_BF16
@@ -212,6 +213,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         } else if (ep.act == 2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+        }
+        if (ep.emask != nullptr && row_ok) {
+          const float* mrow = ep.emask + (long long)row * ep.ldm + n0;
+          if (full && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
+              f[j] *= mk.x; f[j + 1] *= mk.y; f[j + 2] *= mk.z; f[j + 3] *= mk.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < N) f[j] *= __ldg(mrow + j);
+          }
         }
         if (ep.colscale != nullptr) {
 #pragma unroll
@@ -392,7 +407,6 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return g.M == 0 ? CCX_OK : CCX_ERR_SHAPE;
   const bool tf32 = (g.in_dtype == CCX_F32);
   const int BK = tf32 ? 32 : 64;
-  if (g.K % 8) return CCX_ERR_SHAPE;
   if (!tf32 && g.out_dtype == CCX_F32 && g.split) return CCX_ERR_DTYPE;
   if (tf32 && g.out_dtype != CCX_F32) return CCX_ERR_DTYPE;
   (void)BK;
@@ -426,8 +440,10 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   ep.colscale = g.colscale;
   ep.rowscale = g.rowscale;
   ep.residual = g.residual;
+  ep.emask = g.emask;
   ep.ldc = g.ldc;
   ep.ldr = g.ldr;
+  ep.ldm = g.ldm;
   ep.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
   ep.act = g.act;
   ep.out_dtype = g.out_dtype;

@@ -1,0 +1,456 @@
+// train_kernels.cu — backward / optimizer kernels of the teacher-forced train step
+// (reference: the autograd graph behind trainMultiGPU.py:357-394 and utils/utils.py:183-192).
+//
+//   convert_operand   fp32 [R,C] (x optional element-wise multiplier / ReLU mask) -> GEMM operand, optionally
+//                     transposed ([C, Rpad], zero padded) — feeds dgrad (dY . W) and wgrad (dY^T . X) GEMMs
+//   colsum_acc        bias gradients: out[c] += sum_r x[r,c]
+//   ln_bwd            LayerNorm backward (recomputes mean / rstd from the saved input)
+//   mha_bwd           small-sequence attention backward, one CTA per (batch, head)
+//   softmax_ce        fused CrossEntropyLoss forward + backward over the rows selected by pack_padded_sequence
+//   embedding_bwd     dense nn.Embedding gradient (atomic scatter-add)
+//   adam_clamp        clip_gradient(+-c) fused with torch.optim.Adam's update, multi-tensor
+#include "ccx_common.cuh"
+#include "ccx_ops.h"
+#include "ccx_prof.h"
+
+namespace ccx {
+
+// ---------------------------------------------------------------------------------------------
+// convert / transpose to GEMM operand
+// ---------------------------------------------------------------------------------------------
+struct OpDst {
+  void* hi;
+  float* lo;
+  int dtype;
+};
+__device__ __forceinline__ void put(const OpDst& o, long long idx, float v) {
+  if (o.dtype == CCX_BF16) {
+    reinterpret_cast<__nv_bfloat16*>(o.hi)[idx] = __float2bfloat16_rn(v);
+  } else if (o.lo != nullptr) {
+    const float h = tf32_hi(v);
+    reinterpret_cast<float*>(o.hi)[idx] = h;
+    o.lo[idx] = v - h;
+  } else {
+    reinterpret_cast<float*>(o.hi)[idx] = v;
+  }
+}
+
+// mul_mode: 0 none, 1 multiply by mul[r,c], 2 multiply by (mul[r,c] > 0) (ReLU mask from the saved output)
+// (mode 2 also scales by mul_scale: a ReLU output that went through dropout is > 0 exactly where both the ReLU
+// and the keep-mask let it through, and the keep multiplier 1/(1-p) is a constant)
+__device__ __forceinline__ float apply_mul(float v, const float* mul, long long ldm, int r, int c, int mode,
+                                           float mul_scale) {
+  if (mode == 0) return v;
+  const float m = mul[r * ldm + c];
+  return mode == 1 ? v * m : (m > 0.f ? v * mul_scale : 0.f);
+}
+
+// source element: fp32 plain (lo == nullptr), tf32 (hi, lo) pair, or bf16
+struct OpSrc {
+  const void* hi;
+  const float* lo;
+  int dtype;
+};
+__device__ __forceinline__ float get(const OpSrc& s, long long idx) {
+  if (s.dtype == CCX_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s.hi)[idx]);
+  const float h = reinterpret_cast<const float*>(s.hi)[idx];
+  return s.lo ? h + s.lo[idx] : h;
+}
+
+__global__ void __launch_bounds__(256)
+convert_rows_kernel(OpSrc x, long long ldx, const float* __restrict__ mul, long long ldm,
+                    int mul_mode, float mul_scale, OpDst o, long long ldo, int R, int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(R) * C) return;
+  const int r = static_cast<int>(i / C), c = static_cast<int>(i % C);
+  put(o, r * ldo + c, apply_mul(get(x, r * ldx + c), mul, ldm, r, c, mul_mode, mul_scale));
+}
+
+// out[c, r] = x[r, c] for r < R, 0 for R <= r < Rpad
+__global__ void __launch_bounds__(256)
+convert_transpose_kernel(OpSrc x, long long ldx, const float* __restrict__ mul, long long ldm,
+                         int mul_mode, float mul_scale, OpDst o, long long ldo, int R, int C, int Rpad) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? apply_mul(get(x, r * ldx + c), mul, ldm, r, c, mul_mode, mul_scale) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + tx;
+    if (c < C && r < Rpad) put(o, c * ldo + r, tile[tx][j]);
+  }
+}
+
+int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long ldx, const float* mul,
+                    long long ldm, int mul_mode, float mul_scale, void* o_hi, float* o_lo, int o_dtype, long long ldo,
+                    int R, int C, int transpose, int Rpad, cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return CCX_OK;
+  OpDst o{o_hi, o_lo, o_dtype};
+  OpSrc x{x_hi, x_lo, x_dtype};
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 8.0);
+  if (!transpose) {
+    const long long n = static_cast<long long>(R) * C;
+    convert_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale,
+                                                                                  o, ldo, R, C);
+  } else {
+    if (Rpad < R) return CCX_ERR_SHAPE;
+    dim3 grid((Rpad + 31) / 32, (C + 31) / 32);
+    convert_transpose_kernel<<<grid, 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale, o, ldo, R, C, Rpad);
+  }
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums (bias gradient), accumulating
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_acc_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mul, long long ldm,
+                  int mul_mode, float mul_scale, float* __restrict__ out, int R, int C, int rows_per_block) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ty = threadIdx.x >> 5;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(R, r_begin + rows_per_block);
+  float acc = 0.f;
+  if (c < C)
+    for (int r = r_begin + ty; r < r_end; r += 8) acc += apply_mul(x[r * ldx + c], mul, ldm, r, c, mul_mode, mul_scale);
+  red[ty][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
+               float* out, int R, int C, cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return CCX_OK;
+  const int rpb = 256;
+  dim3 grid((C + 31) / 32, (R + rpb - 1) / rpb);
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 4.0);
+  colsum_acc_kernel<<<grid, 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, rpb);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward: one warp per row; dgamma / dbeta reduced per block then atomically accumulated
+// ---------------------------------------------------------------------------------------------
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+              float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C,
+              float eps) {
+  __shared__ float s_dg[VPL * 128], s_db[VPL * 128];
+  for (int i = threadIdx.x; i < VPL * 128; i += 256) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long m = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (m < M) {
+    float4 xv[VPL], gv[VPL], dv[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xv[i] = __ldg(reinterpret_cast<const float4*>(x + m * C) + i * 32 + lane);
+      dv[i] = __ldg(reinterpret_cast<const float4*>(dy + m * C) + i * 32 + lane);
+      gv[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+      s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      q += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    // xhat = (x-mean)*rstd ; g = dy*gamma ; dx = rstd * (g - mean(g) - xhat * mean(g*xhat))
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;
+      const float g0 = dv[i].x * gv[i].x, g1 = dv[i].y * gv[i].y, g2 = dv[i].z * gv[i].z, g3 = dv[i].w * gv[i].w;
+      sg += g0 + g1 + g2 + g3;
+      sgx += g0 * xv[i].x + g1 * xv[i].y + g2 * xv[i].z + g3 * xv[i].w;
+    }
+    sg = warp_sum(sg) / C;
+    sgx = warp_sum(sgx) / C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 o;
+      o.x = rstd * (dv[i].x * gv[i].x - sg - xv[i].x * sgx);
+      o.y = rstd * (dv[i].y * gv[i].y - sg - xv[i].y * sgx);
+      o.z = rstd * (dv[i].z * gv[i].z - sg - xv[i].z * sgx);
+      o.w = rstd * (dv[i].w * gv[i].w - sg - xv[i].w * sgx);
+      reinterpret_cast<float4*>(dx + m * C)[i * 32 + lane] = o;
+      const int c = (i * 32 + lane) * 4;
+      atomicAdd(&s_dg[c + 0], dv[i].x * xv[i].x); atomicAdd(&s_db[c + 0], dv[i].x);
+      atomicAdd(&s_dg[c + 1], dv[i].y * xv[i].y); atomicAdd(&s_db[c + 1], dv[i].y);
+      atomicAdd(&s_dg[c + 2], dv[i].z * xv[i].z); atomicAdd(&s_db[c + 2], dv[i].z);
+      atomicAdd(&s_dg[c + 3], dv[i].w * xv[i].w); atomicAdd(&s_db[c + 3], dv[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    if (dgamma) atomicAdd(dgamma + i, s_dg[i]);
+    if (dbeta) atomicAdd(dbeta + i, s_db[i]);
+  }
+}
+
+int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+           long long M, int C, float eps, cudaStream_t stream) {
+  if (M <= 0) return CCX_OK;
+  if (C % 128 != 0 || C > 1024) return CCX_ERR_SHAPE;
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  ProfScope prof(PROF_LN_ROWS, stream, (double)M * C * 12.0);
+#define CCX_LNB_CASE(V)                                                                              \
+  case V:                                                                                            \
+    ln_bwd_kernel<V><<<grid, 256, 0, stream>>>(dy, x, gamma, dx, dgamma, dbeta, M, C, eps);          \
+    break;
+  switch (C / 128) {
+    CCX_LNB_CASE(1) CCX_LNB_CASE(2) CCX_LNB_CASE(3) CCX_LNB_CASE(4) CCX_LNB_CASE(5) CCX_LNB_CASE(6)
+    CCX_LNB_CASE(7) CCX_LNB_CASE(8)
+    default: return CCX_ERR_SHAPE;
+  }
+#undef CCX_LNB_CASE
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention backward, one CTA per (batch, head)
+// ---------------------------------------------------------------------------------------------
+struct MhaBwdArgs {
+  const float* q; long long q_sb, q_st;
+  const float* k; long long k_sb, k_st;
+  const float* v; long long v_sb, v_st;
+  const float* dctx; long long d_sb, d_st;   // [B, Tq, H*hd] fp32
+  const float* probs;                        // [B,H,Tq,Tk] softmax (before dropout)
+  const float* prob_mask;                    // dropout multiplier or nullptr
+  float* dq; long long dq_sb, dq_st;
+  float* dk; long long dk_sb, dk_st;         // written (not accumulated): one CTA owns (b, h)
+  float* dv; long long dv_sb, dv_st;
+  int B, H, Tq, Tk, hd;
+  float scale;
+};
+
+__global__ void __launch_bounds__(128)
+mha_bwd_kernel(MhaBwdArgs a) {
+  extern __shared__ float bsm[];
+  const int hd = a.hd, ld = hd + 1;
+  float* s_q = bsm;                       // [Tq][ld]
+  float* s_do = s_q + a.Tq * ld;          // [Tq][ld]
+  float* s_k = s_do + a.Tq * ld;          // [Tk][ld]
+  float* s_v = s_k + a.Tk * ld;           // [Tk][ld]
+  float* s_p = s_v + a.Tk * ld;           // [Tq][Tk]  P*mask   (then reused)
+  float* s_ds = s_p + a.Tq * a.Tk;        // [Tq][Tk]  dS
+  const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.Tq * hd; i += 128) {
+    const int r = i / hd, d = i - r * hd;
+    s_q[r * ld + d] = a.q[b * a.q_sb + r * a.q_st + h * hd + d];
+    s_do[r * ld + d] = a.dctx[b * a.d_sb + r * a.d_st + h * hd + d];
+  }
+  for (int i = tid; i < a.Tk * hd; i += 128) {
+    const int r = i / hd, d = i - r * hd;
+    s_k[r * ld + d] = a.k[b * a.k_sb + r * a.k_st + h * hd + d];
+    s_v[r * ld + d] = a.v[b * a.v_sb + r * a.v_st + h * hd + d];
+  }
+  const long long pbase = (static_cast<long long>(b) * a.H + h) * a.Tq * a.Tk;
+  __syncthreads();
+  // dPd[i,j] = dctx_i . v_j ; dP = dPd*mask ; dS = P * (dP - sum_j dP*P)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int i = warp; i < a.Tq; i += 4) {
+    float rowdot = 0.f;
+    for (int j = lane; j < a.Tk; j += 32) {
+      float acc = 0.f;
+      for (int d = 0; d < hd; ++d) acc = fmaf(s_do[i * ld + d], s_v[j * ld + d], acc);
+      const float p = a.probs[pbase + i * a.Tk + j];
+      const float m = a.prob_mask ? a.prob_mask[pbase + i * a.Tk + j] : 1.f;
+      const float dp = acc * m;
+      s_p[i * a.Tk + j] = p * m;     // Pd for dV
+      s_ds[i * a.Tk + j] = dp;       // dP for now
+      rowdot += dp * p;
+    }
+    rowdot = warp_sum(rowdot);
+    for (int j = lane; j < a.Tk; j += 32) {
+      const float p = a.probs[pbase + i * a.Tk + j];
+      s_ds[i * a.Tk + j] = p * (s_ds[i * a.Tk + j] - rowdot);
+    }
+  }
+  __syncthreads();
+  // dq[i,d] = scale * sum_j dS[i,j] k[j,d]
+  for (int idx = tid; idx < a.Tq * hd; idx += 128) {
+    const int i = idx / hd, d = idx - i * hd;
+    float acc = 0.f;
+    for (int j = 0; j < a.Tk; ++j) acc = fmaf(s_ds[i * a.Tk + j], s_k[j * ld + d], acc);
+    a.dq[b * a.dq_sb + i * a.dq_st + h * hd + d] = acc * a.scale;
+  }
+  // dk[j,d] = scale * sum_i dS[i,j] q[i,d] ; dv[j,d] = sum_i Pd[i,j] dctx[i,d]
+  for (int idx = tid; idx < a.Tk * hd; idx += 128) {
+    const int j = idx / hd, d = idx - j * hd;
+    float ak = 0.f, av = 0.f;
+    for (int i = 0; i < a.Tq; ++i) {
+      ak = fmaf(s_ds[i * a.Tk + j], s_q[i * ld + d], ak);
+      av = fmaf(s_p[i * a.Tk + j], s_do[i * ld + d], av);
+    }
+    a.dk[b * a.dk_sb + j * a.dk_st + h * hd + d] = ak * a.scale;
+    a.dv[b * a.dv_sb + j * a.dv_st + h * hd + d] = av;
+  }
+}
+
+int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
+            const float* v, long long v_sb, long long v_st, const float* dctx, long long d_sb, long long d_st,
+            const float* probs, const float* prob_mask, float* dq, long long dq_sb, long long dq_st, float* dk,
+            long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
+            int Tk, int hd, float scale, cudaStream_t stream) {
+  if (B <= 0 || Tq <= 0 || Tk <= 0) return CCX_OK;
+  const size_t smem = (static_cast<size_t>(2) * (Tq + Tk) * (hd + 1) + 2 * static_cast<size_t>(Tq) * Tk) * 4;
+  if (smem > 200 * 1024) return CCX_ERR_SHAPE;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return CCX_ERR_CUDA;
+    configured = true;
+  }
+  MhaBwdArgs a;
+  a.q = q; a.q_sb = q_sb; a.q_st = q_st; a.k = k; a.k_sb = k_sb; a.k_st = k_st; a.v = v; a.v_sb = v_sb; a.v_st = v_st;
+  a.dctx = dctx; a.d_sb = d_sb; a.d_st = d_st; a.probs = probs; a.prob_mask = prob_mask;
+  a.dq = dq; a.dq_sb = dq_sb; a.dq_st = dq_st; a.dk = dk; a.dk_sb = dk_sb; a.dk_st = dk_st;
+  a.dv = dv; a.dv_sb = dv_sb; a.dv_st = dv_st;
+  a.B = B; a.H = H; a.Tq = Tq; a.Tk = Tk; a.hd = hd; a.scale = scale;
+  ProfScope prof(PROF_ATTENTION, stream, (double)B * H * (Tq + Tk) * hd * 16.0);
+  mha_bwd_kernel<<<B * H, 128, smem, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused softmax cross-entropy (mean over the selected rows) forward + backward, one CTA per row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_ce_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ targets, int V,
+                  float inv_n, float* __restrict__ loss_sum, float* __restrict__ dlogits, long long ldd,
+                  float* __restrict__ correct_top1) {
+  __shared__ float red[8];
+  __shared__ float s_b;
+  const long long r = blockIdx.x;
+  const long long tgt = targets[r];
+  float* drow = dlogits ? dlogits + r * ldd : nullptr;
+  if (tgt < 0) {
+    if (drow) for (int v = threadIdx.x; v < V; v += 256) drow[v] = 0.f;
+    return;
+  }
+  const float* row = logits + r * ld;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += 256) mx = fmaxf(mx, row[v]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) { float m = red[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]); s_b = m; }
+  __syncthreads();
+  mx = s_b;
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) sum += expf(row[v] - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; s_b = s; }
+  __syncthreads();
+  sum = s_b;
+  const float lse = mx + logf(sum);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_sum, (lse - row[tgt]) * inv_n);
+    if (correct_top1) atomicAdd(correct_top1, row[tgt] >= mx ? 1.f : 0.f);
+  }
+  if (drow) {
+    const float inv = inv_n / sum;
+    for (int v = threadIdx.x; v < V; v += 256) drow[v] = expf(row[v] - mx) * inv - (v == tgt ? inv_n : 0.f);
+  }
+}
+
+int softmax_ce(const float* logits, long long ld, const long long* targets, long long R, int V, float inv_n,
+               float* loss_sum, float* dlogits, long long ldd, float* correct_top1, cudaStream_t stream) {
+  if (R <= 0) return CCX_OK;
+  ProfScope prof(PROF_LOSS, stream, (double)R * V * (dlogits ? 8.0 : 4.0));
+  softmax_ce_kernel<<<static_cast<unsigned>(R), 256, 0, stream>>>(logits, ld, targets, V, inv_n, loss_sum, dlogits,
+                                                                 ldd, correct_top1);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// embedding backward: dTable[token[r]] += dX[r] * mul[r]   (dense gradient like nn.Embedding(sparse=False))
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const long long* __restrict__ tokens, long long tok_ld, int t0, const float* __restrict__ dx,
+                     long long sb, long long st, const float* __restrict__ dropmask, float* __restrict__ dtable,
+                     int V, int D, int nb, int nt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (r >= static_cast<long long>(nb) * nt) return;
+  const int b = static_cast<int>(r / nt), t = static_cast<int>(r % nt);
+  long long tok = tokens[b * tok_ld + t0 + t];
+  if (tok < 0 || tok >= V) return;
+  for (int d = lane; d < D; d += 32) {
+    float g = dx[b * sb + t * st + d];
+    if (dropmask) g *= dropmask[r * D + d];
+    atomicAdd(dtable + tok * D + d, g);
+  }
+}
+
+int embedding_bwd(const long long* tokens, long long tok_ld, int t0, const float* dx, long long sb, long long st,
+                  const float* dropmask, float* dtable, int V, int D, int nb, int nt, cudaStream_t stream) {
+  if (nb <= 0 || nt <= 0) return CCX_OK;
+  const long long rows = static_cast<long long>(nb) * nt;
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)rows * D * 12.0);
+  embedding_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(tokens, tok_ld, t0, dx, sb, st,
+                                                                                dropmask, dtable, V, D, nb, nt);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// clamp(+-clip) + Adam, multi-tensor.  Table entry: {param, grad, exp_avg, exp_avg_sq, n}
+// ---------------------------------------------------------------------------------------------
+struct AdamEntry {
+  float* p;
+  float* g;
+  float* m;
+  float* v;
+  long long n;
+};
+
+__global__ void __launch_bounds__(256)
+adam_clamp_kernel(const AdamEntry* __restrict__ table, const int* __restrict__ block_entry,
+                  const long long* __restrict__ block_offset, float lr, float beta1, float beta2, float eps,
+                  float bc1, float bc2_sqrt, float clip, int chunk) {
+  const AdamEntry e = table[block_entry[blockIdx.x]];
+  const long long begin = block_offset[blockIdx.x];
+  const long long end = min(e.n, begin + chunk);
+  const float step = lr / bc1;
+  for (long long i = begin + threadIdx.x; i < end; i += 256) {
+    float g = e.g[i];
+    if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);     // utils/utils.py:189-192
+    e.g[i] = g;
+    const float m = beta1 * e.m[i] + (1.f - beta1) * g;   // torch/optim/adam.py _single_tensor_adam
+    const float v = beta2 * e.v[i] + (1.f - beta2) * g * g;
+    e.m[i] = m;
+    e.v[i] = v;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    e.p[i] -= step * (m / denom);
+  }
+}
+
+int adam_clamp(const void* table, const int* block_entry, const long long* block_offset, int n_blocks, float lr,
+               float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip, int chunk,
+               double total_params, cudaStream_t stream) {
+  if (n_blocks <= 0) return CCX_OK;
+  ProfScope prof(PROF_OPTIM, stream, total_params * 28.0);
+  adam_clamp_kernel<<<n_blocks, 256, 0, stream>>>(reinterpret_cast<const AdamEntry*>(table), block_entry,
+                                                  block_offset, lr, beta1, beta2, eps, bc1, bc2_sqrt, clip, chunk);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+}  // namespace ccx

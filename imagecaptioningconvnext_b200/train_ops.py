@@ -1,0 +1,87 @@
+"""Backward building blocks shared by the decoders' autograd Functions (all compute on libccx).
+
+Linear backward re-uses the forward tcgen05 GEMM (``ccx_linear``):
+    dX[M,K] = dY[M,N] . W[N,K]        -> A = dY (row-major, contraction over N), B = W^T [K, N]
+    dW[N,K] = dY^T[N,M] . X[M,K]      -> A = dY^T [N, M], B = X^T [K, M]   (+= through the `residual` epilogue)
+    db[N]   = column sums of dY
+with the transposed / converted operands produced by ``ccx_convert_operand`` (optionally fused with a dropout
+multiplier or the ReLU mask).
+"""
+import torch
+
+from . import _lib
+from ._lib import Operand, ptr
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def _src(x):
+    """(hi ptr, lo ptr, dtype code, ld) of a 2-D source: fp32 tensor or Operand."""
+    if isinstance(x, Operand):
+        return ptr(x.hi), x.lo_ptr, _lib.dt_code(x.dtype), x.hi.stride(0)
+    return ptr(x), None, _lib.CCX_F32, x.stride(0)
+
+
+def to_operand(x, cd, mul=None, mul_mode=0, mul_scale=1.0, transpose=False):
+    """2-D fp32 tensor / Operand [R, C] -> Operand in compute dtype `cd`.
+    Plain: [R, pad8(C)] storage viewed as [R, C].  Transposed: [C, pad8(R)] with zero padding, viewed [C, pad8(R)]
+    (the padded contraction columns are zeros on both GEMM operands)."""
+    hi, lo, code, ldx = _src(x)
+    R, C = (x.hi.shape if isinstance(x, Operand) else x.shape)
+    dev = x.hi.device if isinstance(x, Operand) else x.device
+    if transpose:
+        Rp = _pad8(R)
+        out = Operand.empty((C, Rp), cd, dev)
+        view = out
+        ldo = Rp
+    else:
+        Cp = _pad8(C)
+        out = Operand.empty((R, Cp), cd, dev)
+        view = out.map(lambda t: t[:, :C]) if Cp != C else out
+        ldo = Cp
+        Rp = 0
+    _lib.check(_lib.lib().ccx_convert_operand(hi, lo, code, ldx, ptr(mul), mul.stride(0) if mul is not None else 0,
+                                              mul_mode, mul_scale, ptr(out.hi), out.lo_ptr, _lib.dt_code(cd), ldo, R, C,
+                                              1 if transpose else 0, Rp, _lib.stream_ptr()), "convert_operand")
+    return view
+
+
+def colsum_acc(dy, out, mul=None, mul_mode=0, mul_scale=1.0):
+    R, C = dy.shape
+    _lib.check(_lib.lib().ccx_colsum_acc(ptr(dy), dy.stride(0), ptr(mul), mul.stride(0) if mul is not None else 0,
+                                         mul_mode, mul_scale, ptr(out), R, C, _lib.stream_ptr()), "colsum_acc")
+
+
+def linear_bwd(dy, x, wt, cd, w_grad=None, b_grad=None, need_dx=True, dx_residual=None, mul=None, mul_mode=0,
+               mul_scale=1.0):
+    """Backward of y = x . W^T + b.
+    dy: fp32 [M, N] (upstream gradient, multiplied element-wise by `mul` per mul_mode before use);
+    x: the forward's A operand (Operand or fp32 tensor) [M, K]; wt: Operand holding W^T [K, pad8(N)];
+    w_grad [N, K] / b_grad [N]: fp32 accumulators (+=).  Returns dX [M, K] fp32 (+ dx_residual) or None."""
+    M, N = dy.shape
+    dx = None
+    if need_dx:
+        dy_op = to_operand(dy, cd, mul, mul_mode, mul_scale)
+        dx = _lib.linear(dy_op, wt, residual=dx_residual, k=N)
+    if w_grad is not None:
+        dy_t = to_operand(dy, cd, mul, mul_mode, mul_scale, transpose=True)      # [N, Mp]
+        x_t = to_operand(x, cd, transpose=True)                                   # [K, Mp]
+        _lib.linear(dy_t, x_t, residual=w_grad, out=w_grad)
+    if b_grad is not None:
+        colsum_acc(dy, b_grad, mul, mul_mode, mul_scale)
+    return dx
+
+
+def ln_bwd(dy, x_in, gamma, dgamma, dbeta, eps):
+    M, C = x_in.shape
+    dx = torch.empty_like(x_in)
+    _lib.check(_lib.lib().ccx_ln_bwd(ptr(dy), ptr(x_in), ptr(gamma), ptr(dx), ptr(dgamma), ptr(dbeta), M, C, eps,
+                                     _lib.stream_ptr()), "ln_bwd")
+    return dx
+
+
+def weight_t(w, cd):
+    """W [N, K] fp32 parameter -> Operand W^T [K, pad8(N)] for dgrad GEMMs."""
+    return to_operand(w.detach(), cd, transpose=True)

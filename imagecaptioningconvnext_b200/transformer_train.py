@@ -1,0 +1,187 @@
+"""Teacher-forced TransformerDecoder forward WITH autograd (train mode): one ``torch.autograd.Function`` whose forward
+and backward are libccx launches only (reference: models/transformerDecoder.py:88-108 under trainMultiGPU.py:371-384).
+
+Dropout (p = 0.5 everywhere the reference has it: embedding, both attention-probability dropouts, dropout1/2/3 and
+the FFN hidden dropout — torch/nn/modules/transformer.py:1158-1199) uses multiplier tensors drawn with
+torch.bernoulli (or injected by tests) and applied inside the GEMM epilogues / attention kernel.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import Operand, ptr
+from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t
+
+_SITES = ("sa_p", "d1", "ca_p", "d2", "ff", "d3")
+
+
+def _masks(dec, B, T, Pn, dev):
+    """Dropout multipliers for one forward (None entries in eval mode)."""
+    D, H, Dff, L = dec.embed_dim, dec.num_heads, dec.decoder_dim, dec.num_layers
+    if not dec.training or dec.dropout_p == 0:
+        return None
+    if dec.inject_dropout is not None:
+        return {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in dec.inject_dropout.items()}
+    keep = 1.0 - dec.dropout_p
+
+    def draw(*shape):
+        return (torch.bernoulli(torch.full(shape, keep, device=dev)) / keep).contiguous()
+
+    m = {"emb": draw(B * T, D)}
+    for l in range(L):
+        m[(l, "sa_p")] = draw(B, H, T, T)
+        m[(l, "d1")] = draw(B * T, D)
+        m[(l, "ca_p")] = draw(B, H, T, Pn)
+        m[(l, "d2")] = draw(B * T, D)
+        m[(l, "ff")] = draw(B * T, Dff)
+        m[(l, "d3")] = draw(B * T, D)
+    return m
+
+
+class _TransformerTF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, encoder_out, caps, kpm, *params):
+        L, st = _lib.lib(), _lib.stream_ptr()
+        cd = dec.compute_dtype
+        code = _lib.dt_code(cd)
+        B = encoder_out.size(0)
+        D, V, H, T = dec.embed_dim, dec.vocab_size, dec.num_heads, caps.size(1)
+        dev = encoder_out.device
+        Pw = dec._cache.get()
+        E = encoder_out.size(-1)
+        enc = encoder_out.reshape(B, -1, E).float().contiguous()
+        Pn = enc.size(1)
+        enc_op = Operand.prepare(enc.view(B * Pn, E), cd)
+        mem = dec._linear_op(enc_op, Pw["proj"], Pw["proj_b"]) if Pw["proj"] is not None else enc_op
+        masks = _masks(dec, B, T, Pn, dev)
+        mk = (lambda k: None) if masks is None else (lambda k: masks.get(k))
+        scale = 1.0 / math.sqrt(D // H)
+
+        x_plain = torch.empty((B * T, D), dtype=torch.float32, device=dev)
+        x_op = Operand.empty((B * T, D), cd, dev)
+        _lib.check(L.ccx_embed_rows(ptr(caps), T, 0, ptr(dec.embedding.weight), V, D, ptr(Pw["pe"]), ptr(mk("emb")),
+                                    ptr(x_plain), T * D, D, ptr(x_op.hi), x_op.lo_ptr, code, T * D, D, B, T, st),
+                   "embed_rows")
+        saved = []
+        for li, lw in enumerate(Pw["layers"]):
+            S = {"x0_op": x_op}
+            qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
+            probs1 = torch.empty((B, H, T, T), dtype=torch.float32, device=dev)
+            ctx1 = dec._mha(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
+                            qkv.data_ptr() + 8 * D, B, T, T, 1, 0, kpm, mk((li, "sa_p")), 1, dev, probs_out=probs1)
+            y1 = _lib.linear(ctx1, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain, emask=mk((li, "d1")))
+            x1_plain, x1_op = dec._ln(y1, lw["n"][0], B * T)
+            q2 = _lib.linear(x1_op, lw["ca_q"], bias=lw["ca_q_b"])
+            kv = _lib.linear(mem, lw["ca_kv"], bias=lw["ca_kv_b"])
+            probs2 = torch.empty((B, H, T, Pn), dtype=torch.float32, device=dev)
+            ctx2 = dec._mha(ptr(q2), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, B, T, Pn, 0, 0,
+                            None, mk((li, "ca_p")), 1, dev, probs_out=probs2)
+            y2 = _lib.linear(ctx2, lw["ca_out"], bias=lw["ca_out_b"], residual=x1_plain, emask=mk((li, "d2")))
+            x2_plain, x2_op = dec._ln(y2, lw["n"][1], B * T)
+            h_plain = _lib.linear(x2_op, lw["l1"], bias=lw["l1_b"], act=_lib.ACT_RELU, emask=mk((li, "ff")))
+            h_op = to_operand(h_plain, cd)
+            y3 = _lib.linear(h_op, lw["l2"], bias=lw["l2_b"], residual=x2_plain, emask=mk((li, "d3")))
+            x_plain, x_op = dec._ln(y3, lw["n"][2], B * T)
+            S.update(qkv=qkv, probs1=probs1, ctx1=ctx1, y1=y1, x1_op=x1_op, q2=q2, kv=kv, probs2=probs2, ctx2=ctx2,
+                     y2=y2, x2_op=x2_op, h_plain=h_plain, h_op=h_op, y3=y3)
+            saved.append(S)
+        predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)
+        _lib.linear(x_op, Pw["fc"], bias=Pw["fc_b"], out=predictions.view(B * T, V))
+        ctx.dec, ctx.saved, ctx.masks, ctx.kpm = dec, saved, masks, kpm
+        ctx.x_last_op, ctx.mem, ctx.enc_op, ctx.caps = x_op, mem, enc_op, caps
+        ctx.dims = (B, T, Pn, E)
+        ctx.enc_needs_grad = encoder_out.requires_grad
+        ctx.enc_shape = encoder_out.shape
+        return predictions
+
+    @staticmethod
+    def backward(ctx, dpred):
+        dec = ctx.dec
+        L, st = _lib.lib(), _lib.stream_ptr()
+        cd = dec.compute_dtype
+        B, T, Pn, E = ctx.dims
+        D, V, H, Dff = dec.embed_dim, dec.vocab_size, dec.num_heads, dec.decoder_dim
+        dev = dpred.device
+        masks = ctx.masks
+        mk = (lambda k: None) if masks is None else (lambda k: masks.get(k))
+        mode = 0 if masks is None else 1
+        keep_scale = 1.0 if masks is None else 1.0 / (1.0 - dec.dropout_p)
+        scale = 1.0 / math.sqrt(D // H)
+        names = [n for n, _ in dec.named_parameters()]
+        params = dict(dec.named_parameters())
+        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in params.items() if p.requires_grad}
+        g = lambda n: grads.get(n)
+        M = B * T
+
+        dpred = dpred.contiguous().view(M, V)
+        dx = linear_bwd(dpred, ctx.x_last_op, weight_t(dec.fc_out.weight, cd), cd, g("fc_out.weight"),
+                        g("fc_out.bias"))
+        dmem = torch.zeros((B * Pn, D), dtype=torch.float32, device=dev)
+        for li in reversed(range(dec.num_layers)):
+            S, lyr = ctx.saved[li], dec.transformer_decoder.layers[li]
+            pre = f"transformer_decoder.layers.{li}."
+            # LN3 / FFN
+            dy3 = ln_bwd(dx, S["y3"], lyr.norm3.weight.detach(), g(pre + "norm3.weight"), g(pre + "norm3.bias"), 1e-5)
+            dh = linear_bwd(dy3, S["h_op"], weight_t(lyr.linear2.weight, cd), cd, g(pre + "linear2.weight"),
+                            g(pre + "linear2.bias"), mul=mk((li, "d3")), mul_mode=mode)
+            dx2 = linear_bwd(dh, S["x2_op"], weight_t(lyr.linear1.weight, cd), cd, g(pre + "linear1.weight"),
+                             g(pre + "linear1.bias"), dx_residual=dy3, mul=S["h_plain"], mul_mode=2,
+                             mul_scale=keep_scale)
+            # LN2 / cross attention
+            dy2 = ln_bwd(dx2, S["y2"], lyr.norm2.weight.detach(), g(pre + "norm2.weight"), g(pre + "norm2.bias"), 1e-5)
+            ca = lyr.multihead_attn
+            dctx2 = linear_bwd(dy2, S["ctx2"], weight_t(ca.out_proj.weight, cd), cd, g(pre + "multihead_attn.out_proj.weight"),
+                               g(pre + "multihead_attn.out_proj.bias"), mul=mk((li, "d2")), mul_mode=mode)
+            dq2 = torch.empty((M, D), dtype=torch.float32, device=dev)
+            dkv = torch.empty((B * Pn, 2 * D), dtype=torch.float32, device=dev)
+            q2, kv = S["q2"], S["kv"]
+            _lib.check(L.ccx_mha_bwd(ptr(q2), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, Pn * 2 * D,
+                                     2 * D, ptr(dctx2), T * D, D, ptr(S["probs2"]), ptr(mk((li, "ca_p"))),
+                                     ptr(dq2), T * D, D, ptr(dkv), Pn * 2 * D, 2 * D, dkv.data_ptr() + 4 * D,
+                                     Pn * 2 * D, 2 * D, B, H, T, Pn, D // H, scale, st), "mha_bwd")
+            gw, gb = g(pre + "multihead_attn.in_proj_weight"), g(pre + "multihead_attn.in_proj_bias")
+            w_in = ca.in_proj_weight.detach()
+            dx1 = linear_bwd(dq2, S["x1_op"], weight_t(w_in[:D], cd), cd, None if gw is None else gw[:D],
+                             None if gb is None else gb[:D], dx_residual=dy2)
+            dmem = linear_bwd(dkv, ctx.mem, weight_t(w_in[D:], cd), cd, None if gw is None else gw[D:],
+                              None if gb is None else gb[D:], dx_residual=dmem)
+            # LN1 / self attention
+            dy1 = ln_bwd(dx1, S["y1"], lyr.norm1.weight.detach(), g(pre + "norm1.weight"), g(pre + "norm1.bias"), 1e-5)
+            sa = lyr.self_attn
+            dctx1 = linear_bwd(dy1, S["ctx1"], weight_t(sa.out_proj.weight, cd), cd, g(pre + "self_attn.out_proj.weight"),
+                               g(pre + "self_attn.out_proj.bias"), mul=mk((li, "d1")), mul_mode=mode)
+            qkv = S["qkv"]
+            dqkv = torch.empty((M, 3 * D), dtype=torch.float32, device=dev)
+            _lib.check(L.ccx_mha_bwd(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
+                                     qkv.data_ptr() + 8 * D, T * 3 * D, 3 * D, ptr(dctx1), T * D, D,
+                                     ptr(S["probs1"]), ptr(mk((li, "sa_p"))), ptr(dqkv), T * 3 * D, 3 * D,
+                                     dqkv.data_ptr() + 4 * D, T * 3 * D, 3 * D, dqkv.data_ptr() + 8 * D, T * 3 * D,
+                                     3 * D, B, H, T, T, D // H, scale, st), "mha_bwd")
+            dx = linear_bwd(dqkv, S["x0_op"], weight_t(sa.in_proj_weight, cd), cd, g(pre + "self_attn.in_proj_weight"),
+                            g(pre + "self_attn.in_proj_bias"), dx_residual=dy1)
+        # embedding (dense gradient, times the embedding-dropout multiplier; the PE add has no parameters)
+        ge = g("embedding.weight")
+        if ge is not None:
+            _lib.check(L.ccx_embedding_bwd(ptr(ctx.caps), T, 0, ptr(dx), T * D, D, ptr(mk("emb")), ptr(ge), V, D, B, T,
+                                           st), "embedding_bwd")
+        # encoder_proj
+        denc = None
+        if isinstance(dec.encoder_proj, torch.nn.Identity):
+            denc = dmem if ctx.enc_needs_grad else None
+        else:
+            denc = linear_bwd(dmem, ctx.enc_op, weight_t(dec.encoder_proj.weight, cd), cd, g("encoder_proj.weight"),
+                              g("encoder_proj.bias"), need_dx=ctx.enc_needs_grad)
+        if denc is not None:
+            denc = denc.view(ctx.enc_shape)
+        return (None, denc, None, None) + tuple(grads.get(n) for n in names)
+
+
+def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
+    _lib.require_cuda(encoder_out, "encoder_out")
+    decode_lengths = (caption_lengths.squeeze(1) - 1).tolist()
+    caps = encoded_captions.contiguous()
+    kpm = None if tgt_key_padding_mask is None else tgt_key_padding_mask.to(torch.uint8).contiguous()
+    params = [p for _, p in dec.named_parameters()]
+    predictions = _TransformerTF.apply(dec, encoder_out, caps, kpm, *params)
+    return predictions, encoded_captions, decode_lengths

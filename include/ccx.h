@@ -55,7 +55,8 @@ CCX_API int ccx_num_sms(void);
  * Replaces every nn.Linear / 1x1-equivalent conv on the path:
  *   torchvision/models/convnext.py:55-57 (CNBlock MLP), :146-151 (downsample conv as patch-merge GEMM),
  *   models/decoder.py:19-21,50-54, models/transformerDecoder.py:84-85, torch/nn/modules/transformer.py.
- * epilogue(y) = act(y + bias[n]) * colscale[n] * rowscale[m / rows_per_group] + residual[m,n]
+ * epilogue(y) = act(y + bias[n]) * emask[m,n] * colscale[n] * rowscale[m / rows_per_group] + residual[m,n]
+ * (emask = dropout multiplier, train mode).  K may be any size; lda/ldw (bytes) must be multiples of 16.
  * in_dtype CCX_BF16: A, W bf16; A_lo/W_lo ignored.  in_dtype CCX_F32: A/W are tf32-hi parts, A_lo/W_lo
  * the fp32 remainders (3xTF32); if both *_lo are NULL a single TF32 pass is run.
  * split != 0 (fp32 out only): C receives tf32-hi(y), C_lo the remainder (ready to be the next A operand).
@@ -71,7 +72,8 @@ typedef struct ccx_linear_desc {
   const float* colscale; /* [N] or NULL (layer_scale) */
   const float* rowscale; /* [ceil(M/rows_per_group)] or NULL (stochastic-depth noise/(1-p)) */
   const void* residual;  /* [M, ldr] dtype of C, or NULL */
-  int64_t lda, ldw, ldc, ldr; /* leading dimensions in elements */
+  const float* emask;    /* [M, ldm] fp32 or NULL */
+  int64_t lda, ldw, ldc, ldr, ldm; /* leading dimensions in elements */
   int32_t M, N, K;
   int32_t rows_per_group;
   int32_t act;
@@ -244,6 +246,47 @@ CCX_API int ccx_beam_update(int32_t NI, int32_t k, int32_t Tcap, int32_t step, i
  * KV caches; src_row NULL = identity.  16-byte granules; strides in bytes. */
 CCX_API int ccx_gather_rows(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,
                             const int32_t* src_row, int64_t row_bytes, int32_t rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Train step (autograd graph behind trainMultiGPU.py:357-394; clip_gradient utils/utils.py:183-192; Adam).
+ * Linear backward uses ccx_linear itself: dX = dY . W (B operand = W^T) and dW = dY^T . X (operands transposed by
+ * ccx_convert_operand), accumulating into .grad through the `residual` epilogue.
+ * ------------------------------------------------------------------------------------------------ */
+/* x[R,C] (fp32 plain: x_lo NULL / tf32 pair / bf16 per x_dtype) times an optional multiplier (mul_mode 1:
+ * * mul[r,c] (dropout); 2: * mul_scale where mul[r,c] > 0 else 0 (ReLU mask from the saved, possibly
+ * dropped-out, output)) -> GEMM operand (bf16 / tf32
+ * hi+lo / fp32); transpose != 0 writes out[c, r] with r zero-padded up to Rpad. */
+CCX_API int ccx_convert_operand(const void* x_hi, const float* x_lo, int32_t x_dtype, int64_t ldx,
+                                const float* mul, int64_t ldm, int32_t mul_mode, float mul_scale, void* o_hi,
+                                float* o_lo, int32_t o_dtype, int64_t ldo, int32_t R, int32_t C, int32_t transpose,
+                                int32_t Rpad, void* stream);
+/* out[c] += sum_r x[r,c] (* multiplier as above): bias gradients. */
+CCX_API int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode,
+                           float mul_scale, float* out, int32_t R, int32_t C, void* stream);
+/* LayerNorm backward over rows of x[M,C]; dgamma/dbeta are accumulated (+=). */
+CCX_API int ccx_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
+                       int64_t M, int32_t C, float eps, void* stream);
+/* Backward of ccx_mha_small (same strided addressing; probs = its probs_out). */
+CCX_API int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
+                        const float* v, int64_t v_sb, int64_t v_st, const float* dctx, int64_t d_sb, int64_t d_st,
+                        const float* probs, const float* prob_mask, float* dq, int64_t dq_sb, int64_t dq_st,
+                        float* dk, int64_t dk_sb, int64_t dk_st, float* dv, int64_t dv_sb, int64_t dv_st, int32_t B,
+                        int32_t H, int32_t Tq, int32_t Tk, int32_t hd, float scale, void* stream);
+/* CrossEntropyLoss(mean) over the rows with targets[r] >= 0 (= pack_padded_sequence's selection,
+ * trainMultiGPU.py:365-367): *loss_sum += sum_r (lse_r - logit_r[target]) * inv_n;
+ * dlogits[r] = (softmax_r - onehot) * inv_n, zero rows for targets < 0; correct_top1 counts argmax hits. */
+CCX_API int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V, float inv_n,
+                           float* loss_sum, float* dlogits, int64_t ldd, float* correct_top1, void* stream);
+/* nn.Embedding dense gradient: dtable[token(b,t)] += dx[b*sb + t*st + :] * dropmask[(b*nt+t), :]. */
+CCX_API int ccx_embedding_bwd(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* dx, int64_t sb,
+                              int64_t st, const float* dropmask, float* dtable, int32_t V, int32_t D, int32_t nb,
+                              int32_t nt, void* stream);
+/* clip_gradient (grad.clamp_(-clip, clip), utils/utils.py:189-192) fused with torch.optim.Adam's single-tensor
+ * update (no weight decay / amsgrad), over a device table of {param, grad, exp_avg, exp_avg_sq, n} entries;
+ * block i handles elements [block_offset[i], +chunk) of entry block_entry[i]. */
+CCX_API int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t* block_offset,
+                           int32_t n_blocks, float lr, float beta1, float beta2, float eps, float bc1,
+                           float bc2_sqrt, float clip, int32_t chunk, double total_params, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the
