@@ -17,7 +17,7 @@ class CcxLinear(nn.Linear):
         self._key, self._w = None, None
 
     def operand(self):
-        key = (self.weight.data_ptr(), self.weight._version, self.compute_dtype)
+        key = (self.weight.data_ptr(), self.weight._version + getattr(self.weight, "_ccx_epoch", 0), self.compute_dtype)
         if key != self._key:
             self._w, self._key = Operand.prepare(self.weight.detach(), self.compute_dtype), key
         return self._w
@@ -54,7 +54,8 @@ class PreparedCache:
     def get(self):
         owner = self._owner[0]
         params = list(owner.parameters())
-        key = (owner.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(), sum(p._version for p in params))
+        key = (owner.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(),
+               sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params))
         if key != self._key:
             for p in params:
                 if not p.is_cuda or p.dtype != torch.float32:

@@ -80,6 +80,11 @@ SIGNATURES = {
                               _f32, _vp]),
     "ccx_softmax_ce": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
     "ccx_embedding_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_lstm_pointwise_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32,
+                                         _vp]),
+    "ccx_bahdanau_attention_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
+                                             _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_bcast_add_rows": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, _vp]),
     "ccx_adam_clamp": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_double,
                                  _vp]),
     "ccx_prof_begin": (C.c_int, []),

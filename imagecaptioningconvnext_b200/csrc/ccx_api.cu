@@ -168,6 +168,24 @@ int ccx_embedding_bwd(const int64_t* tokens, int64_t tok_ld, int32_t t0, const f
   return embedding_bwd(reinterpret_cast<const long long*>(tokens), tok_ld, t0, dx, sb, st, dropmask, dtable, V, D,
                        nb, nt, as_stream(stream));
 }
+int ccx_lstm_pointwise_bwd(const float* gates, int64_t ldg, const float* c_prev, const float* c_new,
+                           const float* dh_fc, int64_t ld_fc, const float* dropmask, int64_t ld_dm,
+                           const float* dh_carry, float* dc_carry, float* dgates, int64_t lddg, int32_t bt,
+                           int32_t D, void* stream) {
+  return lstm_pointwise_bwd(gates, ldg, c_prev, c_new, dh_fc, ld_fc, dropmask, ld_dm, dh_carry, dc_carry, dgates,
+                            lddg, bt, D, as_stream(stream));
+}
+int ccx_bahdanau_attention_bwd(const float* att1, const float* hg, int64_t ldhg, const float* w_f, const float* enc,
+                               const float* alpha, int64_t alpha_ld, const float* d_out, int64_t ld_dout,
+                               const float* d_alpha_ext, int64_t dalpha_ld, float* d_hg, int64_t ld_dhg,
+                               float* d_att1, float* d_enc, float* d_wf, int32_t bt, int32_t P, int32_t A,
+                               int32_t E, void* stream) {
+  return bahdanau_attention_bwd(att1, hg, ldhg, w_f, enc, alpha, alpha_ld, d_out, ld_dout, d_alpha_ext, dalpha_ld,
+                                d_hg, ld_dhg, d_att1, d_enc, d_wf, bt, P, A, E, as_stream(stream));
+}
+int ccx_bcast_add_rows(float* out, const float* v, float scale, int32_t B, int32_t P, int32_t E, void* stream) {
+  return bcast_add_rows(out, v, scale, B, P, E, as_stream(stream));
+}
 int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t* block_offset, int32_t n_blocks,
                    float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip,
                    int32_t chunk, double total_params, void* stream) {

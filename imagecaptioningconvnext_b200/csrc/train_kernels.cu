@@ -15,6 +15,8 @@
 
 namespace ccx {
 
+static constexpr int ATT_MAX_P_BWD = 256;
+
 // ---------------------------------------------------------------------------------------------
 // convert / transpose to GEMM operand
 // ---------------------------------------------------------------------------------------------
@@ -408,6 +410,163 @@ int embedding_bwd(const long long* tokens, long long tok_ld, int t0, const float
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)rows * D * 12.0);
   embedding_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(tokens, tok_ld, t0, dx, sb, st,
                                                                                 dropmask, dtable, V, D, nb, nt);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSTM cell backward (point-wise half).  dh = dh_fc * dropmask + dh_carry ; see lstm_pointwise_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lstm_pointwise_bwd_kernel(const float* __restrict__ gates, long long ldg, const float* __restrict__ c_prev,
+                          const float* __restrict__ c_new, const float* __restrict__ dh_fc, long long ld_fc,
+                          const float* __restrict__ dropmask, long long ld_dm, const float* __restrict__ dh_carry,
+                          float* __restrict__ dc_carry,  // in: dL/dc_new, out: dL/dc_prev   [bt, D]
+                          float* __restrict__ dgates, long long lddg, int bt, int D) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(bt) * D) return;
+  const int b = static_cast<int>(idx / D), j = static_cast<int>(idx % D);
+  const float* g = gates + b * ldg;
+  const float i_ = 1.0f / (1.0f + expf(-g[j]));
+  const float f_ = 1.0f / (1.0f + expf(-g[D + j]));
+  const float g_ = tanhf(g[2 * D + j]);
+  const float o_ = 1.0f / (1.0f + expf(-g[3 * D + j]));
+  const float tc = tanhf(c_new[static_cast<long long>(b) * D + j]);
+  float dh = dh_carry ? dh_carry[static_cast<long long>(b) * D + j] : 0.f;
+  if (dh_fc) dh += dh_fc[b * ld_fc + j] * (dropmask ? dropmask[b * ld_dm + j] : 1.f);
+  const float dc = dc_carry[static_cast<long long>(b) * D + j] + dh * o_ * (1.f - tc * tc);
+  float* dg = dgates + b * lddg;
+  dg[j] = dc * g_ * i_ * (1.f - i_);
+  dg[D + j] = dc * c_prev[static_cast<long long>(b) * D + j] * f_ * (1.f - f_);
+  dg[2 * D + j] = dc * i_ * (1.f - g_ * g_);
+  dg[3 * D + j] = dh * tc * o_ * (1.f - o_);
+  dc_carry[static_cast<long long>(b) * D + j] = dc * f_;
+}
+
+int lstm_pointwise_bwd(const float* gates, long long ldg, const float* c_prev, const float* c_new,
+                       const float* dh_fc, long long ld_fc, const float* dropmask, long long ld_dm,
+                       const float* dh_carry, float* dc_carry, float* dgates, long long lddg, int bt, int D,
+                       cudaStream_t stream) {
+  if (bt <= 0) return CCX_OK;
+  const long long n = static_cast<long long>(bt) * D;
+  ProfScope prof(PROF_LSTM, stream, (double)n * 48.0);
+  lstm_pointwise_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      gates, ldg, c_prev, c_new, dh_fc, ld_fc, dropmask, ld_dm, dh_carry, dc_carry, dgates, lddg, bt, D);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bahdanau attention step backward, one CTA per sample (mirror of bahdanau_attention_kernel)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bahdanau_attention_bwd_kernel(const float* __restrict__ att1, const float* __restrict__ hg, long long ldhg,
+                              const float* __restrict__ w_f, const float* __restrict__ enc,
+                              const float* __restrict__ alpha, long long alpha_ld,       // saved softmax [b, p]
+                              const float* __restrict__ d_out, long long ld_dout,        // grad wrt gated awe [b, E]
+                              const float* __restrict__ d_alpha_ext, long long dalpha_ld,  // external grad wrt alpha or null
+                              float* __restrict__ d_hg, long long ld_dhg,                // out [b, A+E]
+                              float* __restrict__ d_att1,                                // += [B, P, A]
+                              float* __restrict__ d_enc,                                 // += [B, P, E] or null
+                              float* __restrict__ d_wf,                                  // += [A] (atomic)
+                              int P, int A, int E) {
+  extern __shared__ float bw_sm[];
+  float* s_att2 = bw_sm;          // [A]
+  float* s_wf = s_att2 + A;       // [A]
+  float* s_draw = s_wf + A;       // [E]  d_awe_raw = d_out * gate
+  float* s_datt2 = s_draw + E;    // [A]
+  __shared__ float s_a[ATT_MAX_P_BWD], s_de[ATT_MAX_P_BWD];
+  __shared__ float s_dot;
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < A; i += 256) {
+    s_att2[i] = hg[b * ldhg + i];
+    s_wf[i] = __ldg(w_f + i);
+    s_datt2[i] = 0.f;
+  }
+  for (int p = threadIdx.x; p < P; p += 256) s_a[p] = alpha[b * alpha_ld + p];
+  __syncthreads();
+  // un-gated awe, gate, d_gate_pre, d_awe_raw
+  for (int e = threadIdx.x; e < E; e += 256) {
+    float awe = 0.f;
+    for (int p = 0; p < P; ++p) awe = fmaf(__ldg(enc + (static_cast<long long>(b) * P + p) * E + e), s_a[p], awe);
+    const float gate = 1.0f / (1.0f + expf(-hg[b * ldhg + A + e]));
+    const float dout = d_out[b * ld_dout + e];
+    d_hg[b * ld_dhg + A + e] = dout * awe * gate * (1.f - gate);
+    s_draw[e] = dout * gate;
+  }
+  __syncthreads();
+  // d_alpha[p] = d_awe_raw . enc_p (+ external), and d_enc += alpha_p * d_awe_raw
+  for (int p = warp; p < P; p += 8) {
+    const float* er = enc + (static_cast<long long>(b) * P + p) * E;
+    float acc = 0.f;
+    for (int e = lane; e < E; e += 32) acc = fmaf(__ldg(er + e), s_draw[e], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_de[p] = acc + (d_alpha_ext ? d_alpha_ext[b * dalpha_ld + p] : 0.f);
+    if (d_enc != nullptr) {
+      float* dr = d_enc + (static_cast<long long>(b) * P + p) * E;
+      const float a = s_a[p];
+      for (int e = lane; e < E; e += 32) dr[e] += a * s_draw[e];
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int p = lane; p < P; p += 32) dot += s_a[p] * s_de[p];
+    dot = warp_sum(dot);
+    if (lane == 0) s_dot = dot;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += 256) s_de[p] = s_a[p] * (s_de[p] - s_dot);   // de_p
+  __syncthreads();
+  // through w_f . relu(att1 + att2): per (p, a)
+  for (int a = threadIdx.x; a < A; a += 256) {
+    float datt2 = 0.f, dwf = 0.f;
+    const float h2 = s_att2[a], wf = s_wf[a];
+    for (int p = 0; p < P; ++p) {
+      const long long i1 = (static_cast<long long>(b) * P + p) * A + a;
+      const float pre = att1[i1] + h2;
+      if (pre > 0.f) {
+        const float de = s_de[p];
+        const float gpre = de * wf;
+        datt2 += gpre;
+        d_att1[i1] += gpre;
+        dwf = fmaf(de, pre, dwf);
+      }
+    }
+    d_hg[b * ld_dhg + a] = datt2;
+    atomicAdd(d_wf + a, dwf);
+  }
+}
+
+int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* enc,
+                           const float* alpha, long long alpha_ld, const float* d_out, long long ld_dout,
+                           const float* d_alpha_ext, long long dalpha_ld, float* d_hg, long long ld_dhg,
+                           float* d_att1, float* d_enc, float* d_wf, int bt, int P, int A, int E,
+                           cudaStream_t stream) {
+  if (bt <= 0) return CCX_OK;
+  if (P <= 0 || P > ATT_MAX_P_BWD) return CCX_ERR_SHAPE;
+  const size_t smem = (3 * static_cast<size_t>(A) + E) * sizeof(float);
+  if (smem > 48 * 1024) return CCX_ERR_SHAPE;
+  ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (2.0 * A + 3.0 * E) * 4.0);
+  bahdanau_attention_bwd_kernel<<<bt, 256, smem, stream>>>(att1, hg, ldhg, w_f, enc, alpha, alpha_ld, d_out, ld_dout,
+                                                           d_alpha_ext, dalpha_ld, d_hg, ld_dhg, d_att1, d_enc, d_wf,
+                                                           P, A, E);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// out[b, p, :] += v[b, :] * scale   (backward of mean over pixels)
+__global__ void __launch_bounds__(256)
+bcast_add_rows_kernel(float* __restrict__ out, const float* __restrict__ v, float scale, int P, int E, int B) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * P * E) return;
+  const int e = static_cast<int>(i % E);
+  const int b = static_cast<int>(i / (static_cast<long long>(P) * E));
+  out[i] += v[static_cast<long long>(b) * E + e] * scale;
+}
+int bcast_add_rows(float* out, const float* v, float scale, int B, int P, int E, cudaStream_t stream) {
+  if (B <= 0) return CCX_OK;
+  const long long n = static_cast<long long>(B) * P * E;
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)n * 8.0);
+  bcast_add_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(out, v, scale, P, E, B);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -163,6 +163,7 @@ class DecoderWithAttention(nn.Module):
         else:
             _lib.linear(m, Pw["w_init_h"], bias=self.init_h.bias.detach(), out=h0, split=True)
         _lib.linear(m, Pw["w_init_c"], bias=self.init_c.bias.detach(), out=C_all[0])
+        self._setup_extras = (m, enc_op)        # kept for the backward pass (decoder_train.py)
         return Pw, att1, XH, C_all
 
     def _step(self, Pw, enc, att1, XH, C_all, HG, G, t, bt, alphas_t, alpha_ld, active, h_all, ha_ld, dm, dm_ld,
@@ -242,7 +243,9 @@ class DecoderWithAttention(nn.Module):
         _lib.linear(H_all.map(lambda x: x.view(B * T, D)), Pw["w_fc"], bias=self.fc.bias.detach(), rowscale=valid,
                     rows_per_group=1, out=predictions.view(B * T, V))
         saved = dict(enc=enc, att1=att1, XH=XH, C_all=C_all, HG=HG, G=G, H_all=H_all, dm=dm, valid=valid, bts=bts,
-                     sort_ind=sort_ind, caps=encoded_captions, Pw=Pw)
+                     sort_ind=sort_ind, caps=encoded_captions, Pw=Pw, m_op=self._setup_extras[0],
+                     enc_op=self._setup_extras[1], alphas=alphas, T=T)
+        self._setup_extras = None
         return predictions, encoded_captions, decode_lengths, alphas, sort_ind, saved
 
     @torch.no_grad()

@@ -1,0 +1,123 @@
+"""Teacher-forced DecoderWithAttention forward WITH autograd: explicit back-propagation through time on libccx
+(reference: models/decoder.py:69-113 under trainMultiGPU.py:363-384).
+
+Per backward step (t = T-1 .. 0): LSTM point-wise backward, ONE dgrad GEMM dgates . [W_ih | W_hh] giving
+[d emb_t | d awe_t | d h_{t-1}], the fused attention backward, ONE dgrad GEMM through [decoder_att | f_beta].
+All weight gradients are batched over time into single GEMMs after the loop (the reference's autograd runs
+~5,100 small kernels for this).
+"""
+import torch
+
+from . import _lib
+from ._lib import Operand, ptr
+from .train_ops import linear_bwd, to_operand, weight_t
+
+
+class _LstmTF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, holder, encoder_out, caps, lens, *params):
+        preds, caps_sorted, decode_lengths, alphas, sort_ind, saved = dec._tf_forward(encoder_out, caps, lens)
+        holder["caps_sorted"], holder["decode_lengths"], holder["sort_ind"] = caps_sorted, decode_lengths, sort_ind
+        ctx.dec, ctx.saved = dec, saved
+        ctx.enc_needs_grad = encoder_out.requires_grad
+        ctx.enc_shape = encoder_out.shape
+        return preds, alphas
+
+    @staticmethod
+    def backward(ctx, dpred, dalphas):
+        dec, S = ctx.dec, ctx.saved
+        L, st = _lib.lib(), _lib.stream_ptr()
+        cd = dec.compute_dtype
+        enc, att1, XH, C_all, HG, G, H_all = S["enc"], S["att1"], S["XH"], S["C_all"], S["HG"], S["G"], S["H_all"]
+        dm, bts, T, alphas, Pw = S["dm"], S["bts"], S["T"], S["alphas"], S["Pw"]
+        B, Pn, E = enc.shape
+        D, A, V, Emb = dec.decoder_dim, dec.attention_dim, dec.vocab_size, dec.embed_dim
+        K, hoff = Emb + E + D, Emb + E
+        dev = enc.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        names = [n for n, _ in dec.named_parameters()]
+        params = dict(dec.named_parameters())
+        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in params.items() if p.requires_grad}
+        g = lambda n: grads.get(n)
+        need_enc = ctx.enc_needs_grad
+
+        # hoisted fc: dH_all[b,t,:] = dpred[b,t,:] . W_fc   (rows past a caption's length carry zero gradient)
+        dpred = dpred.contiguous().view(B * T, V)
+        dH_all = linear_bwd(dpred, H_all.map(lambda x: x.view(B * T, D)), weight_t(dec.fc.weight, cd), cd,
+                            g("fc.weight"), g("fc.bias"))
+        w_lstm_t = weight_t(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd)
+        w_h_t = weight_t(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd)
+        dG_all = torch.zeros((T, B, 4 * D), **f32)
+        dHG_all = torch.zeros((T, B, A + E), **f32)
+        dXH_all = torch.zeros((T, B, K), **f32)
+        d_att1 = torch.zeros((B * Pn, A), **f32)
+        d_enc = torch.zeros((B, Pn, E), **f32) if need_enc else None
+        d_wf = torch.zeros((A,), **f32)
+        dc = torch.zeros((B, D), **f32)
+        dh = torch.zeros((B, D), **f32)
+        dal = None if dalphas is None else dalphas.contiguous()
+        for t in reversed(range(T)):
+            bt = bts[t]
+            _lib.check(L.ccx_lstm_pointwise_bwd(ptr(G[t]), 4 * D, ptr(C_all[t]), ptr(C_all[t + 1]),
+                                                dH_all.data_ptr() + 4 * t * D, T * D,
+                                                None if dm is None else dm.data_ptr() + 4 * t * D, T * D,
+                                                ptr(dh), ptr(dc), ptr(dG_all[t]), 4 * D, bt, D, st), "lstm_bwd")
+            _lib.linear(to_operand(dG_all[t, :bt], cd), w_lstm_t, out=dXH_all[t, :bt], k=4 * D)
+            _lib.check(L.ccx_bahdanau_attention_bwd(
+                ptr(att1), ptr(HG[t]), A + E, ptr(Pw["w_f"]), ptr(enc), alphas.data_ptr() + 4 * t * Pn, T * Pn,
+                dXH_all.data_ptr() + 4 * (t * B * K + Emb), K,
+                None if dal is None else dal.data_ptr() + 4 * t * Pn, T * Pn, ptr(dHG_all[t]), A + E, ptr(d_att1),
+                ptr(d_enc), ptr(d_wf), bt, Pn, A, E, st), "attention_bwd")
+            _lib.linear(to_operand(dHG_all[t, :bt], cd), w_h_t, residual=dXH_all[t, :bt, hoff:], out=dh[:bt],
+                        k=A + E)
+        # ---- weight gradients, batched over time -------------------------------------------------------------
+        TB = T * B
+        x_all = XH.map(lambda x: x[:T].view(TB, K))
+        if g("decode_step.weight_ih") is not None:
+            gw = torch.zeros((4 * D, K), **f32)
+            gb = torch.zeros((4 * D,), **f32)
+            linear_bwd(dG_all.view(TB, 4 * D), x_all, None, cd, gw, gb, need_dx=False)
+            grads["decode_step.weight_ih"], grads["decode_step.weight_hh"] = gw[:, :hoff].contiguous(), gw[:, hoff:].contiguous()
+            grads["decode_step.bias_ih"], grads["decode_step.bias_hh"] = gb, gb.clone()
+        if g("f_beta.weight") is not None:
+            gw = torch.zeros((A + E, D), **f32)
+            gb = torch.zeros((A + E,), **f32)
+            h_prev_all = XH.map(lambda x: x[:T].view(TB, K)[:, hoff:])
+            linear_bwd(dHG_all.view(TB, A + E), h_prev_all, None, cd, gw, gb, need_dx=False)
+            grads["attention.decoder_att.weight"], grads["f_beta.weight"] = gw[:A].contiguous(), gw[A:].contiguous()
+            grads["attention.decoder_att.bias"], grads["f_beta.bias"] = gb[:A].contiguous(), gb[A:].contiguous()
+        if g("attention.full_att.weight") is not None:
+            grads["attention.full_att.weight"] = d_wf.view(1, A)
+            # d/d b_f of softmax(e + b_f) is identically zero (softmax is shift invariant)
+        ge = g("embedding.weight")
+        if ge is not None:
+            caps = S["caps"]
+            _lib.check(L.ccx_embedding_bwd(ptr(caps), caps.stride(0), 0, ptr(dXH_all), K, B * K, None, ptr(ge), V,
+                                           Emb, B, T, st), "embedding_bwd")
+        # ---- initial state and hoisted encoder_att -------------------------------------------------------------
+        dmean = linear_bwd(dh, S["m_op"], weight_t(dec.init_h.weight, cd), cd, g("init_h.weight"), g("init_h.bias"),
+                           need_dx=need_enc)
+        dmean = linear_bwd(dc, S["m_op"], weight_t(dec.init_c.weight, cd), cd, g("init_c.weight"), g("init_c.bias"),
+                           need_dx=need_enc, dx_residual=dmean)
+        if need_enc:
+            _lib.check(L.ccx_bcast_add_rows(ptr(d_enc), ptr(dmean), 1.0 / Pn, B, Pn, E, st), "bcast_add_rows")
+        d_enc_flat = linear_bwd(d_att1, S["enc_op"], weight_t(dec.attention.encoder_att.weight, cd), cd,
+                                g("attention.encoder_att.weight"), g("attention.encoder_att.bias"), need_dx=need_enc,
+                                dx_residual=None if d_enc is None else d_enc.view(B * Pn, E))
+        d_encoder_out = None
+        if need_enc:
+            inv = torch.empty_like(S["sort_ind"])
+            inv[S["sort_ind"]] = torch.arange(B, device=dev)          # un-sort (index plumbing)
+            inv32 = inv.to(torch.int32)
+            d_unsorted = torch.empty_like(d_enc_flat)
+            _lib.check(L.ccx_gather_rows(ptr(d_enc_flat), Pn * E * 4, ptr(d_unsorted), Pn * E * 4, ptr(inv32),
+                                         Pn * E * 4, B, st), "gather_rows")
+            d_encoder_out = d_unsorted.view(ctx.enc_shape)
+        return (None, None, d_encoder_out, None, None) + tuple(grads.get(n) for n in names)
+
+
+def lstm_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths):
+    holder = {}
+    params = [p for _, p in dec.named_parameters()]
+    preds, alphas = _LstmTF.apply(dec, holder, encoder_out, encoded_captions, caption_lengths, *params)
+    return preds, holder["caps_sorted"], holder["decode_lengths"], alphas, holder["sort_ind"]

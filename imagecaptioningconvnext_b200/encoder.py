@@ -136,7 +136,8 @@ class Encoder(nn.Module):
     def prepared(self):
         """Kernel-side weight table (re-laid-out / bf16 or tf32-split copies), rebuilt when parameters change."""
         params = list(self.convnext.parameters())
-        key = (self.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(), sum(p._version for p in params))
+        key = (self.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(),
+               sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params))
         if self._prep_key == key:
             return self._prep[0]
         cd = self.compute_dtype

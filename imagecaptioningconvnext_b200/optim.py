@@ -1,0 +1,68 @@
+"""``ClampAdam`` — ``clip_gradient`` (utils/utils.py:183-192: grad.clamp_(-c, c)) fused with ``torch.optim.Adam``'s
+update (trainMultiGPU.py:387-394) in ONE multi-tensor kernel launch per parameter group (``ccx_adam_clamp``).
+
+State layout and ``state_dict`` keys equal torch.optim.Adam's (``step``, ``exp_avg``, ``exp_avg_sq``), so optimizer
+states from reference checkpoints load unchanged.  No weight decay / amsgrad (the reference uses neither).
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+_CHUNK = 16384
+
+
+class ClampAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_clip=None):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_clip=grad_clip))
+        self._tables = {}
+
+    def _table(self, gi, ps):
+        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        cached = self._tables.get(gi)
+        if cached is not None and cached[0] == key:
+            return cached[1:]
+        rows, be, bo = [], [], []
+        for i, p in enumerate(ps):
+            stt = self.state[p]
+            n = p.numel()
+            rows.append([p.data_ptr(), p.grad.data_ptr(), stt["exp_avg"].data_ptr(), stt["exp_avg_sq"].data_ptr(), n])
+            for off in range(0, n, _CHUNK):
+                be.append(i)
+                bo.append(off)
+        dev = ps[0].device
+        table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        block_entry = torch.tensor(be, dtype=torch.int32).to(dev)
+        block_offset = torch.tensor(bo, dtype=torch.int64).to(dev)
+        total = float(sum(p.numel() for p in ps))
+        self._tables[gi] = (key, table, block_entry, block_offset, len(be), total)
+        return self._tables[gi][1:]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise ValueError("ClampAdam needs contiguous float32 CUDA parameters and gradients")
+                stt = self.state[p]
+                if len(stt) == 0:
+                    stt["step"] = torch.tensor(0.0)
+                    stt["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    stt["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                stt["step"] += 1
+            step = int(self.state[ps[0]]["step"])
+            b1, b2 = group["betas"]
+            table, be, bo, nblk, total = self._table(gi, ps)
+            clip = group["grad_clip"] if group["grad_clip"] is not None else 0.0
+            _lib.check(_lib.lib().ccx_adam_clamp(ptr(table), ptr(be), ptr(bo), nblk, group["lr"], b1, b2, group["eps"],
+                                                 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step), clip, _CHUNK, total,
+                                                 _lib.stream_ptr()), "adam_clamp")
+            for p in ps:          # the weights changed behind torch's back: invalidate kernel-side copies
+                p._ccx_epoch = getattr(p, "_ccx_epoch", 0) + 1
+        return loss

@@ -281,6 +281,23 @@ CCX_API int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targe
 CCX_API int ccx_embedding_bwd(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* dx, int64_t sb,
                               int64_t st, const float* dropmask, float* dtable, int32_t V, int32_t D, int32_t nb,
                               int32_t nt, void* stream);
+/* Backward of ccx_lstm_pointwise for one step: dh = dh_fc*dropmask + dh_carry; dc_carry is dL/dc' on entry and
+ * dL/dc on exit; dgates [bt,4D] are the pre-activation gradients (feed the dgrad / batched wgrad GEMMs). */
+CCX_API int ccx_lstm_pointwise_bwd(const float* gates, int64_t ldg, const float* c_prev, const float* c_new,
+                                   const float* dh_fc, int64_t ld_fc, const float* dropmask, int64_t ld_dm,
+                                   const float* dh_carry, float* dc_carry, float* dgates, int64_t lddg, int32_t bt,
+                                   int32_t D, void* stream);
+/* Backward of ccx_bahdanau_attention for one step (alpha = its saved output): d_hg = [d att2 | d gate pre-act],
+ * d_att1 / d_enc accumulate over steps (+=), d_wf accumulates atomically; d_alpha_ext = gradient reaching alpha
+ * from outside (the doubly-stochastic regulariser, trainMultiGPU.py:369). */
+CCX_API int ccx_bahdanau_attention_bwd(const float* att1, const float* hg, int64_t ldhg, const float* w_f,
+                                       const float* enc, const float* alpha, int64_t alpha_ld, const float* d_out,
+                                       int64_t ld_dout, const float* d_alpha_ext, int64_t dalpha_ld, float* d_hg,
+                                       int64_t ld_dhg, float* d_att1, float* d_enc, float* d_wf, int32_t bt,
+                                       int32_t P, int32_t A, int32_t E, void* stream);
+/* out[b,p,:] += v[b,:] * scale — backward of encoder_out.mean(dim=1) (models/decoder.py:64). */
+CCX_API int ccx_bcast_add_rows(float* out, const float* v, float scale, int32_t B, int32_t P, int32_t E,
+                               void* stream);
 /* clip_gradient (grad.clamp_(-clip, clip), utils/utils.py:189-192) fused with torch.optim.Adam's single-tensor
  * update (no weight decay / amsgrad), over a device table of {param, grad, exp_avg, exp_avg_sq, n} entries;
  * block i handles elements [block_offset[i], +chunk) of entry block_entry[i]. */
