@@ -111,7 +111,10 @@ def test_lstm_teacher_forcing_gradients_bptt(dtype, train_mode):
     loss.backward()
     tol = GRAD_TOL[dtype]
     assert abs(float(loss) - ref_loss) < tol * 5
-    _compare_grads(m, ref_grads, tol, dtype=dtype)
+    # softmax over pixels is shift invariant: d loss / d full_att.bias is identically 0 (torch gets ~1e-10 noise)
+    assert float(ref_grads["attention.full_att.bias"].abs().max()) < 1e-7
+    assert float(m.attention.full_att.bias.grad.abs().max()) == 0.0
+    _compare_grads(m, ref_grads, tol, skip=("attention.full_att.bias",), dtype=dtype)
     assert _grad_err(enc_g.grad, enc_leaf.grad, dtype) < tol
 
 
