@@ -85,6 +85,12 @@ SIGNATURES = {
     "ccx_bahdanau_attention_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64,
                                              _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ccx_bcast_add_rows": (C.c_int, [_vp, _vp, _f32, _i32, _i32, _i32, _vp]),
+    "ccx_dwconv7_plain": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_scale_rows_cols": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
+    "ccx_gelu_bwd": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "ccx_cnblock_param_grads": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "ccx_dwconv7_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_avgpool_nhwc_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ccx_adam_clamp": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_double,
                                  _vp]),
     "ccx_prof_begin": (C.c_int, []),

@@ -62,6 +62,29 @@ int ccx_dwconv7_ln(const float* x, const float* w_tap_major, const float* bias, 
   return dwconv7_ln(x, w_tap_major, bias, ln_g, ln_b, out, out_lo, B, H, W, C, eps, out_dtype, as_stream(stream));
 }
 
+int ccx_dwconv7_plain(const float* x, const float* w_tap_major, const float* bias, const float* addend, float* out,
+                      int32_t B, int32_t H, int32_t W, int32_t C, void* stream) {
+  return dwconv7_ln(x, w_tap_major, bias, nullptr, nullptr, out, nullptr, B, H, W, C, 0.f, CCX_F32, as_stream(stream),
+                    addend);
+}
+int ccx_scale_rows_cols(const float* x, const float* colscale, const float* rowscale, int32_t rows_per_group,
+                        float* out, int64_t M, int32_t C, void* stream) {
+  return scale_rows_cols(x, colscale, rowscale, rows_per_group, out, M, C, as_stream(stream));
+}
+int ccx_gelu_bwd(const float* pre, float* dh, int64_t n, void* stream) { return gelu_bwd(pre, dh, n, as_stream(stream)); }
+int ccx_cnblock_param_grads(const float* G, const float* W2, const float* b2, const float* gamma, const float* s,
+                            float* dW2, float* dgamma, float* db2, int32_t C, int32_t K, void* stream) {
+  return cnblock_param_grads(G, W2, b2, gamma, s, dW2, dgamma, db2, C, K, as_stream(stream));
+}
+int ccx_dwconv7_wgrad(const float* x, const float* du, float* dw_tap_major, int32_t B, int32_t H, int32_t W,
+                      int32_t C, void* stream) {
+  return dwconv7_wgrad(x, du, dw_tap_major, B, H, W, C, as_stream(stream));
+}
+int ccx_avgpool_nhwc_bwd(const float* dout, float* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
+                         void* stream) {
+  return avgpool_nhwc_bwd(dout, dx, B, H, W, C, S, as_stream(stream));
+}
+
 int ccx_ln_rows(const float* x, const float* ln_g, const float* ln_b, void* out, float* out_lo, float* out_plain,
                 int64_t M, int32_t C, float eps, int32_t out_dtype, int32_t merge, int32_t H, int32_t W,
                 void* stream) {

@@ -7,7 +7,7 @@ namespace ccx {
 // dwconv_ln.cu
 int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float* gamma, const float* beta,
                void* out, float* out_lo, int B, int H, int W, int C, float eps, int out_dtype,
-               cudaStream_t stream);
+               cudaStream_t stream, const float* addend = nullptr);
 
 // encoder_misc.cu
 int stem_ln(const float* img, const float* wk, const float* bias, const float* gamma, const float* beta,
@@ -80,5 +80,14 @@ int bcast_add_rows(float* out, const float* v, float scale, int B, int P, int E,
 int adam_clamp(const void* table, const int* block_entry, const long long* block_offset, int n_blocks, float lr,
                float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip, int chunk,
                double total_params, cudaStream_t stream);
+
+// encoder_bwd.cu
+int scale_rows_cols(const float* x, const float* colscale, const float* rowscale, int rows_per_group, float* out,
+                    long long M, int C, cudaStream_t stream);
+int gelu_bwd(const float* pre, float* dh, long long n, cudaStream_t stream);
+int cnblock_param_grads(const float* G, const float* W2, const float* b2, const float* gamma, const float* s,
+                        float* dW2, float* dgamma, float* db2, int C, int K, cudaStream_t stream);
+int dwconv7_wgrad(const float* x, const float* du, float* dw49c, int B, int H, int W, int C, cudaStream_t stream);
+int avgpool_nhwc_bwd(const float* dout, float* dx, int B, int H, int W, int C, int S, cudaStream_t stream);
 
 }  // namespace ccx

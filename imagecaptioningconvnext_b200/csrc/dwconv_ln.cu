@@ -39,6 +39,7 @@ struct DwArgs {
   const float* beta;   // [C]
   void* out;           // [B*H*W, C] bf16 or fp32 (hi)
   float* out_lo;       // fp32 lo part or nullptr
+  const float* addend; // plain mode only: out = conv + addend (residual-gradient accumulation), or nullptr
   int B, H, W, C;
   int tiles_w, tiles_h;
   float eps;
@@ -97,9 +98,10 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   float wt[49];
 #pragma unroll
   for (int t = 0; t < 49; ++t) wt[t] = __ldg(a.w + t * a.C + ch);
-  const float bias = __ldg(a.bias + ch);
-  const float gam = __ldg(a.gamma + ch);
-  const float bet = __ldg(a.beta + ch);
+  const bool plain = (a.gamma == nullptr);   // no LayerNorm: raw conv output (LN recompute / data-gradient use)
+  const float bias = a.bias ? __ldg(a.bias + ch) : 0.f;
+  const float gam = plain ? 1.f : __ldg(a.gamma + ch);
+  const float bet = plain ? 0.f : __ldg(a.beta + ch);
 
   float acc[32];
 #pragma unroll
@@ -128,7 +130,7 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   }
 
   // ---- LayerNorm statistics: per pixel over all C channels (this warp: 32 of them) ----
-  {
+  if (!plain) {
     float s1[32], s2[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { s1[i] = acc[i]; s2[i] = acc[i] * acc[i]; }
@@ -137,6 +139,10 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
     part[((0 * 2 + p) * 4 + g) * 32 + lane] = s1[0];
     part[((1 * 2 + p) * 4 + g) * 32 + lane] = s2[0];
   }
+  if (plain) {   // uniform over the whole cluster: nobody reaches the cluster barrier below
+    if (threadIdx.x < 64) { s_mean[threadIdx.x] = 0.f; s_rstd[threadIdx.x] = 1.f; }
+    __syncthreads();
+  } else {
   __syncthreads();
   if (threadIdx.x < 128) {
     // thread -> (stat, p, px): sum the 4 channel-group partials, publish to every CTA of the cluster
@@ -162,6 +168,7 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
     s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
   }
   __syncthreads();
+  }
 
   // ---- normalise + write ----
 #pragma unroll
@@ -171,9 +178,10 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
     for (int ow = 0; ow < 8; ++ow) {
       const int w = w0 + ow;
       const int px = p * 32 + oh * 8 + ow;
-      const float y = (acc[oh * 8 + ow] - s_mean[px]) * s_rstd[px] * gam + bet;
+      float y = (acc[oh * 8 + ow] - s_mean[px]) * s_rstd[px] * gam + bet;
       if (h < a.H && w < a.W) {
         const long long m = (static_cast<long long>(b) * a.H + h) * a.W + w;
+        if (plain && a.addend != nullptr) y += a.addend[m * a.C + ch];
         if (a.out_dtype == CCX_BF16) {
           reinterpret_cast<__nv_bfloat16*>(a.out)[m * a.C + ch] = __float2bfloat16_rn(y);
         } else if (a.out_lo != nullptr) {
@@ -191,7 +199,7 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
 
 int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float* gamma, const float* beta,
                void* out, float* out_lo, int B, int H, int W, int C, float eps, int out_dtype,
-               cudaStream_t stream) {
+               cudaStream_t stream, const float* addend) {
   if (B <= 0 || H <= 0 || W <= 0 || B > 65535) return CCX_ERR_SHAPE;
   if (C % DW_CH != 0 || C / DW_CH > 8 || C < DW_CH) return CCX_ERR_SHAPE;
   if (out_dtype != CCX_F32 && out_dtype != CCX_BF16) return CCX_ERR_DTYPE;
@@ -218,7 +226,7 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   }
   DwArgs a;
   a.w = w49c; a.bias = bias; a.gamma = gamma; a.beta = beta;
-  a.out = out; a.out_lo = out_lo;
+  a.out = out; a.out_lo = out_lo; a.addend = addend;
   a.B = B; a.H = H; a.W = W; a.C = C;
   a.tiles_w = (W + DW_TILE - 1) / DW_TILE;
   a.tiles_h = (H + DW_TILE - 1) / DW_TILE;

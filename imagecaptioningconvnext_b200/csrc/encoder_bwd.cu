@@ -1,0 +1,165 @@
+// encoder_bwd.cu — backward kernels of the fine-tuned ConvNeXt stage (reference: autograd through
+// torchvision/models/convnext.py:51-67 for `Encoder.fine_tune(True, startingLayer)`, models/encoder.py:29-34).
+//
+//   scale_rows_cols     d(block output) -> d(layer_scale * stochastic_depth branch):  x * colscale[c] * rowscale[m/g]
+//   gelu_bwd            dpre = dh * gelu'(pre)   (exact erf GELU)
+//   cnblock_param_grads dW2 / d layer_scale / d b2 from the un-scaled wgrad G = dout'^T . h  (no recompute of z)
+//   dwconv7_wgrad       depthwise filter gradient, NHWC
+//   avgpool_nhwc_bwd    AdaptiveAvgPool2d backward
+// The depthwise-conv data gradient re-uses dwconv7_ln_kernel in "plain" mode with flipped taps.
+#include "ccx_common.cuh"
+#include "ccx_ops.h"
+#include "ccx_prof.h"
+
+namespace ccx {
+
+__global__ void __launch_bounds__(256)
+scale_rows_cols_kernel(const float* __restrict__ x, const float* __restrict__ colscale,
+                       const float* __restrict__ rowscale, int rows_per_group, float* __restrict__ out, long long M,
+                       int C) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * (C / 4)) return;
+  const long long m = i / (C / 4);
+  const int c4 = static_cast<int>(i % (C / 4));
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  float rs = rowscale ? __ldg(rowscale + m / rows_per_group) : 1.f;
+  if (colscale) {
+    const float4 cs = __ldg(reinterpret_cast<const float4*>(colscale) + c4);
+    v.x *= cs.x; v.y *= cs.y; v.z *= cs.z; v.w *= cs.w;
+  }
+  v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs;
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+int scale_rows_cols(const float* x, const float* colscale, const float* rowscale, int rows_per_group, float* out,
+                    long long M, int C, cudaStream_t stream) {
+  if (M <= 0) return CCX_OK;
+  if (C % 4) return CCX_ERR_SHAPE;
+  const long long n = M * (C / 4);
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)M * C * 8.0);
+  scale_rows_cols_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      x, colscale, rowscale, rows_per_group > 0 ? rows_per_group : 1, out, M, C);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const float* __restrict__ pre, float* __restrict__ dh, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float x = pre[i];
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    dh[i] *= cdf + x * pdf;
+  }
+}
+int gelu_bwd(const float* pre, float* dh, long long n, cudaStream_t stream) {
+  if (n <= 0) return CCX_OK;
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256 > 148 * 32 ? 148 * 32 : (n + 255) / 256);
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)n * 12.0);
+  gelu_bwd_kernel<<<grid, 256, 0, stream>>>(pre, dh, n);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// G[c, :] = sum_m dout'[m,c] h[m,:]  (dout' = dout * rowscale).  With z = h W2^T + b2 and out = x + gamma*rs*z:
+//   dW2[c,:] += gamma[c] * G[c,:] ;  d gamma[c] += W2[c,:] . G[c,:] + b2[c] * s[c] ;  d b2[c] += gamma[c] * s[c]
+// where s[c] = sum_m dout'[m,c].  One warp per output channel c.
+__global__ void __launch_bounds__(256)
+cnblock_param_grads_kernel(const float* __restrict__ G, const float* __restrict__ W2, const float* __restrict__ b2,
+                           const float* __restrict__ gamma, const float* __restrict__ s, float* __restrict__ dW2,
+                           float* __restrict__ dgamma, float* __restrict__ db2, int C, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= C) return;
+  const float g = gamma[c];
+  float dot = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float gv = G[static_cast<long long>(c) * K + k];
+    dot = fmaf(W2[static_cast<long long>(c) * K + k], gv, dot);
+    dW2[static_cast<long long>(c) * K + k] += g * gv;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    dgamma[c] += dot + b2[c] * s[c];
+    db2[c] += g * s[c];
+  }
+}
+int cnblock_param_grads(const float* G, const float* W2, const float* b2, const float* gamma, const float* s,
+                        float* dW2, float* dgamma, float* db2, int C, int K, cudaStream_t stream) {
+  if (C <= 0) return CCX_OK;
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)C * K * 16.0);
+  cnblock_param_grads_kernel<<<(C + 7) / 8, 256, 0, stream>>>(G, W2, b2, gamma, s, dW2, dgamma, db2, C, K);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// dw[tap][c] += sum_{b,h,w} du[b,h,w,c] * x[b,h+kh-3,w+kw-3,c];  one CTA = 128 channels of one image
+__global__ void __launch_bounds__(128)
+dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ dw, int H, int W,
+                     int C) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int b = blockIdx.y;
+  if (c >= C) return;
+  float acc[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) acc[t] = 0.f;
+  const float* xb = x + static_cast<long long>(b) * H * W * C + c;
+  const float* db = du + static_cast<long long>(b) * H * W * C + c;
+  for (int h = 0; h < H; ++h)
+    for (int w = 0; w < W; ++w) {
+      const float d = db[(static_cast<long long>(h) * W + w) * C];
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+        const int ih = h + kh - 3;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) {
+          const int iw = w + kw - 3;
+          if (iw < 0 || iw >= W) continue;
+          acc[kh * 7 + kw] = fmaf(d, xb[(static_cast<long long>(ih) * W + iw) * C], acc[kh * 7 + kw]);
+        }
+      }
+    }
+#pragma unroll
+  for (int t = 0; t < 49; ++t) atomicAdd(dw + static_cast<long long>(t) * C + c, acc[t]);
+}
+int dwconv7_wgrad(const float* x, const float* du, float* dw49c, int B, int H, int W, int C, cudaStream_t stream) {
+  if (B <= 0) return CCX_OK;
+  if (B > 65535) return CCX_ERR_SHAPE;
+  ProfScope prof(PROF_DWCONV_LN, stream, (double)B * H * W * C * 8.0);
+  dwconv7_wgrad_kernel<<<dim3((C + 127) / 128, B), 128, 0, stream>>>(x, du, dw49c, H, W, C);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// adaptive average pool backward: dx[b,h,w,:] = sum over bins containing (h,w) of dout[b,oh,ow,:] / bin_size
+__global__ void __launch_bounds__(256)
+avgpool_nhwc_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, int B, int H, int W, int C, int S) {
+  const long long total = static_cast<long long>(B) * H * W * (C / 4);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % (C / 4));
+    const int w = static_cast<int>((i / (C / 4)) % W);
+    const int h = static_cast<int>((i / (static_cast<long long>(C / 4) * W)) % H);
+    const int b = static_cast<int>(i / (static_cast<long long>(C / 4) * W * H));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int oh = 0; oh < S; ++oh) {
+      const int hs = (oh * H) / S, he = ((oh + 1) * H + S - 1) / S;
+      if (h < hs || h >= he) continue;
+      for (int ow = 0; ow < S; ++ow) {
+        const int ws = (ow * W) / S, we = ((ow + 1) * W + S - 1) / S;
+        if (w < ws || w >= we) continue;
+        const float inv = 1.0f / static_cast<float>((he - hs) * (we - ws));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dout + ((static_cast<long long>(b) * S + oh) * S + ow) * C) + c4);
+        acc.x += v.x * inv; acc.y += v.y * inv; acc.z += v.z * inv; acc.w += v.w * inv;
+      }
+    }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+int avgpool_nhwc_bwd(const float* dout, float* dx, int B, int H, int W, int C, int S, cudaStream_t stream) {
+  if (B <= 0 || (C % 4)) return B <= 0 ? CCX_OK : CCX_ERR_SHAPE;
+  const long long total = static_cast<long long>(B) * H * W * (C / 4);
+  const unsigned grid = static_cast<unsigned>(total / 256 + 1 > 148 * 16 ? 148 * 16 : total / 256 + 1);
+  ProfScope prof(PROF_POOL, stream, (double)B * (H * W + S * S) * C * 4.0);
+  avgpool_nhwc_bwd_kernel<<<grid, 256, 0, stream>>>(dout, dx, B, H, W, C, S);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+}  // namespace ccx

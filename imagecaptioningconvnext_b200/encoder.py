@@ -109,10 +109,8 @@ class Encoder(nn.Module):
         noise = self._stochastic_depth_noise(B, images.device)
         if needs_grad:
             from .encoder_train import encoder_features_with_grad  # backward kernels live there
-            feat = encoder_features_with_grad(self, images, noise)
-        else:
-            feat = self.run_children(images, 0, 8, noise)
-        return self._pool(feat)
+            return encoder_features_with_grad(self, images, noise)   # pooled inside the autograd Function
+        return self._pool(self.run_children(images, 0, 8, noise))
 
     # ---- implementation ------------------------------------------------------------------------------------
     def _stochastic_depth_noise(self, B, device):
@@ -151,10 +149,15 @@ class Encoder(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
+        ops = []
+
         def operand(t2d):
             op = Operand.prepare(t2d.detach().contiguous(), cd)
             keep.append(op)
+            ops.append(op)
             return op.hi.data_ptr(), (op.lo.data_ptr() if op.lo is not None else None)
+
+        self._block_ops = []   # per CNBlock: dict(dw_w, w1, w2) python-side handles (used by encoder_train.py)
 
         w = _lib.EncoderWeights()
         ch = list(self.convnext.children())
@@ -176,6 +179,7 @@ class Encoder(nn.Module):
                 bw.w2, bw.w2_lo = operand(blk.block[5].weight)
                 bw.b2 = f32(blk.block[5].bias)
                 bw.layer_scale = f32(blk.layer_scale.view(Cc))
+                self._block_ops.append({"dw_w": dw, "w1": ops[-2], "w2": ops[-1]})
                 bi += 1
             if s > 0:
                 d = ch[2 * s]

@@ -298,6 +298,27 @@ CCX_API int ccx_bahdanau_attention_bwd(const float* att1, const float* hg, int64
 /* out[b,p,:] += v[b,:] * scale — backward of encoder_out.mean(dim=1) (models/decoder.py:64). */
 CCX_API int ccx_bcast_add_rows(float* out, const float* v, float scale, int32_t B, int32_t P, int32_t E,
                                void* stream);
+/* ---- fine-tuned ConvNeXt stage backward (autograd through torchvision/models/convnext.py:51-67) ---- */
+/* Depthwise 7x7 conv without the LayerNorm: out = conv(x, w) + bias + addend (bias/addend may be NULL).  Used to
+ * recompute the LayerNorm input and, with flipped taps, as the data gradient of the depthwise conv. */
+CCX_API int ccx_dwconv7_plain(const float* x, const float* w_tap_major, const float* bias, const float* addend,
+                              float* out, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* out[m,c] = x[m,c] * colscale[c] * rowscale[m / rows_per_group] (either scale may be NULL). */
+CCX_API int ccx_scale_rows_cols(const float* x, const float* colscale, const float* rowscale, int32_t rows_per_group,
+                                float* out, int64_t M, int32_t C, void* stream);
+/* dh[i] *= gelu'(pre[i]) (exact erf GELU, convnext.py:56). */
+CCX_API int ccx_gelu_bwd(const float* pre, float* dh, int64_t n, void* stream);
+/* From G = (dout*rowscale)^T . h and s = colsum(dout*rowscale): dW2 += gamma*G, d layer_scale += W2.G + b2*s,
+ * d b2 += gamma*s — the layer_scale / second Linear gradients without recomputing the branch output. */
+CCX_API int ccx_cnblock_param_grads(const float* G, const float* W2, const float* b2, const float* gamma,
+                                    const float* s, float* dW2, float* dgamma, float* db2, int32_t C, int32_t K,
+                                    void* stream);
+/* dw[tap][c] += sum du[b,h,w,c] * x[b,h+kh-3,w+kw-3,c]  (depthwise filter gradient, tap-major). */
+CCX_API int ccx_dwconv7_wgrad(const float* x, const float* du, float* dw_tap_major, int32_t B, int32_t H, int32_t W,
+                              int32_t C, void* stream);
+/* AdaptiveAvgPool2d((S,S)) backward over NHWC. */
+CCX_API int ccx_avgpool_nhwc_bwd(const float* dout, float* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
+                                 void* stream);
 /* clip_gradient (grad.clamp_(-clip, clip), utils/utils.py:189-192) fused with torch.optim.Adam's single-tensor
  * update (no weight decay / amsgrad), over a device table of {param, grad, exp_avg, exp_avg_sq, n} entries;
  * block i handles elements [block_offset[i], +chunk) of entry block_entry[i]. */

@@ -154,3 +154,57 @@ def test_clamp_adam_matches_clip_gradient_plus_torch_adam():
     for rp, op in zip(ref_p, our_p):
         assert rel_err(op, rp) < 1e-6
     assert set(our_opt.state_dict()["state"][0]) == set(ref_opt.state_dict()["state"][0])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("train_mode", [False, True])
+def test_encoder_stage4_fine_tune_gradients(dtype, train_mode):
+    """Encoder.fine_tune(True, startingLayer=7): gradients of the three C=1024 CNBlocks vs torch autograd."""
+    import torch.nn.functional as F
+    from imagecaptioningconvnext_b200 import Encoder
+    from imagecaptioningconvnext_b200.encoder import stochastic_depth_probs
+    from oracle import encoder_oracle as eo
+    sd = eo.random_encoder_state(seed=2, layer_scale=1.0)
+    g = torch.Generator().manual_seed(4)
+    for k in sd:                                     # non-trivial LN / bias / layer_scale values in the trainable stage
+        if k.startswith("convnext.7.") and sd[k].dim() <= 3 and "block.0.weight" not in k:
+            sd[k] = sd[k] + 0.2 * torch.randn(sd[k].shape, generator=g)
+    B = 3
+    x = torch.randn(B, 3, 64, 64, generator=g)
+    wgt = torch.randn(B, 7, 7, 1024, generator=g)
+    noise, nz = None, None
+    if train_mode:
+        keep = 1.0 - torch.tensor(stochastic_depth_probs()).view(-1, 1)
+        noise = torch.bernoulli(keep.expand(-1, B), generator=g) / keep
+        noise[33:, 0] = 2.0                                      # make sure stage 4 sees both 0 and non-zero rows
+        noise[33:, 1] = 0.0
+        nz, bi = {}, 0
+        for child, _, nblk in eo.STAGES:
+            for i in range(nblk):
+                nz[(child, i)] = noise[bi]
+                bi += 1
+    leaf = {k: v.clone().requires_grad_(k.startswith("convnext.7.")) for k, v in sd.items()}
+    ref_out = eo.encoder_forward(leaf, x, 7, noise=nz)
+    (ref_out * wgt).sum().backward()
+    ref_grads = {k[len("convnext."):]: v.grad for k, v in leaf.items() if v.requires_grad}
+    e = Encoder(compute_dtype=dtype)
+    e.load_state_dict(sd)
+    e = e.cuda()
+    e.train(train_mode)
+    e.fine_tune(True, 7)
+    e.sd_noise = noise
+    out = e(x.cuda())
+    assert out.requires_grad
+    (out * wgt.cuda()).sum().backward()
+    tol_f = 1e-3 if dtype == torch.float32 else 2e-2
+    assert rel_err(out, ref_out) < tol_f
+    errs = []
+    for n, p in e.convnext.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and p.grad.shape == p.shape, n
+            errs.append((_grad_err(p.grad, ref_grads[n], dtype), n))
+        else:
+            assert p.grad is None
+    errs.sort(reverse=True)
+    print("encoder worst grad errs", errs[:4])
+    assert errs[0][0] < GRAD_TOL[dtype], errs[:4]
