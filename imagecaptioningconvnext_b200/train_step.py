@@ -1,0 +1,47 @@
+"""One teacher-forced train step — the body of the reference's hot loop (trainMultiGPU.py:357-394 = train.py:257-291):
+encoder -> decoder(teacherForcing=True) -> packed cross-entropy (+ doubly-stochastic attention regulariser for the
+LSTM decoder) -> zero_grad -> backward -> clip_gradient(+-5) -> Adam.  Everything heavy runs on libccx; wrap the
+modules in ``torch.nn.parallel.DistributedDataParallel`` (as the reference does, trainMultiGPU.py:233-235) and the
+gradient all-reduce over NCCL overlaps with the explicit backward.
+"""
+import torch
+
+from .decoder import DecoderWithAttention
+from .losses import packed_cross_entropy
+from .optim import ClampAdam
+
+
+def _unwrap(m):
+    return m.module if hasattr(m, "module") else m
+
+
+def make_optimizers(encoder, decoder, decoder_lr=1e-4, encoder_lr=1e-4, grad_clip=5.0):
+    """trainMultiGPU.py:191-198,254: Adam over the trainable parameters; clip_gradient fused into the update."""
+    dec_opt = ClampAdam([p for p in decoder.parameters() if p.requires_grad], lr=decoder_lr, grad_clip=grad_clip)
+    enc_params = [p for p in encoder.parameters() if p.requires_grad]
+    enc_opt = ClampAdam(enc_params, lr=encoder_lr, grad_clip=grad_clip) if enc_params else None
+    return dec_opt, enc_opt
+
+
+def caption_train_step(encoder, decoder, imgs, caps, caplens, decoder_optimizer, encoder_optimizer=None, pad_token=0,
+                       alpha_c=1.0):
+    """Returns the loss tensor (no host sync).  imgs (B,3,256,256) fp32, caps (B,52) int64, caplens (B,1) int64."""
+    feats = encoder(imgs)                                                              # trainMultiGPU.py:361
+    if isinstance(_unwrap(decoder), DecoderWithAttention):
+        scores, caps_sorted, decode_lengths, alphas, _ = decoder(teacherForcing=True, encoder_out=feats,
+                                                                 encoded_captions=caps, caption_lengths=caplens)
+        loss = packed_cross_entropy(scores, caps_sorted, decode_lengths)              # :364-367
+        loss = loss + alpha_c * ((1.0 - alphas.sum(dim=1)) ** 2).mean()               # :369
+    else:
+        kpm = caps == pad_token                                                        # :371
+        scores, caps_out, decode_lengths = decoder(teacherForcing=True, encoder_out=feats, encoded_captions=caps,
+                                                   caption_lengths=caplens, tgt_key_padding_mask=kpm)
+        loss = packed_cross_entropy(scores, caps_out, decode_lengths)                 # :373-377
+    if encoder_optimizer is not None:
+        encoder_optimizer.zero_grad(set_to_none=False)
+    decoder_optimizer.zero_grad(set_to_none=False)                                     # :381-383
+    loss.backward()                                                                    # :384 (DDP all-reduce inside)
+    if encoder_optimizer is not None:
+        encoder_optimizer.step()                                                       # :387-394 (clamp fused)
+    decoder_optimizer.step()
+    return loss.detach()

@@ -208,3 +208,56 @@ def test_encoder_stage4_fine_tune_gradients(dtype, train_mode):
     errs.sort(reverse=True)
     print("encoder worst grad errs", errs[:4])
     assert errs[0][0] < GRAD_TOL[dtype], errs[:4]
+
+
+@pytest.mark.parametrize("kind", ["lstm", "transformer"])
+def test_train_step_matches_reference_step_body(kind):
+    """Two full steps (fwd, packed CE [+alpha reg], backward, clamp +-5, Adam) vs the oracle restatement of
+    trainMultiGPU.py:357-394 on CPU: losses and updated weights agree."""
+    from imagecaptioningconvnext_b200 import Encoder
+    from imagecaptioningconvnext_b200.train_step import caption_train_step, make_optimizers
+    from oracle import decoder_oracle as do
+    from oracle import encoder_oracle as eo
+    torch.manual_seed(0)
+    B = 4
+    esd = eo.random_encoder_state(seed=0, layer_scale=1.0)
+    dsd = do.random_lstm_decoder_state(7, V) if kind == "lstm" else do.random_transformer_decoder_state(7, V)
+    imgs = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    caps, lens = do.synthetic_captions(B, 2, V)
+    # ---- oracle: plain torch autograd + clamp + torch.optim.Adam (eval-mode math: no dropout / stochastic depth)
+    e_leaf = {k: v.clone().requires_grad_(k.startswith("convnext.7.")) for k, v in esd.items()}
+    d_leaf = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_encoding.pe") for k, v in dsd.items()}
+    tr_e = [v for v in e_leaf.values() if v.requires_grad]
+    tr_d = [v for v in d_leaf.values() if v.requires_grad]
+    opt_e, opt_d = torch.optim.Adam(tr_e, lr=1e-3), torch.optim.Adam(tr_d, lr=1e-3)
+    ref_losses = []
+    for _ in range(2):
+        feats = eo.encoder_forward(e_leaf, imgs, 7)
+        if kind == "lstm":
+            p, cs, dl, al, _ = do.lstm_teacher_forcing(d_leaf, feats, caps, lens)
+            loss = do.train_loss_lstm(p, cs, dl, al)
+        else:
+            p, _, dl = do.transformer_teacher_forcing(d_leaf, feats, caps, lens, caps == 0)
+            loss = do.train_loss_transformer(p, caps, dl)
+        opt_e.zero_grad(); opt_d.zero_grad()
+        loss.backward()
+        for prm in tr_e + tr_d:
+            prm.grad.clamp_(-5.0, 5.0)
+        opt_e.step(); opt_d.step()
+        ref_losses.append(float(loss))
+    # ---- ours
+    enc = Encoder()
+    enc.load_state_dict(esd)
+    enc = enc.cuda().eval()
+    enc.fine_tune(True, 7)
+    dec = (_lstm(dsd, torch.float32) if kind == "lstm" else _transformer(dsd, torch.float32))
+    dec.dropout_p = 0.0
+    dec.train()
+    d_opt, e_opt = make_optimizers(enc, dec, decoder_lr=1e-3, encoder_lr=1e-3)
+    losses = [float(caption_train_step(enc, dec, imgs.cuda(), caps.cuda(), lens.cuda(), d_opt, e_opt)) for _ in range(2)]
+    print(kind, "losses", losses, ref_losses)
+    assert abs(losses[0] - ref_losses[0]) < 1e-3 and abs(losses[1] - ref_losses[1]) < 2e-3
+    worst = max(rel_err(p, d_leaf[n]) for n, p in dec.named_parameters())
+    worst_e = max(rel_err(p, e_leaf["convnext." + n]) for n, p in enc.convnext.named_parameters())
+    print("weights after 2 steps: worst rel err", worst, worst_e)
+    assert worst < 2e-3 and worst_e < 2e-3
