@@ -245,6 +245,15 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    extra = None
+    if not args.no_extras:
+        try:
+            del enc
+            torch.cuda.empty_cache()
+            extra = run_extras(args, dev, world, rank, local)
+        except Exception as ex:  # the headline line must survive a failing secondary workload
+            extra = {"error": f"{type(ex).__name__}: {ex}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -290,21 +299,126 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches),
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
         "model_tflops": value / world * ENCODER_GFLOP_PER_IMAGE / 1e3,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs[2..4]) reported under "extra" in the same JSON line
+# ------------------------------------------------------------------------------------------------
+V = 9490
+WORDMAP = {"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1}
+
+
+def _timed(fn, steps, warmup, dev, world):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / steps
+
+
+def run_extras(args, dev, world, rank, local):
+    """train images/s (configs[2], configs[3]) and beam-search captions/s (configs[4]); device-resident inputs."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from imagecaptioningconvnext_b200 import DecoderWithAttention, Encoder, TransformerDecoder
+    from imagecaptioningconvnext_b200.beam import beam_search_transformer
+    from imagecaptioningconvnext_b200.train_step import caption_train_step, make_optimizers
+    from oracle.decoder_oracle import (random_lstm_decoder_state, random_transformer_decoder_state,
+                                       synthetic_captions)
+    from oracle.encoder_oracle import random_encoder_state
+    out = {}
+    B = 32
+    bf16 = torch.bfloat16
+    esd = random_encoder_state(seed=0, layer_scale=1.0)
+    imgs = synthetic_images(B, 99 + rank).to(dev)
+    caps, lens = synthetic_captions(B, 7 + rank, V)
+    caps, lens = caps.to(dev), lens.to(dev)
+
+    def wrap(m):
+        return DDP(m, device_ids=[local]) if world > 1 and any(p.requires_grad for p in m.parameters()) else m
+
+    # configs[3]: encoder fine-tuned from child 7 + LSTM-attention decoder, bf16, DDP
+    enc = Encoder(compute_dtype=bf16)
+    enc.load_state_dict(esd)
+    enc = enc.to(dev).train()
+    enc.fine_tune(True, 7)
+    dec = DecoderWithAttention(512, 512, 512, V, dev, compute_dtype=bf16)
+    dec.load_state_dict(random_lstm_decoder_state(0, V))
+    dec = dec.to(dev).train()
+    d_opt, e_opt = make_optimizers(enc, dec)
+    enc_w, dec_w = wrap(enc), wrap(dec)
+    ms = _timed(lambda: caption_train_step(enc_w, dec_w, imgs, caps, lens, d_opt, e_opt), 6, 3, dev, world)
+    out["train_lstm_finetune7_bf16"] = {"images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms,
+                                        "batch_per_gpu": B, "config": "BASELINE.json configs[3]: encoder "
+                                        "fine_tune(True,7) + DecoderWithAttention, teacher forcing, captions uniform "
+                                        "7..52 tokens, dropout/stochastic depth on, clamp+Adam"
+                                        + (", DDP/NCCL" if world > 1 else "")}
+    del enc_w, dec_w, d_opt, e_opt, dec
+    # configs[2]: frozen encoder + TransformerDecoder teacher forcing
+    for name, cd in (("bf16", bf16), ("fp32", torch.float32)):
+        enc2 = Encoder(compute_dtype=cd)
+        enc2.load_state_dict(esd)
+        enc2 = enc2.to(dev).train()
+        enc2.fine_tune(False)
+        tr = TransformerDecoder(512, 512, V, 52, dev, None, None, True, compute_dtype=cd)
+        tr.load_state_dict(random_transformer_decoder_state(0, V))
+        tr = tr.to(dev).train()
+        d_opt, _ = make_optimizers(enc2, tr)
+        tr_w = wrap(tr)
+        ms = _timed(lambda: caption_train_step(enc2, tr_w, imgs, caps, lens, d_opt, None), 6, 3, dev, world)
+        out[f"train_transformer_frozen_encoder_{name}"] = {
+            "images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms, "batch_per_gpu": B,
+            "config": "BASELINE.json configs[2]: frozen encoder + TransformerDecoder, teacher forcing, 52-token "
+                      "rows (captions uniform 7..52), dropout on, clamp+Adam" + (", DDP/NCCL" if world > 1 else "")}
+        del tr_w, d_opt
+    # configs[4]: batched beam search k=5, 128 images per GPU, TransformerDecoder (encoder included)
+    NI = 128
+    enc3 = Encoder(compute_dtype=bf16)
+    enc3.load_state_dict(esd)
+    enc3 = enc3.to(dev).eval()
+    tr = TransformerDecoder(512, 512, V, 52, dev, None, None, True, compute_dtype=bf16)
+    tr.load_state_dict(random_transformer_decoder_state(0, V, end_bias=3.2))
+    tr = tr.to(dev).eval()
+    big = synthetic_images(NI, 5 + rank).to(dev)
+
+    def beam():
+        with torch.no_grad():
+            return beam_search_transformer(tr, enc3(big), WORDMAP, beamSize=5)
+    ms = _timed(beam, 2, 1, dev, world)
+    out["beam_search_transformer_k5_bf16"] = {"captions_per_sec": world * NI / (ms * 1e-3), "ms_per_batch": ms,
+                                              "images_per_gpu": NI, "beam": 5, "max_steps": 51,
+                                              "config": "BASELINE.json configs[4]: Encoder + TransformerDecoder beam "
+                                                        "search (KV cache), replicas only, no collective"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary train / beam-search workloads")
     ap.add_argument("--spans", default=None, help="write the per-launch timing table of the instrumented pass here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

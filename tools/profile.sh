@@ -3,7 +3,7 @@
 # 1) plain run must exit 0, 2) ncu launch list (durations), 3) ncu --set full of the dominant kernels.
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
