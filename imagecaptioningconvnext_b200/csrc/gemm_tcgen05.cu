@@ -28,7 +28,8 @@ namespace ccx {
 
 static constexpr int BM = 128;          // UMMA M (one TMEM lane per row)
 static constexpr int ROW_BYTES = 128;   // one swizzle row = 64 bf16 or 32 tf32 elements
-static constexpr int NUM_THREADS = 256; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+static constexpr int NUM_THREADS = 384; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-11 epilogue (2 per TMEM lane quarter)
+static constexpr int EPI_WARPS = 8;
 
 template <int BN>
 struct GemmSmem {
@@ -111,7 +112,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -172,7 +173,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    const int ew = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
+    const int half = (warp - 4) >> 2;  // two warps share a quarter and split the 32-column chunks by parity
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -184,7 +186,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float rs = 1.0f;
       if (ep.rowscale != nullptr && row_ok) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int n0 = n_blk * BN + c * 32;
         if (n0 >= N) break;  // warp-uniform
         uint32_t v[32];
@@ -208,8 +210,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         if (ep.act == 1) {
+          if (ep.out_dtype == CCX_BF16) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          }
         } else if (ep.act == 2) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
