@@ -90,6 +90,20 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def max_over_ranks(ms_local, dev, world):
+    """Device-timed milliseconds -> max over ranks (the contract's multi-GPU timing rule)."""
+    import torch.distributed as dist
+    t = torch.tensor([ms_local], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_throughput(units_per_rank_step, steps, world, ms_total):
+    """Whole-job units per second: every rank processed units_per_rank_step * steps in ms_total (max over ranks)."""
+    return world * units_per_rank_step * steps / (ms_total * 1e-3)
+
+
 def synthetic_images(batch, seed):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(batch, 3, 256, 256, generator=g)
@@ -200,11 +214,8 @@ def run_ours(args):
         t_end = time.time()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = world * B * args.steps / (ms_total * 1e-3)
+    ms_total = max_over_ranks(ms, dev, world)
+    value = aggregate_throughput(B, args.steps, world, ms_total)
 
     # ---- end to end through the public call, host buffers ----------------------------------------
     with torch.no_grad():
@@ -221,10 +232,7 @@ def run_ours(args):
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+    e2e_value = aggregate_throughput(B, args.steps, world, max_over_ranks(ms_e2e, dev, world))
 
     # ---- instrumented pass: per-kernel CUDA events (same steps, same data) -------------------------
     with torch.no_grad():

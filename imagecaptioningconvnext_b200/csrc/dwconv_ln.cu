@@ -30,7 +30,7 @@ static constexpr int DW_HALO = DW_TILE + 6;  // 14
 static constexpr int DW_CH = 128;            // channels per CTA
 static constexpr int DW_THREADS = 256;
 static constexpr int DW_TILE_BYTES = DW_HALO * DW_HALO * DW_CH * 4;  // 100,352
-static constexpr int DW_SMEM = DW_TILE_BYTES + 128 /*align*/ + 6144 /*stats*/;
+static constexpr int DW_SMEM = DW_TILE_BYTES + 6144 /*stats*/;
 
 struct DwArgs {
   const float* w;      // [49][C]  tap-major depthwise filter
@@ -62,10 +62,11 @@ __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane
 
 __global__ void __launch_bounds__(DW_THREADS, 2)
 dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
-  extern __shared__ uint8_t dw_smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
-  float* tile = reinterpret_cast<float*>(sm);                        // [14][14][128]
-  float* part = reinterpret_cast<float*>(sm + DW_TILE_BYTES);        // [2 stat][2 p][4 g][32 px] = 512 f
+  // declared aligned (not re-aligned through integer arithmetic) so the compiler keeps the shared address space
+  // and emits LDS for the tile reads instead of generic LD
+  extern __shared__ __align__(1024) float dw_smem[];
+  float* tile = dw_smem;                                             // [14][14][128]
+  float* part = dw_smem + DW_TILE_BYTES / 4;                         // [2 stat][2 p][4 g][32 px] = 512 f
   float* clpart = part + 512;                                        // [8 rank][2 stat][64 px]   = 1024 f (max)
   __shared__ uint64_t bar;
   __shared__ float s_mean[64], s_rstd[64];
@@ -171,6 +172,23 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   }
 
   // ---- normalise + write ----
+  const long long base = ((static_cast<long long>(b) * a.H + h0 + p * 4) * a.W + w0) * a.C + ch;  // pixel (p*4, 0)
+  const int row_stride = a.W * a.C;   // < 2^31 elements per image row is guaranteed by the launcher
+  const bool interior = (h0 + DW_TILE <= a.H) && (w0 + DW_TILE <= a.W);
+  if (interior && a.out_dtype == CCX_BF16 && !plain) {
+    // fast path (every tile of the 256x256 configurations): no per-pixel bounds checks, bf16 out
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + base;
+#pragma unroll
+    for (int oh = 0; oh < 4; ++oh) {
+#pragma unroll
+      for (int ow = 0; ow < 8; ++ow) {
+        const int px = p * 32 + oh * 8 + ow;
+        const float y = (acc[oh * 8 + ow] - s_mean[px]) * s_rstd[px] * gam + bet;
+        o[oh * row_stride + ow * a.C] = __float2bfloat16_rn(y);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int oh = 0; oh < 4; ++oh) {
     const int h = h0 + p * 4 + oh;
@@ -180,16 +198,16 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
       const int px = p * 32 + oh * 8 + ow;
       float y = (acc[oh * 8 + ow] - s_mean[px]) * s_rstd[px] * gam + bet;
       if (h < a.H && w < a.W) {
-        const long long m = (static_cast<long long>(b) * a.H + h) * a.W + w;
-        if (plain && a.addend != nullptr) y += a.addend[m * a.C + ch];
+        const long long idx = base + oh * row_stride + ow * a.C;
+        if (plain && a.addend != nullptr) y += a.addend[idx];
         if (a.out_dtype == CCX_BF16) {
-          reinterpret_cast<__nv_bfloat16*>(a.out)[m * a.C + ch] = __float2bfloat16_rn(y);
+          reinterpret_cast<__nv_bfloat16*>(a.out)[idx] = __float2bfloat16_rn(y);
         } else if (a.out_lo != nullptr) {
           const float hi = tf32_hi(y);
-          reinterpret_cast<float*>(a.out)[m * a.C + ch] = hi;
-          a.out_lo[m * a.C + ch] = y - hi;
+          reinterpret_cast<float*>(a.out)[idx] = hi;
+          a.out_lo[idx] = y - hi;
         } else {
-          reinterpret_cast<float*>(a.out)[m * a.C + ch] = y;
+          reinterpret_cast<float*>(a.out)[idx] = y;
         }
       }
     }
@@ -206,6 +224,7 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return CCX_ERR_TMA;
   if (reinterpret_cast<uintptr_t>(x) & 15) return CCX_ERR_SHAPE;
+  if (static_cast<long long>(W) * C * 8 >= 0x7fffffffLL) return CCX_ERR_SHAPE;
 
   CUtensorMap tm;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
