@@ -148,7 +148,7 @@ def run_reference(args):
                                    f"torch {torch.__version__} CPU ops, flush-denormal on"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, sample_note=None):
@@ -311,7 +311,7 @@ def run_ours(args):
         "model_tflops": value / world * ENCODER_GFLOP_PER_IMAGE / 1e3,
         "extra": extra,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -419,6 +419,15 @@ def run_extras(args, dev, world, rank, local):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -432,6 +441,11 @@ def main():
     ap.add_argument("--spans", default=None, help="write the per-launch timing table of the instrumented pass here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE JSON line: anything libraries print (e.g. "NCCL version ...") goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
