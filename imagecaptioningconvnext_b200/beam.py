@@ -80,7 +80,8 @@ def _gather(src, dst, src_row, rows):
 
 
 @torch.no_grad()
-def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, trace=None, return_all=False):
+def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, trace=None, return_all=False,
+                     _state_only=False):
     """caption.py:39-155 for a batch of images.  encoder_out (NI, s, s, E) from ``Encoder``; eval-mode decoder."""
     _lib.require_cuda(encoder_out, "encoder_out")
     NI, E = encoder_out.size(0), encoder_out.size(-1)
@@ -135,14 +136,16 @@ def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, tr
                                              D * es, rows, st), "gather_rows")
         _gather(c_new, Cs[1 - cur], bs.src_row, rows)
         cur = 1 - cur
-        if step % 8 == 0 and not bool(bs.k_rem.any()):   # caption.py:135-136: k == 0 -> break (per image)
+        if not _state_only and step % 8 == 0 and not bool(bs.k_rem.any()):   # caption.py:135-136: k == 0 -> break
             break
+    if _state_only:
+        return bs
     return (bs.results(), bs.all_done()) if return_all else bs.results()
 
 
 @torch.no_grad()
 def beam_search_transformer(decoder, encoder_out, wordMap, beamSize=3, max_decode_len=51, trace=None,
-                            return_all=False):
+                            return_all=False, _state_only=False):
     """caption.py:160-255 for a batch of images, with a KV cache re-ordered along the surviving beams."""
     _lib.require_cuda(encoder_out, "encoder_out")
     NI = encoder_out.size(0)
@@ -169,6 +172,47 @@ def beam_search_transformer(decoder, encoder_out, wordMap, beamSize=3, max_decod
             _lib.check(L.ccx_gather_rows(ptr(src), src.stride(0) * 4, ptr(dst), dst.stride(0) * 4, ptr(bs.src_row),
                                          (t + 1) * 3 * D * 4, rows, st), "gather_rows")
             state["cache"][li], spare[li] = dst, src
-        if t % 8 == 7 and not bool(bs.k_rem.any()):
+        if not _state_only and t % 8 == 7 and not bool(bs.k_rem.any()):
             break
+    if _state_only:
+        return bs
     return (bs.results(), bs.all_done()) if return_all else bs.results()
+
+
+class CapturedBeamSearch:
+    """The whole fixed-shape decode loop (51 steps x ~75 launches for the Transformer) captured ONCE into a CUDA graph
+    and replayed per batch: the per-step work is launch-bound at these sizes (640 rows), so removing the host from
+    the loop is worth more than any single kernel.  Shapes are fixed at construction (n_images, beamSize, pixels);
+    the first call runs eagerly once (warm-up: kernel attributes, weight preparation) and then captures.
+    Results equal the eager functions' (same kernels, same order); early exit is replaced by running all steps, which
+    cannot change the outcome (finished images have k_rem == 0 and are skipped by the kernels)."""
+
+    def __init__(self, decoder, wordMap, kind, beamSize=3, max_len=None):
+        self.decoder, self.wordMap, self.kind, self.k = decoder, wordMap, kind, int(beamSize)
+        self.max_len = max_len
+        self.graph, self.static_in, self.state = None, None, None
+
+    def _run(self, feats):
+        if self.kind == "lstm":
+            return beam_search_lstm(self.decoder, feats, self.wordMap, self.k,
+                                    max_steps=50 if self.max_len is None else self.max_len, _state_only=True)
+        return beam_search_transformer(self.decoder, feats, self.wordMap, self.k,
+                                       max_decode_len=51 if self.max_len is None else self.max_len, _state_only=True)
+
+    @torch.no_grad()
+    def __call__(self, encoder_out, return_all=False):
+        _lib.require_cuda(encoder_out, "encoder_out")
+        if self.graph is None or self.static_in.shape != encoder_out.shape:
+            self.static_in = encoder_out.detach().clone().float().contiguous()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._run(self.static_in)                       # eager warm-up on the side stream
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.state = self._run(self.static_in)
+        self.static_in.copy_(encoder_out)
+        self.graph.replay()
+        return (self.state.results(), self.state.all_done()) if return_all else self.state.results()

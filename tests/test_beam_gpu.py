@@ -92,3 +92,23 @@ def test_full_pipeline_matches_reference_caption_py_golden(golden_dir):
     tsd = do.random_transformer_decoder_state(0, V, end_bias=gold["transformer_end_bias"])
     assert beam_search_lstm(_lstm(lsd, torch.float32), f, WORDMAP, beamSize=gold["k"]) == gold["lstm"]
     assert beam_search_transformer(_transformer(tsd, torch.float32), f, WORDMAP, beamSize=gold["k"]) == gold["transformer"]
+
+
+@pytest.mark.parametrize("kind", ["lstm", "transformer"])
+def test_cuda_graph_captured_beam_search_equals_eager(kind):
+    from imagecaptioningconvnext_b200.beam import CapturedBeamSearch, beam_search_lstm, beam_search_transformer
+    from oracle import decoder_oracle as do
+    if kind == "lstm":
+        sd = do.random_lstm_decoder_state(0, V, end_bias=0.21)
+        m, fn = _lstm(sd, torch.float32), beam_search_lstm
+    else:
+        sd = do.random_transformer_decoder_state(0, V, end_bias=3.2)
+        m, fn = _transformer(sd, torch.float32), beam_search_transformer
+    cap = CapturedBeamSearch(m, WORDMAP, kind, beamSize=5)
+    for seed in (300, 301):                      # second batch re-uses the captured graph with new features
+        feats = do.synthetic_features(4, seed).cuda()
+        eager = fn(m, feats, WORDMAP, beamSize=5, return_all=True)
+        graphed = cap(feats, return_all=True)
+        assert graphed[0] == eager[0]
+        for (gs, gsc), (es, esc) in zip(graphed[1], eager[1]):
+            assert gs == es and gsc == esc
