@@ -42,6 +42,22 @@ class EncoderWeights(C.Structure):
                 ("depths", _i32 * 4), ("dims", _i32 * 4), ("compute_dtype", _i32)]
 
 
+class LstmTF(C.Structure):
+    _fields_ = [("XH_hi", _vp), ("XH_lo", _vp), ("C_all", _vp), ("HG", _vp), ("G", _vp), ("alphas", _vp),
+                ("H_all_hi", _vp), ("H_all_lo", _vp), ("dropmask", _vp), ("att1", _vp), ("enc", _vp),
+                ("w_h", _vp), ("w_h_lo", _vp), ("b_h", _vp), ("w_f", _vp), ("b_f", _vp),
+                ("w_lstm", _vp), ("w_lstm_lo", _vp), ("b_lstm", _vp), ("bts_host", C.POINTER(_i32)),
+                ("B", _i32), ("T", _i32), ("P", _i32), ("E", _i32), ("A", _i32), ("D", _i32), ("Emb", _i32),
+                ("compute_dtype", _i32)]
+
+
+class LstmTFBwd(C.Structure):
+    _fields_ = [("dH_all", _vp), ("dalphas", _vp), ("dG_all", _vp), ("dHG_all", _vp), ("dXH_all", _vp),
+                ("dh", _vp), ("dc", _vp), ("d_att1", _vp), ("d_enc", _vp), ("d_wf", _vp),
+                ("w_lstm_t", _vp), ("w_lstm_t_lo", _vp), ("w_h_t", _vp), ("w_h_t_lo", _vp),
+                ("scratch_hi", _vp), ("scratch_lo", _vp)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ccx.h declares (tests/test_abi.py checks it)
 SIGNATURES = {
     "ccx_version": (C.c_int, []),
@@ -91,6 +107,8 @@ SIGNATURES = {
     "ccx_cnblock_param_grads": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "ccx_dwconv7_wgrad": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ccx_avgpool_nhwc_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "ccx_lstm_tf_forward": (C.c_int, [C.POINTER(LstmTF), _vp]),
+    "ccx_lstm_tf_backward": (C.c_int, [C.POINTER(LstmTF), C.POINTER(LstmTFBwd), _vp]),
     "ccx_adam_clamp": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_double,
                                  _vp]),
     "ccx_prof_begin": (C.c_int, []),

@@ -15,6 +15,8 @@ What runs underneath (all libccx kernels, no torch compute on the path):
     ``nonzero()`` host sync per step.
 Extra ctor kwarg: ``compute_dtype`` (float32 = 3xTF32, bfloat16).  There is no CPU path.
 """
+import ctypes
+
 import torch
 from torch import nn
 
@@ -187,6 +189,24 @@ class DecoderWithAttention(nn.Module):
                                         ptr(h_all.hi), h_all.lo_ptr, ha_ld, code, ptr(dm), dm_ld, None, 0, bt, D,
                                         st), "lstm_pointwise")
 
+    def _loop_desc(self, Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts):
+        """ccx_lstm_tf descriptor over the step buffers (kept alive by the caller)."""
+        d = _lib.LstmTF()
+        d.XH_hi, d.XH_lo = ptr(XH.hi), XH.lo_ptr
+        d.C_all, d.HG, d.G, d.alphas = ptr(C_all), ptr(HG), ptr(G), ptr(alphas)
+        d.H_all_hi, d.H_all_lo = ptr(H_all.hi), H_all.lo_ptr
+        d.dropmask, d.att1, d.enc = ptr(dm), ptr(att1), ptr(enc)
+        d.w_h, d.w_h_lo, d.b_h = ptr(Pw["w_h"].hi), Pw["w_h"].lo_ptr, ptr(Pw["b_h"])
+        d.w_f, d.b_f = ptr(Pw["w_f"]), ptr(Pw["b_f"])
+        d.w_lstm, d.w_lstm_lo, d.b_lstm = ptr(Pw["w_lstm"].hi), Pw["w_lstm"].lo_ptr, ptr(Pw["b_lstm"])
+        arr = (ctypes.c_int32 * max(len(bts), 1))(*bts)
+        d.bts_host = arr
+        d._keep = arr                                   # ctypes does not keep the array alive by itself
+        d.B, d.T, d.P, d.E = enc.shape[0], len(bts), enc.shape[1], enc.shape[2]
+        d.A, d.D, d.Emb = self.attention_dim, self.decoder_dim, self.embed_dim
+        d.compute_dtype = _lib.dt_code(self.compute_dtype)
+        return d
+
     def _dropout_mask(self, B, T, dev):
         """nn.Dropout(p) of models/decoder.py:109 as a multiplier tensor (None in eval mode)."""
         if not self.training or self.dropout_p == 0:
@@ -231,12 +251,9 @@ class DecoderWithAttention(nn.Module):
                                     V, self.embed_dim, None, None, None, 0, 0, ptr(XH.hi), XH.lo_ptr, code,
                                     K, B * K, B, T, st), "embed_rows")
         bts = [sum(l > t for l in decode_lengths) for t in range(T)]
-        for t in range(T):
-            bt = bts[t]
-            h_all_t = H_all.map(lambda x: x[:, t])
-            dm_t = None if dm is None else dm[:, t]
-            self._step(Pw, enc, att1, XH, C_all, HG, G, t, bt, alphas[:, t], T * Pn, None, h_all_t, T * D,
-                       dm_t, T * D)
+        # the whole time loop in ONE FFI call (csrc/lstm_runner.cu): same kernels/order as self._step per step
+        desc = self._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
+        _lib.check(L.ccx_lstm_tf_forward(ctypes.byref(desc), st), "lstm_tf_forward")
         valid = (torch.arange(T, device=dev).unsqueeze(0) <
                  torch.tensor(decode_lengths, device=dev).unsqueeze(1)).to(torch.float32).reshape(-1).contiguous()
         predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)

@@ -6,6 +6,8 @@ Per backward step (t = T-1 .. 0): LSTM point-wise backward, ONE dgrad GEMM dgate
 All weight gradients are batched over time into single GEMMs after the loop (the reference's autograd runs
 ~5,100 small kernels for this).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -56,20 +58,18 @@ class _LstmTF(torch.autograd.Function):
         dc = torch.zeros((B, D), **f32)
         dh = torch.zeros((B, D), **f32)
         dal = None if dalphas is None else dalphas.contiguous()
-        for t in reversed(range(T)):
-            bt = bts[t]
-            _lib.check(L.ccx_lstm_pointwise_bwd(ptr(G[t]), 4 * D, ptr(C_all[t]), ptr(C_all[t + 1]),
-                                                dH_all.data_ptr() + 4 * t * D, T * D,
-                                                None if dm is None else dm.data_ptr() + 4 * t * D, T * D,
-                                                ptr(dh), ptr(dc), ptr(dG_all[t]), 4 * D, bt, D, st), "lstm_bwd")
-            _lib.linear(to_operand(dG_all[t, :bt], cd), w_lstm_t, out=dXH_all[t, :bt], k=4 * D)
-            _lib.check(L.ccx_bahdanau_attention_bwd(
-                ptr(att1), ptr(HG[t]), A + E, ptr(Pw["w_f"]), ptr(enc), alphas.data_ptr() + 4 * t * Pn, T * Pn,
-                dXH_all.data_ptr() + 4 * (t * B * K + Emb), K,
-                None if dal is None else dal.data_ptr() + 4 * t * Pn, T * Pn, ptr(dHG_all[t]), A + E, ptr(d_att1),
-                ptr(d_enc), ptr(d_wf), bt, Pn, A, E, st), "attention_bwd")
-            _lib.linear(to_operand(dHG_all[t, :bt], cd), w_h_t, residual=dXH_all[t, :bt, hoff:], out=dh[:bt],
-                        k=A + E)
+        # the whole BPTT loop in ONE FFI call (csrc/lstm_runner.cu): per step LSTM point-wise backward, dgrad GEMM
+        # through [W_ih | W_hh], attention backward, dgrad GEMM through [decoder_att ; f_beta]
+        scratch = Operand.empty((B, max(4 * D, A + E)), cd, dev)
+        fwd = dec._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
+        bd = _lib.LstmTFBwd()
+        bd.dH_all, bd.dalphas = ptr(dH_all), ptr(dal)
+        bd.dG_all, bd.dHG_all, bd.dXH_all = ptr(dG_all), ptr(dHG_all), ptr(dXH_all)
+        bd.dh, bd.dc, bd.d_att1, bd.d_enc, bd.d_wf = ptr(dh), ptr(dc), ptr(d_att1), ptr(d_enc), ptr(d_wf)
+        bd.w_lstm_t, bd.w_lstm_t_lo = ptr(w_lstm_t.hi), w_lstm_t.lo_ptr
+        bd.w_h_t, bd.w_h_t_lo = ptr(w_h_t.hi), w_h_t.lo_ptr
+        bd.scratch_hi, bd.scratch_lo = ptr(scratch.hi), scratch.lo_ptr
+        _lib.check(L.ccx_lstm_tf_backward(ctypes.byref(fwd), ctypes.byref(bd), st), "lstm_tf_backward")
         # ---- weight gradients, batched over time -------------------------------------------------------------
         TB = T * B
         x_all = XH.map(lambda x: x[:T].view(TB, K))

@@ -319,6 +319,61 @@ CCX_API int ccx_dwconv7_wgrad(const float* x, const float* du, float* dw_tap_maj
 /* AdaptiveAvgPool2d((S,S)) backward over NHWC. */
 CCX_API int ccx_avgpool_nhwc_bwd(const float* dout, float* dx, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
                                  void* stream);
+/* ---- teacher-forced LSTM-attention time loop driven from C++ (models/decoder.py:100-111 and its backward) ----
+ * One call launches every step's kernels (GEMM [decoder_att|f_beta], attention, GEMM gates, LSTM point-wise);
+ * bts_host[t] = number of active (length-sorted) rows at step t.  Buffer layouts as in decoder.py:
+ * XH [T+1][B][Emb+E+D] operand (hi/lo), C_all [T+1][B][D], HG [T][B][A+E], G [T][B][4D], alphas [B][T][P],
+ * H_all [B][T][D] operand, dropmask [B][T][D] or NULL. */
+typedef struct ccx_lstm_tf {
+  void* XH_hi;
+  float* XH_lo;
+  float* C_all;
+  float* HG;
+  float* G;
+  float* alphas;
+  void* H_all_hi;
+  float* H_all_lo;
+  const float* dropmask;
+  const float* att1; /* [B*P, A] hoisted encoder_att(enc) */
+  const float* enc;  /* [B, P, E] length-sorted */
+  const void* w_h;   /* [A+E, D] operand */
+  const void* w_h_lo;
+  const float* b_h;
+  const float* w_f;
+  const float* b_f;
+  const void* w_lstm; /* [4D, Emb+E+D] operand */
+  const void* w_lstm_lo;
+  const float* b_lstm;
+  const int32_t* bts_host; /* HOST array [T] */
+  int32_t B, T, P, E, A, D, Emb;
+  int32_t compute_dtype;
+} ccx_lstm_tf;
+CCX_API int ccx_lstm_tf_forward(const ccx_lstm_tf* s, void* stream);
+
+/* BPTT over the same buffers: dH_all [B][T][D] (fc dgrad), dalphas [B][T][P] or NULL; work buffers dG_all
+ * [T][B][4D], dHG_all [T][B][A+E], dXH_all [T][B][Emb+E+D] (zero-initialised by the caller), dh / dc [B][D]
+ * (zero-initialised; on return dL/dh_0, dL/dc_0), d_att1 [B*P,A] (+=), d_enc [B,P,E] (+=, may be NULL), d_wf [A];
+ * w_*_t = transposed weight operands [in, out]; scratch = operand staging of max(4D, A+E) * B elements. */
+typedef struct ccx_lstm_tf_bwd {
+  const float* dH_all;
+  const float* dalphas;
+  float* dG_all;
+  float* dHG_all;
+  float* dXH_all;
+  float* dh;
+  float* dc;
+  float* d_att1;
+  float* d_enc;
+  float* d_wf;
+  const void* w_lstm_t; /* [Emb+E+D, 4D] operand */
+  const void* w_lstm_t_lo;
+  const void* w_h_t; /* [D, A+E] operand */
+  const void* w_h_t_lo;
+  void* scratch_hi;
+  float* scratch_lo;
+} ccx_lstm_tf_bwd;
+CCX_API int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* stream);
+
 /* clip_gradient (grad.clamp_(-clip, clip), utils/utils.py:189-192) fused with torch.optim.Adam's single-tensor
  * update (no weight decay / amsgrad), over a device table of {param, grad, exp_avg, exp_avg_sq, n} entries;
  * block i handles elements [block_offset[i], +chunk) of entry block_entry[i]. */
