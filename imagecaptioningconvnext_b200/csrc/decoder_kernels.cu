@@ -339,10 +339,19 @@ mha_small_kernel(MhaArgs a) {
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const long long bk = b / a.kv_group;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int idx = threadIdx.x; idx < a.Tk * hd; idx += 128) {
-    const int j = idx / hd, d = idx - j * hd;
-    s_k[j * ldk + d] = a.k[bk * a.k_sb + j * a.k_st + h * hd + d];
-    s_v[j * ldk + d] = a.v[bk * a.v_sb + j * a.v_st + h * hd + d];
+  {
+    // 16-byte loads, four in flight per thread: the staging loop is latency bound (one CTA has 4 warps)
+    const int hd4 = hd >> 2;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < a.Tk * hd4; idx += 128) {
+      const int j = idx / hd4, d = (idx - j * hd4) * 4;
+      const float4 kk = __ldg(reinterpret_cast<const float4*>(a.k + bk * a.k_sb + j * a.k_st + h * hd + d));
+      const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + bk * a.v_sb + j * a.v_st + h * hd + d));
+      float* dk = s_k + j * ldk + d;
+      float* dv = s_v + j * ldk + d;
+      dk[0] = kk.x; dk[1] = kk.y; dk[2] = kk.z; dk[3] = kk.w;
+      dv[0] = vv.x; dv[1] = vv.y; dv[2] = vv.z; dv[3] = vv.w;
+    }
   }
   __syncthreads();
   float* q = s_q + warp * hd;
@@ -391,7 +400,9 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
               int kv_group, cudaStream_t stream) {
   if (B <= 0 || Tq <= 0) return CCX_OK;
-  if (Tk <= 0 || hd <= 0 || H <= 0) return CCX_ERR_SHAPE;
+  if (Tk <= 0 || hd <= 0 || H <= 0 || (hd & 3) || (k_sb & 3) || (k_st & 3) || (v_sb & 3) || (v_st & 3) ||
+      (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
+    return CCX_ERR_SHAPE;
   const size_t smem = (static_cast<size_t>(2) * Tk * (hd + 1) + 4 * hd + 4 * Tk) * sizeof(float);
   if (smem > 200 * 1024) return CCX_ERR_SHAPE;
   static size_t configured = 0;

@@ -251,15 +251,26 @@ mha_bwd_kernel(MhaBwdArgs a) {
   float* s_ds = s_p + a.Tq * a.Tk;        // [Tq][Tk]  dS
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const int tid = threadIdx.x;
-  for (int i = tid; i < a.Tq * hd; i += 128) {
-    const int r = i / hd, d = i - r * hd;
-    s_q[r * ld + d] = a.q[b * a.q_sb + r * a.q_st + h * hd + d];
-    s_do[r * ld + d] = a.dctx[b * a.d_sb + r * a.d_st + h * hd + d];
+  const int hd4 = hd >> 2;   // 16-byte loads, several in flight (the staging loops are latency bound)
+#pragma unroll 4
+  for (int i = tid; i < a.Tq * hd4; i += 128) {
+    const int r = i / hd4, d = (i - r * hd4) * 4;
+    const float4 qq = __ldg(reinterpret_cast<const float4*>(a.q + b * a.q_sb + r * a.q_st + h * hd + d));
+    const float4 dd = __ldg(reinterpret_cast<const float4*>(a.dctx + b * a.d_sb + r * a.d_st + h * hd + d));
+    float* pq = s_q + r * ld + d;
+    float* pd = s_do + r * ld + d;
+    pq[0] = qq.x; pq[1] = qq.y; pq[2] = qq.z; pq[3] = qq.w;
+    pd[0] = dd.x; pd[1] = dd.y; pd[2] = dd.z; pd[3] = dd.w;
   }
-  for (int i = tid; i < a.Tk * hd; i += 128) {
-    const int r = i / hd, d = i - r * hd;
-    s_k[r * ld + d] = a.k[b * a.k_sb + r * a.k_st + h * hd + d];
-    s_v[r * ld + d] = a.v[b * a.v_sb + r * a.v_st + h * hd + d];
+#pragma unroll 4
+  for (int i = tid; i < a.Tk * hd4; i += 128) {
+    const int r = i / hd4, d = (i - r * hd4) * 4;
+    const float4 kk = __ldg(reinterpret_cast<const float4*>(a.k + b * a.k_sb + r * a.k_st + h * hd + d));
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(a.v + b * a.v_sb + r * a.v_st + h * hd + d));
+    float* pk = s_k + r * ld + d;
+    float* pv = s_v + r * ld + d;
+    pk[0] = kk.x; pk[1] = kk.y; pk[2] = kk.z; pk[3] = kk.w;
+    pv[0] = vv.x; pv[1] = vv.y; pv[2] = vv.z; pv[3] = vv.w;
   }
   const long long pbase = (static_cast<long long>(b) * a.H + h) * a.Tq * a.Tk;
   __syncthreads();
@@ -310,6 +321,7 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
             long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
             int Tk, int hd, float scale, cudaStream_t stream) {
   if (B <= 0 || Tq <= 0 || Tk <= 0) return CCX_OK;
+  if ((hd & 3) || ((q_sb | q_st | k_sb | k_st | v_sb | v_st | d_sb | d_st) & 3)) return CCX_ERR_SHAPE;
   const size_t smem = (static_cast<size_t>(2) * (Tq + Tk) * (hd + 1) + 2 * static_cast<size_t>(Tq) * Tk) * 4;
   if (smem > 200 * 1024) return CCX_ERR_SHAPE;
   static bool configured = false;
@@ -455,72 +467,76 @@ int lstm_pointwise_bwd(const float* gates, long long ldg, const float* c_prev, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bahdanau attention step backward, one CTA per sample (mirror of bahdanau_attention_kernel)
+// Bahdanau attention step backward (mirror of bahdanau_attention_kernel), two kernels so that a step with only
+// <= 32 active samples still fills the machine:
+//   K1  grid (bt, E/128), one thread per encoder channel e: the 49 enc values of (b, :, e) live in registers;
+//       un-gated awe, gate, d gate-pre-activation, d_awe_raw, d_enc += alpha_p * d_awe_raw, and the partial
+//       d alpha_p = sum_e d_awe_raw[e] enc[p,e] (warp reduce + atomicAdd into d_hg[b, 0:P], used as scratch)
+//   K2  grid bt, one thread per attention unit a: softmax backward, then through w_f . relu(att1 + att2)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-bahdanau_attention_bwd_kernel(const float* __restrict__ att1, const float* __restrict__ hg, long long ldhg,
-                              const float* __restrict__ w_f, const float* __restrict__ enc,
-                              const float* __restrict__ alpha, long long alpha_ld,       // saved softmax [b, p]
-                              const float* __restrict__ d_out, long long ld_dout,        // grad wrt gated awe [b, E]
-                              const float* __restrict__ d_alpha_ext, long long dalpha_ld,  // external grad wrt alpha or null
-                              float* __restrict__ d_hg, long long ld_dhg,                // out [b, A+E]
-                              float* __restrict__ d_att1,                                // += [B, P, A]
-                              float* __restrict__ d_enc,                                 // += [B, P, E] or null
-                              float* __restrict__ d_wf,                                  // += [A] (atomic)
-                              int P, int A, int E) {
-  extern __shared__ float bw_sm[];
-  float* s_att2 = bw_sm;          // [A]
-  float* s_wf = s_att2 + A;       // [A]
-  float* s_draw = s_wf + A;       // [E]  d_awe_raw = d_out * gate
-  float* s_datt2 = s_draw + E;    // [A]
-  __shared__ float s_a[ATT_MAX_P_BWD], s_de[ATT_MAX_P_BWD];
-  __shared__ float s_dot;
+static constexpr int ATTB_P = 64;   // register-resident pixel count of K1 (P <= 64 fast path)
+
+template <int PMAX>
+__global__ void __launch_bounds__(128)
+attention_bwd_enc_kernel(const float* __restrict__ hg, long long ldhg, const float* __restrict__ enc,
+                         const float* __restrict__ alpha, long long alpha_ld, const float* __restrict__ d_out,
+                         long long ld_dout, float* __restrict__ d_hg, long long ld_dhg, float* __restrict__ d_enc,
+                         int P, int A, int E) {
+  __shared__ float s_a[PMAX];
   const int b = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < A; i += 256) {
-    s_att2[i] = hg[b * ldhg + i];
-    s_wf[i] = __ldg(w_f + i);
-    s_datt2[i] = 0.f;
-  }
-  for (int p = threadIdx.x; p < P; p += 256) s_a[p] = alpha[b * alpha_ld + p];
+  const int e = blockIdx.y * 128 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  for (int p = threadIdx.x; p < P; p += 128) s_a[p] = alpha[b * alpha_ld + p];
   __syncthreads();
-  // un-gated awe, gate, d_gate_pre, d_awe_raw
-  for (int e = threadIdx.x; e < E; e += 256) {
-    float awe = 0.f;
-    for (int p = 0; p < P; ++p) awe = fmaf(__ldg(enc + (static_cast<long long>(b) * P + p) * E + e), s_a[p], awe);
+  const bool ok = e < E;
+  float x[PMAX];
+  float awe = 0.f;
+#pragma unroll
+  for (int p = 0; p < PMAX; ++p) {
+    x[p] = (ok && p < P) ? __ldg(enc + (static_cast<long long>(b) * P + p) * E + e) : 0.f;
+    awe = fmaf(x[p], (p < P) ? s_a[p] : 0.f, awe);
+  }
+  float draw = 0.f;
+  if (ok) {
     const float gate = 1.0f / (1.0f + expf(-hg[b * ldhg + A + e]));
     const float dout = d_out[b * ld_dout + e];
     d_hg[b * ld_dhg + A + e] = dout * awe * gate * (1.f - gate);
-    s_draw[e] = dout * gate;
+    draw = dout * gate;
   }
-  __syncthreads();
-  // d_alpha[p] = d_awe_raw . enc_p (+ external), and d_enc += alpha_p * d_awe_raw
-  for (int p = warp; p < P; p += 8) {
-    const float* er = enc + (static_cast<long long>(b) * P + p) * E;
-    float acc = 0.f;
-    for (int e = lane; e < E; e += 32) acc = fmaf(__ldg(er + e), s_draw[e], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) s_de[p] = acc + (d_alpha_ext ? d_alpha_ext[b * dalpha_ld + p] : 0.f);
-    if (d_enc != nullptr) {
-      float* dr = d_enc + (static_cast<long long>(b) * P + p) * E;
-      const float a = s_a[p];
-      for (int e = lane; e < E; e += 32) dr[e] += a * s_draw[e];
-    }
+#pragma unroll
+  for (int p = 0; p < PMAX; ++p) {
+    if (p >= P) break;
+    const float part = warp_sum(draw * x[p]);
+    if (lane == 0) atomicAdd(d_hg + b * ld_dhg + p, part);          // d alpha_p accumulator (scratch)
+    if (ok && d_enc != nullptr) d_enc[(static_cast<long long>(b) * P + p) * E + e] += s_a[p] * draw;
   }
-  __syncthreads();
-  if (warp == 0) {
-    float dot = 0.f;
-    for (int p = lane; p < P; p += 32) dot += s_a[p] * s_de[p];
-    dot = warp_sum(dot);
-    if (lane == 0) s_dot = dot;
+}
+
+__global__ void __launch_bounds__(512)
+attention_bwd_att_kernel(const float* __restrict__ att1, const float* __restrict__ hg, long long ldhg,
+                         const float* __restrict__ w_f, const float* __restrict__ alpha, long long alpha_ld,
+                         const float* __restrict__ d_alpha_ext, long long dalpha_ld, float* __restrict__ d_hg,
+                         long long ld_dhg, float* __restrict__ d_att1, float* __restrict__ d_wf, int P, int A) {
+  __shared__ float s_de[ATT_MAX_P_BWD];
+  __shared__ float s_red[16];
+  const int b = blockIdx.x;
+  // de_p = alpha_p * (dalpha_p - sum_q alpha_q dalpha_q)
+  float mine = 0.f, a_p = 0.f, da_p = 0.f;
+  if (threadIdx.x < P) {
+    a_p = alpha[b * alpha_ld + threadIdx.x];
+    da_p = d_hg[b * ld_dhg + threadIdx.x] + (d_alpha_ext ? d_alpha_ext[b * dalpha_ld + threadIdx.x] : 0.f);
+    mine = a_p * da_p;
   }
+  mine = warp_sum(mine);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mine;
   __syncthreads();
-  for (int p = threadIdx.x; p < P; p += 256) s_de[p] = s_a[p] * (s_de[p] - s_dot);   // de_p
-  __syncthreads();
-  // through w_f . relu(att1 + att2): per (p, a)
-  for (int a = threadIdx.x; a < A; a += 256) {
+  float dot = 0.f;
+  for (int w = 0; w < (P + 31) / 32; ++w) dot += s_red[w];
+  if (threadIdx.x < P) s_de[threadIdx.x] = a_p * (da_p - dot);
+  __syncthreads();   // every read of the d_hg[b, 0:P] scratch is done before it is overwritten below
+  for (int a = threadIdx.x; a < A; a += 512) {
     float datt2 = 0.f, dwf = 0.f;
-    const float h2 = s_att2[a], wf = s_wf[a];
+    const float h2 = hg[b * ldhg + a], wf = __ldg(w_f + a);
     for (int p = 0; p < P; ++p) {
       const long long i1 = (static_cast<long long>(b) * P + p) * A + a;
       const float pre = att1[i1] + h2;
@@ -543,13 +559,19 @@ int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, c
                            float* d_att1, float* d_enc, float* d_wf, int bt, int P, int A, int E,
                            cudaStream_t stream) {
   if (bt <= 0) return CCX_OK;
-  if (P <= 0 || P > ATT_MAX_P_BWD) return CCX_ERR_SHAPE;
-  const size_t smem = (3 * static_cast<size_t>(A) + E) * sizeof(float);
-  if (smem > 48 * 1024) return CCX_ERR_SHAPE;
+  if (P <= 0 || P > ATT_MAX_P_BWD || P > A || bt > 65535) return CCX_ERR_SHAPE;
   ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (2.0 * A + 3.0 * E) * 4.0);
-  bahdanau_attention_bwd_kernel<<<bt, 256, smem, stream>>>(att1, hg, ldhg, w_f, enc, alpha, alpha_ld, d_out, ld_dout,
-                                                           d_alpha_ext, dalpha_ld, d_hg, ld_dhg, d_att1, d_enc, d_wf,
-                                                           P, A, E);
+  if (cudaMemset2DAsync(d_hg, ld_dhg * sizeof(float), 0, P * sizeof(float), bt, stream) != cudaSuccess)
+    return CCX_ERR_CUDA;
+  dim3 g1(bt, (E + 127) / 128);
+  if (P <= ATTB_P)
+    attention_bwd_enc_kernel<ATTB_P><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout, d_hg,
+                                                             ld_dhg, d_enc, P, A, E);
+  else
+    attention_bwd_enc_kernel<ATT_MAX_P_BWD><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout,
+                                                                    d_hg, ld_dhg, d_enc, P, A, E);
+  attention_bwd_att_kernel<<<bt, 512, 0, stream>>>(att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld, d_hg,
+                                                   ld_dhg, d_att1, d_wf, P, A);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
