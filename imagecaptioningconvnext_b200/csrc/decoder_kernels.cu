@@ -334,13 +334,17 @@ mha_small_kernel(MhaArgs a) {
   const int hd = a.hd, ldk = hd + 1;
   float* s_k = mha_sm;                    // [Tk][hd+1]
   float* s_v = s_k + a.Tk * ldk;          // [Tk][hd+1]
-  float* s_q = s_v + a.Tk * ldk;          // [4 warps][hd]
-  float* s_p = s_q + 4 * hd;              // [4 warps][Tk]
+  float* s_q = s_v + a.Tk * ldk;          // [rows of this CTA][hd]   (pre-scaled)
+  const int rows_per_cta = (a.Tq + gridDim.y - 1) / gridDim.y;
+  float* s_p = s_q + rows_per_cta * hd;   // [4 warps][Tk]
   const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
   const long long bk = b / a.kv_group;
+  const int i_begin = blockIdx.y * rows_per_cta;
+  const int i_end = min(a.Tq, i_begin + rows_per_cta);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
-    // 16-byte loads, four in flight per thread: the staging loop is latency bound (one CTA has 4 warps)
+    // stage K, V and this CTA's Q rows with 16-byte loads, several in flight per thread: everything the row loop
+    // touches afterwards is in shared memory (the loop used to pay a global round trip per query row)
     const int hd4 = hd >> 2;
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < a.Tk * hd4; idx += 128) {
@@ -352,16 +356,23 @@ mha_small_kernel(MhaArgs a) {
       dk[0] = kk.x; dk[1] = kk.y; dk[2] = kk.z; dk[3] = kk.w;
       dv[0] = vv.x; dv[1] = vv.y; dv[2] = vv.z; dv[3] = vv.w;
     }
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < (i_end - i_begin) * hd4; idx += 128) {
+      const int r = idx / hd4, d = (idx - r * hd4) * 4;
+      const float4 qq = __ldg(reinterpret_cast<const float4*>(a.q + b * a.q_sb + (i_begin + r) * a.q_st + h * hd + d));
+      float* dq = s_q + r * hd + d;
+      dq[0] = qq.x * a.scale; dq[1] = qq.y * a.scale; dq[2] = qq.z * a.scale; dq[3] = qq.w * a.scale;
+    }
   }
   __syncthreads();
-  float* q = s_q + warp * hd;
   float* p = s_p + warp * a.Tk;
-  for (int i = warp; i < a.Tq; i += 4) {
-    for (int d = lane; d < hd; d += 32) q[d] = a.q[b * a.q_sb + i * a.q_st + h * hd + d] * a.scale;
-    __syncwarp();
+  for (int i = i_begin + warp; i < i_end; i += 4) {
+    const float* q = s_q + (i - i_begin) * hd;
+    const long long prow = ((static_cast<long long>(b) * a.H + h) * a.Tq + i) * a.Tk;
     float mx = -INFINITY;
     for (int j = lane; j < a.Tk; j += 32) {
       float s = 0.f;
+#pragma unroll 8
       for (int d = 0; d < hd; ++d) s = fmaf(q[d], s_k[j * ldk + d], s);
       const bool masked = (a.causal && j > a.q_pos0 + i) || (a.key_pad && a.key_pad[b * a.Tk + j]);
       s = masked ? -INFINITY : s;
@@ -377,16 +388,16 @@ mha_small_kernel(MhaArgs a) {
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    const long long prow = ((static_cast<long long>(b) * a.H + h) * a.Tq + i) * a.Tk;
     for (int j = lane; j < a.Tk; j += 32) {
       float pr = p[j] * inv;
       if (a.probs_out) a.probs_out[prow + j] = pr;
-      if (a.prob_mask) pr *= a.prob_mask[prow + j];
+      if (a.prob_mask) pr *= __ldg(a.prob_mask + prow + j);
       p[j] = pr;
     }
     __syncwarp();
     for (int d = lane; d < hd; d += 32) {
       float acc = 0.f;
+#pragma unroll 4
       for (int j = 0; j < a.Tk; ++j) acc = fmaf(p[j], s_v[j * ldk + d], acc);
       store_op(a.ctx, b * a.c_sb + i * a.c_st + h * hd + d, acc);
     }
@@ -401,9 +412,14 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               int kv_group, cudaStream_t stream) {
   if (B <= 0 || Tq <= 0) return CCX_OK;
   if (Tk <= 0 || hd <= 0 || H <= 0 || (hd & 3) || (k_sb & 3) || (k_st & 3) || (v_sb & 3) || (v_st & 3) ||
-      (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15))
+      (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15) || (q_sb & 3) || (q_st & 3) ||
+      (reinterpret_cast<uintptr_t>(q) & 15))
     return CCX_ERR_SHAPE;
-  const size_t smem = (static_cast<size_t>(2) * Tk * (hd + 1) + 4 * hd + 4 * Tk) * sizeof(float);
+  int ysplit = 1;
+  while (ysplit < 4 && static_cast<long long>(B) * H * ysplit < 2 * 148 && Tq / (ysplit * 2) >= 8) ysplit *= 2;
+  const int rows_per_cta = (Tq + ysplit - 1) / ysplit;
+  const size_t smem = (static_cast<size_t>(2) * Tk * (hd + 1) + static_cast<size_t>(rows_per_cta) * hd + 4 * Tk) *
+                      sizeof(float);
   if (smem > 200 * 1024) return CCX_ERR_SHAPE;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -422,7 +438,7 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
   a.causal = causal; a.q_pos0 = q_pos0; a.scale = scale;
   a.kv_group = kv_group > 0 ? kv_group : 1;
   ProfScope prof(PROF_ATTENTION, stream, (double)B * H * (Tq + 2.0 * Tk) * hd * 4.0);
-  mha_small_kernel<<<B * H, 128, smem, stream>>>(a);
+  mha_small_kernel<<<dim3(B * H, ysplit), 128, smem, stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -273,25 +273,34 @@ mha_bwd_kernel(MhaBwdArgs a) {
     pv[0] = vv.x; pv[1] = vv.y; pv[2] = vv.z; pv[3] = vv.w;
   }
   const long long pbase = (static_cast<long long>(b) * a.H + h) * a.Tq * a.Tk;
+  // stage softmax probabilities (and the dropout multipliers) once, coalesced, instead of a global round trip per
+  // (row, key) inside the reduction loops:  s_ds <- P,  s_p <- mask (or 1)
+  for (int i = tid; i < a.Tq * a.Tk; i += 128) {
+    s_ds[i] = __ldg(a.probs + pbase + i);
+    s_p[i] = a.prob_mask ? __ldg(a.prob_mask + pbase + i) : 1.f;
+  }
   __syncthreads();
-  // dPd[i,j] = dctx_i . v_j ; dP = dPd*mask ; dS = P * (dP - sum_j dP*P)
+  // dPd[i,j] = dctx_i . v_j ; dP = dPd*mask ; dS = P * (dP - sum_j dP*P) ; afterwards s_p = P*mask, s_ds = dS
   const int warp = tid >> 5, lane = tid & 31;
   for (int i = warp; i < a.Tq; i += 4) {
     float rowdot = 0.f;
-    for (int j = lane; j < a.Tk; j += 32) {
+    float dp_keep[8];   // Tk <= 256 keys -> at most 8 per lane
+    int n = 0;
+    for (int j = lane; j < a.Tk; j += 32, ++n) {
       float acc = 0.f;
+#pragma unroll 8
       for (int d = 0; d < hd; ++d) acc = fmaf(s_do[i * ld + d], s_v[j * ld + d], acc);
-      const float p = a.probs[pbase + i * a.Tk + j];
-      const float m = a.prob_mask ? a.prob_mask[pbase + i * a.Tk + j] : 1.f;
+      const float pr = s_ds[i * a.Tk + j], m = s_p[i * a.Tk + j];
       const float dp = acc * m;
-      s_p[i * a.Tk + j] = p * m;     // Pd for dV
-      s_ds[i * a.Tk + j] = dp;       // dP for now
-      rowdot += dp * p;
+      dp_keep[n & 7] = dp;
+      rowdot += dp * pr;
     }
     rowdot = warp_sum(rowdot);
-    for (int j = lane; j < a.Tk; j += 32) {
-      const float p = a.probs[pbase + i * a.Tk + j];
-      s_ds[i * a.Tk + j] = p * (s_ds[i * a.Tk + j] - rowdot);
+    n = 0;
+    for (int j = lane; j < a.Tk; j += 32, ++n) {
+      const float pr = s_ds[i * a.Tk + j], m = s_p[i * a.Tk + j];
+      s_p[i * a.Tk + j] = pr * m;                       // Pd for dV
+      s_ds[i * a.Tk + j] = pr * (dp_keep[n & 7] - rowdot);
     }
   }
   __syncthreads();
@@ -321,7 +330,7 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
             long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
             int Tk, int hd, float scale, cudaStream_t stream) {
   if (B <= 0 || Tq <= 0 || Tk <= 0) return CCX_OK;
-  if ((hd & 3) || ((q_sb | q_st | k_sb | k_st | v_sb | v_st | d_sb | d_st) & 3)) return CCX_ERR_SHAPE;
+  if ((hd & 3) || ((q_sb | q_st | k_sb | k_st | v_sb | v_st | d_sb | d_st) & 3) || Tk > 256) return CCX_ERR_SHAPE;
   const size_t smem = (static_cast<size_t>(2) * (Tq + Tk) * (hd + 1) + 2 * static_cast<size_t>(Tq) * Tk) * 4;
   if (smem > 200 * 1024) return CCX_ERR_SHAPE;
   static bool configured = false;
