@@ -74,9 +74,35 @@ class _Layer(nn.Module):
 
 
 class _Stack(nn.Module):
+    """Parameter tree of nn.TransformerDecoder; ``forward`` keeps its seq-first signature for external callers
+    (caption.py:204-213 pokes ``decoder.transformer_decoder(tgt, memory, tgt_mask=...)``) and runs on libccx."""
+
     def __init__(self, d, dff, n):
         super().__init__()
         self.layers = nn.ModuleList([_Layer(d, dff) for _ in range(n)])
+        self._owner = []     # [TransformerDecoder]; a list so the parent is not registered as a sub-module
+
+    @torch.no_grad()
+    def forward(self, tgt, memory, tgt_mask=None, tgt_key_padding_mask=None):
+        """tgt (T,B,D), memory (P,B,D) seq-first -> (T,B,D).  Inference only (eval-mode math, no autograd).
+        tgt_mask must be None or the causal mask (the only masks the reference ever passes)."""
+        dec = self._owner[0]
+        T, B, D = tgt.shape
+        causal = 0
+        if tgt_mask is not None:
+            want = torch.ones(T, T, dtype=torch.bool, device=tgt.device).triu(1)
+            got = tgt_mask if tgt_mask.dtype == torch.bool else (tgt_mask == float("-inf"))
+            if got.shape != (T, T) or not torch.equal(got, want):
+                raise ValueError("only the causal tgt_mask (generate_square_subsequent_mask) is supported")
+            causal = 1
+        Pw = dec._cache.get()
+        cd = dec.compute_dtype
+        x_plain = tgt.permute(1, 0, 2).contiguous().float().view(B * T, D)          # batch-first rows
+        x_op = Operand.prepare(x_plain, cd)
+        mem = Operand.prepare(memory.permute(1, 0, 2).contiguous().float().view(-1, D), cd)
+        kpm = None if tgt_key_padding_mask is None else tgt_key_padding_mask.to(torch.uint8).contiguous()
+        x_plain, _ = dec._run_layers(Pw, x_plain, x_op, mem, B, T, memory.shape[0], causal, kpm)
+        return x_plain.view(B, T, D).permute(1, 0, 2)
 
 
 class TransformerDecoder(nn.Module):
@@ -103,6 +129,7 @@ class TransformerDecoder(nn.Module):
                              if encoder_dim != embed_dim else nn.Identity())
         self.device = device
         self._cache = PreparedCache(self)
+        self.transformer_decoder._owner.append(self)
         self.inject_dropout = None   # tests: dict of multipliers, see _drop()
 
     # ---- prepared weights ---------------------------------------------------------------------------------------
@@ -180,6 +207,27 @@ class TransformerDecoder(nn.Module):
         every layer call of every greedy step)."""
         return [_lib.linear(mem, lw["ca_kv"], bias=lw["ca_kv_b"]) for lw in Pw["layers"]]
 
+    def _run_layers(self, Pw, x_plain, x_op, mem, B, T, Pn, causal, kpm):
+        """The 6 post-norm layers on batch-first rows (eval-mode math): torch/nn/modules/transformer.py:1089-1199."""
+        D = self.embed_dim
+        dev = x_plain.device
+        kvs = self._cross_kv(Pw, mem)
+        for lw, kv in zip(Pw["layers"], kvs):
+            qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
+            ctx = self._mha(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
+                            qkv.data_ptr() + 8 * D, B, T, T, causal, 0, kpm, None, 1, dev)
+            y = _lib.linear(ctx, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain)
+            x_plain, x_op = self._ln(y, lw["n"][0], B * T)
+            q = _lib.linear(x_op, lw["ca_q"], bias=lw["ca_q_b"])
+            ctx = self._mha(ptr(q), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, B, T, Pn, 0, 0,
+                            None, None, 1, dev)
+            y = _lib.linear(ctx, lw["ca_out"], bias=lw["ca_out_b"], residual=x_plain)
+            x_plain, x_op = self._ln(y, lw["n"][1], B * T)
+            h = self._linear_op(x_op, lw["l1"], lw["l1_b"], act=_lib.ACT_RELU)
+            y = _lib.linear(h, lw["l2"], bias=lw["l2_b"], residual=x_plain)
+            x_plain, x_op = self._ln(y, lw["n"][2], B * T)
+        return x_plain, x_op
+
     def _drop(self, name, shape, dev):
         if not self.training or self.dropout_p == 0:
             return None
@@ -216,21 +264,7 @@ class TransformerDecoder(nn.Module):
         kpm = None
         if tgt_key_padding_mask is not None:
             kpm = tgt_key_padding_mask.to(torch.uint8).contiguous()
-        kvs = self._cross_kv(Pw, mem)
-        for lw, kv in zip(Pw["layers"], kvs):
-            qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
-            ctx = self._mha(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
-                            qkv.data_ptr() + 8 * D, B, T, T, 1, 0, kpm, None, 1, dev)
-            y = _lib.linear(ctx, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain)
-            x_plain, x_op = self._ln(y, lw["n"][0], B * T)
-            q = _lib.linear(x_op, lw["ca_q"], bias=lw["ca_q_b"])
-            ctx = self._mha(ptr(q), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, B, T, Pn, 0, 0,
-                            None, None, 1, dev)
-            y = _lib.linear(ctx, lw["ca_out"], bias=lw["ca_out_b"], residual=x_plain)
-            x_plain, x_op = self._ln(y, lw["n"][1], B * T)
-            h = self._linear_op(x_op, lw["l1"], lw["l1_b"], act=_lib.ACT_RELU)
-            y = _lib.linear(h, lw["l2"], bias=lw["l2_b"], residual=x_plain)
-            x_plain, x_op = self._ln(y, lw["n"][2], B * T)
+        x_plain, x_op = self._run_layers(Pw, x_plain, x_op, mem, B, T, Pn, 1, kpm)
         predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)
         _lib.linear(x_op, Pw["fc"], bias=Pw["fc_b"], out=predictions.view(B * T, V))
         return predictions, encoded_captions, decode_lengths

@@ -178,3 +178,21 @@ def test_poked_submodules_run_on_libccx():
     hr, cr, _ = do.lstm_step(sd, enc, sd["embedding.weight"][tok.squeeze(1)], h0, c0)
     assert rel_err(h2, hr) < 1e-4 and rel_err(c2, cr) < 1e-4
     assert rel_err(m.fc(h2), torch.nn.functional.linear(hr, sd["fc.weight"], sd["fc.bias"])) < 1e-4
+
+
+def test_poked_transformer_submodules_run_on_libccx():
+    """caption.py:181,204-216 pokes encoder_proj / embedding / pos_encoding / transformer_decoder / fc_out directly."""
+    import torch.nn as nn
+    from oracle import decoder_oracle as do
+    sd = do.random_transformer_decoder_state(6, V)
+    m = _transformer(sd, torch.float32)
+    enc = do.synthetic_features(2, 11).view(2, 49, 1024)
+    toks = torch.randint(1, V - 4, (2, 9), generator=torch.Generator().manual_seed(2))
+    mem = m.encoder_proj(enc.cuda()).permute(1, 0, 2)                       # (P, B, D) as caption.py:181
+    emb = m.pos_encoding(m.dropout(m.embedding(toks.cuda())))
+    tgt = emb.permute(1, 0, 2)
+    mask = nn.Transformer.generate_square_subsequent_mask(9).cuda().bool()
+    out = m.transformer_decoder(tgt, mem, tgt_mask=mask)
+    logits = m.fc_out(out[-1])
+    ref = do.transformer_last_logits(sd, do.transformer_memory(sd, enc), toks)
+    assert rel_err(logits, ref) < 1e-3
