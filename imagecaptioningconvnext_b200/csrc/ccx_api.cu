@@ -181,9 +181,16 @@ int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float* k, int6
                  dk, dk_sb, dk_st, dv, dv_sb, dv_st, B, H, Tq, Tk, hd, scale, as_stream(stream));
 }
 int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V, float inv_n,
-                   float* loss_sum, float* dlogits, int64_t ldd, float* correct_top1, void* stream) {
+                   float* loss_sum, float* dlogits, int64_t ldd, float* stats, int32_t topk, void* stream) {
   return softmax_ce(logits, ld, reinterpret_cast<const long long*>(targets), R, V, inv_n, loss_sum, dlogits, ldd,
-                    correct_top1, as_stream(stream));
+                    stats, topk, as_stream(stream));
+}
+int ccx_free_running_targets(const int64_t* sequences, const int64_t* caps, int64_t cap_ld, int64_t* targets,
+                             int32_t* decode_len, int32_t B, int32_t T, int32_t cap_T, int64_t end_tok,
+                             int64_t pad_tok, void* stream) {
+  return free_running_targets(reinterpret_cast<const long long*>(sequences), reinterpret_cast<const long long*>(caps),
+                              cap_ld, reinterpret_cast<long long*>(targets), decode_len, B, T, cap_T, end_tok, pad_tok,
+                              as_stream(stream));
 }
 int ccx_embedding_bwd(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* dx, int64_t sb, int64_t st,
                       const float* dropmask, float* dtable, int32_t V, int32_t D, int32_t nb, int32_t nt,

@@ -64,7 +64,10 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
             long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
             int Tk, int hd, float scale, cudaStream_t stream);
 int softmax_ce(const float* logits, long long ld, const long long* targets, long long R, int V, float inv_n,
-               float* loss_sum, float* dlogits, long long ldd, float* correct_top1, cudaStream_t stream);
+               float* loss_sum, float* dlogits, long long ldd, float* stats, int topk, cudaStream_t stream);
+int free_running_targets(const long long* sequences, const long long* caps, long long cap_ld, long long* targets,
+                         int* decode_len, int B, int T, int cap_T, long long end_tok, long long pad_tok,
+                         cudaStream_t stream);
 int embedding_bwd(const long long* tokens, long long tok_ld, int t0, const float* dx, long long sb, long long st,
                   const float* dropmask, float* dtable, int V, int D, int nb, int nt, cudaStream_t stream);
 int lstm_pointwise_bwd(const float* gates, long long ldg, const float* c_prev, const float* c_new,

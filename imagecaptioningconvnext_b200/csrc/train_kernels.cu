@@ -356,17 +356,18 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ targets, int V,
                   float inv_n, float* __restrict__ loss_sum, float* __restrict__ dlogits, long long ldd,
-                  float* __restrict__ correct_top1) {
-  __shared__ float red[8];
-  __shared__ float s_b;
+                  float* __restrict__ stats, int topk) {
+  __shared__ float red[8], red2[8];
+  __shared__ float s_b, s_c;
   const long long r = blockIdx.x;
   const long long tgt = targets[r];
   float* drow = dlogits ? dlogits + r * ldd : nullptr;
-  if (tgt < 0) {
+  if (tgt < 0 || tgt >= V) {
     if (drow) for (int v = threadIdx.x; v < V; v += 256) drow[v] = 0.f;
     return;
   }
   const float* row = logits + r * ld;
+  const float tval = row[tgt];
   float mx = -INFINITY;
   for (int v = threadIdx.x; v < V; v += 256) mx = fmaxf(mx, row[v]);
   mx = warp_max(mx);
@@ -375,19 +376,32 @@ softmax_ce_kernel(const float* __restrict__ logits, long long ld, const long lon
   if (threadIdx.x == 0) { float m = red[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]); s_b = m; }
   __syncthreads();
   mx = s_b;
-  float sum = 0.f;
-  for (int v = threadIdx.x; v < V; v += 256) sum += expf(row[v] - mx);
+  float sum = 0.f, gt = 0.f;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float x = row[v];
+    sum += expf(x - mx);
+    gt += (x > tval) ? 1.f : 0.f;     // rank of the target = number of strictly larger logits
+  }
   sum = warp_sum(sum);
+  gt = warp_sum(gt);
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = sum; red2[threadIdx.x >> 5] = gt; }
   __syncthreads();
-  if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; s_b = s; }
+  if (threadIdx.x == 0) {
+    float s = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { s += red[w]; c += red2[w]; }
+    s_b = s; s_c = c;
+  }
   __syncthreads();
   sum = s_b;
   const float lse = mx + logf(sum);
   if (threadIdx.x == 0) {
-    atomicAdd(loss_sum, (lse - row[tgt]) * inv_n);
-    if (correct_top1) atomicAdd(correct_top1, row[tgt] >= mx ? 1.f : 0.f);
+    if (loss_sum) atomicAdd(loss_sum, (lse - tval) * inv_n);
+    if (stats) {
+      atomicAdd(stats + 0, lse - tval);                       // un-normalised token loss sum
+      atomicAdd(stats + 1, 1.f);                              // valid rows (tokens)
+      atomicAdd(stats + 2, s_c < static_cast<float>(topk) ? 1.f : 0.f);   // top-k hits (utils/utils.py:239-254)
+    }
   }
   if (drow) {
     const float inv = inv_n / sum;
@@ -396,11 +410,43 @@ softmax_ce_kernel(const float* __restrict__ logits, long long ld, const long lon
 }
 
 int softmax_ce(const float* logits, long long ld, const long long* targets, long long R, int V, float inv_n,
-               float* loss_sum, float* dlogits, long long ldd, float* correct_top1, cudaStream_t stream) {
+               float* loss_sum, float* dlogits, long long ldd, float* stats, int topk, cudaStream_t stream) {
   if (R <= 0) return CCX_OK;
   ProfScope prof(PROF_LOSS, stream, (double)R * V * (dlogits ? 8.0 : 4.0));
   softmax_ce_kernel<<<static_cast<unsigned>(R), 256, 0, stream>>>(logits, ld, targets, V, inv_n, loss_sum, dlogits,
-                                                                 ldd, correct_top1);
+                                                                 ldd, stats, topk);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// Targets of the free-running (no teacher forcing) evaluation, utils/utils.py:261-295
+// (preprocessDecoderOutputForMetrics) without the per-sample Python loop: row i is scored for t < L_i where
+// L_i = (first <end> in sequences[i]) + 1, or maxDecodeLen if none; positions whose ground truth is <pad> are dropped.
+__global__ void free_running_targets_kernel(const long long* __restrict__ sequences, const long long* __restrict__ caps,
+                                            long long cap_ld, long long* __restrict__ targets,
+                                            int* __restrict__ decode_len, int B, int T, int cap_T, long long end_tok,
+                                            long long pad_tok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  int L = T;
+  for (int t = 0; t < T; ++t)
+    if (sequences[static_cast<long long>(i) * T + t] == end_tok) { L = t + 1; break; }
+  if (decode_len) decode_len[i] = L;
+  for (int t = 0; t < T; ++t) {
+    long long g = -1;
+    if (t < L && 1 + t < cap_T) {
+      g = caps[i * cap_ld + 1 + t];
+      if (g == pad_tok) g = -1;
+    }
+    targets[static_cast<long long>(i) * T + t] = g;
+  }
+}
+int free_running_targets(const long long* sequences, const long long* caps, long long cap_ld, long long* targets,
+                         int* decode_len, int B, int T, int cap_T, long long end_tok, long long pad_tok,
+                         cudaStream_t stream) {
+  if (B <= 0) return CCX_OK;
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)B * T * 24.0);
+  free_running_targets_kernel<<<(B + 127) / 128, 128, 0, stream>>>(sequences, caps, cap_ld, targets, decode_len, B, T,
+                                                                 cap_T, end_tok, pad_tok);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

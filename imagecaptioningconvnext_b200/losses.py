@@ -15,7 +15,7 @@ class _PackedCE(torch.autograd.Function):
         need_grad = scores.requires_grad
         dlogits = torch.empty_like(s2) if need_grad else None
         _lib.check(_lib.lib().ccx_softmax_ce(ptr(s2), V, ptr(targets), B * T, V, 1.0 / n_valid, ptr(loss),
-                                             ptr(dlogits), V, None, _lib.stream_ptr()), "softmax_ce")
+                                             ptr(dlogits), V, None, 0, _lib.stream_ptr()), "softmax_ce")
         ctx.dlogits, ctx.shape = dlogits, scores.shape
         return loss[0]
 
@@ -36,3 +36,43 @@ def packed_cross_entropy(scores, captions, decode_lengths):
     valid = torch.arange(T, device=dev).unsqueeze(0) < dl.unsqueeze(1)
     targets = torch.where(valid, tgt, torch.full_like(tgt, -1)).contiguous().view(-1)
     return _PackedCE.apply(scores, targets, float(sum(decode_lengths)))
+
+
+def packed_targets(captions, decode_lengths, T):
+    """int64 (B*T,) targets for ``ccx_softmax_ce``: captions[b, 1+t] for t < decode_lengths[b], else -1."""
+    dev = captions.device
+    dl = torch.as_tensor(decode_lengths, device=dev)
+    tgt = captions[:, 1:T + 1].to(torch.long)
+    if tgt.shape[1] < T:
+        tgt = torch.nn.functional.pad(tgt, (0, T - tgt.shape[1]), value=0)
+    valid = torch.arange(T, device=dev).unsqueeze(0) < dl.unsqueeze(1)
+    return torch.where(valid, tgt, torch.full_like(tgt, -1)).contiguous().view(-1)
+
+
+@torch.no_grad()
+def step_metrics(scores, targets, topk=5, group=None):
+    """Loss / token count / top-k hits of one step in ONE kernel pass and ONE 12-byte all-reduce, with no host sync
+    until the caller reads the result (the reference: 4 scalar all-reduces + 5 ``.item()`` syncs per step,
+    trainMultiGPU.py:96-108,396-403).  scores (B,T,V); targets (B*T,) with -1 = ignored.
+    Returns a device tensor [global mean token loss, total tokens, top-k accuracy in percent]."""
+    B, T, V = scores.shape
+    s2 = scores.detach().contiguous().view(B * T, V)
+    stats = torch.zeros(3, dtype=torch.float32, device=scores.device)
+    _lib.check(_lib.lib().ccx_softmax_ce(ptr(s2), V, ptr(targets), B * T, V, 1.0, None, None, 0, ptr(stats), topk,
+                                         _lib.stream_ptr()), "softmax_ce")
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.all_reduce(stats, group=group)
+    return torch.stack([stats[0] / stats[1], stats[1], 100.0 * stats[2] / stats[1]])
+
+
+@torch.no_grad()
+def free_running_targets(sequences, captions, end_token, pad_token):
+    """Device-side ``preprocessDecoderOutputForMetrics`` (utils/utils.py:261-295): -> (targets (B*T,), decode_len (B,))."""
+    B, T = sequences.shape
+    caps = captions.contiguous()
+    targets = torch.empty(B * T, dtype=torch.long, device=sequences.device)
+    dlen = torch.empty(B, dtype=torch.int32, device=sequences.device)
+    _lib.check(_lib.lib().ccx_free_running_targets(ptr(sequences.contiguous()), ptr(caps), caps.stride(0), ptr(targets),
+                                                   ptr(dlen), B, T, caps.shape[1], end_token, pad_token,
+                                                   _lib.stream_ptr()), "free_running_targets")
+    return targets, dlen

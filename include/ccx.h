@@ -274,9 +274,18 @@ CCX_API int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float*
                         int32_t H, int32_t Tq, int32_t Tk, int32_t hd, float scale, void* stream);
 /* CrossEntropyLoss(mean) over the rows with targets[r] >= 0 (= pack_padded_sequence's selection,
  * trainMultiGPU.py:365-367): *loss_sum += sum_r (lse_r - logit_r[target]) * inv_n;
- * dlogits[r] = (softmax_r - onehot) * inv_n, zero rows for targets < 0; correct_top1 counts argmax hits. */
+ * dlogits[r] = (softmax_r - onehot) * inv_n, zero rows for targets < 0 (loss_sum / dlogits may be NULL).
+ * stats (3 floats, may be NULL) += {sum of token losses, number of valid rows, top-k hits}: the step metrics of
+ * trainMultiGPU.py:396-403 (reduceLossAndTokens + accuracy(scores, targets, 5), utils/utils.py:239-254) in the same
+ * pass; a hit = fewer than topk logits strictly larger than the target's. */
 CCX_API int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V, float inv_n,
-                           float* loss_sum, float* dlogits, int64_t ldd, float* correct_top1, void* stream);
+                           float* loss_sum, float* dlogits, int64_t ldd, float* stats, int32_t topk, void* stream);
+/* Targets of the free-running evaluation (utils/utils.py:261-295 preprocessDecoderOutputForMetrics) on the device:
+ * targets[i,t] = caps[i,1+t] for t < L_i (L_i = first <end> in sequences[i] + 1, else T) and != <pad>, else -1;
+ * decode_len[i] = L_i (may be NULL).  Feed targets to ccx_softmax_ce. */
+CCX_API int ccx_free_running_targets(const int64_t* sequences, const int64_t* caps, int64_t cap_ld, int64_t* targets,
+                                     int32_t* decode_len, int32_t B, int32_t T, int32_t cap_T, int64_t end_tok,
+                                     int64_t pad_tok, void* stream);
 /* nn.Embedding dense gradient: dtable[token(b,t)] += dx[b*sb + t*st + :] * dropmask[(b*nt+t), :]. */
 CCX_API int ccx_embedding_bwd(const int64_t* tokens, int64_t tok_ld, int32_t t0, const float* dx, int64_t sb,
                               int64_t st, const float* dropmask, float* dtable, int32_t V, int32_t D, int32_t nb,
