@@ -282,9 +282,13 @@ def run_ours(args):
     g = prof["gemm"]
     achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"] if dtype == torch.bfloat16 else peaks["bf16_tflops_sustained"] / 6.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and dtype == torch.bfloat16:
+        traffic = json.load(open(tpath))["gemm_tn_kernel"]["dram_bytes_per_launch"]   # from the committed ncu capture
     roofline = {"kernel": "gemm_tn_kernel (tcgen05, all encoder pointwise/downsample GEMMs)", "bound": "tensor",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peaks["source"] + (" bf16 sustained" if dtype == torch.bfloat16
+                "traffic": traffic, "peak_source": peaks["source"] + (" bf16 sustained" if dtype == torch.bfloat16
                                                                      else " bf16 sustained / 6 (3xTF32 at half rate)"),
                 "flops_per_launch": g["work"] / max(g["launches"], 1),
                 "us_per_launch": g["ms"] * 1e3 / max(g["launches"], 1)}
