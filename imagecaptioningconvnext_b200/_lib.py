@@ -67,6 +67,7 @@ SIGNATURES = {
     "ccx_split_tf32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "ccx_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ccx_stem_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
+    "ccx_stem_ln_u8": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),
     "ccx_dwconv7_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "ccx_ln_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _i32, _vp]),
     "ccx_embed_rows": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _i64,

@@ -53,7 +53,14 @@ int ccx_cast_bf16(const float* x, void* y, int64_t n, void* stream) {
 
 int ccx_stem_ln(const float* images, const float* w_k, const float* bias, const float* ln_g, const float* ln_b,
                 float* out, int32_t B, int32_t Hin, int32_t Win, float eps, void* stream) {
-  return stem_ln(images, w_k, bias, ln_g, ln_b, out, B, Hin, Win, eps, as_stream(stream));
+  return stem_ln(images, nullptr, nullptr, nullptr, w_k, bias, ln_g, ln_b, out, B, Hin, Win, eps, as_stream(stream));
+}
+
+int ccx_stem_ln_u8(const uint8_t* images_u8, const float* mean3, const float* inv_std3, const float* w_k,
+                   const float* bias, const float* ln_g, const float* ln_b, float* out, int32_t B, int32_t Hin,
+                   int32_t Win, float eps, void* stream) {
+  return stem_ln(nullptr, images_u8, mean3, inv_std3, w_k, bias, ln_g, ln_b, out, B, Hin, Win, eps,
+                 as_stream(stream));
 }
 
 int ccx_dwconv7_ln(const float* x, const float* w_tap_major, const float* bias, const float* ln_g,
@@ -284,7 +291,8 @@ int ccx_encoder_run(const ccx_encoder_weights* w, const float* in, float* out, i
     const bool last_child = (child == child_end - 1);
     if (child == 0) {
       float* dst = last_child ? out : X0;
-      if ((rc = stem_ln(cur, w->stem_w, w->stem_b, w->stem_ln_g, w->stem_ln_b, dst, B, Hin, Win, 1e-6f, stream)))
+      if ((rc = stem_ln(cur, nullptr, nullptr, nullptr, w->stem_w, w->stem_b, w->stem_ln_g, w->stem_ln_b, dst, B, Hin,
+                        Win, 1e-6f, stream)))
         return rc;
       cur = dst;
       continue;

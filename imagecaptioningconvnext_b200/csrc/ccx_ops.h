@@ -10,8 +10,9 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
                cudaStream_t stream, const float* addend = nullptr);
 
 // encoder_misc.cu
-int stem_ln(const float* img, const float* wk, const float* bias, const float* gamma, const float* beta,
-            float* out, int B, int Hin, int Win, float eps, cudaStream_t stream);
+int stem_ln(const float* img, const unsigned char* img_u8, const float* mean, const float* inv_std, const float* wk,
+            const float* bias, const float* gamma, const float* beta, float* out, int B, int Hin, int Win, float eps,
+            cudaStream_t stream);
 int ln_rows(const float* x, const float* gamma, const float* beta, void* out, float* out_lo, float* out_plain,
             long long M, int C, float eps, int out_dtype, int merge, int H, int W, cudaStream_t stream);
 int avgpool_nhwc(const float* x, float* out, int B, int H, int W, int C, int S, cudaStream_t stream);

@@ -19,8 +19,12 @@ namespace ccx {
 static constexpr int STEM_PX = 64;
 static constexpr int STEM_C = 128;
 
+// img_u8 != nullptr: raw uint8 pixels; (x/255 - mean[c]) * inv_std[c] is applied while staging
+// (dataLoader.py:43-45: FloatTensor(img / 255.) then transforms.Normalize(mean, std))
 __global__ void __launch_bounds__(256)
-stem_ln_kernel(const float* __restrict__ img, const float* __restrict__ wk,  // wk [48][128], k = c*16+kh*4+kw
+stem_ln_kernel(const float* __restrict__ img, const unsigned char* __restrict__ img_u8,
+               const float* __restrict__ mean, const float* __restrict__ inv_std,
+               const float* __restrict__ wk,  // wk [48][128], k = c*16+kh*4+kw
                const float* __restrict__ bias, const float* __restrict__ gamma,
                const float* __restrict__ beta, float* __restrict__ out, int B, int Hin, int Win, int Hout,
                int Wout, float eps) {
@@ -39,7 +43,13 @@ stem_ln_kernel(const float* __restrict__ img, const float* __restrict__ wk,  // 
     const int c = rowi >> 2, kh = rowi & 3;
     const int ih = oh * 4 + kh, iw = ow0 * 4 + col;
     float v = 0.f;
-    if (iw < Wout * 4) v = __ldg(img + ((static_cast<long long>(b) * 3 + c) * Hin + ih) * Win + iw);
+    if (iw < Wout * 4) {
+      const long long gi = ((static_cast<long long>(b) * 3 + c) * Hin + ih) * Win + iw;
+      if (img_u8 != nullptr)
+        v = (static_cast<float>(img_u8[gi]) / 255.0f - __ldg(mean + c)) * __ldg(inv_std + c);
+      else
+        v = __ldg(img + gi);
+    }
     in_s[rowi][col] = v;
   }
   __syncthreads();
@@ -89,16 +99,20 @@ stem_ln_kernel(const float* __restrict__ img, const float* __restrict__ wk,  // 
   }
 }
 
-int stem_ln(const float* img, const float* wk, const float* bias, const float* gamma, const float* beta,
-            float* out, int B, int Hin, int Win, float eps, cudaStream_t stream) {
+int stem_ln(const float* img, const unsigned char* img_u8, const float* mean, const float* inv_std, const float* wk,
+            const float* bias, const float* gamma, const float* beta, float* out, int B, int Hin, int Win, float eps,
+            cudaStream_t stream) {
   if (B <= 0 || Hin < 4 || Win < 4) return CCX_ERR_SHAPE;
   const int Hout = Hin / 4, Wout = Win / 4;
   const int segs = (Wout + STEM_PX - 1) / STEM_PX;
   const long long grid = static_cast<long long>(B) * Hout * segs;
   if (grid > 0x7fffffffLL) return CCX_ERR_SHAPE;
-  ProfScope prof(PROF_STEM, stream, (double)B * (3.0 * Hin * Win + (double)Hout * Wout * STEM_C) * 4.0);
-  stem_ln_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(img, wk, bias, gamma, beta, out, B, Hin, Win,
-                                                                   Hout, Wout, eps);
+  if ((img == nullptr) == (img_u8 == nullptr)) return CCX_ERR_DTYPE;
+  if (img_u8 != nullptr && (mean == nullptr || inv_std == nullptr)) return CCX_ERR_SHAPE;
+  ProfScope prof(PROF_STEM, stream,
+                 (double)B * (3.0 * Hin * Win * (img_u8 ? 1.0 : 4.0) + (double)Hout * Wout * STEM_C * 4.0));
+  stem_ln_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(img, img_u8, mean, inv_std, wk, bias, gamma, beta,
+                                                                   out, B, Hin, Win, Hout, Wout, eps);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

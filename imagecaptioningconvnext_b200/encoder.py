@@ -22,6 +22,8 @@ from ._lib import Operand
 
 DEPTHS = (3, 3, 27, 3)
 DIMS = (128, 256, 512, 1024)
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # the Normalize constants of train.py:152-153 / caption.py:62
+IMAGENET_STD = (0.229, 0.224, 0.225)
 SD_PROB = 0.5  # torchvision convnext_base default stochastic_depth_prob (tv:models/convnext.py:356-382)
 
 
@@ -99,14 +101,20 @@ class Encoder(nn.Module):
     def forward(self, images):
         """models/encoder.py:23-27: (B,3,H,W) fp32 -> (B,s,s,1024) fp32."""
         _lib.require_cuda(images, "images")
-        if images.dim() != 4 or images.shape[1] != 3 or images.dtype != torch.float32:
-            raise ValueError(f"images must be float32 (B,3,H,W); got {tuple(images.shape)} {images.dtype}")
+        if images.dim() != 4 or images.shape[1] != 3 or images.dtype not in (torch.float32, torch.uint8):
+            raise ValueError(f"images must be float32 (or raw uint8) (B,3,H,W); got {tuple(images.shape)} {images.dtype}")
         B, _, H, W = images.shape
         if H % 32 or W % 32:
             raise ValueError("image height/width must be multiples of 32 (ConvNeXt total stride)")
         images = images.contiguous()
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.convnext.parameters())
         noise = self._stochastic_depth_noise(B, images.device)
+        if images.dtype == torch.uint8:
+            # raw dataset pixels: /255 and Normalize(mean, std) (dataLoader.py:43-45) are fused into the stem kernel
+            if needs_grad:
+                raise NotImplementedError("uint8 input with encoder fine-tuning: normalise on the host side instead")
+            x1 = self._stem_u8(images)
+            return self._pool(self.run_children(x1, 1, 8, noise, image_hw=(H, W)))
         if needs_grad:
             from .encoder_train import encoder_features_with_grad  # backward kernels live there
             return encoder_features_with_grad(self, images, noise)   # pooled inside the autograd Function
@@ -122,6 +130,21 @@ class Encoder(nn.Module):
         p = torch.tensor(stochastic_depth_probs(), device=device, dtype=torch.float32).view(-1, 1)
         keep = 1.0 - p
         return (torch.bernoulli(keep.expand(-1, B)) / keep).contiguous()
+
+    def _stem_u8(self, images_u8):
+        B, _, H, W = images_u8.shape
+        w = self.prepared()
+        dev = images_u8.device
+        if getattr(self, "_norm_consts", None) is None or self._norm_consts[0].device != dev:
+            mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32, device=dev)
+            inv_std = (1.0 / torch.tensor(IMAGENET_STD, dtype=torch.float64)).to(torch.float32).to(dev)
+            self._norm_consts = (mean, inv_std)
+        out = torch.empty((B, H // 4, W // 4, DIMS[0]), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().ccx_stem_ln_u8(images_u8.data_ptr(), self._norm_consts[0].data_ptr(),
+                                             self._norm_consts[1].data_ptr(), w.stem_w, w.stem_b, w.stem_ln_g,
+                                             w.stem_ln_b, out.data_ptr(), B, H, W, 1e-6, _lib.stream_ptr()),
+                   "stem_ln_u8")
+        return out
 
     def _pool(self, feat):
         B, h, w, Cc = feat.shape

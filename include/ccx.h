@@ -95,6 +95,13 @@ CCX_API int ccx_cast_bf16(const float* x, void* y_bf16, int64_t n, void* stream)
 CCX_API int ccx_stem_ln(const float* images, const float* w_k, const float* bias, const float* ln_g, const float* ln_b,
                 float* out, int32_t B, int32_t Hin, int32_t Win, float eps, void* stream);
 
+/* Same with the input pipeline fused in: images are the dataset's raw uint8 NCHW pixels
+ * (utils/utils.py:107,134 stores uint8 (N,3,256,256)) and (x/255 - mean[c]) * inv_std[c] — dataLoader.py:43-45 —
+ * is applied while the patch is staged, so the host->device copy is 4x smaller and no normalised fp32 image exists. */
+CCX_API int ccx_stem_ln_u8(const uint8_t* images_u8, const float* mean3, const float* inv_std3, const float* w_k,
+                           const float* bias, const float* ln_g, const float* ln_b, float* out, int32_t B,
+                           int32_t Hin, int32_t Win, float eps, void* stream);
+
 /* Depthwise Conv2d(C,C,7,padding=3,groups=C)+bias -> LayerNorm(C): torchvision/models/convnext.py:52-54.
  * x NHWC fp32; w_tap_major [49][C]; out [B*H*W, C] as bf16 (out_lo NULL) or tf32 (hi, lo) fp32 pair, or plain
  * fp32 when out_dtype == CCX_F32 and out_lo == NULL.  C must be a multiple of 128, at most 1024. */

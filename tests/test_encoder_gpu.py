@@ -105,3 +105,18 @@ def test_encoder_batch_and_determinism():
         c = e(x[1:3])
     assert torch.equal(a, b)                      # bit-reproducible run to run
     assert torch.equal(a[1:3], c)                 # per-sample independence (no cross-batch leakage)
+
+
+def test_encoder_uint8_input_fuses_dataset_normalisation():
+    """raw uint8 pixels in, /255 + Normalize(mean, std) (dataLoader.py:43-45) inside the stem."""
+    from oracle import encoder_oracle as eo
+    e, sd = _enc(0, torch.float32)
+    u8 = torch.randint(0, 256, (2, 3, 64, 96), generator=torch.Generator().manual_seed(9), dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = (torch.from_numpy(u8.numpy() / 255.).float() - mean) / std
+    ref = eo.encoder_forward(sd, x, 7)
+    with torch.no_grad():
+        y = e(u8.cuda())
+        y2 = e(x.cuda())
+    assert rel_err(y, ref) < FP32_TOL and rel_err(y, y2) < 1e-4
