@@ -91,7 +91,7 @@ SIGNATURES = {
     "ccx_convert_operand": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i32, _i64, _i32, _i32,
                                       _i32, _i32, _vp]),
     "ccx_colsum_acc": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i32, _i32, _vp]),
-    "ccx_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "ccx_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "ccx_mha_bwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
                               _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
                               _f32, _vp]),

@@ -176,8 +176,9 @@ int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, i
   return colsum_acc(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, as_stream(stream));
 }
 int ccx_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
-               int64_t M, int32_t C, float eps, void* stream) {
-  return ln_bwd(dy, x, gamma, dx, dgamma, dbeta, M, C, eps, as_stream(stream));
+               int64_t M, int32_t C, float eps, int32_t merge, int32_t H, int32_t W, void* stream) {
+  if (merge && ((H & 1) || (W & 1) || H <= 0 || W <= 0)) return CCX_ERR_SHAPE;
+  return ln_bwd(dy, x, gamma, dx, dgamma, dbeta, M, C, eps, as_stream(stream), merge, H, W);
 }
 int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
                 const float* v, int64_t v_sb, int64_t v_st, const float* dctx, int64_t d_sb, int64_t d_st,

@@ -58,7 +58,7 @@ int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long 
 int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
                float* out, int R, int C, cudaStream_t stream);
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
-           long long M, int C, float eps, cudaStream_t stream);
+           long long M, int C, float eps, cudaStream_t stream, int merge = 0, int H = 1, int W = 1);
 int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
             const float* v, long long v_sb, long long v_st, const float* dctx, long long d_sb, long long d_st,
             const float* probs, const float* prob_mask, float* dq, long long dq_sb, long long dq_st, float* dk,

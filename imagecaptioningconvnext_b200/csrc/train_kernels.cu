@@ -146,19 +146,27 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C,
-              float eps) {
+              float eps, int merge, int H, int W) {
   __shared__ float s_dg[VPL * 128], s_db[VPL * 128];
   for (int i = threadIdx.x; i < VPL * 128; i += 256) { s_dg[i] = 0.f; s_db[i] = 0.f; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (m < M) {
+    // dy addressing: plain rows, or the 2x2 patch-merged layout written by ln_rows_kernel(merge=1)
+    const float* dyr = dy + m * C;
+    if (merge) {
+      const int w = static_cast<int>(m % W);
+      const int h = static_cast<int>((m / W) % H);
+      const long long b = m / (static_cast<long long>(W) * H);
+      dyr = dy + ((b * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * (4LL * C) + ((h & 1) * 2 + (w & 1)) * C;
+    }
     float4 xv[VPL], gv[VPL], dv[VPL];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       xv[i] = __ldg(reinterpret_cast<const float4*>(x + m * C) + i * 32 + lane);
-      dv[i] = __ldg(reinterpret_cast<const float4*>(dy + m * C) + i * 32 + lane);
+      dv[i] = __ldg(reinterpret_cast<const float4*>(dyr) + i * 32 + lane);
       gv[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
       s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
     }
@@ -204,14 +212,14 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
 }
 
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
-           long long M, int C, float eps, cudaStream_t stream) {
+           long long M, int C, float eps, cudaStream_t stream, int merge, int H, int W) {
   if (M <= 0) return CCX_OK;
   if (C % 128 != 0 || C > 1024) return CCX_ERR_SHAPE;
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
   ProfScope prof(PROF_LN_ROWS, stream, (double)M * C * 12.0);
 #define CCX_LNB_CASE(V)                                                                              \
   case V:                                                                                            \
-    ln_bwd_kernel<V><<<grid, 256, 0, stream>>>(dy, x, gamma, dx, dgamma, dbeta, M, C, eps);          \
+    ln_bwd_kernel<V><<<grid, 256, 0, stream>>>(dy, x, gamma, dx, dgamma, dbeta, M, C, eps, merge, H, W); \
     break;
   switch (C / 128) {
     CCX_LNB_CASE(1) CCX_LNB_CASE(2) CCX_LNB_CASE(3) CCX_LNB_CASE(4) CCX_LNB_CASE(5) CCX_LNB_CASE(6)

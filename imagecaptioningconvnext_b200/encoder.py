@@ -181,6 +181,7 @@ class Encoder(nn.Module):
             return op.hi.data_ptr(), (op.lo.data_ptr() if op.lo is not None else None)
 
         self._block_ops = []   # per CNBlock: dict(dw_w, w1, w2) python-side handles (used by encoder_train.py)
+        self._down_ops = {}    # downsample child index (2, 4, 6) -> Operand of the re-ordered conv weight
 
         w = _lib.EncoderWeights()
         ch = list(self.convnext.children())
@@ -210,6 +211,7 @@ class Encoder(nn.Module):
                 dwn.ln_g, dwn.ln_b = f32(d[0].weight), f32(d[0].bias)
                 wm = d[1].weight.detach().permute(0, 2, 3, 1).reshape(Cc, 4 * DIMS[s - 1])
                 dwn.w, dwn.w_lo = operand(wm)
+                self._down_ops[2 * s] = ops[-1]
                 dwn.b = f32(d[1].bias)
         for s in range(4):
             w.depths[s], w.dims[s] = DEPTHS[s], DIMS[s]

@@ -1,18 +1,19 @@
-"""Encoder forward WITH autograd for ``Encoder.fine_tune(True, startingLayer=7)`` — the reference's default
-fine-tuning extent (trainMultiGPU.py:68: children()[7:] = the three C=1024 CNBlocks at 8x8; models/encoder.py:29-34).
+"""Encoder forward WITH autograd for ``Encoder.fine_tune(True, startingLayer)`` (models/encoder.py:29-34), for any
+``startingLayer`` in 1..7 (trainMultiGPU.py:68 defaults to 7, train.py:63 to 5; 0 = stem is not built and raises).
 
-Children [0, 7) run frozen through ``ccx_encoder_run``; the trainable blocks run op by op so their inputs can be
-kept, and the backward is explicit (libccx launches only):
-  layer_scale / stochastic-depth / residual -> second Linear (dgrad + un-scaled wgrad, layer_scale gradient derived
-  from it without recomputing the branch) -> GELU' (pre-activation recomputed by one GEMM) -> first Linear ->
-  LayerNorm backward (its input recomputed by the conv kernel in plain mode) -> depthwise conv data gradient (same
-  TMA/cluster kernel with flipped taps) and filter gradient.
-Fine-tuning from an earlier child (downsample / stem backward) is not built yet and raises.
+Children [0, startingLayer) run frozen through ``ccx_encoder_run``; the trainable children run op by op so their
+inputs can be kept, and the backward is explicit (libccx launches only):
+  CNBlock:   layer_scale / stochastic-depth / residual -> second Linear (dgrad + un-scaled wgrad; the layer_scale
+             gradient is derived from it without recomputing the branch) -> GELU' (pre-activation recomputed by one
+             GEMM) -> first Linear -> LayerNorm backward (its input recomputed by the conv kernel in plain mode) ->
+             depthwise-conv data gradient (the same TMA/cluster kernel with flipped taps) and filter gradient;
+  downsample: patch-merge GEMM dgrad/wgrad -> LayerNorm2d backward reading dy in the merged layout.
 """
 import torch
 
 from . import _lib
 from ._lib import Operand, ptr
+from .encoder import DIMS
 from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t
 
 
@@ -23,39 +24,55 @@ def _first_trainable_child(enc):
     return 8
 
 
+def _block_index0(enc, child):
+    """Global index (stage-major) of the first CNBlock of stage child `child` (1, 3, 5 or 7)."""
+    return sum(len(enc.convnext[i]) for i in (1, 3, 5, 7) if i < child)
+
+
 class _EncoderTail(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc, x7, noise, *params):
+    def forward(ctx, enc, x_in, first, noise, *params):
         L, st = _lib.lib(), _lib.stream_ptr()
         cd = enc.compute_dtype
         code = _lib.dt_code(cd)
         enc.prepared()
-        B, H, W, C = x7.shape
-        M = B * H * W
-        blocks = list(enc.convnext[7])
-        nb0 = sum(len(enc.convnext[i]) for i in (1, 3, 5))       # index of the first stage-4 block
-        saved = []
-        x = x7
-        for i, blk in enumerate(blocks):
-            ops = enc._block_ops[nb0 + i]
-            y_op = Operand.empty((M, C), cd, x.device)
-            _lib.check(L.ccx_dwconv7_ln(ptr(x), ptr(ops["dw_w"]), ptr(blk.block[0].bias.detach()),
-                                        ptr(blk.block[2].weight.detach()), ptr(blk.block[2].bias.detach()),
-                                        ptr(y_op.hi), y_op.lo_ptr, B, H, W, C, 1e-6, code, st), "dwconv7_ln")
-            if cd == torch.bfloat16:
-                h_op = Operand(_lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach(), act=_lib.ACT_GELU,
-                                           out_dtype=torch.bfloat16), None, torch.bfloat16)
-            else:
-                h_op = _lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach(), act=_lib.ACT_GELU, split=True)
-            rs = None if noise is None else noise[nb0 + i]
-            x_out = _lib.linear(h_op, ops["w2"], bias=blk.block[5].bias.detach(),
-                                colscale=blk.layer_scale.detach().view(C), rowscale=rs, rows_per_group=H * W,
-                                residual=x.view(M, C)).view(B, H, W, C)
-            saved.append((x, y_op, h_op, rs))
-            x = x_out
+        saved = []          # one entry per op, in execution order
+        x = x_in
+        for child in range(first, 8):
+            B, H, W, C = x.shape
+            M = B * H * W
+            if child % 2 == 0:
+                # downsample: LayerNorm2d + 2x2/s2 conv as patch-merge GEMM (convnext.py:146-151)
+                mod = enc.convnext[child]
+                y_op = Operand.empty((M // 4, 4 * C), cd, x.device)
+                _lib.check(L.ccx_ln_rows(ptr(x), ptr(mod[0].weight.detach()), ptr(mod[0].bias.detach()), ptr(y_op.hi),
+                                         y_op.lo_ptr, None, M, C, 1e-6, code, 1, H, W, st), "ln_rows")
+                Cout = DIMS[child // 2]
+                x_out = _lib.linear(y_op, enc._down_ops[child], bias=mod[1].bias.detach()).view(B, H // 2, W // 2, Cout)
+                saved.append(("down", child, x, y_op))
+                x = x_out
+                continue
+            nb0 = _block_index0(enc, child)
+            for i, blk in enumerate(enc.convnext[child]):
+                ops = enc._block_ops[nb0 + i]
+                y_op = Operand.empty((M, C), cd, x.device)
+                _lib.check(L.ccx_dwconv7_ln(ptr(x), ptr(ops["dw_w"]), ptr(blk.block[0].bias.detach()),
+                                            ptr(blk.block[2].weight.detach()), ptr(blk.block[2].bias.detach()),
+                                            ptr(y_op.hi), y_op.lo_ptr, B, H, W, C, 1e-6, code, st), "dwconv7_ln")
+                if cd == torch.bfloat16:
+                    h_op = Operand(_lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach(), act=_lib.ACT_GELU,
+                                               out_dtype=torch.bfloat16), None, torch.bfloat16)
+                else:
+                    h_op = _lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach(), act=_lib.ACT_GELU, split=True)
+                rs = None if noise is None else noise[nb0 + i]
+                x_out = _lib.linear(h_op, ops["w2"], bias=blk.block[5].bias.detach(),
+                                    colscale=blk.layer_scale.detach().view(C), rowscale=rs, rows_per_group=H * W,
+                                    residual=x.view(M, C)).view(B, H, W, C)
+                saved.append(("block", (child, i, nb0 + i), x, y_op, h_op, rs))
+                x = x_out
         out = enc._pool(x)
-        ctx.enc, ctx.saved, ctx.dims, ctx.nb0 = enc, saved, (B, H, W, C), nb0
-        ctx.x7_needs_grad = x7.requires_grad
+        ctx.enc, ctx.saved, ctx.first, ctx.feat_shape = enc, saved, first, x.shape
+        ctx.x_needs_grad = x_in.requires_grad
         return out
 
     @staticmethod
@@ -63,23 +80,36 @@ class _EncoderTail(torch.autograd.Function):
         enc = ctx.enc
         L, st = _lib.lib(), _lib.stream_ptr()
         cd = enc.compute_dtype
-        B, H, W, C = ctx.dims
-        M, K4 = B * H * W, 4 * C
         dev = dpooled.device
         f32 = dict(dtype=torch.float32, device=dev)
-        blocks = list(enc.convnext[7])
-        names = [n for n, _ in enc.convnext[7].named_parameters()]
-        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in enc.convnext[7].named_parameters()}
-        dout = torch.empty((M, C), **f32)
+        tail = [(f"{c}.{n}", p) for c in range(ctx.first, 8) for n, p in enc.convnext[c].named_parameters()]
+        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in tail}
+        B, H, W, C = ctx.feat_shape
+        dout = torch.empty((B * H * W, C), **f32)
         _lib.check(L.ccx_avgpool_nhwc_bwd(ptr(dpooled.contiguous()), ptr(dout), B, H, W, C, enc.enc_image_size, st),
                    "avgpool_bwd")
-        for i in reversed(range(len(blocks))):
-            blk = blocks[i]
-            x_in, y_op, h_op, rs = ctx.saved[i]
-            ops = enc._block_ops[ctx.nb0 + i]
+        for entry in reversed(ctx.saved):
+            if entry[0] == "down":
+                _, child, x_in, y_op = entry
+                B, H, W, C = x_in.shape
+                M = B * H * W
+                mod = enc.convnext[child]
+                Cout = mod[1].weight.shape[0]
+                gw = torch.zeros((Cout, 4 * C), **f32)
+                w_perm = mod[1].weight.detach().permute(0, 2, 3, 1).reshape(Cout, 4 * C)       # (Cout, kh, kw, Cin)
+                dmerged = linear_bwd(dout, y_op, weight_t(w_perm, cd), cd, gw, grads[f"{child}.1.bias"])
+                grads[f"{child}.1.weight"] = gw.view(Cout, 2, 2, C).permute(0, 3, 1, 2).contiguous()
+                dout = ln_bwd(dmerged, x_in.view(M, C), mod[0].weight.detach(), grads[f"{child}.0.weight"],
+                              grads[f"{child}.0.bias"], 1e-6, merge_hw=(H, W))
+                continue
+            _, (child, i, gi), x_in, y_op, h_op, rs = entry
+            B, H, W, C = x_in.shape
+            M, K4 = B * H * W, 4 * C
+            blk = enc.convnext[child][i]
+            ops = enc._block_ops[gi]
             gamma = blk.layer_scale.detach().view(C)
             W1, W2 = blk.block[3].weight.detach(), blk.block[5].weight.detach()
-            pre_n = f"{i}."
+            pre_n = f"{child}.{i}."
             # layer_scale * stochastic depth
             dz = torch.empty((M, C), **f32)
             _lib.check(L.ccx_scale_rows_cols(ptr(dout), ptr(gamma), ptr(rs), H * W, ptr(dz), M, C, st), "scale")
@@ -102,6 +132,7 @@ class _EncoderTail(torch.autograd.Function):
             _lib.check(L.ccx_gelu_bwd(ptr(pre), ptr(dh), M * K4, st), "gelu_bwd")
             dy = linear_bwd(dh, y_op, weight_t(W1, cd), cd, grads[pre_n + "block.3.weight"],
                             grads[pre_n + "block.3.bias"])
+            del pre, dh
             # LayerNorm backward on the recomputed conv output
             u = torch.empty((M, C), **f32)
             _lib.check(L.ccx_dwconv7_plain(ptr(x_in), ptr(ops["dw_w"]), ptr(blk.block[0].bias.detach()), None, ptr(u),
@@ -118,19 +149,20 @@ class _EncoderTail(torch.autograd.Function):
             _lib.check(L.ccx_dwconv7_plain(ptr(du), ptr(w_flip), None, ptr(dout), ptr(dprev), B, H, W, C, st),
                        "dwconv7_dgrad")
             dout = dprev
-        dx7 = dout.view(B, H, W, C) if ctx.x7_needs_grad else None
-        return (None, dx7, None) + tuple(grads[n] for n in names)
+        dx = None
+        if ctx.x_needs_grad:
+            dx = dout.view(ctx.saved[0][2].shape)
+        return (None, dx, None, None) + tuple(grads[n] for n, _ in tail)
 
 
 def encoder_features_with_grad(enc, images, noise):
     """Returns the POOLED features (B,s,s,C); Encoder.forward must not pool again."""
     first = _first_trainable_child(enc)
-    if first < 7:
-        raise NotImplementedError(
-            f"fine-tuning from child {first} needs the downsample/stem backward kernels, which are not built yet; "
-            "the reference's default (trainMultiGPU.py --startingLayer 7) is supported")
+    if first < 1:
+        raise NotImplementedError("fine-tuning the stem (startingLayer=0) is not built: its backward kernel is missing; "
+                                  "startingLayer 1..7 are supported (reference defaults: 7 and 5)")
     B, _, H, W = images.shape
     with torch.no_grad():
-        x7 = enc.run_children(images, 0, 7, noise)
-    params = [p for _, p in enc.convnext[7].named_parameters()]
-    return _EncoderTail.apply(enc, x7, noise, *params)
+        x = enc.run_children(images, 0, first, noise)
+    params = [p for c in range(first, 8) for _, p in enc.convnext[c].named_parameters()]
+    return _EncoderTail.apply(enc, x, first, noise, *params)

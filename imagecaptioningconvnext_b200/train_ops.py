@@ -74,11 +74,13 @@ def linear_bwd(dy, x, wt, cd, w_grad=None, b_grad=None, need_dx=True, dx_residua
     return dx
 
 
-def ln_bwd(dy, x_in, gamma, dgamma, dbeta, eps):
+def ln_bwd(dy, x_in, gamma, dgamma, dbeta, eps, merge_hw=None):
+    """merge_hw=(H, W): dy is in the 2x2 patch-merged layout of the downsample LayerNorm (see ccx_ln_bwd)."""
     M, C = x_in.shape
     dx = torch.empty_like(x_in)
+    mg, H, W = (0, 1, 1) if merge_hw is None else (1, merge_hw[0], merge_hw[1])
     _lib.check(_lib.lib().ccx_ln_bwd(ptr(dy), ptr(x_in), ptr(gamma), ptr(dx), ptr(dgamma), ptr(dbeta), M, C, eps,
-                                     _lib.stream_ptr()), "ln_bwd")
+                                     mg, H, W, _lib.stream_ptr()), "ln_bwd")
     return dx
 
 

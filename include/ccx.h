@@ -270,9 +270,10 @@ CCX_API int ccx_convert_operand(const void* x_hi, const float* x_lo, int32_t x_d
 /* out[c] += sum_r x[r,c] (* multiplier as above): bias gradients. */
 CCX_API int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode,
                            float mul_scale, float* out, int32_t R, int32_t C, void* stream);
-/* LayerNorm backward over rows of x[M,C]; dgamma/dbeta are accumulated (+=). */
+/* LayerNorm backward over rows of x[M,C]; dgamma/dbeta are accumulated (+=).  merge != 0: dy is read in the 2x2
+ * patch-merged [M/4, 4C] layout that ccx_ln_rows(merge=1) wrote (downsample LayerNorm2d, convnext.py:146-151). */
 CCX_API int ccx_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
-                       int64_t M, int32_t C, float eps, void* stream);
+                       int64_t M, int32_t C, float eps, int32_t merge, int32_t H, int32_t W, void* stream);
 /* Backward of ccx_mha_small (same strided addressing; probs = its probs_out). */
 CCX_API int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
                         const float* v, int64_t v_sb, int64_t v_st, const float* dctx, int64_t d_sb, int64_t d_st,

@@ -156,10 +156,13 @@ def test_clamp_adam_matches_clip_gradient_plus_torch_adam():
     assert set(our_opt.state_dict()["state"][0]) == set(ref_opt.state_dict()["state"][0])
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("train_mode", [False, True])
-def test_encoder_stage4_fine_tune_gradients(dtype, train_mode):
-    """Encoder.fine_tune(True, startingLayer=7): gradients of the three C=1024 CNBlocks vs torch autograd."""
+@pytest.mark.parametrize("dtype,train_mode,start", [(torch.float32, False, 7), (torch.float32, True, 7),
+                                                    (torch.bfloat16, False, 7), (torch.bfloat16, True, 7),
+                                                    (torch.float32, True, 5), (torch.float32, False, 2),
+                                                    (torch.bfloat16, True, 5)])
+def test_encoder_fine_tune_gradients(dtype, train_mode, start):
+    """Encoder.fine_tune(True, startingLayer): gradients of children[startingLayer:] vs torch autograd
+    (trainMultiGPU.py default 7 = three C=1024 CNBlocks; train.py default 5 adds stage 3 and a downsample)."""
     import torch.nn.functional as F
     from imagecaptioningconvnext_b200 import Encoder
     from imagecaptioningconvnext_b200.encoder import stochastic_depth_probs
@@ -167,7 +170,7 @@ def test_encoder_stage4_fine_tune_gradients(dtype, train_mode):
     sd = eo.random_encoder_state(seed=2, layer_scale=1.0)
     g = torch.Generator().manual_seed(4)
     for k in sd:                                     # non-trivial LN / bias / layer_scale values in the trainable stage
-        if k.startswith("convnext.7.") and sd[k].dim() <= 3 and "block.0.weight" not in k:
+        if int(k.split(".")[1]) >= start and sd[k].dim() <= 3 and "block.0.weight" not in k:
             sd[k] = sd[k] + 0.2 * torch.randn(sd[k].shape, generator=g)
     B = 3
     x = torch.randn(B, 3, 64, 64, generator=g)
@@ -183,7 +186,7 @@ def test_encoder_stage4_fine_tune_gradients(dtype, train_mode):
             for i in range(nblk):
                 nz[(child, i)] = noise[bi]
                 bi += 1
-    leaf = {k: v.clone().requires_grad_(k.startswith("convnext.7.")) for k, v in sd.items()}
+    leaf = {k: v.clone().requires_grad_(int(k.split(".")[1]) >= start) for k, v in sd.items()}
     ref_out = eo.encoder_forward(leaf, x, 7, noise=nz)
     (ref_out * wgt).sum().backward()
     ref_grads = {k[len("convnext."):]: v.grad for k, v in leaf.items() if v.requires_grad}
@@ -191,7 +194,7 @@ def test_encoder_stage4_fine_tune_gradients(dtype, train_mode):
     e.load_state_dict(sd)
     e = e.cuda()
     e.train(train_mode)
-    e.fine_tune(True, 7)
+    e.fine_tune(True, start)
     e.sd_noise = noise
     out = e(x.cuda())
     assert out.requires_grad
