@@ -16,6 +16,7 @@
 //     owns ONE channel, keeps its 49 filter taps in registers and 32 fp32 accumulators, so each halo value is
 //     read from shared memory exactly once per thread (140 conflict-free LDS.32 for 1568 FFMA).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "ccx_common.cuh"
 #include "ccx_gemm.h"
@@ -215,6 +216,175 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   // no trailing cluster barrier: every remote store into a CTA's clpart happened before the barrier above
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v2: packed fp32x2 math.  Same tile / TMA / cluster scheme, but a CTA is 4 warps and every lane owns TWO adjacent
+// channels: halo values are read with LDS.64 and accumulated with Blackwell's FFMA2 (fma.rn.f32x2), which halves
+// the issue slots per MAC — v1 is issue-bound (~1.7 instructions per FFMA), not FMA-pipe or HBM bound.
+//   warp = (p, g): p = pixel half (4x8 output patch), g = 64-channel group; 32 float2 accumulators, 49 float2 taps.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int DW2_THREADS = 128;
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return d;
+}
+
+__global__ void __launch_bounds__(DW2_THREADS, 2)
+dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
+  extern __shared__ __align__(1024) float dw_smem[];
+  float* tile = dw_smem;                                             // [14][14][128]
+  float* part = dw_smem + DW_TILE_BYTES / 4;                         // [2 stat][2 p][2 g][32 px] = 256 f
+  float* clpart = part + 512;                                        // [8 rank][2 stat][64 px]
+  __shared__ uint64_t bar;
+  __shared__ float s_mean[64], s_rstd[64];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nc = a.C / DW_CH;
+  const int crank = blockIdx.x;
+  const int b = blockIdx.z;
+  const int th = blockIdx.y / a.tiles_w, tw = blockIdx.y - th * a.tiles_w;
+  const int h0 = th * DW_TILE, w0 = tw * DW_TILE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = warp >> 1;   // pixel half
+  const int g = warp & 1;    // 64-channel group
+  const int ch_local = g * 64 + lane * 2;
+  const int ch = crank * DW_CH + ch_local;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, DW_TILE_BYTES);
+    tma_load_4d(tile, &tmX, &bar, crank * DW_CH, w0 - 3, h0 - 3, b);
+  }
+  float2 wt[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wt[t] = __ldg(reinterpret_cast<const float2*>(a.w + t * a.C + ch));
+  const bool plain = (a.gamma == nullptr);
+  const float2 bias = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + ch)) : make_float2(0.f, 0.f);
+  const float2 gam = plain ? make_float2(1.f, 1.f) : __ldg(reinterpret_cast<const float2*>(a.gamma + ch));
+  const float2 bet = plain ? make_float2(0.f, 0.f) : __ldg(reinterpret_cast<const float2*>(a.beta + ch));
+  float2 acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = bias;
+
+  mbar_wait(&bar, 0);
+  const float* tp = tile + (p * 4) * DW_HALO * DW_CH + ch_local;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#pragma unroll
+    for (int c = 0; c < DW_HALO; ++c) {
+      const float2 v = *reinterpret_cast<const float2*>(tp + (r * DW_HALO + c) * DW_CH);
+#pragma unroll
+      for (int oh = 0; oh < 4; ++oh) {
+        const int kr = r - oh;
+        if (kr < 0 || kr > 6) continue;
+#pragma unroll
+        for (int ow = 0; ow < 8; ++ow) {
+          const int kc = c - ow;
+          if (kc < 0 || kc > 6) continue;
+          acc[oh * 8 + ow] = ffma2(v, wt[kr * 7 + kc], acc[oh * 8 + ow]);
+        }
+      }
+    }
+  }
+  if (!plain) {
+    float s1[32], s2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      s1[i] = acc[i].x + acc[i].y;
+      s2[i] = fmaf(acc[i].x, acc[i].x, acc[i].y * acc[i].y);
+    }
+    warp_transpose_reduce32(s1, lane);
+    warp_transpose_reduce32(s2, lane);
+    part[((0 * 2 + p) * 2 + g) * 32 + lane] = s1[0];
+    part[((1 * 2 + p) * 2 + g) * 32 + lane] = s2[0];
+  }
+  if (plain) {
+    if (threadIdx.x < 64) { s_mean[threadIdx.x] = 0.f; s_rstd[threadIdx.x] = 1.f; }
+    __syncthreads();
+  } else {
+    __syncthreads();
+    {
+      // thread -> (stat, p, px): sum the 2 channel-group partials, publish to every CTA of the cluster
+      const int stat = threadIdx.x >> 6, pp = (threadIdx.x >> 5) & 1, px = threadIdx.x & 31;
+      const float* src = part + ((stat * 2 + pp) * 2) * 32 + px;
+      const float tot = src[0] + src[32];
+      for (int r = 0; r < nc; ++r) {
+        float* dst = cluster.map_shared_rank(clpart, r);
+        dst[(crank * 2 + stat) * 64 + pp * 32 + px] = tot;
+      }
+    }
+    cluster.sync();
+    if (threadIdx.x < 64) {
+      float s = 0.f, q = 0.f;
+      for (int r = 0; r < nc; ++r) {
+        s += clpart[(r * 2 + 0) * 64 + threadIdx.x];
+        q += clpart[(r * 2 + 1) * 64 + threadIdx.x];
+      }
+      const float inv = 1.0f / static_cast<float>(a.C);
+      const float mean = s * inv;
+      const float var = fmaxf(q * inv - mean * mean, 0.0f);
+      s_mean[threadIdx.x] = mean;
+      s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+  }
+  const long long base = ((static_cast<long long>(b) * a.H + h0 + p * 4) * a.W + w0) * a.C + ch;
+  const int row_stride = a.W * a.C;
+  const bool interior = (h0 + DW_TILE <= a.H) && (w0 + DW_TILE <= a.W);
+  if (interior && a.out_dtype == CCX_BF16 && !plain) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + base;
+#pragma unroll
+    for (int oh = 0; oh < 4; ++oh) {
+#pragma unroll
+      for (int ow = 0; ow < 8; ++ow) {
+        const int px = p * 32 + oh * 8 + ow;
+        const float m = s_mean[px], rs = s_rstd[px];
+        const float y0 = (acc[oh * 8 + ow].x - m) * rs * gam.x + bet.x;
+        const float y1 = (acc[oh * 8 + ow].y - m) * rs * gam.y + bet.y;
+        *reinterpret_cast<uint32_t*>(o + oh * row_stride + ow * a.C) = pack_bf16x2(y0, y1);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int oh = 0; oh < 4; ++oh) {
+    const int h = h0 + p * 4 + oh;
+#pragma unroll
+    for (int ow = 0; ow < 8; ++ow) {
+      const int w = w0 + ow;
+      const int px = p * 32 + oh * 8 + ow;
+      const float m = s_mean[px], rs = s_rstd[px];
+      float y0 = (acc[oh * 8 + ow].x - m) * rs * gam.x + bet.x;
+      float y1 = (acc[oh * 8 + ow].y - m) * rs * gam.y + bet.y;
+      if (h < a.H && w < a.W) {
+        const long long idx = base + oh * row_stride + ow * a.C;
+        if (plain && a.addend != nullptr) {
+          const float2 ad = *reinterpret_cast<const float2*>(a.addend + idx);
+          y0 += ad.x; y1 += ad.y;
+        }
+        if (a.out_dtype == CCX_BF16) {
+          *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.out) + idx) = pack_bf16x2(y0, y1);
+        } else if (a.out_lo != nullptr) {
+          const float h0v = tf32_hi(y0), h1v = tf32_hi(y1);
+          *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out) + idx) = make_float2(h0v, h1v);
+          *reinterpret_cast<float2*>(a.out_lo + idx) = make_float2(y0 - h0v, y1 - h1v);
+        } else {
+          *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out) + idx) = make_float2(y0, y1);
+        }
+      }
+    }
+  }
+}
+
 int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float* gamma, const float* beta,
                void* out, float* out_lo, int B, int H, int W, int C, float eps, int out_dtype,
                cudaStream_t stream, const float* addend) {
@@ -239,10 +409,13 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
-        cudaSuccess)
+            cudaSuccess ||
+        cudaFuncSetAttribute(dwconv7_ln_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
+            cudaSuccess)
       return CCX_ERR_CUDA;
     configured = true;
   }
+  static const bool use_v1 = (getenv("CCX_DWCONV_V1") != nullptr);   // A/B switch for profiling
   DwArgs a;
   a.w = w49c; a.bias = bias; a.gamma = gamma; a.beta = beta;
   a.out = out; a.out_lo = out_lo; a.addend = addend;
@@ -255,7 +428,7 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   const int nc = C / DW_CH;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nc, a.tiles_w * a.tiles_h, B);
-  cfg.blockDim = dim3(DW_THREADS, 1, 1);
+  cfg.blockDim = dim3(use_v1 ? DW_THREADS : DW2_THREADS, 1, 1);
   cfg.dynamicSmemBytes = DW_SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -267,7 +440,11 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   cfg.numAttrs = 1;
   const double bytes = (double)B * H * W * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0)));
   ProfScope prof(PROF_DWCONV_LN, stream, bytes);
-  if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+  if (use_v1) {
+    if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+  } else {
+    if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel_v2, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+  }
   return CCX_OK;
 }
 
