@@ -86,7 +86,15 @@ class Encoder(nn.Module):
         self._prep = None      # (EncoderWeights struct, list of tensors kept alive)
         self._ws = None
         self.sd_noise = None   # tests may inject a (36, B) tensor of stochastic-depth row factors
+        self._graphs = None    # {input shape/dtype: (CUDAGraph, static_in, static_out, weights key)} when enabled
         self.fine_tune()
+
+    def enable_cuda_graph(self, enabled=True):
+        """Inference-only option: capture the whole forward (117 launches, TMA descriptors included) into one CUDA
+        graph per input shape and replay it, so a slow or busy host cannot starve the GPU.  Eval mode / no-grad calls
+        only; train-mode or grad-enabled calls keep the eager path.  Results are bit-identical to the eager path."""
+        self._graphs = {} if enabled else None
+        return self
 
     # ---- reference API -------------------------------------------------------------------------------------
     def fine_tune(self, fine_tune=True, startingLayer=7):
@@ -109,6 +117,8 @@ class Encoder(nn.Module):
         images = images.contiguous()
         needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.convnext.parameters())
         noise = self._stochastic_depth_noise(B, images.device)
+        if self._graphs is not None and not needs_grad and noise is None:
+            return self._forward_graphed(images)
         if images.dtype == torch.uint8:
             # raw dataset pixels: /255 and Normalize(mean, std) (dataLoader.py:43-45) are fused into the stem kernel
             if needs_grad:
@@ -130,6 +140,35 @@ class Encoder(nn.Module):
         p = torch.tensor(stochastic_depth_probs(), device=device, dtype=torch.float32).view(-1, 1)
         keep = 1.0 - p
         return (torch.bernoulli(keep.expand(-1, B)) / keep).contiguous()
+
+    def _forward_eager_nograd(self, images):
+        B, _, H, W = images.shape
+        if images.dtype == torch.uint8:
+            return self._pool(self.run_children(self._stem_u8(images), 1, 8, None, image_hw=(H, W)))
+        return self._pool(self.run_children(images, 0, 8, None))
+
+    @torch.no_grad()
+    def _forward_graphed(self, images):
+        self.prepared()
+        key = (tuple(images.shape), images.dtype, images.device)
+        entry = self._graphs.get(key)
+        if entry is None or entry[3] != self._prep_key:
+            static_in = images.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._forward_eager_nograd(static_in)          # warm-up: kernel attributes, workspace, weight prep
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._forward_eager_nograd(static_in)
+            entry = (g, static_in, static_out, self._prep_key)
+            self._graphs[key] = entry
+        g, static_in, static_out, _ = entry
+        static_in.copy_(images)
+        g.replay()
+        return static_out.clone()
 
     def _stem_u8(self, images_u8):
         B, _, H, W = images_u8.shape

@@ -120,3 +120,17 @@ def test_encoder_uint8_input_fuses_dataset_normalisation():
         y = e(u8.cuda())
         y2 = e(x.cuda())
     assert rel_err(y, ref) < FP32_TOL and rel_err(y, y2) < 1e-4
+
+
+def test_encoder_cuda_graph_replay_is_bit_identical():
+    e, _ = _enc(0, torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(3, 3, 64, 64, generator=g).cuda() for _ in range(3)]
+    with torch.no_grad():
+        eager = [e(x) for x in xs]
+        e.enable_cuda_graph()
+        graphed = [e(x) for x in xs]            # first call captures, the others replay
+        other = e(torch.randn(2, 3, 96, 64, generator=g).cuda())      # a second shape gets its own graph
+    for a, b in zip(eager, graphed):
+        assert torch.equal(a, b)
+    assert other.shape == (2, 7, 7, 1024) and len(e._graphs) == 2
