@@ -156,22 +156,31 @@ def beam_search_transformer(decoder, encoder_out, wordMap, beamSize=3, max_decod
     rows = NI * k
     Pw = decoder._cache.get()
     state = decoder.new_decode_state(Pw, encoder_out, rows, max_decode_len, kv_group=k)
-    spare = [torch.empty_like(c) for c in state["cache"]]
+    # beams are re-ordered by rewriting a (rows x positions) map of physical cache rows, not by copying the caches:
+    # logical row r reads position j from cache row kv_rows[r, j]; its new token's K/V go to cache row r.
+    Tm = max_decode_len
+    Tpad = (Tm + 3) // 4 * 4
+    ident = torch.arange(rows, dtype=torch.int32, device=dev)
+    maps = [ident.view(-1, 1).expand(rows, Tpad).contiguous() for _ in range(2)]
+    state["kv_rows"] = maps[0]
     tokens = state["tokens"]
     tokens[:, 0] = wordMap['<start>']
     bs = _BeamState(NI, k, max_decode_len + 1, wordMap['<start>'], dev)
     logits = torch.empty((rows, V), dtype=torch.float32, device=dev)
     L, st = _lib.lib(), _lib.stream_ptr()
+    cur = 0
     for t in range(max_decode_len):                       # caption.py:249: `if step + 1 >= max_decode_len: break`
         x_op = decoder.decode_step_cached(Pw, state, t, rows)
         _lib.linear(x_op, Pw["fc"], bias=Pw["fc_b"], out=logits)
         bs.advance(logits, V, t + 1, wordMap['<end>'], tokens.data_ptr() + 8 * (t + 1), tokens.stride(0), trace)
-        # re-order the self-attention caches (positions 0..t) along the surviving beams
-        for li in range(decoder.num_layers):
-            src, dst = state["cache"][li], spare[li]
-            _lib.check(L.ccx_gather_rows(ptr(src), src.stride(0) * 4, ptr(dst), dst.stride(0) * 4, ptr(bs.src_row),
-                                         (t + 1) * 3 * D * 4, rows, st), "gather_rows")
-            state["cache"][li], spare[li] = dst, src
+        # new_map[r, :] = old_map[parent(r), :]; position t+1 of every row will live in its own cache row
+        src, dst = maps[cur], maps[1 - cur]
+        _lib.check(L.ccx_gather_rows(ptr(src), Tpad * 4, ptr(dst), Tpad * 4, ptr(bs.src_row), Tpad * 4, rows, st),
+                   "gather_rows")
+        if t + 1 < Tpad:
+            dst[:, t + 1] = ident
+        cur = 1 - cur
+        state["kv_rows"] = maps[cur]
         if not _state_only and t % 8 == 7 and not bool(bs.k_rem.any()):
             break
     if _state_only:

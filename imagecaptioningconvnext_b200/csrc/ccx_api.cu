@@ -231,6 +231,14 @@ int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t*
                     eps, bc1, bc2_sqrt, clip, chunk, total_params, as_stream(stream));
 }
 
+int ccx_mha_decode(const float* q, int64_t q_sb, const float* k, int64_t k_sb, int64_t k_st, const float* v,
+                   int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo, int32_t ctx_dtype, int64_t c_sb,
+                   const int32_t* kv_rows, int64_t ld_map, int32_t rows, int32_t H, int32_t Tk, int32_t hd,
+                   int32_t kv_group, float scale, void* stream) {
+  return mha_decode(q, q_sb, k, k_sb, k_st, v, v_sb, v_st, ctx_hi, ctx_lo, ctx_dtype, c_sb, kv_rows, ld_map, rows, H,
+                    Tk, hd, kv_group, scale, as_stream(stream));
+}
+
 int ccx_avgpool_nhwc(const float* x, float* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t S,
                      void* stream) {
   return avgpool_nhwc(x, out, B, H, W, C, S, as_stream(stream));

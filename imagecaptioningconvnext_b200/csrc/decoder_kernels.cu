@@ -442,4 +442,104 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------
+// single-query attention for KV-cache decoding: one WARP per (row, head), no shared-memory staging.
+//   scores: lanes own keys (float4 loads of the 64-wide head slice), softmax by shuffles,
+//   context: lanes own output dims, keys streamed (coalesced 256 B per key).
+// kv_rows (optional) [rows, ld_map]: physical cache row holding position j of logical row r — beam search
+// re-orders beams by re-writing this small map instead of copying the caches (caption.py:138-145 semantics).
+// ---------------------------------------------------------------------------------------------
+struct MhaDecArgs {
+  const float* q; long long q_sb;            // (r, h*hd + d) at q[r*q_sb + h*hd + d]
+  const float* k; long long k_sb, k_st;      // (row, j, h*hd + d) at k[row*k_sb + j*k_st + h*hd + d]
+  const float* v; long long v_sb, v_st;
+  OpOut ctx; long long c_sb;
+  const int* kv_rows; long long ld_map;
+  int rows, H, Tk, hd, kv_group;
+  float scale;
+};
+
+__global__ void __launch_bounds__(256)
+mha_decode_kernel(MhaDecArgs a) {
+  const int warp_global = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= a.rows * a.H) return;
+  const int r = warp_global / a.H, h = warp_global % a.H;
+  const int hd = a.hd;          // multiple of 4, <= 128
+  const float* qp = a.q + r * a.q_sb + h * hd;
+  // scores for keys lane, lane+32, ... (Tk <= 256 -> at most 8 per lane)
+  float sc[8];
+  int prow[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int j = lane + n * 32;
+    sc[n] = -INFINITY;
+    prow[n] = 0;
+    if (j < a.Tk) {
+      const long long row = a.kv_rows ? a.kv_rows[r * a.ld_map + j] : (r / a.kv_group);
+      prow[n] = static_cast<int>(row);
+      const float4* kp = reinterpret_cast<const float4*>(a.k + row * a.k_sb + j * a.k_st + h * hd);
+      float s = 0.f;
+      for (int d4 = 0; d4 < hd / 4; ++d4) {
+        const float4 kk = __ldg(kp + d4);
+        const float4 qq = __ldg(reinterpret_cast<const float4*>(qp) + d4);
+        s = fmaf(qq.x, kk.x, s); s = fmaf(qq.y, kk.y, s); s = fmaf(qq.z, kk.z, s); s = fmaf(qq.w, kk.w, s);
+      }
+      sc[n] = s * a.scale;
+      mx = fmaxf(mx, sc[n]);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int j = lane + n * 32;
+    sc[n] = (j < a.Tk) ? expf(sc[n] - mx) : 0.f;
+    sum += sc[n];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  // context: lane owns dims d = lane, lane+32, ... ; probabilities / rows broadcast by shuffle
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = 0; n < 8; ++n) {
+    if (n * 32 >= a.Tk) break;
+    const int cnt = min(32, a.Tk - n * 32);
+    for (int jj = 0; jj < cnt; ++jj) {
+      const float p = __shfl_sync(0xffffffffu, sc[n], jj) * inv;
+      const long long row = __shfl_sync(0xffffffffu, prow[n], jj);
+      const float* vp = a.v + row * a.v_sb + static_cast<long long>(n * 32 + jj) * a.v_st + h * hd;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane + i * 32;
+        if (d < hd) acc[i] = fmaf(p, __ldg(vp + d), acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + i * 32;
+    if (d < hd) store_op(a.ctx, r * a.c_sb + h * hd + d, acc[i]);
+  }
+}
+
+int mha_decode(const float* q, long long q_sb, const float* k, long long k_sb, long long k_st, const float* v,
+               long long v_sb, long long v_st, void* ctx_hi, float* ctx_lo, int ctx_dtype, long long c_sb,
+               const int* kv_rows, long long ld_map, int rows, int H, int Tk, int hd, int kv_group, float scale,
+               cudaStream_t stream) {
+  if (rows <= 0) return CCX_OK;
+  if (Tk <= 0 || Tk > 256 || hd <= 0 || hd > 128 || (hd & 3) || H <= 0 || ((q_sb | k_sb | k_st | v_sb | v_st) & 3) ||
+      (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15))
+    return CCX_ERR_SHAPE;
+  MhaDecArgs a;
+  a.q = q; a.q_sb = q_sb; a.k = k; a.k_sb = k_sb; a.k_st = k_st; a.v = v; a.v_sb = v_sb; a.v_st = v_st;
+  a.ctx = OpOut{ctx_hi, ctx_lo, ctx_dtype}; a.c_sb = c_sb;
+  a.kv_rows = kv_rows; a.ld_map = ld_map;
+  a.rows = rows; a.H = H; a.Tk = Tk; a.hd = hd; a.kv_group = kv_group > 0 ? kv_group : 1; a.scale = scale;
+  const long long warps = static_cast<long long>(rows) * H;
+  ProfScope prof(PROF_ATTENTION, stream, (double)rows * H * (2.0 * Tk + 2.0) * hd * 4.0);
+  mha_decode_kernel<<<static_cast<unsigned>((warps + 7) / 8), 256, 0, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
 }  // namespace ccx

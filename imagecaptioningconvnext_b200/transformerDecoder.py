@@ -196,6 +196,16 @@ class TransformerDecoder(nn.Module):
                                             1.0 / math.sqrt(D // H), kv_group, _lib.stream_ptr()), "mha_small")
         return ctx
 
+    def _mha_decode(self, q, q_sb, k, k_sb, k_st, v, rows, Tk, kv_rows, kv_group, dev):
+        """Single-query attention over the KV cache / image memory (ccx_mha_decode)."""
+        D, H, cd = self.embed_dim, self.num_heads, self.compute_dtype
+        ctx = Operand.empty((rows, D), cd, dev)
+        _lib.check(_lib.lib().ccx_mha_decode(q, q_sb, k, k_sb, k_st, v, k_sb, k_st, ptr(ctx.hi), ctx.lo_ptr,
+                                             _lib.dt_code(cd), D, ptr(kv_rows),
+                                             0 if kv_rows is None else kv_rows.stride(0), rows, H, Tk, D // H,
+                                             kv_group, 1.0 / math.sqrt(D // H), _lib.stream_ptr()), "mha_decode")
+        return ctx
+
     def _linear_op(self, a, w, bias, act=_lib.ACT_NONE):
         """GEMM whose output is directly the next GEMM's operand."""
         if self.compute_dtype == torch.bfloat16:
@@ -288,13 +298,13 @@ class TransformerDecoder(nn.Module):
             # qkv of the new token is written straight into the cache row (b, t, :)
             _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"], out=cache[:rows, t])
             base = cache.data_ptr()
-            ctx = self._mha(base + 4 * (t * 3 * D), Tm * 3 * D, 3 * D, base + 4 * D, Tm * 3 * D, 3 * D,
-                            base + 8 * D, rows, 1, t + 1, 0, 0, None, None, 1, dev)
+            ctx = self._mha_decode(base + 4 * (t * 3 * D), Tm * 3 * D, base + 4 * D, Tm * 3 * D, 3 * D, base + 8 * D,
+                                   rows, t + 1, state.get("kv_rows"), 1, dev)
             y = _lib.linear(ctx, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain)
             x_plain, x_op = self._ln(y, lw["n"][0], rows)
             q = _lib.linear(x_op, lw["ca_q"], bias=lw["ca_q_b"])
-            ctx = self._mha(ptr(q), D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows, 1, Pn, 0, 0,
-                            None, None, g, dev)
+            ctx = self._mha_decode(ptr(q), D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows, Pn, None, g,
+                                   dev)
             y = _lib.linear(ctx, lw["ca_out"], bias=lw["ca_out_b"], residual=x_plain)
             x_plain, x_op = self._ln(y, lw["n"][1], rows)
             h = self._linear_op(x_op, lw["l1"], lw["l1_b"], act=_lib.ACT_RELU)

@@ -228,6 +228,15 @@ CCX_API int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const floa
                           int32_t hd, int32_t causal, int32_t q_pos0, float scale, int32_t kv_group,
                           void* stream);
 
+/* Single-query attention for KV-cache decoding (one warp per (row, head), no staging): q row r attends to Tk
+ * cached positions.  kv_rows [rows, ld_map] (optional): physical cache row that holds position j of logical row
+ * r — beam search re-orders beams by rewriting this map instead of copying caches; without it rows read cache
+ * row r / kv_group (cross-attention over the shared image memory). */
+CCX_API int ccx_mha_decode(const float* q, int64_t q_sb, const float* k, int64_t k_sb, int64_t k_st, const float* v,
+                           int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo, int32_t ctx_dtype, int64_t c_sb,
+                           const int32_t* kv_rows, int64_t ld_map, int32_t rows, int32_t H, int32_t Tk, int32_t hd,
+                           int32_t kv_group, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Batched beam search (caption.py:96-155 LSTM, caption.py:197-251 Transformer), NI images x k beams (k <= 8) as
  * NI*k decode rows; row img*k + j is beam j of image img, alive beams compacted to the front.
