@@ -481,6 +481,7 @@ mha_decode_kernel(MhaDecArgs a) {
       prow[n] = static_cast<int>(row);
       const float4* kp = reinterpret_cast<const float4*>(a.k + row * a.k_sb + j * a.k_st + h * hd);
       float s = 0.f;
+#pragma unroll 8
       for (int d4 = 0; d4 < hd / 4; ++d4) {
         const float4 kk = __ldg(kp + d4);
         const float4 qq = __ldg(reinterpret_cast<const float4*>(qp) + d4);
@@ -500,20 +501,34 @@ mha_decode_kernel(MhaDecArgs a) {
   }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-  // context: lane owns dims d = lane, lane+32, ... ; probabilities / rows broadcast by shuffle
+  // context: lane owns dims d = lane, lane+32, ... ; probabilities / rows broadcast by shuffle.  Keys are handled
+  // in batches of 8 with all V loads issued before the FMAs (the loop is otherwise one exposed global round trip
+  // per key).
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int nd = (hd + 31) / 32;   // dims per lane (<= 4)
   for (int n = 0; n < 8; ++n) {
     if (n * 32 >= a.Tk) break;
     const int cnt = min(32, a.Tk - n * 32);
-    for (int jj = 0; jj < cnt; ++jj) {
-      const float p = __shfl_sync(0xffffffffu, sc[n], jj) * inv;
-      const long long row = __shfl_sync(0xffffffffu, prow[n], jj);
-      const float* vp = a.v + row * a.v_sb + static_cast<long long>(n * 32 + jj) * a.v_st + h * hd;
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+      float pw[8];
+      float vv[8][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = lane + i * 32;
-        if (d < hd) acc[i] = fmaf(p, __ldg(vp + d), acc[i]);
+      for (int u = 0; u < 8; ++u) {
+        const int jj = min(j0 + u, cnt - 1);
+        const float p = __shfl_sync(0xffffffffu, sc[n], jj);
+        const long long row = __shfl_sync(0xffffffffu, prow[n], jj);
+        pw[u] = (j0 + u < cnt) ? p * inv : 0.f;
+        const float* vp = a.v + row * a.v_sb + static_cast<long long>(n * 32 + jj) * a.v_st + h * hd;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int d = lane + i * 32;
+          vv[u][i] = (i < nd && d < hd) ? __ldg(vp + d) : 0.f;
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(pw[u], vv[u][i], acc[i]);
     }
   }
 #pragma unroll
