@@ -303,8 +303,14 @@ class TransformerDecoder(nn.Module):
             y = _lib.linear(ctx, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain)
             x_plain, x_op = self._ln(y, lw["n"][0], rows)
             q = _lib.linear(x_op, lw["ca_q"], bias=lw["ca_q_b"])
-            ctx = self._mha_decode(ptr(q), D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows, Pn, None, g,
-                                   dev)
+            if g > 1:
+                # beam search: the g beams of an image are g query rows of ONE (image, head) CTA, so the image's K/V
+                # head slice is staged once instead of being re-read by every beam
+                ctx = self._mha(ptr(q), g * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows // g, g, Pn,
+                                0, 0, None, None, 1, dev)
+            else:
+                ctx = self._mha_decode(ptr(q), D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows, Pn, None,
+                                       1, dev)
             y = _lib.linear(ctx, lw["ca_out"], bias=lw["ca_out_b"], residual=x_plain)
             x_plain, x_op = self._ln(y, lw["n"][1], rows)
             h = self._linear_op(x_op, lw["l1"], lw["l1_b"], act=_lib.ACT_RELU)
