@@ -20,8 +20,11 @@
 //   torchvision/models/convnext.py:55-57 (CNBlock MLP), :146-151 (downsample conv),
 //   models/decoder.py:19-21,50-54 (attention / init / f_beta / fc Linear layers),
 //   models/transformerDecoder.py:84-85 + torch/nn/modules/transformer.py (QKV/FFN/out-proj).
+#include <stdlib.h>
+
 #include "ccx_common.cuh"
 #include "ccx_gemm.h"
+#include "ccx_gemm_epilogue.cuh"
 #include "ccx_prof.h"
 
 namespace ccx {
@@ -41,20 +44,7 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
-struct EpiArgs {
-  void* out;            // [M, ldc] bf16 or fp32
-  float* out_lo;        // fp32 split output (lo part) or nullptr
-  const float* bias;    // [N] or nullptr
-  const float* colscale;  // [N] or nullptr   (layer_scale)
-  const float* rowscale;  // [M / rows_per_group] or nullptr (stochastic-depth noise/(1-p))
-  const void* residual;   // [M, ldr] same dtype as out, or nullptr
-  const float* emask;     // [M, ldm] element-wise multiplier applied after the activation (dropout), or nullptr
-  long long ldc, ldr, ldm;
-  int rows_per_group;
-  int act;              // 0 none, 1 gelu(erf), 2 relu
-  int out_dtype;        // CCX_F32 / CCX_BF16
-  int split;            // 1: write tf32 hi to out, residual lo to out_lo
-};
+
 
 template <typename T>
 __device__ __forceinline__ float ld_as_float(const T* p);
@@ -195,142 +185,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const bool full = (n0 + 32 <= N);
-        if (ep.bias != nullptr) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) f[j] += __ldg(ep.bias + n0 + j);
-          }
-        }
-        if (ep.act == 1) {
-          if (ep.out_dtype == CCX_BF16) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
-        } else if (ep.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-        }
-        if (ep.emask != nullptr && row_ok) {
-          const float* mrow = ep.emask + (long long)row * ep.ldm + n0;
-          if (full && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
-              f[j] *= mk.x; f[j + 1] *= mk.y; f[j + 2] *= mk.z; f[j + 3] *= mk.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) f[j] *= __ldg(mrow + j);
-          }
-        }
-        if (ep.colscale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < N) f[j] *= __ldg(ep.colscale + n0 + j) * rs;
-        } else if (ep.rowscale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= rs;
-        }
-        if (row_ok) {
-        if (ep.out_dtype == CCX_BF16) {
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldc + n0;
-          const __nv_bfloat16* rrow =
-              ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + n0
-                          : nullptr;
-          const bool vec = full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
-                           (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-          if (vec) {
-            if (rrow) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint4 r = __ldg(reinterpret_cast<const uint4*>(rrow + j));
-                float2 t;
-                t = unpack_bf16x2(r.x); f[j] += t.x; f[j + 1] += t.y;
-                t = unpack_bf16x2(r.y); f[j + 2] += t.x; f[j + 3] += t.y;
-                t = unpack_bf16x2(r.z); f[j + 4] += t.x; f[j + 5] += t.y;
-                t = unpack_bf16x2(r.w); f[j + 6] += t.x; f[j + 7] += t.y;
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 o;
-              o.x = pack_bf16x2(f[j], f[j + 1]);
-              o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(orow + j) = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + j < N) {
-                float y = f[j];
-                if (rrow) y += __bfloat162float(rrow[j]);
-                orow[j] = __float2bfloat16_rn(y);
-              }
-            }
-          }
-        } else {
-          float* orow = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n0;
-          float* lrow = ep.split ? ep.out_lo + (long long)row * ep.ldc + n0 : nullptr;
-          const float* rrow =
-              ep.residual ? reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0 : nullptr;
-          const bool vec = full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
-                           (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-          if (vec) {
-            if (rrow) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
-                f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-              }
-            }
-            if (ep.split) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 h, l;
-                h.x = tf32_hi(f[j]);     l.x = f[j] - h.x;
-                h.y = tf32_hi(f[j + 1]); l.y = f[j + 1] - h.y;
-                h.z = tf32_hi(f[j + 2]); l.z = f[j + 2] - h.z;
-                h.w = tf32_hi(f[j + 3]); l.w = f[j + 3] - h.w;
-                *reinterpret_cast<float4*>(orow + j) = h;
-                *reinterpret_cast<float4*>(lrow + j) = l;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n0 + j < N) {
-                float y = f[j];
-                if (rrow) y += __ldg(rrow + j);
-                if (ep.split) {
-                  const float h = tf32_hi(y);
-                  orow[j] = h;
-                  lrow[j] = y - h;
-                } else {
-                  orow[j] = y;
-                }
-              }
-            }
-          }
-        }
-        }  // row_ok
+        epilogue_chunk(ep, f, row, row_ok, n0, N, rs);
         __syncwarp();
       }
       tc_fence_before();
@@ -410,6 +265,9 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtens
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
+int gemm_tn_2cta(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
+                 int M, int N, int K, int nseg, const EpiArgs& ep, bool tf32, cudaStream_t stream);
+
 int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return g.M == 0 ? CCX_OK : CCX_ERR_SHAPE;
   const bool tf32 = (g.in_dtype == CCX_F32);
@@ -426,6 +284,12 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
     else bn = 64;
     if (g.N <= 64) bn = 64;
   }
+  // CTA-pair (cta_group::2, 256x256 tiles) path for the GEMMs that fill the machine with pair tiles
+  static const int pair_mode = getenv("CCX_GEMM_2CTA") ? atoi(getenv("CCX_GEMM_2CTA")) : 1;
+  const long long pair_tiles = ((g.M + 255LL) / 256) * (g.N / 256);
+  const bool use_pair = pair_mode && g.force_bn == 0 && (g.N % 256 == 0) && g.M >= 256 &&
+                        pair_tiles >= num_sms() / 2;
+  if (use_pair) bn = 128;   // B box = this CTA's half of the 256-row B tile
   CUtensorMap a_hi, b_hi, a_lo, b_lo;
   int rc;
   if ((rc = make_map_2d(&a_hi, g.A, tf32, g.M, g.K, g.lda, BM))) return rc;
@@ -455,6 +319,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   ep.act = g.act;
   ep.out_dtype = g.out_dtype;
   ep.split = (g.split && g.C_lo != nullptr) ? 1 : 0;
+  if (use_pair) return gemm_tn_2cta(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, tf32, stream);
   if (tf32) {
     if (bn == 256) return launch<256, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
     if (bn == 128) return launch<128, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);

@@ -101,8 +101,10 @@ def test_avgpool_nhwc(H, S):
     assert rel_err(out, ref) < 1e-6
 
 
+# the last three shapes fill the machine with 256x256 pair tiles and take the cta_group::2 kernel
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 192), (77, 9490, 512), (4096, 512, 128),
-                                   (1000, 512, 2048), (5, 1536, 512), (1, 512, 1024)])
+                                   (1000, 512, 2048), (5, 1536, 512), (1, 512, 1024),
+                                   (16384, 512, 2048), (9472, 2048, 512), (20000, 1024, 96)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_linear_epilogues(M, N, K, dtype):
     from imagecaptioningconvnext_b200 import _lib
