@@ -21,7 +21,7 @@ struct EpiArgs {
 };
 
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, float (&f)[32], int row, bool row_ok, int n0, int N,
-                                               float rs) {
+                                               float rs, const float4* res_pre = nullptr) {
   const bool full = (n0 + 32 <= N);
   if (ep.bias != nullptr) {
     if (full) {
@@ -63,9 +63,17 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, float (&f)[32]
     }
   }
   if (ep.colscale != nullptr) {
+    if (full && ((reinterpret_cast<uintptr_t>(ep.colscale + n0) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (full || n0 + j < N) f[j] *= __ldg(ep.colscale + n0 + j) * rs;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.colscale + n0 + j));
+        f[j] *= cs.x * rs; f[j + 1] *= cs.y * rs; f[j + 2] *= cs.z * rs; f[j + 3] *= cs.w * rs;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < N) f[j] *= __ldg(ep.colscale + n0 + j) * rs;
+    }
   } else if (ep.rowscale != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= rs;
@@ -118,10 +126,18 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, float (&f)[32]
                      (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
     if (vec) {
       if (rrow) {
+        if (res_pre != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
-          f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 r = res_pre[j >> 2];
+            f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
+            f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+          }
         }
       }
       if (ep.split) {
@@ -158,6 +174,51 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, float (&f)[32]
     }
   }
   }  // row_ok
+}
+
+// Residual rows of an fp32 output tile are prefetched one 32-column chunk ahead (the first chunk BEFORE the wait on
+// the accumulator), so the global-load latency hides behind the main loop / the previous chunk instead of stalling
+// every chunk (ncu: the residual FADDs were the top stall of the Linear(4C->C)+residual GEMMs).
+__device__ __forceinline__ bool residual_prefetch(const EpiArgs& ep, int row, bool row_ok, int n0, int N,
+                                                  float4 (&r)[8]) {
+  if (ep.residual == nullptr || ep.out_dtype != CCX_F32 || !row_ok || n0 + 32 > N) return false;
+  const float* rrow = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0;
+  const float* orow = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0;
+  if ((reinterpret_cast<uintptr_t>(rrow) & 15) || (reinterpret_cast<uintptr_t>(orow) & 15)) return false;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __ldg(reinterpret_cast<const float4*>(rrow) + j);
+  return true;
+}
+
+// Drain one accumulator stage: chunks c = half, half+2, ... of 32 columns each.  tmem_addr = TMEM address of
+// (this warp's lane quarter, first column of the stage).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_addr, int half, int row, bool row_ok,
+                                              int n_blk, int N, uint64_t* tfull_bar, uint32_t acc_phase) {
+  float rs = 1.0f;
+  if (ep.rowscale != nullptr && row_ok) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
+  float4 rnext[8];
+  bool have_next = residual_prefetch(ep, row, row_ok, n_blk * BN + half * 32, N, rnext);
+  mbar_wait(tfull_bar, acc_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = half; c < BN / 32; c += 2) {
+    const int n0 = n_blk * BN + c * 32;
+    if (n0 >= N) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(tmem_addr + c * 32, v);
+    float4 rcur[8];
+    const bool have_cur = have_next;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+    have_next = (c + 2 < BN / 32) && residual_prefetch(ep, row, row_ok, n0 + 64, N, rnext);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    epilogue_chunk(ep, f, row, row_ok, n0, N, rs, have_cur ? rcur : nullptr);
+    __syncwarp();
+  }
 }
 
 }  // namespace ccx

@@ -218,23 +218,8 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int ms = tile / n_tiles, n_blk = tile % n_tiles;
       const int row = (ms * 2 + static_cast<int>(rank)) * BM2 + ew * 32 + lane;
       const bool row_ok = row < M;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      float rs = 1.0f;
-      if (ep.rowscale != nullptr && row_ok) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
-#pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= N) break;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        epilogue_chunk(ep, f, row, row_ok, n0, N, rs);
-        __syncwarp();
-      }
+      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half, row, row_ok, n_blk, N,
+                        &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
