@@ -191,14 +191,17 @@ __device__ __forceinline__ bool residual_prefetch(const EpiArgs& ep, int row, bo
 }
 
 // Drain one accumulator stage: chunks c = half, half+2, ... of 32 columns each.  tmem_addr = TMEM address of
-// (this warp's lane quarter, first column of the stage).
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_addr, int half, int row, bool row_ok,
-                                              int n_blk, int N, uint64_t* tfull_bar, uint32_t acc_phase) {
+// (this warp's lane quarter, first column of the stage).  PREFETCH_RES is a compile-time switch so that GEMMs
+// without an fp32 residual keep the lean loop (fewer live registers).
+template <int BN, bool PREFETCH_RES>
+__device__ __forceinline__ void epilogue_tile_impl(const EpiArgs& ep, uint32_t tmem_addr, int half, int row,
+                                                   bool row_ok, int n_blk, int N, uint64_t* tfull_bar,
+                                                   uint32_t acc_phase) {
   float rs = 1.0f;
   if (ep.rowscale != nullptr && row_ok) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
   float4 rnext[8];
-  bool have_next = residual_prefetch(ep, row, row_ok, n_blk * BN + half * 32, N, rnext);
+  bool have_next = false;
+  if constexpr (PREFETCH_RES) have_next = residual_prefetch(ep, row, row_ok, n_blk * BN + half * 32, N, rnext);
   mbar_wait(tfull_bar, acc_phase);
   tc_fence_after();
 #pragma unroll 1
@@ -207,18 +210,35 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_a
     if (n0 >= N) break;  // warp-uniform
     uint32_t v[32];
     tmem_ld32(tmem_addr + c * 32, v);
-    float4 rcur[8];
-    const bool have_cur = have_next;
+    if constexpr (PREFETCH_RES) {
+      float4 rcur[8];
+      const bool have_cur = have_next;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
-    have_next = (c + 2 < BN / 32) && residual_prefetch(ep, row, row_ok, n0 + 64, N, rnext);
-    tmem_ld_wait();
-    float f[32];
+      for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
+      have_next = (c + 2 < BN / 32) && residual_prefetch(ep, row, row_ok, n0 + 64, N, rnext);
+      tmem_ld_wait();
+      float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    epilogue_chunk(ep, f, row, row_ok, n0, N, rs, have_cur ? rcur : nullptr);
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      epilogue_chunk(ep, f, row, row_ok, n0, N, rs, have_cur ? rcur : nullptr);
+    } else {
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      epilogue_chunk(ep, f, row, row_ok, n0, N, rs, nullptr);
+    }
     __syncwarp();
   }
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_addr, int half, int row, bool row_ok,
+                                              int n_blk, int N, uint64_t* tfull_bar, uint32_t acc_phase) {
+  if (ep.residual != nullptr && ep.out_dtype == CCX_F32)   // uniform over the kernel
+    epilogue_tile_impl<BN, true>(ep, tmem_addr, half, row, row_ok, n_blk, N, tfull_bar, acc_phase);
+  else
+    epilogue_tile_impl<BN, false>(ep, tmem_addr, half, row, row_ok, n_blk, N, tfull_bar, acc_phase);
 }
 
 }  // namespace ccx
