@@ -44,6 +44,11 @@ int ccx_linear(const ccx_linear_desc* d, void* stream) {
   return gemm_tn(g, as_stream(stream));
 }
 
+int ccx_set_gemm_pair_mode(int32_t mode) {
+  set_gemm_pair_mode(mode);
+  return CCX_OK;
+}
+
 int ccx_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
   return split_tf32(x, hi, lo, n, as_stream(stream));
 }

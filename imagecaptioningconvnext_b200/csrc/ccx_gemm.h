@@ -29,6 +29,7 @@ struct GemmDesc {
 };
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream);
+void set_gemm_pair_mode(int mode);
 
 // driver entry point for building TMA descriptors (resolved through the runtime; no -lcuda needed)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -253,6 +253,9 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtens
 int gemm_tn_2cta(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
                  int M, int N, int K, int nseg, const EpiArgs& ep, bool tf32, cudaStream_t stream);
 
+static int g_pair_mode = -1;
+void set_gemm_pair_mode(int mode) { g_pair_mode = mode ? 1 : 0; }
+
 int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return g.M == 0 ? CCX_OK : CCX_ERR_SHAPE;
   const bool tf32 = (g.in_dtype == CCX_F32);
@@ -270,7 +273,11 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
     if (g.N <= 64) bn = 64;
   }
   // CTA-pair (cta_group::2, 256x256 tiles) path for the GEMMs that fill the machine with pair tiles
-  static const int pair_mode = getenv("CCX_GEMM_2CTA") ? atoi(getenv("CCX_GEMM_2CTA")) : 1;
+  // measured on B200 (profiles/r01_spans_*): the pair kernel does not beat the single-CTA kernel on these shapes
+  // (the GEMMs are epilogue / HBM bound, not operand-traffic bound), so it is opt-in: ccx_set_gemm_pair_mode(1)
+  // or CCX_GEMM_2CTA=1
+  if (g_pair_mode < 0) g_pair_mode = getenv("CCX_GEMM_2CTA") ? atoi(getenv("CCX_GEMM_2CTA")) : 0;
+  const int pair_mode = g_pair_mode;
   const long long pair_tiles = ((g.M + 255LL) / 256) * (g.N / 256);
   const bool use_pair = pair_mode && g.force_bn == 0 && (g.N % 256 == 0) && g.M >= 256 &&
                         pair_tiles >= num_sms() / 2;

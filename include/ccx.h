@@ -82,6 +82,10 @@ typedef struct ccx_linear_desc {
   int32_t split;
 } ccx_linear_desc;
 CCX_API int ccx_linear(const ccx_linear_desc* d, void* stream);
+/* mode != 0: GEMMs that fill the machine with 256x256 tiles use the CTA-pair kernel (tcgen05 cta_group::2, UMMA
+ * M=256 across two SMs, each SM streaming half of the B tile).  Off by default: on the ConvNeXt shapes it measures
+ * equal or slower than the single-CTA kernel (profiles/r01_spans_v5*.txt). */
+CCX_API int ccx_set_gemm_pair_mode(int32_t mode);
 
 /* fp32 -> (tf32 hi, fp32 lo) and fp32 -> bf16 operand preparation (weights once, activations in epilogues) */
 CCX_API int ccx_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);

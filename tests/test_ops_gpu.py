@@ -101,12 +101,23 @@ def test_avgpool_nhwc(H, S):
     assert rel_err(out, ref) < 1e-6
 
 
-# the last three shapes fill the machine with 256x256 pair tiles and take the cta_group::2 kernel
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 192), (77, 9490, 512), (4096, 512, 128),
-                                   (1000, 512, 2048), (5, 1536, 512), (1, 512, 1024),
-                                   (16384, 512, 2048), (9472, 2048, 512), (20000, 1024, 96)])
+# the last three shapes fill the machine with 256x256 pair tiles; pair=True runs them on the cta_group::2 kernel
+@pytest.mark.parametrize("M,N,K,pair", [(128, 128, 64, False), (300, 200, 192, False), (77, 9490, 512, False),
+                                        (4096, 512, 128, False), (1000, 512, 2048, False), (5, 1536, 512, False),
+                                        (1, 512, 1024, False), (16384, 512, 2048, False), (16384, 512, 2048, True),
+                                        (9472, 2048, 512, True), (20000, 1024, 96, True)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_linear_epilogues(M, N, K, dtype):
+def test_linear_epilogues(M, N, K, pair, dtype):
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import Operand
+    _lib.lib().ccx_set_gemm_pair_mode(1 if pair else 0)
+    try:
+        _linear_epilogue_checks(M, N, K, dtype)
+    finally:
+        _lib.lib().ccx_set_gemm_pair_mode(0)
+
+
+def _linear_epilogue_checks(M, N, K, dtype):
     from imagecaptioningconvnext_b200 import _lib
     from imagecaptioningconvnext_b200._lib import Operand
     g = _g(M + N)
