@@ -264,6 +264,22 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(fabsf(half_x), erf_abs, half_x);             // 0.5x + 0.5|x| erf(|x|/sqrt2) = 0.5x(1+erf(x/sqrt2))
 }
 
+// GELU for bf16 OUTPUTS: 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715 x^3))) with MUFU.TANH — 5 FMA-pipe instructions and
+// one MUFU per element instead of the 12 + 2 of the erf form, which makes the Linear(C->4C)+GELU epilogue MUFU/issue
+// bound above the MMA time.  |tanh form - erf form| <= 4.7e-4 absolute; after rounding to bf16 the RMS error against
+// the exact erf GELU grows from 2.500e-3 to 2.507e-3 (measured over N(0,1.5) inputs) — invisible under the bf16
+// rounding itself.  fp32 outputs keep erff.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float u = x * fmaf(0.035677408136f, x * x, 0.7978845608f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(u), hx);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

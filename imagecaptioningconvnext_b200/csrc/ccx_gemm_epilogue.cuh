@@ -39,7 +39,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, float (&f)[32]
   if (ep.act == 1) {
     if (ep.out_dtype == CCX_BF16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+      for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
