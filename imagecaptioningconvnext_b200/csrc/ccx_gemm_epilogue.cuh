@@ -1,5 +1,11 @@
-// ccx_gemm_epilogue.cuh — the fused GEMM epilogue for one 32-column chunk of one accumulator row, shared by the
-// 1-CTA and the 2-CTA (cta_group::2) tcgen05 kernels.  f[] holds the fp32 accumulators of columns n0..n0+31 of `row`.
+// ccx_gemm_epilogue.cuh — the fused GEMM epilogue shared by the 1-CTA and the 2-CTA (cta_group::2) tcgen05 kernels.
+//
+// tcgen05.ld hands every thread ONE accumulator row (32 consecutive columns).  Writing / reading global memory in
+// that layout makes each warp instruction touch 32 different lines (16 B out of each), which made the epilogue —
+// not the MMA — the bottleneck of every encoder GEMM (ncu r01: LSU-transaction bound, residual loads the top stall).
+// So each 32x32 chunk is transposed through a warp-private, XOR-swizzled shared-memory scratch: afterwards a lane owns
+// a COLUMN, and every global access of the epilogue (residual, dropout mask, output hi/lo) is one coalesced line per
+// warp instruction; bias / layer-scale become per-lane scalars.
 #pragma once
 #include "ccx_common.cuh"
 
@@ -20,188 +26,117 @@ struct EpiArgs {
   int split;            // 1: write tf32 hi to out, residual lo to out_lo
 };
 
-__device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, float (&f)[32], int row, bool row_ok, int n0, int N,
-                                               float rs, const float4* res_pre = nullptr) {
-  const bool full = (n0 + 32 <= N);
-  if (ep.bias != nullptr) {
-    if (full) {
+static constexpr int EPI_SCRATCH_FLOATS = 32 * 32;   // per epilogue warp
+
+// f[j] = accumulator (row0 + lane, n0 + j).  scratch: this warp's 32x32 floats.
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&f)[32], float* scratch, int row0,
+                                               int lane, int n0, int M, int N) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+  for (int j = 0; j < 32; ++j) scratch[lane * 32 + (j ^ lane)] = f[j];
+  __syncwarp();
+  const int col = n0 + lane;
+  const bool col_ok = col < N;
+  const int rows = min(32, M - row0);          // warp-uniform
+  const float b = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.0f;
+  const float cs = (ep.colscale != nullptr && col_ok) ? __ldg(ep.colscale + col) : 1.0f;
+  const bool scale = (ep.colscale != nullptr) || (ep.rowscale != nullptr);
+  if (rows == 32 && col_ok) {
+    // full chunk: all global loads of the 32 rows are issued before they are consumed
+    float y[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) y[r] = scratch[r * 32 + (lane ^ r)] + b;
+    if (ep.act == 1) {
+      if (ep.out_dtype == CCX_BF16) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) y[r] = gelu_tanh_fast(y[r]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) y[r] = gelu_erf(y[r]);
       }
-    } else {
+    } else if (ep.act == 2) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) f[j] += __ldg(ep.bias + n0 + j);
+      for (int r = 0; r < 32; ++r) y[r] = fmaxf(y[r], 0.0f);
     }
-  }
-  if (ep.act == 1) {
+    if (ep.emask != nullptr) {
+      const float* mp = ep.emask + (long long)row0 * ep.ldm + col;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) y[r] *= __ldg(mp + r * ep.ldm);
+    }
+    if (scale) {
+      if (ep.rowscale != nullptr) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) y[r] *= cs * __ldg(ep.rowscale + (row0 + r) / ep.rows_per_group);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) y[r] *= cs;
+      }
+    }
     if (ep.out_dtype == CCX_BF16) {
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row0 * ep.ldc + col;
+      if (ep.residual != nullptr) {
+        const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row0 * ep.ldr + col;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
+        for (int r = 0; r < 32; ++r) y[r] += __bfloat162float(rp[r * ep.ldr]);
+      }
+#pragma unroll
+      for (int r = 0; r < 32; ++r) op[r * ep.ldc] = __float2bfloat16_rn(y[r]);
     } else {
+      float* op = reinterpret_cast<float*>(ep.out) + (long long)row0 * ep.ldc + col;
+      if (ep.residual != nullptr) {
+        const float* rp = reinterpret_cast<const float*>(ep.residual) + (long long)row0 * ep.ldr + col;
+        float rv[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-    }
-  } else if (ep.act == 2) {
+        for (int r = 0; r < 32; ++r) rv[r] = __ldg(rp + r * ep.ldr);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-  }
-  if (ep.emask != nullptr && row_ok) {
-    const float* mrow = ep.emask + (long long)row * ep.ldm + n0;
-    if (full && ((reinterpret_cast<uintptr_t>(mrow) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow + j));
-        f[j] *= mk.x; f[j + 1] *= mk.y; f[j + 2] *= mk.z; f[j + 3] *= mk.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) f[j] *= __ldg(mrow + j);
-    }
-  }
-  if (ep.colscale != nullptr) {
-    if (full && ((reinterpret_cast<uintptr_t>(ep.colscale + n0) & 15) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 cs = __ldg(reinterpret_cast<const float4*>(ep.colscale + n0 + j));
-        f[j] *= cs.x * rs; f[j + 1] *= cs.y * rs; f[j + 2] *= cs.z * rs; f[j + 3] *= cs.w * rs;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < N) f[j] *= __ldg(ep.colscale + n0 + j) * rs;
-    }
-  } else if (ep.rowscale != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] *= rs;
-  }
-  if (row_ok) {
-  if (ep.out_dtype == CCX_BF16) {
-    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row * ep.ldc + n0;
-    const __nv_bfloat16* rrow =
-        ep.residual ? reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row * ep.ldr + n0
-                    : nullptr;
-    const bool vec = full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
-                     (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-    if (vec) {
-      if (rrow) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 r = __ldg(reinterpret_cast<const uint4*>(rrow + j));
-          float2 t;
-          t = unpack_bf16x2(r.x); f[j] += t.x; f[j + 1] += t.y;
-          t = unpack_bf16x2(r.y); f[j + 2] += t.x; f[j + 3] += t.y;
-          t = unpack_bf16x2(r.z); f[j + 4] += t.x; f[j + 5] += t.y;
-          t = unpack_bf16x2(r.w); f[j + 6] += t.x; f[j + 7] += t.y;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 o;
-        o.x = pack_bf16x2(f[j], f[j + 1]);
-        o.y = pack_bf16x2(f[j + 2], f[j + 3]);
-        o.z = pack_bf16x2(f[j + 4], f[j + 5]);
-        o.w = pack_bf16x2(f[j + 6], f[j + 7]);
-        *reinterpret_cast<uint4*>(orow + j) = o;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (n0 + j < N) {
-          float y = f[j];
-          if (rrow) y += __bfloat162float(rrow[j]);
-          orow[j] = __float2bfloat16_rn(y);
-        }
-      }
-    }
-  } else {
-    float* orow = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldc + n0;
-    float* lrow = ep.split ? ep.out_lo + (long long)row * ep.ldc + n0 : nullptr;
-    const float* rrow =
-        ep.residual ? reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0 : nullptr;
-    const bool vec = full && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
-                     (rrow == nullptr || (reinterpret_cast<uintptr_t>(rrow) & 15) == 0);
-    if (vec) {
-      if (rrow) {
-        if (res_pre != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 r = res_pre[j >> 2];
-            f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(rrow + j));
-            f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-          }
-        }
+        for (int r = 0; r < 32; ++r) y[r] += rv[r];
       }
       if (ep.split) {
+        float* lp = ep.out_lo + (long long)row0 * ep.ldc + col;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 h, l;
-          h.x = tf32_hi(f[j]);     l.x = f[j] - h.x;
-          h.y = tf32_hi(f[j + 1]); l.y = f[j + 1] - h.y;
-          h.z = tf32_hi(f[j + 2]); l.z = f[j + 2] - h.z;
-          h.w = tf32_hi(f[j + 3]); l.w = f[j + 3] - h.w;
-          *reinterpret_cast<float4*>(orow + j) = h;
-          *reinterpret_cast<float4*>(lrow + j) = l;
+        for (int r = 0; r < 32; ++r) {
+          const float h = tf32_hi(y[r]);
+          op[r * ep.ldc] = h;
+          lp[r * ep.ldc] = y[r] - h;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        for (int r = 0; r < 32; ++r) op[r * ep.ldc] = y[r];
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (n0 + j < N) {
-          float y = f[j];
-          if (rrow) y += __ldg(rrow + j);
-          if (ep.split) {
-            const float h = tf32_hi(y);
-            orow[j] = h;
-            lrow[j] = y - h;
-          } else {
-            orow[j] = y;
-          }
+    }
+  } else if (col_ok) {
+    // ragged chunk (last rows of M): same math, row by row
+    for (int r = 0; r < rows; ++r) {
+      const int row = row0 + r;
+      float y = scratch[r * 32 + (lane ^ r)] + b;
+      if (ep.act == 1) y = (ep.out_dtype == CCX_BF16) ? gelu_tanh_fast(y) : gelu_erf(y);
+      else if (ep.act == 2) y = fmaxf(y, 0.0f);
+      if (ep.emask != nullptr) y *= __ldg(ep.emask + (long long)row * ep.ldm + col);
+      if (scale) y *= cs * (ep.rowscale ? __ldg(ep.rowscale + row / ep.rows_per_group) : 1.0f);
+      if (ep.out_dtype == CCX_BF16) {
+        if (ep.residual != nullptr)
+          y += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ep.residual)[(long long)row * ep.ldr + col]);
+        reinterpret_cast<__nv_bfloat16*>(ep.out)[(long long)row * ep.ldc + col] = __float2bfloat16_rn(y);
+      } else {
+        if (ep.residual != nullptr) y += __ldg(reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col);
+        if (ep.split) {
+          const float h = tf32_hi(y);
+          reinterpret_cast<float*>(ep.out)[(long long)row * ep.ldc + col] = h;
+          ep.out_lo[(long long)row * ep.ldc + col] = y - h;
+        } else {
+          reinterpret_cast<float*>(ep.out)[(long long)row * ep.ldc + col] = y;
         }
       }
     }
   }
-  }  // row_ok
-}
-
-// Residual rows of an fp32 output tile are prefetched one 32-column chunk ahead (the first chunk BEFORE the wait on
-// the accumulator), so the global-load latency hides behind the main loop / the previous chunk instead of stalling
-// every chunk (ncu: the residual FADDs were the top stall of the Linear(4C->C)+residual GEMMs).
-__device__ __forceinline__ bool residual_prefetch(const EpiArgs& ep, int row, bool row_ok, int n0, int N,
-                                                  float4 (&r)[8]) {
-  if (ep.residual == nullptr || ep.out_dtype != CCX_F32 || !row_ok || n0 + 32 > N) return false;
-  const float* rrow = reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + n0;
-  const float* orow = reinterpret_cast<const float*>(ep.out) + (long long)row * ep.ldc + n0;
-  if ((reinterpret_cast<uintptr_t>(rrow) & 15) || (reinterpret_cast<uintptr_t>(orow) & 15)) return false;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = __ldg(reinterpret_cast<const float4*>(rrow) + j);
-  return true;
+  __syncwarp();   // the scratch is reused by the next chunk
 }
 
 // Drain one accumulator stage: chunks c = half, half+2, ... of 32 columns each.  tmem_addr = TMEM address of
-// (this warp's lane quarter, first column of the stage).  PREFETCH_RES is a compile-time switch so that GEMMs
-// without an fp32 residual keep the lean loop (fewer live registers).
-template <int BN, bool PREFETCH_RES>
-__device__ __forceinline__ void epilogue_tile_impl(const EpiArgs& ep, uint32_t tmem_addr, int half, int row,
-                                                   bool row_ok, int n_blk, int N, uint64_t* tfull_bar,
-                                                   uint32_t acc_phase) {
-  float rs = 1.0f;
-  if (ep.rowscale != nullptr && row_ok) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
-  float4 rnext[8];
-  bool have_next = false;
-  if constexpr (PREFETCH_RES) have_next = residual_prefetch(ep, row, row_ok, n_blk * BN + half * 32, N, rnext);
+// (this warp's lane quarter, first column of the stage); row0 = first row of this warp's 32-row slab.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_addr, int half, int row0, int lane,
+                                              float* scratch, int n_blk, int M, int N, uint64_t* tfull_bar,
+                                              uint32_t acc_phase) {
   mbar_wait(tfull_bar, acc_phase);
   tc_fence_after();
 #pragma unroll 1
@@ -210,35 +145,12 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiArgs& ep, uint32_t t
     if (n0 >= N) break;  // warp-uniform
     uint32_t v[32];
     tmem_ld32(tmem_addr + c * 32, v);
-    if constexpr (PREFETCH_RES) {
-      float4 rcur[8];
-      const bool have_cur = have_next;
+    tmem_ld_wait();
+    float f[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rcur[j] = rnext[j];
-      have_next = (c + 2 < BN / 32) && residual_prefetch(ep, row, row_ok, n0 + 64, N, rnext);
-      tmem_ld_wait();
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      epilogue_chunk(ep, f, row, row_ok, n0, N, rs, have_cur ? rcur : nullptr);
-    } else {
-      tmem_ld_wait();
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      epilogue_chunk(ep, f, row, row_ok, n0, N, rs, nullptr);
-    }
-    __syncwarp();
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (row0 < M) epilogue_chunk(ep, f, scratch, row0, lane, n0, M, N);
   }
-}
-
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_addr, int half, int row, bool row_ok,
-                                              int n_blk, int N, uint64_t* tfull_bar, uint32_t acc_phase) {
-  if (ep.residual != nullptr && ep.out_dtype == CCX_F32)   // uniform over the kernel
-    epilogue_tile_impl<BN, true>(ep, tmem_addr, half, row, row_ok, n_blk, N, tfull_bar, acc_phase);
-  else
-    epilogue_tile_impl<BN, false>(ep, tmem_addr, half, row, row_ok, n_blk, N, tfull_bar, acc_phase);
 }
 
 }  // namespace ccx

@@ -41,7 +41,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int EPI_BYTES = 8 * EPI_SCRATCH_FLOATS * 4;   // transposition scratch of the 8 epilogue warps
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024 alignment slack
 };
 
 
@@ -77,6 +78,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -169,10 +171,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int row = m_blk * BM + ew * 32 + lane;
-      const bool row_ok = row < M;
-      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half, row, row_ok, n_blk, N,
-                        &tfull_bar[acc], acc_phase);
+      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half, m_blk * BM + ew * 32, lane,
+                        epi_scratch + (warp - 4) * EPI_SCRATCH_FLOATS, n_blk, M, N, &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);

@@ -26,7 +26,8 @@ struct Gemm2Smem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int EPI_BYTES = 8 * EPI_SCRATCH_FLOATS * 4;   // transposition scratch of the 8 epilogue warps
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -118,6 +119,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   uint64_t* tfull_bar = bars + 2 * STAGES;      // per CTA: accumulator stage complete
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // leader: both CTAs' epilogues drained the stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -216,10 +218,9 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
       const int ms = tile / n_tiles, n_blk = tile % n_tiles;
-      const int row = (ms * 2 + static_cast<int>(rank)) * BM2 + ew * 32 + lane;
-      const bool row_ok = row < M;
-      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half, row, row_ok, n_blk, N,
-                        &tfull_bar[acc], acc_phase);
+      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half,
+                        (ms * 2 + static_cast<int>(rank)) * BM2 + ew * 32, lane,
+                        epi_scratch + (warp - 4) * EPI_SCRATCH_FLOATS, n_blk, M, N, &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
