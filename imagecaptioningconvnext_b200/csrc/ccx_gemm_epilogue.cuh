@@ -31,9 +31,14 @@ static constexpr int EPI_SCRATCH_FLOATS = 32 * 32;   // per epilogue warp
 // f[j] = accumulator (row0 + lane, n0 + j).  scratch: this warp's 32x32 floats.
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&f)[32], float* scratch, int row0,
                                                int lane, int n0, int M, int N) {
+  // element (row i, col j) lives at i*32 + ((j>>2) ^ (i&7))*4 + (j&3): 8 conflict-free STS.128 per thread on the way
+  // in (16-byte groups swizzled by the row), conflict-free scalar LDS on the way out (a lane = a column)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) scratch[lane * 32 + (j ^ lane)] = f[j];
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<float4*>(scratch + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+        make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
   __syncwarp();
+  const int cq = lane >> 2, cr = lane & 3;   // this lane's column = 4*cq + cr
   const int col = n0 + lane;
   const bool col_ok = col < N;
   const int rows = min(32, M - row0);          // warp-uniform
@@ -44,7 +49,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
     // full chunk: all global loads of the 32 rows are issued before they are consumed
     float y[32];
 #pragma unroll
-    for (int r = 0; r < 32; ++r) y[r] = scratch[r * 32 + (lane ^ r)] + b;
+    for (int r = 0; r < 32; ++r) y[r] = scratch[r * 32 + ((cq ^ (r & 7)) << 2) + cr] + b;
     if (ep.act == 1) {
       if (ep.out_dtype == CCX_BF16) {
 #pragma unroll
@@ -107,7 +112,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
     // ragged chunk (last rows of M): same math, row by row
     for (int r = 0; r < rows; ++r) {
       const int row = row0 + r;
-      float y = scratch[r * 32 + (lane ^ r)] + b;
+      float y = scratch[r * 32 + ((cq ^ (r & 7)) << 2) + cr] + b;
       if (ep.act == 1) y = (ep.out_dtype == CCX_BF16) ? gelu_tanh_fast(y) : gelu_erf(y);
       else if (ep.act == 2) y = fmaxf(y, 0.0f);
       if (ep.emask != nullptr) y *= __ldg(ep.emask + (long long)row * ep.ldm + col);
