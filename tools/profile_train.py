@@ -37,3 +37,33 @@ for k, v in prof.items():
 big = sorted(spans[:len(spans)//5], key=lambda s: -s[1])[:12]
 for k, ms, w in big: print(f"   top: {k:10s} {ms*1e3:8.1f} us work={w:.3g}")
 # host-only cost: time the python side with a CPU profiler-free trick: run under cuda graphs impossible; report wall - gpu
+
+# ---- where does the wall time go: host-side phase timing (each phase followed by a sync, so GPU time is included) ----
+import contextlib
+from imagecaptioningconvnext_b200.losses import packed_cross_entropy
+def phase_times():
+    t = {}
+    def mark(name, t0):
+        torch.cuda.synchronize(); t[name] = t.get(name, 0.0) + time.perf_counter() - t0
+    t0 = time.perf_counter(); feats = enc(imgs); mark("encoder fwd", t0)
+    t0 = time.perf_counter()
+    if kind == "lstm":
+        s, cs, dl, al, _ = dec(teacherForcing=True, encoder_out=feats, encoded_captions=caps, caption_lengths=lens)
+        loss = packed_cross_entropy(s, cs, dl) + ((1.0 - al.sum(dim=1)) ** 2).mean()
+    else:
+        s, co, dl = dec(teacherForcing=True, encoder_out=feats, encoded_captions=caps, caption_lengths=lens, tgt_key_padding_mask=(caps == 0))
+        loss = packed_cross_entropy(s, co, dl)
+    mark("decoder fwd + loss", t0)
+    t0 = time.perf_counter()
+    if e_opt is not None: e_opt.zero_grad(set_to_none=False)
+    d_opt.zero_grad(set_to_none=False)
+    loss.backward(); mark("backward", t0)
+    t0 = time.perf_counter()
+    if e_opt is not None: e_opt.step()
+    d_opt.step(); mark("optimizer", t0)
+    return t
+phase_times()
+acc = {}
+for _ in range(5):
+    for k, v in phase_times().items(): acc[k] = acc.get(k, 0.0) + v / 5
+print("phase wall times (ms, each synced):", {k: round(v * 1e3, 2) for k, v in acc.items()}, "sum", round(sum(acc.values()) * 1e3, 2))
