@@ -194,14 +194,29 @@ class Encoder(nn.Module):
         return out
 
     def prepared(self):
-        """Kernel-side weight table (re-laid-out / bf16 or tf32-split copies), rebuilt when parameters change."""
+        """Kernel-side weight table (re-laid-out / bf16 or tf32-split copies).  Rebuilt when any parameter changes, but
+        only the entries whose OWN parameter changed are re-converted (fine-tuning touches 3 of the 36 blocks per step;
+        re-casting all 88 M weights every step would cost more than the trainable blocks' forward)."""
         params = list(self.convnext.parameters())
         key = (self.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(),
                sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params))
         if self._prep_key == key:
             return self._prep[0]
         cd = self.compute_dtype
+        cache = getattr(self, "_entry_cache", None)
+        if cache is None or cache.get("__dtype__") != cd:
+            cache = {"__dtype__": cd}
+        self._entry_cache = cache
         keep = []
+
+        def cached(name, p, make):
+            k = (p.data_ptr(), p._version + getattr(p, "_ccx_epoch", 0))
+            hit = cache.get(name)
+            if hit is None or hit[0] != k:
+                hit = (k, make(p.detach()))
+                cache[name] = hit
+            keep.append(hit[1])
+            return hit[1]
 
         def f32(p):
             t = p.detach()
@@ -211,12 +226,7 @@ class Encoder(nn.Module):
             keep.append(t)
             return t.data_ptr()
 
-        ops = []
-
-        def operand(t2d):
-            op = Operand.prepare(t2d.detach().contiguous(), cd)
-            keep.append(op)
-            ops.append(op)
+        def op_ptrs(op):
             return op.hi.data_ptr(), (op.lo.data_ptr() if op.lo is not None else None)
 
         self._block_ops = []   # per CNBlock: dict(dw_w, w1, w2) python-side handles (used by encoder_train.py)
@@ -224,8 +234,7 @@ class Encoder(nn.Module):
 
         w = _lib.EncoderWeights()
         ch = list(self.convnext.children())
-        stem_w = ch[0][0].weight.detach().reshape(128, 48).t().contiguous()
-        keep.append(stem_w)
+        stem_w = cached("stem", ch[0][0].weight, lambda t: t.reshape(128, 48).t().contiguous())
         w.stem_w, w.stem_b = stem_w.data_ptr(), f32(ch[0][0].bias)
         w.stem_ln_g, w.stem_ln_b = f32(ch[0][1].weight), f32(ch[0][1].bias)
         bi = 0
@@ -233,24 +242,27 @@ class Encoder(nn.Module):
             Cc = DIMS[s]
             for blk in ch[1 + 2 * s]:
                 bw = w.blocks[bi]
-                dw = blk.block[0].weight.detach().reshape(Cc, 49).t().contiguous()
-                keep.append(dw)
+                dw = cached(f"dw{bi}", blk.block[0].weight, lambda t, Cc=Cc: t.reshape(Cc, 49).t().contiguous())
                 bw.dw_w, bw.dw_b = dw.data_ptr(), f32(blk.block[0].bias)
                 bw.ln_g, bw.ln_b = f32(blk.block[2].weight), f32(blk.block[2].bias)
-                bw.w1, bw.w1_lo = operand(blk.block[3].weight)
+                w1 = cached(f"w1_{bi}", blk.block[3].weight, lambda t: Operand.prepare(t.contiguous(), cd))
+                w2 = cached(f"w2_{bi}", blk.block[5].weight, lambda t: Operand.prepare(t.contiguous(), cd))
+                bw.w1, bw.w1_lo = op_ptrs(w1)
                 bw.b1 = f32(blk.block[3].bias)
-                bw.w2, bw.w2_lo = operand(blk.block[5].weight)
+                bw.w2, bw.w2_lo = op_ptrs(w2)
                 bw.b2 = f32(blk.block[5].bias)
                 bw.layer_scale = f32(blk.layer_scale.view(Cc))
-                self._block_ops.append({"dw_w": dw, "w1": ops[-2], "w2": ops[-1]})
+                self._block_ops.append({"dw_w": dw, "w1": w1, "w2": w2})
                 bi += 1
             if s > 0:
                 d = ch[2 * s]
                 dwn = w.down[s - 1]
                 dwn.ln_g, dwn.ln_b = f32(d[0].weight), f32(d[0].bias)
-                wm = d[1].weight.detach().permute(0, 2, 3, 1).reshape(Cc, 4 * DIMS[s - 1])
-                dwn.w, dwn.w_lo = operand(wm)
-                self._down_ops[2 * s] = ops[-1]
+                wd = cached(f"down{s}", d[1].weight,
+                            lambda t, Cc=Cc, Ci=DIMS[s - 1]: Operand.prepare(
+                                t.permute(0, 2, 3, 1).reshape(Cc, 4 * Ci).contiguous(), cd))
+                dwn.w, dwn.w_lo = op_ptrs(wd)
+                self._down_ops[2 * s] = wd
                 dwn.b = f32(d[1].bias)
         for s in range(4):
             w.depths[s], w.dims[s] = DEPTHS[s], DIMS[s]
