@@ -420,7 +420,7 @@ def run_extras(args, dev, world, rank, local):
     dec = dec.to(dev).train()
     d_opt, e_opt = make_optimizers(enc, dec)
     enc_w, dec_w = wrap(enc), wrap(dec)
-    ms = _timed(lambda: caption_train_step(enc_w, dec_w, imgs, caps, lens, d_opt, e_opt), 6, 3, dev, world)
+    ms = _timed(lambda: caption_train_step(enc_w, dec_w, imgs, caps, lens, d_opt, e_opt), 20, 10, dev, world)
     out["train_lstm_finetune7_bf16"] = {"images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms,
                                         "batch_per_gpu": B, "config": "BASELINE.json configs[3]: encoder "
                                         "fine_tune(True,7) + DecoderWithAttention, teacher forcing, captions uniform "
@@ -438,7 +438,7 @@ def run_extras(args, dev, world, rank, local):
         tr = tr.to(dev).train()
         d_opt, _ = make_optimizers(enc2, tr)
         tr_w = wrap(tr)
-        ms = _timed(lambda: caption_train_step(enc2, tr_w, imgs, caps, lens, d_opt, None), 6, 3, dev, world)
+        ms = _timed(lambda: caption_train_step(enc2, tr_w, imgs, caps, lens, d_opt, None), 20, 10, dev, world)
         out[f"train_transformer_frozen_encoder_{name}"] = {
             "images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms, "batch_per_gpu": B,
             "config": "BASELINE.json configs[2]: frozen encoder + TransformerDecoder, teacher forcing, 52-token "
