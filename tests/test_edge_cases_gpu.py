@@ -96,10 +96,10 @@ def test_single_image_single_beam_and_wide_beam():
     tsd = do.random_transformer_decoder_state(0, V, end_bias=3.2)
     feats = do.synthetic_features(1, 300)
     for k in (1, 8):                                  # beam widths 1 (caption.py's default) and 8 (kernel maximum)
-        assert beam_search_lstm(_lstm(lsd, torch.float32), feats.cuda(), WORDMAP, beamSize=k)[0] == \\
-            do.beam_search(lsd, feats, "lstm", k, V - 2, V - 1, V)[0]
-        assert beam_search_transformer(_transformer(tsd, torch.float32), feats.cuda(), WORDMAP, beamSize=k)[0] == \\
-            do.beam_search(tsd, feats, "transformer", k, V - 2, V - 1, V)[0]
+        got = beam_search_lstm(_lstm(lsd, torch.float32), feats.cuda(), WORDMAP, beamSize=k)[0]
+        assert got == do.beam_search(lsd, feats, "lstm", k, V - 2, V - 1, V)[0]
+        got = beam_search_transformer(_transformer(tsd, torch.float32), feats.cuda(), WORDMAP, beamSize=k)[0]
+        assert got == do.beam_search(tsd, feats, "transformer", k, V - 2, V - 1, V)[0]
     with pytest.raises(RuntimeError):                # beam width above the kernel maximum fails loudly
         beam_search_lstm(_lstm(lsd, torch.float32), feats.cuda(), WORDMAP, beamSize=9)
 
