@@ -136,25 +136,104 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
   __syncwarp();   // the scratch is reused by the next chunk
 }
 
-// Drain one accumulator stage: chunks c = half, half+2, ... of 32 columns each.  tmem_addr = TMEM address of
-// (this warp's lane quarter, first column of the stage); row0 = first row of this warp's 32-row slab.
+// bf16 output without residual / dropout mask (the Linear+GELU of every CNBlock, the decoders' operand outputs):
+// 64 columns at a time.  Bias / activation / scales are applied in the accumulator's row-per-thread layout, the
+// result is packed to bf16x2 and transposed through the same 4 KB scratch as 32 words per row, so every store
+// instruction writes one full 128-byte line of a row (the 32-column path writes 64 B per instruction).
+__device__ __forceinline__ void epilogue_unit_bf16(const EpiArgs& ep, float (&f)[64], float* scratch, int row0,
+                                                   int lane, int n0, int M) {
+  const int row = row0 + lane;
+  float rs = 1.0f;
+  if (ep.rowscale != nullptr && row < M) rs = __ldg(ep.rowscale + row / ep.rows_per_group);
+  if (ep.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+      f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+    }
+  }
+  if (ep.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = gelu_tanh_fast(f[j]);
+  } else if (ep.act == 2) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+  }
+  if (ep.colscale != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 64; j += 4) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(ep.colscale + n0 + j));
+      f[j] *= c.x * rs; f[j + 1] *= c.y * rs; f[j + 2] *= c.z * rs; f[j + 3] *= c.w * rs;
+    }
+  } else if (ep.rowscale != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) f[j] *= rs;
+  }
+  uint32_t* sw = reinterpret_cast<uint32_t*>(scratch);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 pk;
+    pk.x = pack_bf16x2(f[8 * q], f[8 * q + 1]);
+    pk.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+    pk.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+    pk.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+    *reinterpret_cast<uint4*>(sw + lane * 32 + ((q ^ (lane & 7)) << 2)) = pk;
+  }
+  __syncwarp();
+  const int rows = min(32, M - row0);
+  const int wq = lane >> 2, wr = lane & 3;     // this lane's word = columns n0 + 2*lane, +1
+  uint32_t* op = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (long long)row0 * ep.ldc + n0) + lane;
+  const long long ldw = ep.ldc >> 1;           // row stride in 32-bit words (ldc is even on this path)
+  if (rows == 32) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) op[r * ldw] = sw[r * 32 + ((wq ^ (r & 7)) << 2) + wr];
+  } else {
+    for (int r = 0; r < rows; ++r) op[r * ldw] = sw[r * 32 + ((wq ^ (r & 7)) << 2) + wr];
+  }
+  __syncwarp();
+}
+
+// Drain one accumulator stage in units of 64 columns (u = half, half+2, ...): the bf16 fast path above, or two
+// generic 32-column chunks.  tmem_addr = TMEM address of (this warp's lane quarter, first column of the stage);
+// row0 = first row of this warp's 32-row slab.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& ep, uint32_t tmem_addr, int half, int row0, int lane,
                                               float* scratch, int n_blk, int M, int N, uint64_t* tfull_bar,
                                               uint32_t acc_phase) {
   mbar_wait(tfull_bar, acc_phase);
   tc_fence_after();
+  const bool bf16_fast = (ep.out_dtype == CCX_BF16) && ep.residual == nullptr && ep.emask == nullptr &&
+                         ((ep.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(ep.out) & 3) == 0) &&
+                         (ep.bias == nullptr || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) &&
+                         (ep.colscale == nullptr || (reinterpret_cast<uintptr_t>(ep.colscale) & 15) == 0);
+  constexpr int UNITS = (BN + 63) / 64;
 #pragma unroll 1
-  for (int c = half; c < BN / 32; c += 2) {
-    const int n0 = n_blk * BN + c * 32;
+  for (int u = half; u < UNITS; u += 2) {
+    const int n0 = n_blk * BN + u * 64;
     if (n0 >= N) break;  // warp-uniform
-    uint32_t v[32];
-    tmem_ld32(tmem_addr + c * 32, v);
-    tmem_ld_wait();
-    float f[32];
+    if (bf16_fast && n0 + 64 <= N && BN >= 64) {
+      uint32_t v0[32], v1[32];
+      tmem_ld32(tmem_addr + u * 64, v0);
+      tmem_ld32(tmem_addr + u * 64 + 32, v1);
+      tmem_ld_wait();
+      float f[64];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (row0 < M) epilogue_chunk(ep, f, scratch, row0, lane, n0, M, N);
+      for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+      if (row0 < M) epilogue_unit_bf16(ep, f, scratch, row0, lane, n0, M);
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int n1 = n0 + c * 32;
+        if (n1 >= N || u * 64 + c * 32 >= BN) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_addr + u * 64 + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (row0 < M) epilogue_chunk(ep, f, scratch, row0, lane, n1, M, N);
+      }
+    }
   }
 }
 

@@ -267,7 +267,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   int bn = g.force_bn;
   if (bn == 0) {
     const long long mt = (g.M + BM - 1) / BM;
-    if (g.N % 256 == 0 && mt * (g.N / 256) >= num_sms()) bn = 256;
+    if (g.N % 256 == 0 && mt * (g.N / 256) * 5 >= num_sms() * 4) bn = 256;   // >= 0.8 wave of 128x256 tiles
     else if (mt * ((g.N + 127) / 128) >= num_sms() / 2 || g.N <= 64) bn = 128;
     else bn = 64;
     if (g.N <= 64) bn = 64;
