@@ -152,32 +152,45 @@ __device__ __forceinline__ void epilogue_unit_bf16(const EpiArgs& ep, float (&f)
       f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
     }
   }
-  if (ep.act == 1) {
-#pragma unroll
-    for (int j = 0; j < 64; ++j) f[j] = gelu_tanh_fast(f[j]);
-  } else if (ep.act == 2) {
-#pragma unroll
-    for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
-  }
-  if (ep.colscale != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 64; j += 4) {
-      const float4 c = __ldg(reinterpret_cast<const float4*>(ep.colscale + n0 + j));
-      f[j] *= c.x * rs; f[j + 1] *= c.y * rs; f[j + 2] *= c.z * rs; f[j + 3] *= c.w * rs;
-    }
-  } else if (ep.rowscale != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 64; ++j) f[j] *= rs;
-  }
   uint32_t* sw = reinterpret_cast<uint32_t*>(scratch);
+  if (ep.act == 1 && ep.colscale == nullptr && ep.rowscale == nullptr) {
+    // Linear + GELU (CNBlock): packed-fp16 GELU, two columns per instruction
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    uint4 pk;
-    pk.x = pack_bf16x2(f[8 * q], f[8 * q + 1]);
-    pk.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
-    pk.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
-    pk.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
-    *reinterpret_cast<uint4*>(sw + lane * 32 + ((q ^ (lane & 7)) << 2)) = pk;
+    for (int q = 0; q < 8; ++q) {
+      uint4 pk;
+      pk.x = gelu_tanh_f16x2_to_bf16x2(f[8 * q], f[8 * q + 1]);
+      pk.y = gelu_tanh_f16x2_to_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+      pk.z = gelu_tanh_f16x2_to_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+      pk.w = gelu_tanh_f16x2_to_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+      *reinterpret_cast<uint4*>(sw + lane * 32 + ((q ^ (lane & 7)) << 2)) = pk;
+    }
+  } else {
+    if (ep.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = gelu_tanh_fast(f[j]);
+    } else if (ep.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
+    if (ep.colscale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(ep.colscale + n0 + j));
+        f[j] *= c.x * rs; f[j + 1] *= c.y * rs; f[j + 2] *= c.z * rs; f[j + 3] *= c.w * rs;
+      }
+    } else if (ep.rowscale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] *= rs;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 pk;
+      pk.x = pack_bf16x2(f[8 * q], f[8 * q + 1]);
+      pk.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+      pk.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+      pk.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+      *reinterpret_cast<uint4*>(sw + lane * 32 + ((q ^ (lane & 7)) << 2)) = pk;
+    }
   }
   __syncwarp();
   const int rows = min(32, M - row0);
