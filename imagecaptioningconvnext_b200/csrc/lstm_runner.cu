@@ -72,7 +72,7 @@ int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* s
   if (s == nullptr || b == nullptr) return CCX_ERR_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   const int B = s->B, T = s->T, P = s->P, E = s->E, A = s->A, D = s->D, Emb = s->Emb;
-  const int K = Emb + E + D, hoff = Emb + E;
+  const int K = Emb + E + D, hoff = Emb + E, AE = A + E;
   const int cd = s->compute_dtype;
   const bool f32 = (cd == CCX_F32);
   int rc;
@@ -80,19 +80,19 @@ int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* s
     const int bt = s->bts_host[t];
     if (bt <= 0) continue;
     float* dG = b->dG_all + static_cast<long long>(t) * B * 4 * D;
-    float* dHG = b->dHG_all + static_cast<long long>(t) * B * (A + E);
+    float* dHG = b->dHG_all + static_cast<long long>(t) * B * AE;
     float* dXH = b->dXH_all + static_cast<long long>(t) * B * K;
+    // (1) point-wise LSTM backward; also emits dgates as the dgrad GEMM's A operand and clears the attention-backward
+    //     accumulator columns of dHG[t] (two launches fewer per step than separate convert / memset)
     if ((rc = lstm_pointwise_bwd(s->G + static_cast<long long>(t) * B * 4 * D, 4 * D,
                                  s->C_all + static_cast<long long>(t) * B * D,
                                  s->C_all + static_cast<long long>(t + 1) * B * D,
                                  b->dH_all + static_cast<long long>(t) * D, static_cast<long long>(T) * D,
                                  s->dropmask ? s->dropmask + static_cast<long long>(t) * D : nullptr,
-                                 static_cast<long long>(T) * D, b->dh, b->dc, dG, 4 * D, bt, D, st)))
+                                 static_cast<long long>(T) * D, b->dh, b->dc, dG, 4 * D, bt, D, st, b->scratch_hi,
+                                 f32 ? b->scratch_lo : nullptr, cd, 4 * D, dHG, AE, P)))
       return rc;
-    // [d emb | d awe | d h_prev] = dgates . [W_ih | W_hh]
-    if ((rc = convert_operand(dG, nullptr, CCX_F32, 4 * D, nullptr, 0, 0, 1.f, b->scratch_hi, f32 ? b->scratch_lo : nullptr,
-                              cd, 4 * D, bt, 4 * D, 0, 0, st)))
-      return rc;
+    // (2) [d emb | d awe | d h_prev] = dgates . [W_ih | W_hh]
     GemmDesc g1;
     g1.A = b->scratch_hi; g1.A_lo = f32 ? b->scratch_lo : nullptr;
     g1.B = b->w_lstm_t; g1.B_lo = f32 ? b->w_lstm_t_lo : nullptr;
@@ -101,19 +101,16 @@ int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* s
     g1.M = bt; g1.N = K; g1.K = 4 * D;
     g1.in_dtype = cd; g1.out_dtype = CCX_F32;
     if ((rc = gemm_tn(g1, st))) return rc;
-    if ((rc = bahdanau_attention_bwd(s->att1, s->HG + static_cast<long long>(t) * B * (A + E), A + E, s->w_f, s->enc,
+    // (3)+(4) attention backward: writes d[att2 | gate] as fp32 (batched wgrad later) and as the next GEMM's operand
+    if ((rc = bahdanau_attention_bwd(s->att1, s->HG + static_cast<long long>(t) * B * AE, AE, s->w_f, s->enc,
                                      s->alphas + static_cast<long long>(t) * P, static_cast<long long>(T) * P, dXH + Emb,
                                      K, b->dalphas ? b->dalphas + static_cast<long long>(t) * P : nullptr,
-                                     static_cast<long long>(T) * P, dHG, A + E, b->d_att1, b->d_enc, b->d_wf, bt, P, A,
-                                     E, st)))
+                                     static_cast<long long>(T) * P, dHG, AE, b->d_att1, b->d_enc, b->d_wf, bt, P, A, E,
+                                     st, b->scratch2_hi, f32 ? b->scratch2_lo : nullptr, cd, AE, 1)))
       return rc;
-    // d h_{t-1} = d h_prev (from the gates GEMM) + dHG . [decoder_att ; f_beta]
-    const int AE = A + E;
-    if ((rc = convert_operand(dHG, nullptr, CCX_F32, AE, nullptr, 0, 0, 1.f, b->scratch_hi, f32 ? b->scratch_lo : nullptr,
-                              cd, AE, bt, AE, 0, 0, st)))
-      return rc;
+    // (5) d h_{t-1} = d h_prev (from the gates GEMM) + dHG . [decoder_att ; f_beta]
     GemmDesc g2;
-    g2.A = b->scratch_hi; g2.A_lo = f32 ? b->scratch_lo : nullptr;
+    g2.A = b->scratch2_hi; g2.A_lo = f32 ? b->scratch2_lo : nullptr;
     g2.B = b->w_h_t; g2.B_lo = f32 ? b->w_h_t_lo : nullptr;
     g2.C = b->dh; g2.residual = dXH + hoff;
     g2.lda = AE; g2.ldb = AE; g2.ldc = D; g2.ldr = K;

@@ -496,7 +496,8 @@ lstm_pointwise_bwd_kernel(const float* __restrict__ gates, long long ldg, const 
                           const float* __restrict__ c_new, const float* __restrict__ dh_fc, long long ld_fc,
                           const float* __restrict__ dropmask, long long ld_dm, const float* __restrict__ dh_carry,
                           float* __restrict__ dc_carry,  // in: dL/dc_new, out: dL/dc_prev   [bt, D]
-                          float* __restrict__ dgates, long long lddg, int bt, int D) {
+                          float* __restrict__ dgates, long long lddg, OpDst dg_op, long long ld_op,
+                          float* __restrict__ zero_rows, long long ld_zero, int n_zero, int bt, int D) {
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(bt) * D) return;
   const int b = static_cast<int>(idx / D), j = static_cast<int>(idx % D);
@@ -510,22 +511,32 @@ lstm_pointwise_bwd_kernel(const float* __restrict__ gates, long long ldg, const 
   if (dh_fc) dh += dh_fc[b * ld_fc + j] * (dropmask ? dropmask[b * ld_dm + j] : 1.f);
   const float dc = dc_carry[static_cast<long long>(b) * D + j] + dh * o_ * (1.f - tc * tc);
   float* dg = dgates + b * lddg;
-  dg[j] = dc * g_ * i_ * (1.f - i_);
-  dg[D + j] = dc * c_prev[static_cast<long long>(b) * D + j] * f_ * (1.f - f_);
-  dg[2 * D + j] = dc * i_ * (1.f - g_ * g_);
-  dg[3 * D + j] = dh * tc * o_ * (1.f - o_);
+  const float d0 = dc * g_ * i_ * (1.f - i_);
+  const float d1 = dc * c_prev[static_cast<long long>(b) * D + j] * f_ * (1.f - f_);
+  const float d2 = dc * i_ * (1.f - g_ * g_);
+  const float d3 = dh * tc * o_ * (1.f - o_);
+  dg[j] = d0; dg[D + j] = d1; dg[2 * D + j] = d2; dg[3 * D + j] = d3;
+  if (dg_op.hi != nullptr) {   // the same values as the A operand of the dgrad GEMM (saves a conversion launch)
+    put(dg_op, b * ld_op + j, d0); put(dg_op, b * ld_op + D + j, d1);
+    put(dg_op, b * ld_op + 2 * D + j, d2); put(dg_op, b * ld_op + 3 * D + j, d3);
+  }
+  if (zero_rows != nullptr && j < n_zero) zero_rows[b * ld_zero + j] = 0.f;   // attention-backward accumulators
   dc_carry[static_cast<long long>(b) * D + j] = dc * f_;
 }
 
 int lstm_pointwise_bwd(const float* gates, long long ldg, const float* c_prev, const float* c_new,
                        const float* dh_fc, long long ld_fc, const float* dropmask, long long ld_dm,
                        const float* dh_carry, float* dc_carry, float* dgates, long long lddg, int bt, int D,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, void* dg_op_hi, float* dg_op_lo, int dg_op_dtype, long long ld_op,
+                       float* zero_rows, long long ld_zero, int n_zero) {
   if (bt <= 0) return CCX_OK;
+  if (n_zero > D) return CCX_ERR_SHAPE;
+  OpDst dg_op{dg_op_hi, dg_op_lo, dg_op_dtype};
   const long long n = static_cast<long long>(bt) * D;
   ProfScope prof(PROF_LSTM, stream, (double)n * 48.0);
   lstm_pointwise_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      gates, ldg, c_prev, c_new, dh_fc, ld_fc, dropmask, ld_dm, dh_carry, dc_carry, dgates, lddg, bt, D);
+      gates, ldg, c_prev, c_new, dh_fc, ld_fc, dropmask, ld_dm, dh_carry, dc_carry, dgates, lddg, dg_op, ld_op,
+      zero_rows, ld_zero, n_zero, bt, D);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(128)
 attention_bwd_enc_kernel(const float* __restrict__ hg, long long ldhg, const float* __restrict__ enc,
                          const float* __restrict__ alpha, long long alpha_ld, const float* __restrict__ d_out,
                          long long ld_dout, float* __restrict__ d_hg, long long ld_dhg, float* __restrict__ d_enc,
-                         int P, int A, int E) {
+                         OpDst dhg_op, long long ld_op, int P, int A, int E) {
   __shared__ float s_a[PMAX];
   const int b = blockIdx.x;
   const int e = blockIdx.y * 128 + threadIdx.x;
@@ -563,7 +574,9 @@ attention_bwd_enc_kernel(const float* __restrict__ hg, long long ldhg, const flo
   if (ok) {
     const float gate = 1.0f / (1.0f + expf(-hg[b * ldhg + A + e]));
     const float dout = d_out[b * ld_dout + e];
-    d_hg[b * ld_dhg + A + e] = dout * awe * gate * (1.f - gate);
+    const float dgp = dout * awe * gate * (1.f - gate);
+    d_hg[b * ld_dhg + A + e] = dgp;
+    if (dhg_op.hi != nullptr) put(dhg_op, b * ld_op + A + e, dgp);
     draw = dout * gate;
   }
 #pragma unroll
@@ -579,7 +592,8 @@ __global__ void __launch_bounds__(512)
 attention_bwd_att_kernel(const float* __restrict__ att1, const float* __restrict__ hg, long long ldhg,
                          const float* __restrict__ w_f, const float* __restrict__ alpha, long long alpha_ld,
                          const float* __restrict__ d_alpha_ext, long long dalpha_ld, float* __restrict__ d_hg,
-                         long long ld_dhg, float* __restrict__ d_att1, float* __restrict__ d_wf, int P, int A) {
+                         long long ld_dhg, float* __restrict__ d_att1, float* __restrict__ d_wf, OpDst dhg_op,
+                         long long ld_op, int P, int A) {
   __shared__ float s_de[ATT_MAX_P_BWD];
   __shared__ float s_red[16];
   const int b = blockIdx.x;
@@ -612,6 +626,7 @@ attention_bwd_att_kernel(const float* __restrict__ att1, const float* __restrict
       }
     }
     d_hg[b * ld_dhg + a] = datt2;
+    if (dhg_op.hi != nullptr) put(dhg_op, b * ld_op + a, datt2);
     atomicAdd(d_wf + a, dwf);
   }
 }
@@ -620,21 +635,24 @@ int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, c
                            const float* alpha, long long alpha_ld, const float* d_out, long long ld_dout,
                            const float* d_alpha_ext, long long dalpha_ld, float* d_hg, long long ld_dhg,
                            float* d_att1, float* d_enc, float* d_wf, int bt, int P, int A, int E,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, void* op_hi, float* op_lo, int op_dtype, long long ld_op,
+                           int scratch_zeroed) {
   if (bt <= 0) return CCX_OK;
   if (P <= 0 || P > ATT_MAX_P_BWD || P > A || bt > 65535) return CCX_ERR_SHAPE;
+  OpDst dhg_op{op_hi, op_lo, op_dtype};
   ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (2.0 * A + 3.0 * E) * 4.0);
-  if (cudaMemset2DAsync(d_hg, ld_dhg * sizeof(float), 0, P * sizeof(float), bt, stream) != cudaSuccess)
+  if (!scratch_zeroed &&
+      cudaMemset2DAsync(d_hg, ld_dhg * sizeof(float), 0, P * sizeof(float), bt, stream) != cudaSuccess)
     return CCX_ERR_CUDA;
   dim3 g1(bt, (E + 127) / 128);
   if (P <= ATTB_P)
     attention_bwd_enc_kernel<ATTB_P><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout, d_hg,
-                                                             ld_dhg, d_enc, P, A, E);
+                                                             ld_dhg, d_enc, dhg_op, ld_op, P, A, E);
   else
     attention_bwd_enc_kernel<ATT_MAX_P_BWD><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout,
-                                                                    d_hg, ld_dhg, d_enc, P, A, E);
+                                                                    d_hg, ld_dhg, d_enc, dhg_op, ld_op, P, A, E);
   attention_bwd_att_kernel<<<bt, 512, 0, stream>>>(att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld, d_hg,
-                                                   ld_dhg, d_att1, d_wf, P, A);
+                                                   ld_dhg, d_att1, d_wf, dhg_op, ld_op, P, A);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

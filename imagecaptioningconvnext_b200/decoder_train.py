@@ -60,7 +60,8 @@ class _LstmTF(torch.autograd.Function):
         dal = None if dalphas is None else dalphas.contiguous()
         # the whole BPTT loop in ONE FFI call (csrc/lstm_runner.cu): per step LSTM point-wise backward, dgrad GEMM
         # through [W_ih | W_hh], attention backward, dgrad GEMM through [decoder_att ; f_beta]
-        scratch = Operand.empty((B, max(4 * D, A + E)), cd, dev)
+        scratch = Operand.empty((B, 4 * D), cd, dev)
+        scratch2 = Operand.empty((B, A + E), cd, dev)
         fwd = dec._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
         bd = _lib.LstmTFBwd()
         bd.dH_all, bd.dalphas = ptr(dH_all), ptr(dal)
@@ -69,6 +70,7 @@ class _LstmTF(torch.autograd.Function):
         bd.w_lstm_t, bd.w_lstm_t_lo = ptr(w_lstm_t.hi), w_lstm_t.lo_ptr
         bd.w_h_t, bd.w_h_t_lo = ptr(w_h_t.hi), w_h_t.lo_ptr
         bd.scratch_hi, bd.scratch_lo = ptr(scratch.hi), scratch.lo_ptr
+        bd.scratch2_hi, bd.scratch2_lo = ptr(scratch2.hi), scratch2.lo_ptr
         _lib.check(L.ccx_lstm_tf_backward(ctypes.byref(fwd), ctypes.byref(bd), st), "lstm_tf_backward")
         # ---- weight gradients, batched over time -------------------------------------------------------------
         TB = T * B

@@ -383,7 +383,8 @@ CCX_API int ccx_lstm_tf_forward(const ccx_lstm_tf* s, void* stream);
 /* BPTT over the same buffers: dH_all [B][T][D] (fc dgrad), dalphas [B][T][P] or NULL; work buffers dG_all
  * [T][B][4D], dHG_all [T][B][A+E], dXH_all [T][B][Emb+E+D] (zero-initialised by the caller), dh / dc [B][D]
  * (zero-initialised; on return dL/dh_0, dL/dc_0), d_att1 [B*P,A] (+=), d_enc [B,P,E] (+=, may be NULL), d_wf [A];
- * w_*_t = transposed weight operands [in, out]; scratch = operand staging of max(4D, A+E) * B elements. */
+ * w_*_t = transposed weight operands [in, out]; scratch / scratch2 = operand staging buffers (written by the
+ * point-wise and attention backward kernels themselves: 5 launches per step). */
 typedef struct ccx_lstm_tf_bwd {
   const float* dH_all;
   const float* dalphas;
@@ -399,8 +400,10 @@ typedef struct ccx_lstm_tf_bwd {
   const void* w_lstm_t_lo;
   const void* w_h_t; /* [D, A+E] operand */
   const void* w_h_t_lo;
-  void* scratch_hi;
+  void* scratch_hi;  /* [B, 4D] operand staging of dgates */
   float* scratch_lo;
+  void* scratch2_hi; /* [B, A+E] operand staging of d[att2 | gate] */
+  float* scratch2_lo;
 } ccx_lstm_tf_bwd;
 CCX_API int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* stream);
 
