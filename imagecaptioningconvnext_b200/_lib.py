@@ -234,6 +234,18 @@ class Operand:
             op.lo.zero_()
         return op
 
+    def refresh(self, x_fp32):
+        """Re-convert a new fp32 value INTO this operand's buffers (same pointers: weight tables and captured CUDA
+        graphs that reference them stay valid)."""
+        x = x_fp32.contiguous()
+        if x.shape != self.hi.shape:
+            raise ValueError("Operand.refresh: shape changed")
+        if self.dtype == torch.bfloat16:
+            check(lib().ccx_cast_bf16(ptr(x), ptr(self.hi), x.numel(), stream_ptr()), "cast_bf16")
+        else:
+            check(lib().ccx_split_tf32(ptr(x), ptr(self.hi), ptr(self.lo), x.numel(), stream_ptr()), "split_tf32")
+        return self
+
     @staticmethod
     def prepare(x_fp32, compute_dtype):
         if compute_dtype == torch.bfloat16:

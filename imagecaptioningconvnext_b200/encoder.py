@@ -152,7 +152,7 @@ class Encoder(nn.Module):
         self.prepared()
         key = (tuple(images.shape), images.dtype, images.device)
         entry = self._graphs.get(key)
-        if entry is None or entry[3] != self._prep_key:
+        if entry is None or entry[3] != self._prep_key[:3]:
             static_in = images.clone()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -163,7 +163,7 @@ class Encoder(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 static_out = self._forward_eager_nograd(static_in)
-            entry = (g, static_in, static_out, self._prep_key)
+            entry = (g, static_in, static_out, self._prep_key[:3])
             self._graphs[key] = entry
         g, static_in, static_out, _ = entry
         static_in.copy_(images)
@@ -194,47 +194,60 @@ class Encoder(nn.Module):
         return out
 
     def prepared(self):
-        """Kernel-side weight table (re-laid-out / bf16 or tf32-split copies).  Rebuilt when any parameter changes, but
-        only the entries whose OWN parameter changed are re-converted (fine-tuning touches 3 of the 36 blocks per step;
-        re-casting all 88 M weights every step would cost more than the trainable blocks' forward)."""
+        """Kernel-side weight table (re-laid-out / bf16 or tf32-split copies of the fp32 master weights).
+        Built once; afterwards a changed parameter (optimizer step, load_state_dict) is re-converted IN PLACE into
+        its existing buffer, so the table's pointers never change (fine-tuning touches 3 of the 36 blocks per step;
+        rebuilding the table or re-casting all 88 M weights every step costs more than those blocks' forward)."""
         params = list(self.convnext.parameters())
-        key = (self.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(),
-               sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params))
+        vsum = sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params)
+        key = (self.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(), vsum)
         if self._prep_key == key:
             return self._prep[0]
         cd = self.compute_dtype
-        cache = getattr(self, "_entry_cache", None)
-        if cache is None or cache.get("__dtype__") != cd:
-            cache = {"__dtype__": cd}
-        self._entry_cache = cache
-        keep = []
-
-        def cached(name, p, make):
-            k = (p.data_ptr(), p._version + getattr(p, "_ccx_epoch", 0))
-            hit = cache.get(name)
-            if hit is None or hit[0] != k:
-                hit = (k, make(p.detach()))
-                cache[name] = hit
-            keep.append(hit[1])
-            return hit[1]
+        if (self._prep is not None and self._prep_key is not None and self._prep_key[:3] == key[:3]):
+            # same storage, same dtype: refresh only the derived copies whose source parameter changed
+            for ent in self._derived:
+                p = ent["param"]
+                k = p._version + getattr(p, "_ccx_epoch", 0)
+                if k != ent["key"]:
+                    ent["refresh"](p.detach())
+                    ent["key"] = k
+            self._prep_key = key
+            return self._prep[0]
+        keep, derived = [], []
 
         def f32(p):
             t = p.detach()
             if t.dtype != torch.float32 or not t.is_cuda:
                 raise ValueError("Encoder parameters must be float32 CUDA tensors (call .cuda())")
-            t = t.contiguous()
+            if not t.is_contiguous():
+                raise ValueError("Encoder parameters must be contiguous")
             keep.append(t)
             return t.data_ptr()
+
+        def relayout(p, fn):
+            """fp32 re-laid-out copy (depthwise filter tap-major, stem [48][128]) refreshed in place."""
+            buf = fn(p.detach()).contiguous()
+            derived.append({"param": p, "key": p._version + getattr(p, "_ccx_epoch", 0),
+                            "refresh": lambda t, buf=buf, fn=fn: buf.copy_(fn(t))})
+            keep.append(buf)
+            return buf
+
+        def operand(p, fn=lambda t: t):
+            op = Operand.prepare(fn(p.detach()).contiguous(), cd)
+            derived.append({"param": p, "key": p._version + getattr(p, "_ccx_epoch", 0),
+                            "refresh": lambda t, op=op, fn=fn: op.refresh(fn(t))})
+            keep.append(op)
+            return op
 
         def op_ptrs(op):
             return op.hi.data_ptr(), (op.lo.data_ptr() if op.lo is not None else None)
 
         self._block_ops = []   # per CNBlock: dict(dw_w, w1, w2) python-side handles (used by encoder_train.py)
         self._down_ops = {}    # downsample child index (2, 4, 6) -> Operand of the re-ordered conv weight
-
         w = _lib.EncoderWeights()
         ch = list(self.convnext.children())
-        stem_w = cached("stem", ch[0][0].weight, lambda t: t.reshape(128, 48).t().contiguous())
+        stem_w = relayout(ch[0][0].weight, lambda t: t.reshape(128, 48).t())
         w.stem_w, w.stem_b = stem_w.data_ptr(), f32(ch[0][0].bias)
         w.stem_ln_g, w.stem_ln_b = f32(ch[0][1].weight), f32(ch[0][1].bias)
         bi = 0
@@ -242,32 +255,29 @@ class Encoder(nn.Module):
             Cc = DIMS[s]
             for blk in ch[1 + 2 * s]:
                 bw = w.blocks[bi]
-                dw = cached(f"dw{bi}", blk.block[0].weight, lambda t, Cc=Cc: t.reshape(Cc, 49).t().contiguous())
+                dw = relayout(blk.block[0].weight, lambda t, Cc=Cc: t.reshape(Cc, 49).t())
                 bw.dw_w, bw.dw_b = dw.data_ptr(), f32(blk.block[0].bias)
                 bw.ln_g, bw.ln_b = f32(blk.block[2].weight), f32(blk.block[2].bias)
-                w1 = cached(f"w1_{bi}", blk.block[3].weight, lambda t: Operand.prepare(t.contiguous(), cd))
-                w2 = cached(f"w2_{bi}", blk.block[5].weight, lambda t: Operand.prepare(t.contiguous(), cd))
+                w1, w2 = operand(blk.block[3].weight), operand(blk.block[5].weight)
                 bw.w1, bw.w1_lo = op_ptrs(w1)
                 bw.b1 = f32(blk.block[3].bias)
                 bw.w2, bw.w2_lo = op_ptrs(w2)
                 bw.b2 = f32(blk.block[5].bias)
-                bw.layer_scale = f32(blk.layer_scale.view(Cc))
+                bw.layer_scale = f32(blk.layer_scale)          # (C,1,1) contiguous == [C]
                 self._block_ops.append({"dw_w": dw, "w1": w1, "w2": w2})
                 bi += 1
             if s > 0:
                 d = ch[2 * s]
                 dwn = w.down[s - 1]
                 dwn.ln_g, dwn.ln_b = f32(d[0].weight), f32(d[0].bias)
-                wd = cached(f"down{s}", d[1].weight,
-                            lambda t, Cc=Cc, Ci=DIMS[s - 1]: Operand.prepare(
-                                t.permute(0, 2, 3, 1).reshape(Cc, 4 * Ci).contiguous(), cd))
+                wd = operand(d[1].weight, lambda t, Cc=Cc, Ci=DIMS[s - 1]: t.permute(0, 2, 3, 1).reshape(Cc, 4 * Ci))
                 dwn.w, dwn.w_lo = op_ptrs(wd)
                 self._down_ops[2 * s] = wd
                 dwn.b = f32(d[1].bias)
         for s in range(4):
             w.depths[s], w.dims[s] = DEPTHS[s], DIMS[s]
         w.compute_dtype = _lib.dt_code(cd)
-        self._prep, self._prep_key = (w, keep), key
+        self._prep, self._prep_key, self._derived = (w, keep), key, derived
         return w
 
     def _workspace(self, B, H, W, device):

@@ -34,3 +34,24 @@ for i in range(16):
 print("gc disabled:", ts)
 gc.enable()
 print("gc counts", gc.get_count(), "objects", len(gc.get_objects()))
+
+# ---- GPU-time per phase (CUDA events at phase boundaries, no host sync) vs host enqueue time per phase ----
+from imagecaptioningconvnext_b200.losses import packed_cross_entropy
+def one(events, host):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    t = [time.perf_counter()]
+    ev[0].record()
+    feats = enc(imgs); ev[1].record(); t.append(time.perf_counter())
+    s, cs, dl, al, _ = dec(teacherForcing=True, encoder_out=feats, encoded_captions=caps, caption_lengths=lens)
+    loss = packed_cross_entropy(s, cs, dl) + ((1.0 - al.sum(dim=1)) ** 2).mean(); ev[2].record(); t.append(time.perf_counter())
+    e_opt.zero_grad(set_to_none=False); d_opt.zero_grad(set_to_none=False); loss.backward(); ev[3].record(); t.append(time.perf_counter())
+    e_opt.step(); d_opt.step(); ev[4].record(); t.append(time.perf_counter())
+    events.append(ev); host.append([t[i + 1] - t[i] for i in range(4)])
+events, host = [], []
+for _ in range(10): one(events, host)
+torch.cuda.synchronize()
+names = ["encoder fwd", "decoder fwd+loss", "backward", "optimizer"]
+for i, n in enumerate(names):
+    g = sum(ev[i].elapsed_time(ev[i + 1]) for ev in events[3:]) / len(events[3:])
+    h = sum(hh[i] for hh in host[3:]) / len(host[3:]) * 1e3
+    print(f"{n:18s} gpu-span {g:6.2f} ms   host-enqueue {h:6.2f} ms")
