@@ -32,6 +32,7 @@ static constexpr int DW_CH = 128;            // channels per CTA
 static constexpr int DW_THREADS = 256;
 static constexpr int DW_TILE_BYTES = DW_HALO * DW_HALO * DW_CH * 4;  // 100,352
 static constexpr int DW_SMEM = DW_TILE_BYTES + 6144 /*stats*/;
+static constexpr int DW_SMEM64 = DW_TILE_BYTES / 2 + 6144;      // 64-channel tiles: 56,320 B -> 4 CTAs per SM
 
 struct DwArgs {
   const float* w;      // [49][C]  tap-major depthwise filter
@@ -222,7 +223,8 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
 // the issue slots per MAC — v1 is issue-bound (~1.7 instructions per FFMA), not FMA-pipe or HBM bound.
 //   warp = (p, g): p = pixel half (4x8 output patch), g = 64-channel group; 32 float2 accumulators, 49 float2 taps.
 // ---------------------------------------------------------------------------------------------------------
-static constexpr int DW2_THREADS = 128;
+// CH = channels per CTA (64 or 128): 64 halves the halo tile (50 KB) so FOUR CTAs are resident per SM and the
+// TMA-wait / FMA / LayerNorm-exchange phases of different tiles overlap four ways instead of two.
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
@@ -233,26 +235,29 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
-__global__ void __launch_bounds__(DW2_THREADS, 2)
+template <int CH>
+__global__ void __launch_bounds__(CH, 256 / CH)
 dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
+  constexpr int NG = CH / 64;                 // 64-channel groups (warps per pixel half)
+  constexpr int TILE_BYTES = DW_HALO * DW_HALO * CH * 4;
   extern __shared__ __align__(1024) float dw_smem[];
   float* tile = dw_smem;                                             // [14][14][128]
-  float* part = dw_smem + DW_TILE_BYTES / 4;                         // [2 stat][2 p][2 g][32 px] = 256 f
-  float* clpart = part + 512;                                        // [8 rank][2 stat][64 px]
+  float* part = dw_smem + TILE_BYTES / 4;                            // [2 stat][2 p][NG g][32 px]
+  float* clpart = part + 512;                                        // [<=16 rank][2 stat][64 px]
   __shared__ uint64_t bar;
   __shared__ float s_mean[64], s_rstd[64];
 
   cg::cluster_group cluster = cg::this_cluster();
-  const int nc = a.C / DW_CH;
+  const int nc = a.C / CH;
   const int crank = blockIdx.x;
   const int b = blockIdx.z;
   const int th = blockIdx.y / a.tiles_w, tw = blockIdx.y - th * a.tiles_w;
   const int h0 = th * DW_TILE, w0 = tw * DW_TILE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = warp >> 1;   // pixel half
-  const int g = warp & 1;    // 64-channel group
+  const int p = warp / NG;   // pixel half
+  const int g = warp % NG;   // 64-channel group
   const int ch_local = g * 64 + lane * 2;
-  const int ch = crank * DW_CH + ch_local;
+  const int ch = crank * CH + ch_local;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -261,8 +266,8 @@ dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bar, DW_TILE_BYTES);
-    tma_load_4d(tile, &tmX, &bar, crank * DW_CH, w0 - 3, h0 - 3, b);
+    mbar_expect_tx(&bar, TILE_BYTES);
+    tma_load_4d(tile, &tmX, &bar, crank * CH, w0 - 3, h0 - 3, b);
   }
   float2 wt[49];
 #pragma unroll
@@ -276,12 +281,12 @@ dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   for (int i = 0; i < 32; ++i) acc[i] = bias;
 
   mbar_wait(&bar, 0);
-  const float* tp = tile + (p * 4) * DW_HALO * DW_CH + ch_local;
+  const float* tp = tile + (p * 4) * DW_HALO * CH + ch_local;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
 #pragma unroll
     for (int c = 0; c < DW_HALO; ++c) {
-      const float2 v = *reinterpret_cast<const float2*>(tp + (r * DW_HALO + c) * DW_CH);
+      const float2 v = *reinterpret_cast<const float2*>(tp + (r * DW_HALO + c) * CH);
 #pragma unroll
       for (int oh = 0; oh < 4; ++oh) {
         const int kr = r - oh;
@@ -304,19 +309,20 @@ dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
     }
     warp_transpose_reduce32(s1, lane);
     warp_transpose_reduce32(s2, lane);
-    part[((0 * 2 + p) * 2 + g) * 32 + lane] = s1[0];
-    part[((1 * 2 + p) * 2 + g) * 32 + lane] = s2[0];
+    part[((0 * 2 + p) * NG + g) * 32 + lane] = s1[0];
+    part[((1 * 2 + p) * NG + g) * 32 + lane] = s2[0];
   }
   if (plain) {
     if (threadIdx.x < 64) { s_mean[threadIdx.x] = 0.f; s_rstd[threadIdx.x] = 1.f; }
     __syncthreads();
   } else {
     __syncthreads();
-    {
-      // thread -> (stat, p, px): sum the 2 channel-group partials, publish to every CTA of the cluster
-      const int stat = threadIdx.x >> 6, pp = (threadIdx.x >> 5) & 1, px = threadIdx.x & 31;
-      const float* src = part + ((stat * 2 + pp) * 2) * 32 + px;
-      const float tot = src[0] + src[32];
+    for (int idx = threadIdx.x; idx < 128; idx += CH) {
+      // idx -> (stat, p, px): sum the channel-group partials, publish to every CTA of the cluster
+      const int stat = idx >> 6, pp = (idx >> 5) & 1, px = idx & 31;
+      const float* src = part + ((stat * 2 + pp) * NG) * 32 + px;
+      float tot = src[0];
+      if (NG == 2) tot += src[32];
       for (int r = 0; r < nc; ++r) {
         float* dst = cluster.map_shared_rank(clpart, r);
         dst[(crank * 2 + stat) * 64 + pp * 32 + px] = tot;
@@ -390,6 +396,9 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
                cudaStream_t stream, const float* addend) {
   if (B <= 0 || H <= 0 || W <= 0 || B > 65535) return CCX_ERR_SHAPE;
   if (C % DW_CH != 0 || C / DW_CH > 8 || C < DW_CH) return CCX_ERR_SHAPE;
+  static const bool use_v1 = (getenv("CCX_DWCONV_V1") != nullptr);   // A/B switch for profiling
+  // 64 channels per CTA (4 resident CTAs per SM) whenever the LayerNorm cluster stays within the portable size 8
+  const int CH = (!use_v1 && C / 64 <= 8 && getenv("CCX_DWCONV_CH128") == nullptr) ? 64 : DW_CH;
   if (out_dtype != CCX_F32 && out_dtype != CCX_BF16) return CCX_ERR_DTYPE;
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return CCX_ERR_TMA;
@@ -399,7 +408,7 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   CUtensorMap tm;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {DW_CH, DW_HALO, DW_HALO, 1};
+  cuuint32_t box[4] = {(cuuint32_t)CH, DW_HALO, DW_HALO, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -410,12 +419,13 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   if (!configured) {
     if (cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
             cudaSuccess ||
-        cudaFuncSetAttribute(dwconv7_ln_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
+        cudaFuncSetAttribute(dwconv7_ln_kernel_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(dwconv7_ln_kernel_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM64) !=
             cudaSuccess)
       return CCX_ERR_CUDA;
     configured = true;
   }
-  static const bool use_v1 = (getenv("CCX_DWCONV_V1") != nullptr);   // A/B switch for profiling
   DwArgs a;
   a.w = w49c; a.bias = bias; a.gamma = gamma; a.beta = beta;
   a.out = out; a.out_lo = out_lo; a.addend = addend;
@@ -425,11 +435,11 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   a.eps = eps;
   a.out_dtype = out_dtype;
 
-  const int nc = C / DW_CH;
+  const int nc = C / CH;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nc, a.tiles_w * a.tiles_h, B);
-  cfg.blockDim = dim3(use_v1 ? DW_THREADS : DW2_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = DW_SMEM;
+  cfg.blockDim = dim3(use_v1 ? DW_THREADS : CH, 1, 1);
+  cfg.dynamicSmemBytes = (CH == 64) ? DW_SMEM64 : DW_SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -443,7 +453,11 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   if (use_v1) {
     if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
   } else {
-    if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel_v2, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+    if (CH == 64) {
+      if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel_v2<64>, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+    } else {
+      if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel_v2<128>, tm, a) != cudaSuccess) return CCX_ERR_CUDA;
+    }
   }
   return CCX_OK;
 }
