@@ -438,9 +438,12 @@ def run_extras(args, dev, world, rank, local):
         tr = tr.to(dev).train()
         d_opt, _ = make_optimizers(enc2, tr)
         tr_w = wrap(tr)
+        ms_eager = _timed(lambda: caption_train_step(enc2, tr_w, imgs, caps, lens, d_opt, None), 20, 10, dev, world)
+        tr.enable_cuda_graph()       # decoder forward / backward bodies replayed as two CUDA graphs
         ms = _timed(lambda: caption_train_step(enc2, tr_w, imgs, caps, lens, d_opt, None), 20, 10, dev, world)
         out[f"train_transformer_frozen_encoder_{name}"] = {
-            "images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms, "batch_per_gpu": B,
+            "images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms, "ms_per_step_eager_launches": ms_eager,
+            "batch_per_gpu": B,
             "config": "BASELINE.json configs[2]: frozen encoder + TransformerDecoder, teacher forcing, 52-token "
                       "rows (captions uniform 7..52), dropout on, clamp+Adam" + (", DDP/NCCL" if world > 1 else "")}
         del tr_w, d_opt

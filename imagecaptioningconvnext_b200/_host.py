@@ -44,8 +44,41 @@ class CcxEmbedding(nn.Embedding):
         return out.view(*tokens.shape, D)
 
 
+def _refresh_into(old, new):
+    """Copy freshly prepared values into the buffers of a previous preparation (same structure), so that device
+    pointers stay stable across optimizer steps (weight tables, captured CUDA graphs)."""
+    if isinstance(old, dict):
+        for k in old:
+            _refresh_into(old[k], new[k])
+    elif isinstance(old, (list, tuple)):
+        for a, b in zip(old, new):
+            _refresh_into(a, b)
+    elif isinstance(old, Operand):
+        old.hi.copy_(new.hi)
+        if old.lo is not None:
+            old.lo.copy_(new.lo)
+    elif torch.is_tensor(old):
+        if old.data_ptr() != new.data_ptr():      # views of the parameter storage need no copy
+            old.copy_(new)
+
+
+def _same_structure(a, b):
+    if type(a) is not type(b):
+        return False
+    if isinstance(a, dict):
+        return a.keys() == b.keys() and all(_same_structure(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(_same_structure(x, y) for x, y in zip(a, b))
+    if isinstance(a, Operand):
+        return a.hi.shape == b.hi.shape and a.dtype == b.dtype
+    if torch.is_tensor(a):
+        return a.shape == b.shape and a.dtype == b.dtype
+    return True
+
+
 class PreparedCache:
-    """Caches ``owner._prepare()`` (dict of kernel-side weight tensors) until any parameter changes."""
+    """Caches ``owner._prepare()`` (dict of kernel-side weight tensors).  When a parameter changes the new values are
+    copied INTO the existing buffers (pointer-stable), unless storage / dtype / shapes changed."""
 
     def __init__(self, owner):
         self._owner = [owner]   # list: keep the module out of nn.Module's attribute registration
@@ -60,8 +93,17 @@ class PreparedCache:
             for p in params:
                 if not p.is_cuda or p.dtype != torch.float32:
                     raise ValueError("parameters must be float32 CUDA tensors (call .cuda()); there is no CPU path")
-            self._val, self._key = owner._prepare(), key
+            fresh = owner._prepare()
+            if self._val is not None and self._key is not None and self._key[:3] == key[:3] and \
+                    _same_structure(self._val, fresh):
+                _refresh_into(self._val, fresh)
+            else:
+                self._val = fresh
+            self._key = key
         return self._val
+
+    def storage_key(self):
+        return None if self._key is None else self._key[:3]
 
     def invalidate(self):
         self._key = None

@@ -246,6 +246,12 @@ class TransformerDecoder(nn.Module):
         keep = 1.0 - self.dropout_p
         return (torch.bernoulli(torch.full(shape, keep, device=dev)) / keep).contiguous()
 
+    def enable_cuda_graph(self, enabled=True):
+        """Training option (not in the reference): replay the teacher-forced forward / backward as CUDA graphs;
+        see transformer_train.enable_cuda_graph for the static-buffer contract."""
+        from .transformer_train import enable_cuda_graph
+        return enable_cuda_graph(self, enabled)
+
     # ---- reference API ------------------------------------------------------------------------------------------
     def forwardWithTeacherForcing(self, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
         """models/transformerDecoder.py:88-108."""

@@ -6,6 +6,7 @@ the FFN hidden dropout — torch/nn/modules/transformer.py:1158-1199) uses multi
 torch.bernoulli (or injected by tests) and applied inside the GEMM epilogues / attention kernel.
 """
 import math
+import weakref
 
 import torch
 
@@ -39,9 +40,14 @@ def _masks(dec, B, T, Pn, dev):
     return m
 
 
-class _TransformerTF(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, dec, encoder_out, caps, kpm, *params):
+class _Payload:
+    """What the forward keeps for the backward (plain attribute bag; also used as the CUDA-graph static state)."""
+
+
+def _forward_body(dec, encoder_out, caps, kpm):
+    """Train-mode forward on libccx; returns (predictions, payload)."""
+    if True:
+        ctx = _Payload()
         L, st = _lib.lib(), _lib.stream_ptr()
         cd = dec.compute_dtype
         code = _lib.dt_code(cd)
@@ -91,12 +97,13 @@ class _TransformerTF(torch.autograd.Function):
         ctx.dec, ctx.saved, ctx.masks, ctx.kpm = dec, saved, masks, kpm
         ctx.x_last_op, ctx.mem, ctx.enc_op, ctx.caps = x_op, mem, enc_op, caps
         ctx.dims = (B, T, Pn, E)
-        ctx.enc_needs_grad = encoder_out.requires_grad
         ctx.enc_shape = encoder_out.shape
-        return predictions
+        return predictions, ctx
 
-    @staticmethod
-    def backward(ctx, dpred):
+
+def _backward_body(ctx, dpred, enc_needs_grad):
+    """Explicit backward on libccx; returns (d encoder_out or None, {parameter name: gradient})."""
+    if True:
         dec = ctx.dec
         L, st = _lib.lib(), _lib.stream_ptr()
         cd = dec.compute_dtype
@@ -168,13 +175,101 @@ class _TransformerTF(torch.autograd.Function):
         # encoder_proj
         denc = None
         if isinstance(dec.encoder_proj, torch.nn.Identity):
-            denc = dmem if ctx.enc_needs_grad else None
+            denc = dmem if enc_needs_grad else None
         else:
             denc = linear_bwd(dmem, ctx.enc_op, weight_t(dec.encoder_proj.weight, cd), cd, g("encoder_proj.weight"),
-                              g("encoder_proj.bias"), need_dx=ctx.enc_needs_grad)
+                              g("encoder_proj.bias"), need_dx=enc_needs_grad)
         if denc is not None:
             denc = denc.view(ctx.enc_shape)
-        return (None, denc, None, None) + tuple(grads.get(n) for n in names)
+        return denc, grads
+
+
+class _GraphState:
+    """One captured (forward, backward) pair for a fixed shape signature: static input buffers, the payload whose
+    tensors live in the graphs' private memory pool, static gradient outputs."""
+
+    def __init__(self):
+        self.calls = 0
+        self.fwd = self.bwd = None
+        self.owner = None          # weakref to the token of the forward whose backward has not run yet
+
+    @property
+    def pending(self):
+        """True while a graphed forward still waits for its backward (its autograd node is alive): the static
+        buffers belong to it, so another forward has to run eagerly."""
+        return self.owner is not None and self.owner() is not None
+
+
+class _Token:
+    pass
+
+
+def _graph_key(dec, encoder_out, caps, kpm):
+    return (tuple(encoder_out.shape), tuple(caps.shape), kpm is not None, dec.training, encoder_out.requires_grad,
+            dec.compute_dtype, encoder_out.device, dec._cache.storage_key(),
+            tuple(p.requires_grad for p in dec.parameters()))
+
+
+class _TransformerTF(torch.autograd.Function):
+    """Eager path, or — with ``dec.enable_cuda_graph()`` — the forward body and the backward body each replayed as
+    ONE CUDA graph (the step is ~580 tiny launches; replay removes the launch gaps and the host from the loop).
+    The first two calls of a shape signature run eagerly (warm-up), the third captures."""
+
+    @staticmethod
+    def forward(ctx, dec, encoder_out, caps, kpm, use_graph, *params):
+        ctx.enc_needs_grad = encoder_out.requires_grad
+        ctx.names = [n for n, _ in dec.named_parameters()]
+        graphs = getattr(dec, "_train_graphs", None)
+        st = None
+        if graphs is not None and use_graph:
+            dec._cache.get()                                   # weight copies refreshed in place, outside the graph
+            key = _graph_key(dec, encoder_out, caps, kpm)
+            st = graphs.get(key)
+            if st is None:
+                st = graphs[key] = _GraphState()
+            st.calls += 1
+            if st.pending or st.calls <= 2:
+                st = None                                      # buffers busy (two forwards in flight) or warming up
+        ctx.gstate = st
+        if st is None:
+            predictions, ctx.payload = _forward_body(dec, encoder_out, caps, kpm)
+            return predictions
+        if st.fwd is None:
+            st.enc_in, st.caps_in = encoder_out.detach().clone(), caps.clone()
+            st.kpm_in = None if kpm is None else kpm.clone()
+            torch.cuda.synchronize()
+            st.fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.fwd):
+                st.predictions, st.payload = _forward_body(dec, st.enc_in, st.caps_in, st.kpm_in)
+            st.pool = st.fwd.pool()
+        st.enc_in.copy_(encoder_out.detach())
+        st.caps_in.copy_(caps)
+        if kpm is not None:
+            st.kpm_in.copy_(kpm)
+        st.fwd.replay()
+        ctx.token = _Token()
+        st.owner = weakref.ref(ctx.token)
+        ctx.payload = st.payload
+        return st.predictions.detach()          # fresh alias: autograd attaches this call's node to it
+
+    @staticmethod
+    def backward(ctx, dpred):
+        st = ctx.gstate
+        if st is None:
+            denc, grads = _backward_body(ctx.payload, dpred, ctx.enc_needs_grad)
+            return (None, denc, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+        if st.owner is None or st.owner() is not ctx.token:
+            raise RuntimeError("graphed TransformerDecoder backward ran twice, or after its static buffers were reused")
+        if st.bwd is None:
+            st.dpred_in = dpred.detach().contiguous().clone()
+            torch.cuda.synchronize()
+            st.bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.bwd, pool=st.pool):
+                st.denc, st.grads = _backward_body(st.payload, st.dpred_in, ctx.enc_needs_grad)
+        st.dpred_in.copy_(dpred)
+        st.bwd.replay()
+        st.owner = None
+        return (None, st.denc, None, None, None) + tuple(st.grads.get(n) for n in ctx.names)
 
 
 def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
@@ -183,5 +278,15 @@ def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, ca
     caps = encoded_captions.contiguous()
     kpm = None if tgt_key_padding_mask is None else tgt_key_padding_mask.to(torch.uint8).contiguous()
     params = [p for _, p in dec.named_parameters()]
-    predictions = _TransformerTF.apply(dec, encoder_out, caps, kpm, *params)
+    use_graph = torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in params))
+    predictions = _TransformerTF.apply(dec, encoder_out, caps, kpm, use_graph, *params)
     return predictions, encoded_captions, decode_lengths
+
+
+def enable_cuda_graph(dec, enabled=True):
+    """Training option: replay the teacher-forced forward and backward as CUDA graphs (see _TransformerTF).
+    The returned predictions and the gradients handed to autograd are then STATIC buffers, overwritten by the next
+    graphed step of the same shape: consume them (loss, optimizer step, all-reduce) before the next forward, as a
+    normal training loop does.  A second forward issued before the first one's backward runs eagerly."""
+    dec._train_graphs = {} if enabled else None
+    return dec

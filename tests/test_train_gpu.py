@@ -83,6 +83,65 @@ def test_transformer_teacher_forcing_gradients(dtype, train_mode):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_transformer_graph_replayed_steps_equal_eager_steps(dtype):
+    """enable_cuda_graph(): five optimizer steps (fresh inputs each, weights moving under ClampAdam, random dropout
+    from the same generator state) give the eager launches' losses and weights; a forward issued
+    while another one waits for its backward falls back to eager instead of clobbering the static buffers."""
+    from oracle import decoder_oracle as do
+    from imagecaptioningconvnext_b200.optim import ClampAdam
+    sd = do.random_transformer_decoder_state(3, V)
+    B = 4
+    batches = []
+    for s in range(5):
+        caps, lens = do.synthetic_captions(B, 40 + s, V)
+        batches.append((do.synthetic_features(B, 30 + s).cuda(), caps.cuda(), lens.cuda(), (caps == 0).cuda()))
+
+    def run(graphed):
+        m = _transformer(sd, dtype).train()
+        if graphed:
+            m.enable_cuda_graph()
+        opt = ClampAdam([p for p in m.parameters() if p.requires_grad], lr=1e-3, grad_clip=5.0)
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        losses, enc_grads = [], []
+        for enc, caps, lens, kpm in batches:
+            enc_g = enc.clone().requires_grad_(True)
+            preds, _, dl = m(teacherForcing=True, encoder_out=enc_g, encoded_captions=caps, caption_lengths=lens,
+                             tgt_key_padding_mask=kpm)
+            loss = do.train_loss_transformer(preds, caps, dl)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+            enc_grads.append(enc_g.grad.clone())
+        return m, losses, enc_grads
+
+    m0, l0, g0 = run(False)
+    m1, l1, g1 = run(True)
+    st = next(iter(m1._train_graphs.values()))
+    assert st.fwd is not None and st.bwd is not None and st.calls == 5
+    # not bit-equal even eager-vs-eager: the bias / embedding gradient reductions use float atomics
+    assert max(abs(a - b) / abs(a) for a, b in zip(l0, l1)) < (1e-4 if dtype == torch.float32 else 2e-3), (l0, l1)
+    for a, b in zip(g0, g1):
+        # bf16: the trajectories drift apart through weight-rounding flips; fp32 is the strict check
+        assert _grad_err(a, b, dtype) < (2e-3 if dtype == torch.float32 else GRAD_TOL[dtype])
+    for (n, p), (_, q) in zip(m0.named_parameters(), m1.named_parameters()):
+        # an Adam step moves every element by ~lr whatever the gradient's size, so a noise-level gradient may flip
+        moved = ((p - q).abs() > 2e-4).float().mean().item()
+        assert moved < (5e-3 if dtype == torch.float32 else 0.1), (n, moved)
+    # two forwards in flight: the second must not reuse the static buffers
+    enc, caps, lens, kpm = batches[0]
+    pa, _, dla = m1(teacherForcing=True, encoder_out=enc, encoded_captions=caps, caption_lengths=lens,
+                    tgt_key_padding_mask=kpm)
+    keep = pa.clone()
+    pb, _, _ = m1(teacherForcing=True, encoder_out=batches[1][0], encoded_captions=batches[1][1],
+                  caption_lengths=batches[1][2], tgt_key_padding_mask=batches[1][3])
+    assert pb.data_ptr() != pa.data_ptr() and torch.equal(pa, keep)
+    do.train_loss_transformer(pa, caps, dla).backward()
+    do.train_loss_transformer(pb, batches[1][1], (batches[1][2].squeeze(1) - 1).tolist()).backward()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("train_mode", [False, True])
 def test_lstm_teacher_forcing_gradients_bptt(dtype, train_mode):
     from oracle import decoder_oracle as do
