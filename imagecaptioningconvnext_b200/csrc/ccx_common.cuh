@@ -321,4 +321,14 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(r);
 }
 
+// Blackwell packed fp32 FMA: two MACs per issue slot
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return d;
+}
+
 }  // namespace ccx

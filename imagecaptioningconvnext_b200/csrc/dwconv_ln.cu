@@ -226,15 +226,6 @@ dwconv7_ln_kernel(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
 // CH = channels per CTA (64 or 128): 64 halves the halo tile (50 KB) so FOUR CTAs are resident per SM and the
 // TMA-wait / FMA / LayerNorm-exchange phases of different tiles overlap four ways instead of two.
 
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(*reinterpret_cast<unsigned long long*>(&d))
-      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-        "l"(*reinterpret_cast<unsigned long long*>(&c)));
-  return d;
-}
-
 template <int CH>
 __global__ void __launch_bounds__(CH, 256 / CH)
 dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {

@@ -8,6 +8,7 @@
 //   split_tf32        helper: fp32 -> (tf32-representable hi, fp32 lo) pair for the 3xTF32 GEMM path
 //   cast_bf16         helper: fp32 -> bf16
 #include "ccx_common.cuh"
+#include "ccx_gemm.h"
 #include "ccx_ops.h"
 #include "ccx_prof.h"
 
@@ -99,6 +100,111 @@ stem_ln_kernel(const float* __restrict__ img, const unsigned char* __restrict__ 
   }
 }
 
+// v2 (used when rows are 16-byte addressable): persistent CTAs keep the 24 KB filter in shared memory across many
+// 64-pixel row segments, the next segment's pixels are fetched into registers while the current one is computed
+// (double-buffered staging, one barrier per segment), and the MACs are packed FFMA2.
+__global__ void __launch_bounds__(256, 2)
+stem_ln_kernel_v2(const float* __restrict__ img, const unsigned char* __restrict__ img_u8,
+                  const float* __restrict__ mean, const float* __restrict__ inv_std, const float* __restrict__ wk,
+                  const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float* __restrict__ out, int B, int Hin, int Win, int Hout, int Wout, float eps) {
+  __shared__ __align__(16) float w_s[48 * STEM_C];            // 24 KB
+  __shared__ __align__(16) float in_s[2][12][STEM_PX * 4];    // 24 KB
+  const int segs = (Wout + STEM_PX - 1) / STEM_PX;
+  const int items = B * Hout * segs;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool u8 = img_u8 != nullptr;
+
+  for (int i = tid; i < 48 * STEM_C / 4; i += 256)
+    reinterpret_cast<float4*>(w_s)[i] = __ldg(reinterpret_cast<const float4*>(wk) + i);
+
+  // staging slot k of this thread: 4 consecutive input columns of row (c, kh)
+  float4 stage[3];
+  auto fetch = [&](int item) {
+    const int seg = item % segs, oh = (item / segs) % Hout, b = item / (segs * Hout);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = tid + k * 256, rowi = i >> 6, chunk = i & 63;
+      const int c = rowi >> 2, kh = rowi & 3;
+      const int iw = (seg * STEM_PX + chunk) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iw < Wout * 4) {
+        const long long gi = ((static_cast<long long>(b) * 3 + c) * Hin + oh * 4 + kh) * Win + iw;
+        if (u8) {
+          const uchar4 q = __ldg(reinterpret_cast<const uchar4*>(img_u8 + gi));
+          const float m = __ldg(mean + c), is = __ldg(inv_std + c);
+          v.x = (static_cast<float>(q.x) / 255.0f - m) * is;
+          v.y = (static_cast<float>(q.y) / 255.0f - m) * is;
+          v.z = (static_cast<float>(q.z) / 255.0f - m) * is;
+          v.w = (static_cast<float>(q.w) / 255.0f - m) * is;
+        } else {
+          v = __ldg(reinterpret_cast<const float4*>(img + gi));
+        }
+      }
+      stage[k] = v;
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int i = tid + k * 256;
+      *reinterpret_cast<float4*>(&in_s[buf][i >> 6][(i & 63) * 4]) = stage[k];
+    }
+  };
+
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias) + lane);
+  const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  int item = blockIdx.x, buf = 0;
+  if (item < items) { fetch(item); commit(0); }
+  __syncthreads();
+  for (; item < items; item += gridDim.x, buf ^= 1) {
+    const int next = item + gridDim.x;
+    if (next < items) fetch(next);
+    float2 acc[8][2];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) { acc[p][0] = make_float2(bv.x, bv.y); acc[p][1] = make_float2(bv.z, bv.w); }
+#pragma unroll
+    for (int rowi = 0; rowi < 12; ++rowi) {
+      float4 wv[4];
+#pragma unroll
+      for (int kw = 0; kw < 4; ++kw)
+        wv[kw] = *reinterpret_cast<const float4*>(&w_s[(rowi * 4 + kw) * STEM_C + lane * 4]);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const float4 iv = *reinterpret_cast<const float4*>(&in_s[buf][rowi][(warp * 8 + p) * 4]);  // broadcast
+        const float in4[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+          const float2 a = make_float2(in4[kw], in4[kw]);
+          acc[p][0] = ffma2(a, make_float2(wv[kw].x, wv[kw].y), acc[p][0]);
+          acc[p][1] = ffma2(a, make_float2(wv[kw].z, wv[kw].w), acc[p][1]);
+        }
+      }
+    }
+    const int seg = item % segs, oh = (item / segs) % Hout, b = item / (segs * Hout);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const float s = warp_sum(acc[p][0].x + acc[p][0].y + acc[p][1].x + acc[p][1].y);
+      const float mu = s * (1.0f / STEM_C);
+      const float d0 = acc[p][0].x - mu, d1 = acc[p][0].y - mu, d2 = acc[p][1].x - mu, d3 = acc[p][1].y - mu;
+      const float q = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+      const float rstd = rsqrtf(q * (1.0f / STEM_C) + eps);
+      const int ow = seg * STEM_PX + warp * 8 + p;
+      if (ow < Wout) {
+        float4 o;
+        o.x = d0 * rstd * gv.x + be.x;
+        o.y = d1 * rstd * gv.y + be.y;
+        o.z = d2 * rstd * gv.z + be.z;
+        o.w = d3 * rstd * gv.w + be.w;
+        reinterpret_cast<float4*>(out + ((static_cast<long long>(b) * Hout + oh) * Wout + ow) * STEM_C)[lane] = o;
+      }
+    }
+    if (next < items) commit(buf ^ 1);
+    __syncthreads();
+  }
+}
+
 int stem_ln(const float* img, const unsigned char* img_u8, const float* mean, const float* inv_std, const float* wk,
             const float* bias, const float* gamma, const float* beta, float* out, int B, int Hin, int Win, float eps,
             cudaStream_t stream) {
@@ -111,8 +217,16 @@ int stem_ln(const float* img, const unsigned char* img_u8, const float* mean, co
   if (img_u8 != nullptr && (mean == nullptr || inv_std == nullptr)) return CCX_ERR_SHAPE;
   ProfScope prof(PROF_STEM, stream,
                  (double)B * (3.0 * Hin * Win * (img_u8 ? 1.0 : 4.0) + (double)Hout * Wout * STEM_C * 4.0));
-  stem_ln_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(img, img_u8, mean, inv_std, wk, bias, gamma, beta,
-                                                                   out, B, Hin, Win, Hout, Wout, eps);
+  const bool vec_ok = (Win % 4 == 0) && (reinterpret_cast<uintptr_t>(img) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(img_u8) % 4 == 0);
+  if (vec_ok) {
+    const long long cap = 2LL * num_sms();
+    stem_ln_kernel_v2<<<static_cast<unsigned>(grid < cap ? grid : cap), 256, 0, stream>>>(
+        img, img_u8, mean, inv_std, wk, bias, gamma, beta, out, B, Hin, Win, Hout, Wout, eps);
+  } else {
+    stem_ln_kernel<<<static_cast<unsigned>(grid), 256, 0, stream>>>(img, img_u8, mean, inv_std, wk, bias, gamma,
+                                                                     beta, out, B, Hin, Win, Hout, Wout, eps);
+  }
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
