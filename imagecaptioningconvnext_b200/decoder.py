@@ -224,7 +224,9 @@ class DecoderWithAttention(nn.Module):
             return lstm_teacher_forcing_with_grad(self, encoder_out, encoded_captions, caption_lengths)
         return self._tf_forward(encoder_out, encoded_captions, caption_lengths)[:5]
 
-    def _tf_forward(self, encoder_out, encoded_captions, caption_lengths):
+    def _tf_forward(self, encoder_out, encoded_captions, caption_lengths, dropmask_unsorted=None):
+        """dropmask_unsorted: (B, >=T, D) dropout multipliers in the CALLER's row order (the free-running training
+        path re-uses the masks of its greedy pass); default = a fresh draw / the injected mask, sorted order."""
         _lib.require_cuda(encoder_out, "encoder_out")
         B, E = encoder_out.size(0), encoder_out.size(-1)
         V, D = self.vocab_size, self.decoder_dim
@@ -244,7 +246,10 @@ class DecoderWithAttention(nn.Module):
         G = torch.empty((T, B, 4 * D), dtype=torch.float32, device=dev)
         alphas = torch.zeros((B, T, Pn), dtype=torch.float32, device=dev)
         H_all = Operand.zeros((B, T, D), cd, dev)
-        dm = self._dropout_mask(B, T, dev)
+        if dropmask_unsorted is not None:
+            dm = dropmask_unsorted[sort_ind][:, :T].contiguous()
+        else:
+            dm = self._dropout_mask(B, T, dev)
         # all embeddings at once: XH[t, b, 0:embed] = embedding[caps[b, t]]
         K = XH.hi.shape[2]
         _lib.check(L.ccx_embed_rows(ptr(encoded_captions), encoded_captions.stride(0), 0, ptr(self.embedding.weight),
@@ -265,10 +270,19 @@ class DecoderWithAttention(nn.Module):
         self._setup_extras = None
         return predictions, encoded_captions, decode_lengths, alphas, sort_ind, saved
 
-    @torch.no_grad()
     def forwardWithoutTeacherForcing(self, encoder_out, wordMap, maxDecodeLen):
-        """models/decoder.py:119-163 (greedy).  Finished rows are masked on the device instead of being compacted
-        with nonzero(): their predictions/alphas/sequences stay zero exactly as in the reference."""
+        """models/decoder.py:119-163 (greedy).  With autograd enabled (trainWithoutTeacherForcing,
+        trainMultiGPU.py:444-460) the outputs carry gradients to every parameter and to encoder_out."""
+        if torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .decoder_train import lstm_free_running_with_grad
+            return lstm_free_running_with_grad(self, encoder_out, wordMap, maxDecodeLen)
+        return self._greedy(encoder_out, wordMap, maxDecodeLen)
+
+    @torch.no_grad()
+    def _greedy(self, encoder_out, wordMap, maxDecodeLen, dropmask=False):
+        """Finished rows are masked on the device instead of being compacted with nonzero(): their
+        predictions/alphas/sequences stay zero exactly as in the reference.  dropmask: False = draw (train mode) or
+        none (eval); None / tensor (B, T, D) = use exactly this."""
         _lib.require_cuda(encoder_out, "encoder_out")
         B, E = encoder_out.size(0), encoder_out.size(-1)
         V, D, T = self.vocab_size, self.decoder_dim, int(maxDecodeLen)
@@ -287,7 +301,7 @@ class DecoderWithAttention(nn.Module):
         tokens[:, 0] = wordMap['<start>']
         active = torch.ones(B, dtype=torch.float32, device=dev)
         h_cur = Operand.empty((B, D), cd, dev)
-        dm = self._dropout_mask(B, T, dev)
+        dm = self._dropout_mask(B, T, dev) if dropmask is False else dropmask
         K = XH.hi.shape[2]
         for t in range(T):
             _lib.check(L.ccx_embed_rows(ptr(tokens), T + 1, t, ptr(self.embedding.weight), V, self.embed_dim, None,

@@ -18,7 +18,8 @@ from .train_ops import linear_bwd, to_operand, weight_t
 class _LstmTF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dec, holder, encoder_out, caps, lens, *params):
-        preds, caps_sorted, decode_lengths, alphas, sort_ind, saved = dec._tf_forward(encoder_out, caps, lens)
+        preds, caps_sorted, decode_lengths, alphas, sort_ind, saved = dec._tf_forward(
+            encoder_out, caps, lens, dropmask_unsorted=holder.get("dropmask_unsorted"))
         holder["caps_sorted"], holder["decode_lengths"], holder["sort_ind"] = caps_sorted, decode_lengths, sort_ind
         ctx.dec, ctx.saved = dec, saved
         ctx.enc_needs_grad = encoder_out.requires_grad
@@ -118,8 +119,47 @@ class _LstmTF(torch.autograd.Function):
         return (None, None, d_encoder_out, None, None) + tuple(grads.get(n) for n in names)
 
 
-def lstm_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths):
-    holder = {}
+def lstm_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, dropmask_unsorted=None):
+    holder = {"dropmask_unsorted": dropmask_unsorted}
     params = [p for _, p in dec.named_parameters()]
     preds, alphas = _LstmTF.apply(dec, holder, encoder_out, encoded_captions, caption_lengths, *params)
     return preds, holder["caps_sorted"], holder["decode_lengths"], alphas, holder["sort_ind"]
+
+
+def generated_captions(sequences, start_token, end_token, max_len):
+    """Greedy output (B, T) -> the caption tensor a teacher-forced pass would be fed to reproduce the same steps:
+    row = [<start>, generated ids ...] (B, T+1) and caption_lengths (B, 1) = decode length + 1, where the decode
+    length is the position of the first <end> + 1, or T (utils/utils.py:270-276)."""
+    B, T = sequences.shape
+    is_end = sequences == end_token
+    first_end = torch.where(is_end.any(dim=1), is_end.to(torch.int64).argmax(dim=1) + 1,
+                            torch.full((B,), T, dtype=torch.int64, device=sequences.device))
+    start = torch.full((B, 1), start_token, dtype=torch.int64, device=sequences.device)
+    return torch.cat([start, sequences], dim=1), (first_end + 1).unsqueeze(1)
+
+
+def lstm_free_running_with_grad(dec, encoder_out, wordMap, maxDecodeLen):
+    """Free-running TRAINING forward (models/decoder.py:119-163 with autograd, trainMultiGPU.py:444-460).
+
+    No gradient flows through argmax, and rows never interact, so the reference's 51-step autograd graph equals:
+    (1) the greedy pass (inference kernels, no graph kept) that fixes the generated ids and each row's finish step;
+    (2) a teacher-forced pass over [<start>, generated ids] with the SAME dropout masks, whose explicit BPTT
+    (_LstmTF) then yields exactly the gradients of the reference loop — h/c recurrences, attention, the embedding
+    rows of the sampled ids, encoder_out.  Outputs are returned in the caller's row order, zero past each row's
+    finish step like the reference's."""
+    T = int(maxDecodeLen)
+    B = encoder_out.size(0)
+    dev = encoder_out.device
+    dm = dec._dropout_mask(B, T, dev)                  # one draw, shared by both passes (None in eval mode)
+    _, _, sequences = dec._greedy(encoder_out.detach(), wordMap, T, dropmask=dm)
+    caps, lens = generated_captions(sequences, wordMap['<start>'], wordMap['<end>'], T)
+    preds_s, _, decode_lengths, alphas_s, sort_ind = lstm_teacher_forcing_with_grad(dec, encoder_out, caps, lens,
+                                                                                    dropmask_unsorted=dm)
+    inv = torch.empty_like(sort_ind)
+    inv[sort_ind] = torch.arange(B, device=dev)
+    pad_t = T - preds_s.size(1)
+    preds, alphas = preds_s[inv], alphas_s[inv]
+    if pad_t:
+        preds = torch.nn.functional.pad(preds, (0, 0, 0, pad_t))
+        alphas = torch.nn.functional.pad(alphas, (0, 0, 0, pad_t))
+    return preds, alphas, sequences

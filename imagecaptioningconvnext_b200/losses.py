@@ -76,3 +76,12 @@ def free_running_targets(sequences, captions, end_token, pad_token):
                                                    ptr(dlen), B, T, caps.shape[1], end_token, pad_token,
                                                    _lib.stream_ptr()), "free_running_targets")
     return targets, dlen
+
+
+def free_running_cross_entropy(scores, sequences, captions, end_token, pad_token):
+    """Loss of trainWithoutTeacherForcing (trainMultiGPU.py:448-450): CrossEntropyLoss over the rows
+    preprocessDecoderOutputForMetrics keeps — positions before each row's first generated <end> (inclusive) whose
+    ground-truth token is not <pad>.  Returns (loss with autograd, targets (B*T,) with -1 = ignored, token count)."""
+    targets, _ = free_running_targets(sequences, captions, end_token, pad_token)
+    n_valid = int((targets >= 0).sum())                  # the reference syncs here too (totalValidTokenCount)
+    return _PackedCE.apply(scores, targets, float(max(n_valid, 1))), targets, n_valid

@@ -7,7 +7,7 @@ gradient all-reduce over NCCL overlaps with the explicit backward.
 import torch
 
 from .decoder import DecoderWithAttention
-from .losses import packed_cross_entropy
+from .losses import free_running_cross_entropy, packed_cross_entropy
 from .optim import ClampAdam
 
 
@@ -24,10 +24,18 @@ def make_optimizers(encoder, decoder, decoder_lr=1e-4, encoder_lr=1e-4, grad_cli
 
 
 def caption_train_step(encoder, decoder, imgs, caps, caplens, decoder_optimizer, encoder_optimizer=None, pad_token=0,
-                       alpha_c=1.0):
-    """Returns the loss tensor (no host sync).  imgs (B,3,256,256) fp32, caps (B,52) int64, caplens (B,1) int64."""
+                       alpha_c=1.0, teacher_forcing=True, wordMap=None, max_decode_len=51):
+    """Returns the loss tensor (no host sync).  imgs (B,3,256,256) fp32, caps (B,52) int64, caplens (B,1) int64.
+    teacher_forcing=False: the free-running step of trainWithoutTeacherForcing (trainMultiGPU.py:423-460; needs
+    wordMap for <start>/<end>)."""
     feats = encoder(imgs)                                                              # trainMultiGPU.py:361
-    if isinstance(_unwrap(decoder), DecoderWithAttention):
+    if not teacher_forcing:
+        out = decoder(teacherForcing=False, encoder_out=feats, wordMap=wordMap, maxDecodeLen=max_decode_len)  # :445,:451
+        scores, sequences = out[0], out[-1]
+        loss, _, _ = free_running_cross_entropy(scores, sequences, caps, wordMap['<end>'], pad_token)   # :446-450
+        if isinstance(_unwrap(decoder), DecoderWithAttention):
+            loss = loss + alpha_c * ((1.0 - out[1].sum(dim=1)) ** 2).mean()           # :448
+    elif isinstance(_unwrap(decoder), DecoderWithAttention):
         scores, caps_sorted, decode_lengths, alphas, _ = decoder(teacherForcing=True, encoder_out=feats,
                                                                  encoded_captions=caps, caption_lengths=caplens)
         loss = packed_cross_entropy(scores, caps_sorted, decode_lengths)              # :364-367

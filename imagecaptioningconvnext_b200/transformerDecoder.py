@@ -334,11 +334,18 @@ class TransformerDecoder(nn.Module):
                           for _ in range(self.num_layers)],
                 "tokens": torch.zeros((rows, Tmax + 1), dtype=torch.long, device=dev)}
 
-    @torch.no_grad()
     def forwardWithoutTeacherForcing(self, encoder_out, wordMap, maxDecodeLen):
-        """models/transformerDecoder.py:110-160 (greedy), with a KV cache instead of prefix recomputation."""
+        """models/transformerDecoder.py:110-160 (greedy), with a KV cache instead of prefix recomputation.  With
+        autograd enabled (trainWithoutTeacherForcing, trainMultiGPU.py:444-460) the predictions carry gradients."""
+        if torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .transformer_train import transformer_free_running_with_grad
+            return transformer_free_running_with_grad(self, encoder_out, wordMap, maxDecodeLen)
+        return self._greedy(encoder_out, wordMap, maxDecodeLen)
+
+    @torch.no_grad()
+    def _greedy(self, encoder_out, wordMap, maxDecodeLen, dropout_free=False):
         _lib.require_cuda(encoder_out, "encoder_out")
-        if self.training and self.dropout_p > 0:
+        if self.training and self.dropout_p > 0 and not dropout_free:
             raise RuntimeError("free-running decode in train mode (dropout live) is not built; call .eval()")
         B, T, V = encoder_out.size(0), int(maxDecodeLen), self.vocab_size
         if T > self.maxLen:

@@ -283,6 +283,27 @@ def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, ca
     return predictions, encoded_captions, decode_lengths
 
 
+def transformer_free_running_with_grad(dec, encoder_out, wordMap, maxDecodeLen):
+    """Free-running TRAINING forward (models/transformerDecoder.py:110-160 with autograd).
+
+    The reference re-runs the whole prefix at every step and keeps all 51 graphs (O(T^2) forward and backward).
+    Under the causal mask the step-t logits depend only on tokens 0..t, a finished row is never computed again and
+    an active row's prefix holds no <pad>, so — no gradient passing through argmax — the same loss gradient comes
+    from (1) the KV-cached greedy pass that fixes the generated ids and (2) ONE causal teacher-forced pass over
+    [<start>, generated ids] with autograd, its logits zeroed past each row's finish step.  Exact for dropout-free
+    modules (eval mode, dropout=0; parity-tested against the reference's gradients).  DEVIATION with live dropout:
+    the ids are generated dropout-free and pass (2) draws one mask set per sequence, where the reference draws fresh
+    masks at every step's prefix recomputation (a different estimator of the same expectation)."""
+    from .decoder_train import generated_captions
+    T = int(maxDecodeLen)
+    _, sequences = dec._greedy(encoder_out.detach(), wordMap, T, dropout_free=True)
+    caps, lens = generated_captions(sequences, wordMap['<start>'], wordMap['<end>'], T)
+    params = [p for _, p in dec.named_parameters()]
+    preds = _TransformerTF.apply(dec, encoder_out, caps[:, :T].contiguous(), None, True, *params)
+    valid = torch.arange(T, device=preds.device).unsqueeze(0) < (lens - 1)
+    return preds * valid.unsqueeze(-1).to(preds.dtype), sequences
+
+
 def enable_cuda_graph(dec, enabled=True):
     """Training option: replay the teacher-forced forward and backward as CUDA graphs (see _TransformerTF).
     The returned predictions and the gradients handed to autograd are then STATIC buffers, overwritten by the next

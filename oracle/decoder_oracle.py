@@ -174,8 +174,10 @@ def lstm_teacher_forcing(sd, encoder_out, caps, caplens, dropmask=None):
     return preds, caps, dl, alphas, sort_ind
 
 
-def lstm_greedy(sd, encoder_out, start_tok, end_tok, max_len):
-    """models/decoder.py:119-163 (eval mode)."""
+def lstm_greedy(sd, encoder_out, start_tok, end_tok, max_len, dropmask=None):
+    """models/decoder.py:119-163.  dropmask: optional (B, max_len, D) multiplier applied to h before fc (the
+    nn.Dropout of :150 with the mask injected, rows in ORIGINAL order); None = eval mode.  Differentiable: the
+    free-running training mode (trainMultiGPU.py:423-498) back-propagates through this loop."""
     B, E = encoder_out.size(0), encoder_out.size(-1)
     enc = encoder_out.reshape(B, -1, E)
     h, c = init_hidden_state(sd, enc)
@@ -190,7 +192,8 @@ def lstm_greedy(sd, encoder_out, start_tok, end_tok, max_len):
         if len(act) == 0:
             break
         hn, cn, alpha = lstm_step(sd, enc[act], inputs[act], h[act], c[act])
-        p = F.linear(hn, sd["fc.weight"], sd["fc.bias"])
+        hd = hn if dropmask is None else hn * dropmask[act, t]
+        p = F.linear(hd, sd["fc.weight"], sd["fc.bias"])
         preds[act, t] = p
         alphas[act, t] = alpha
         ids = p.argmax(dim=1)
@@ -410,3 +413,14 @@ def train_loss_lstm(preds, caps_sorted, decode_lengths, alphas, alpha_c=1.0):
 def train_loss_transformer(preds, caps, decode_lengths):
     """trainMultiGPU.py:373-377."""
     return packed_cross_entropy(preds, caps[:, 1:], decode_lengths)
+
+
+def free_running_loss(preds, seqs, caps, end_tok, pad_tok, max_len, alphas=None, alpha_c=1.0):
+    """trainMultiGPU.py:448-458 (trainWithoutTeacherForcing): preprocessDecoderOutputForMetrics -> CrossEntropyLoss
+    (+ the alpha regulariser for the LSTM decoder)."""
+    from .metrics_oracle import preprocess_decoder_output_for_metrics
+    scores, targets, _, _ = preprocess_decoder_output_for_metrics(preds, seqs, caps, end_tok, pad_tok, max_len)
+    loss = F.cross_entropy(scores, targets)
+    if alphas is not None:
+        loss = loss + alpha_c * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+    return loss

@@ -134,6 +134,57 @@ def golden_transformer():
     torch.save(out, os.path.join(HERE, "transformer_decoder.pt"))
 
 
+def _grad_digest(named_grads):
+    """Small fingerprint of a gradient set: per tensor its norm and every 499th element."""
+    return {k: {"norm": g.norm(), "sub": g.reshape(-1)[::499].clone()} for k, g in named_grads}
+
+
+def golden_free_running():
+    """Reference free-running TRAINING step body (trainMultiGPU.py:444-460) on both decoders: greedy forward with
+    autograd, preprocessDecoderOutputForMetrics, CrossEntropyLoss (+ alpha term), backward.  Modules in eval mode
+    (dropout is random in train mode; the arithmetic is otherwise identical)."""
+    import torch.nn as nn
+    from models.decoder import DecoderWithAttention
+    from models.transformerDecoder import TransformerDecoder
+    from oracle import decoder_oracle as do
+    from oracle.metrics_oracle import preprocess_decoder_output_for_metrics as restated
+
+    # utils/utils.py cannot be imported (h5py); its preprocessDecoderOutputForMetrics is exec'd from the source text
+    src = open(os.path.join(REF, "utils", "utils.py")).read()
+    a = src.index("def preprocessDecoderOutputForMetrics")
+    ns = {"torch": torch}
+    exec(src[a:], ns)
+    preprocess = ns["preprocessDecoderOutputForMetrics"]
+    crit = nn.CrossEntropyLoss()
+    out = {}
+    B = 4
+    for kind, end_bias, fs in (("lstm", 0.21, 300), ("transformer", 3.2, 310)):
+        if kind == "lstm":
+            ref = DecoderWithAttention(512, 512, 512, V, torch.device("cpu")).eval()
+            sd = do.random_lstm_decoder_state(0, V, end_bias=end_bias)
+        else:
+            ref = TransformerDecoder(512, 512, V, 52, torch.device("cpu"), None, None, True).eval()
+            sd = do.random_transformer_decoder_state(0, V, end_bias=end_bias)
+        ref.load_state_dict(sd)
+        enc = do.synthetic_features(B, fs).requires_grad_(True)
+        caps, lens = do.synthetic_captions(B, fs + 1, V)
+        res = ref(teacherForcing=False, encoder_out=enc, wordMap=WORDMAP, maxDecodeLen=51)
+        scores, seqs = res[0], res[-1]
+        su, tu, ntok, adl = preprocess(scores, seqs, caps, WORDMAP["<end>"], WORDMAP["<pad>"], 51)
+        su2, tu2, ntok2, adl2 = restated(scores, seqs, caps, WORDMAP["<end>"], WORDMAP["<pad>"], 51)
+        assert torch.equal(su, su2) and torch.equal(tu, tu2) and ntok == ntok2 and adl == adl2
+        loss = crit(su, tu)
+        if kind == "lstm":
+            loss = loss + 1.0 * ((1.0 - res[1].sum(dim=1)) ** 2).mean()
+        loss.backward()
+        grads = [(k, p.grad) for k, p in ref.named_parameters() if p.grad is not None]
+        out[kind] = {"B": B, "feat_seed": fs, "cap_seed": fs + 1, "weight_seed": 0, "end_bias": end_bias,
+                     "loss": loss.detach(), "sequences": seqs, "decode_lengths": adl, "tokens": ntok,
+                     "enc_grad_norm": enc.grad.norm(), "enc_grad_sub": enc.grad[..., ::16].clone(), "grads": _grad_digest(grads)}
+        print(kind, "free-running loss", float(loss), "lengths", adl, "tokens", ntok)
+    torch.save(out, os.path.join(HERE, "free_running.pt"))
+
+
 def golden_beam():
     """Reference caption.py beam search (k=5), full pipeline image file -> Encoder -> decoder, both decoders."""
     import numpy as np

@@ -113,3 +113,44 @@ def test_beam_oracle_matches_reference_caption_py_golden(golden_dir):
         assert rel_err(f[0, ::3, ::3, ::64], gold["features"][i]) < 1e-5
         assert do.beam_search(lsd, f, "lstm", gold["k"], V - 2, V - 1, V)[0] == gold["lstm"][i]
         assert do.beam_search(tsd, f, "transformer", gold["k"], V - 2, V - 1, V)[0] == gold["transformer"][i]
+
+
+def _oracle_free_running(kind, g, V=9490):
+    """Oracle greedy forward WITH autograd + the restated trainWithoutTeacherForcing loss -> (loss, seqs, grads)."""
+    from oracle import decoder_oracle as do
+    start, end, pad = V - 2, V - 1, 0
+    if kind == "lstm":
+        sd = do.random_lstm_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    else:
+        sd = do.random_transformer_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    leaf = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_encoding.pe") for k, v in sd.items()}
+    enc = do.synthetic_features(g["B"], g["feat_seed"]).requires_grad_(True)
+    caps, _ = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    if kind == "lstm":
+        preds, alphas, seqs = do.lstm_greedy(leaf, enc, start, end, 51)
+    else:
+        preds, seqs = do.transformer_greedy(leaf, enc, start, end, pad, 51)
+        alphas = None
+    loss = do.free_running_loss(preds, seqs, caps, end, pad, 51, alphas=alphas)
+    loss.backward()
+    return loss.detach(), seqs, enc.grad, {k: v.grad for k, v in leaf.items() if v.requires_grad and v.grad is not None}
+
+
+def test_free_running_training_oracle_matches_reference_golden(golden_dir):
+    """The oracle's differentiable greedy loops + loss reproduce the reference's free-running train-step body
+    (trainMultiGPU.py:444-460): loss, generated sequences and every parameter gradient (digest: norm + strided
+    sample) of both decoders."""
+    gold = torch.load(os.path.join(golden_dir, "free_running.pt"))
+    for kind in ("lstm", "transformer"):
+        g = gold[kind]
+        loss, seqs, enc_grad, grads = _oracle_free_running(kind, g)
+        assert torch.equal(seqs, g["sequences"]), kind
+        assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+        assert rel_err(enc_grad[..., ::16], g["enc_grad_sub"]) < 1e-4
+        assert abs(float(enc_grad.norm()) - float(g["enc_grad_norm"])) < 1e-4 * float(g["enc_grad_norm"])
+        assert set(grads) == set(g["grads"]), (kind, set(grads) ^ set(g["grads"]))
+        for k, d in g["grads"].items():
+            ref_n = float(d["norm"])
+            assert abs(float(grads[k].norm()) - ref_n) <= 1e-4 * ref_n + 1e-9, (kind, k)
+            if ref_n > 0:
+                assert rel_err(grads[k].reshape(-1)[::499], d["sub"]) < 1e-3, (kind, k)

@@ -327,3 +327,106 @@ def test_train_step_matches_reference_step_body(kind):
     worst_e = max(frac_bad(p, e_leaf["convnext." + n]) for n, p in enc.convnext.named_parameters())
     print("weights after 2 steps: worst fraction of elements off by > 0.2*lr", worst, worst_e)
     assert worst < 0.01 and worst_e < 0.01
+
+
+# ---- free-running (no teacher forcing) TRAINING path: SURVEY.md §8(f) rank 3 ----------------------------------------
+def _free_running_case(kind, dtype, train_mode, golden_dir):
+    """GPU free-running train forward + loss + backward vs the oracle's differentiable greedy loop (which
+    tests/test_oracle_golden.py pins against the reference's own gradients on this very configuration)."""
+    import os
+    from oracle import decoder_oracle as do
+    from test_decoders_gpu import WORDMAP
+    from imagecaptioningconvnext_b200.losses import free_running_cross_entropy
+    g = torch.load(os.path.join(golden_dir, "free_running.pt"))[kind]
+    start, end, pad = V - 2, V - 1, 0
+    B = g["B"]
+    enc = do.synthetic_features(B, g["feat_seed"])
+    caps, _ = do.synthetic_captions(B, g["cap_seed"], V)
+    mask = None
+    if kind == "lstm":
+        sd = do.random_lstm_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+        if train_mode:
+            mask = (torch.rand(B, 51, 512, generator=torch.Generator().manual_seed(9)) > 0.5).float() * 2.0
+    else:
+        sd = do.random_transformer_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    enc_leaf = enc.clone().requires_grad_(True)
+    out = {}
+
+    def loss_fn(leaf):
+        if kind == "lstm":
+            preds, alphas, seqs = do.lstm_greedy(leaf, enc_leaf, start, end, 51, dropmask=mask)
+        else:
+            preds, seqs = do.transformer_greedy(leaf, enc_leaf, start, end, pad, 51)
+            alphas = None
+        out["seqs"], out["preds"] = seqs, preds.detach()
+        return do.free_running_loss(preds, seqs, caps, end, pad, 51, alphas=alphas)
+
+    ref_loss, ref_grads = _oracle_grads(sd, loss_fn)
+    if mask is None:
+        assert torch.equal(out["seqs"], g["sequences"])        # the reference's own greedy output
+    m = (_lstm if kind == "lstm" else _transformer)(sd, dtype)
+    m.train(train_mode)
+    if kind == "lstm":
+        m.inject_dropmask = mask
+    else:
+        m.dropout_p = 0.0            # exactness holds for dropout-free modules (see transformer_free_running_with_grad)
+    enc_g = enc.cuda().requires_grad_(True)
+    res = m(teacherForcing=False, encoder_out=enc_g, wordMap=WORDMAP, maxDecodeLen=51)
+    preds, seqs = res[0], res[-1]
+    assert preds.shape == (B, 51, V) and preds.requires_grad
+    if not torch.equal(seqs.cpu(), out["seqs"]):
+        assert dtype == torch.bfloat16, "fp32 greedy ids must equal the oracle's"
+        pytest.skip("bf16 picked a different token at a near-tie: gradients are not comparable")
+    # zero past each row's finish step, like the reference's pre-zeroed buffers
+    assert torch.equal(preds.detach().cpu() == 0, out["preds"] == 0)
+    loss, targets, ntok = free_running_cross_entropy(preds, seqs, caps.cuda(), end, pad)
+    if mask is None:
+        assert ntok == g["tokens"]
+    if kind == "lstm":
+        loss = loss + 1.0 * ((1.0 - res[1].sum(dim=1)) ** 2).mean()
+    loss.backward()
+    tol = GRAD_TOL[dtype]
+    assert abs(float(loss) - ref_loss) < tol * 5
+    skip = ("attention.full_att.bias",) if kind == "lstm" else ()
+    _compare_grads(m, ref_grads, tol, skip=skip, dtype=dtype)
+    assert _grad_err(enc_g.grad, enc_leaf.grad, dtype) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("train_mode", [False, True])
+def test_lstm_free_running_training_gradients(golden_dir, dtype, train_mode):
+    _free_running_case("lstm", dtype, train_mode, golden_dir)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_transformer_free_running_training_gradients(golden_dir, dtype):
+    _free_running_case("transformer", dtype, False, golden_dir)
+
+
+@pytest.mark.parametrize("kind", ["lstm", "transformer"])
+def test_free_running_train_step_runs_with_dropout(kind):
+    """caption_train_step(teacher_forcing=False) in train mode (dropout live): finite loss, every parameter moves."""
+    from oracle import decoder_oracle as do
+    from oracle.encoder_oracle import random_encoder_state
+    from test_decoders_gpu import WORDMAP
+    from imagecaptioningconvnext_b200 import Encoder
+    from imagecaptioningconvnext_b200.train_step import caption_train_step, make_optimizers
+    enc = Encoder(compute_dtype=torch.bfloat16)
+    enc.load_state_dict(random_encoder_state(seed=0, layer_scale=1.0))
+    enc = enc.cuda().train()
+    enc.fine_tune(False)
+    if kind == "lstm":
+        dec = _lstm(do.random_lstm_decoder_state(0, V, end_bias=0.21), torch.bfloat16).train()
+    else:
+        dec = _transformer(do.random_transformer_decoder_state(0, V, end_bias=3.2), torch.bfloat16).train()
+    d_opt, _ = make_optimizers(enc, dec)
+    B = 4
+    imgs = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(3)).cuda()
+    caps, lens = do.synthetic_captions(B, 77, V)
+    before = {n: p.detach().clone() for n, p in dec.named_parameters()}
+    for _ in range(2):
+        loss = caption_train_step(enc, dec, imgs, caps.cuda(), lens.cuda(), d_opt, None, teacher_forcing=False,
+                                  wordMap=WORDMAP)
+        assert torch.isfinite(loss)
+    moved = [n for n, p in dec.named_parameters() if not torch.equal(p, before[n])]
+    assert len(moved) >= len(before) - 1, set(before) - set(moved)       # full_att.bias has an identically-zero grad
