@@ -6,6 +6,8 @@
 """
 from .decoder import Attention, DecoderWithAttention  # noqa: F401
 from .encoder import Encoder  # noqa: F401
-from .transformerDecoder import PositionalEncoding, TransformerDecoder  # noqa: F401
+from .transformerDecoder import (PositionalEncoding, TransformerDecoder,  # noqa: F401
+                                 TransformerDecoderForAttentionViz)
 
-__all__ = ["Encoder", "Attention", "DecoderWithAttention", "PositionalEncoding", "TransformerDecoder"]
+__all__ = ["Encoder", "Attention", "DecoderWithAttention", "PositionalEncoding", "TransformerDecoder",
+           "TransformerDecoderForAttentionViz"]

@@ -85,6 +85,8 @@ SIGNATURES = {
     "ccx_encoder_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ccx_encoder_run": (C.c_int, [C.POINTER(EncoderWeights), _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp,
                                   _sz, _vp]),
+    "ccx_attn_head_mean": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _f32,
+                                     _i32, _vp]),
     "ccx_mha_decode": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _i32, _i64, _vp, _i64, _i32,
                                  _i32, _i32, _i32, _i32, _f32, _vp]),
     "ccx_beam_topk": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),

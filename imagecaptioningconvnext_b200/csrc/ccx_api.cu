@@ -236,6 +236,13 @@ int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t*
                     eps, bc1, bc2_sqrt, clip, chunk, total_params, as_stream(stream));
 }
 
+int ccx_attn_head_mean(const float* probs, int64_t p_sb, int64_t p_sh, int64_t p_st, const float* prob_mask,
+                       const float* row_active, float* alphas, int64_t a_sb, int64_t a_st, int32_t B, int32_t H,
+                       int32_t Tq, int32_t Tk, float scale, int32_t accumulate, void* stream) {
+  return attn_head_mean(probs, p_sb, p_sh, p_st, prob_mask, row_active, alphas, a_sb, a_st, B, H, Tq, Tk, scale,
+                        accumulate, static_cast<cudaStream_t>(stream));
+}
+
 int ccx_mha_decode(const float* q, int64_t q_sb, const float* k, int64_t k_sb, int64_t k_st, const float* v,
                    int64_t v_sb, int64_t v_st, void* ctx_hi, float* ctx_lo, int32_t ctx_dtype, int64_t c_sb,
                    const int32_t* kv_rows, int64_t ld_map, int32_t rows, int32_t H, int32_t Tk, int32_t hd,

@@ -41,6 +41,9 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
               int kv_group, cudaStream_t stream);
 
+int attn_head_mean(const float* probs, long long p_sb, long long p_sh, long long p_st, const float* mask,
+                   const float* row_active, float* alphas, long long a_sb, long long a_st, int B, int H, int Tq, int Tk,
+                   float scale, int accumulate, cudaStream_t stream);
 int mha_decode(const float* q, long long q_sb, const float* k, long long k_sb, long long k_st, const float* v,
                long long v_sb, long long v_st, void* ctx_hi, float* ctx_lo, int ctx_dtype, long long c_sb,
                const int* kv_rows, long long ld_map, int rows, int H, int Tk, int hd, int kv_group, float scale,

@@ -557,4 +557,40 @@ int mha_decode(const float* q, long long q_sb, const float* k, long long k_sb, l
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------
+// attention maps for visualisation (models/transformerDecoderAttVis.py:163-165,223-226): mean over heads (and,
+// by accumulation over calls, over layers) of the cross-attention probabilities.
+//   alphas[b, t, j] (+)= scale * row_active[b] * sum_h probs[b, h, t, j] (* mask[b, h, t, j])
+// ---------------------------------------------------------------------------------------------
+__global__ void attn_head_mean_kernel(const float* __restrict__ probs, long long p_sb, long long p_sh, long long p_st,
+                                      const float* __restrict__ mask, const float* __restrict__ row_active,
+                                      float* __restrict__ alphas, long long a_sb, long long a_st, int B, int H, int Tq,
+                                      int Tk, float scale, int accumulate) {
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * Tq * Tk) return;
+  const int j = static_cast<int>(idx % Tk), t = static_cast<int>((idx / Tk) % Tq), b = static_cast<int>(idx / (static_cast<long long>(Tk) * Tq));
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) {
+    const long long off = b * p_sb + h * p_sh + t * p_st + j;
+    float v = __ldg(probs + off);
+    if (mask != nullptr) v *= __ldg(mask + off);
+    s += v;
+  }
+  s *= scale;
+  if (row_active != nullptr) s *= __ldg(row_active + b);
+  const long long o = b * a_sb + t * a_st + j;
+  alphas[o] = accumulate ? alphas[o] + s : s;
+}
+
+int attn_head_mean(const float* probs, long long p_sb, long long p_sh, long long p_st, const float* mask,
+                   const float* row_active, float* alphas, long long a_sb, long long a_st, int B, int H, int Tq, int Tk,
+                   float scale, int accumulate, cudaStream_t stream) {
+  if (B <= 0 || Tq <= 0) return CCX_OK;
+  if (H <= 0 || Tk <= 0 || probs == nullptr || alphas == nullptr) return CCX_ERR_SHAPE;
+  const long long n = static_cast<long long>(B) * Tq * Tk;
+  attn_head_mean_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      probs, p_sb, p_sh, p_st, mask, row_active, alphas, a_sb, a_st, B, H, Tq, Tk, scale, accumulate);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
 }  // namespace ccx

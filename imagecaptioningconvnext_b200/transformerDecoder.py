@@ -131,6 +131,7 @@ class TransformerDecoder(nn.Module):
         self._cache = PreparedCache(self)
         self.transformer_decoder._owner.append(self)
         self.inject_dropout = None   # tests: dict of multipliers, see _drop()
+        self._want_alphas = False    # TransformerDecoderForAttentionViz: also produce the averaged cross-attention maps
 
     # ---- prepared weights ---------------------------------------------------------------------------------------
     def _prepare(self):
@@ -217,12 +218,31 @@ class TransformerDecoder(nn.Module):
         every layer call of every greedy step)."""
         return [_lib.linear(mem, lw["ca_kv"], bias=lw["ca_kv_b"]) for lw in Pw["layers"]]
 
-    def _run_layers(self, Pw, x_plain, x_op, mem, B, T, Pn, causal, kpm):
-        """The 6 post-norm layers on batch-first rows (eval-mode math): torch/nn/modules/transformer.py:1089-1199."""
+    def _head_mean(self, probs, prob_mask, alphas, a_sb, a_st, B, Tq, Tk, layer, row_active=None, over="heads"):
+        """alphas (+)= one layer's share of the averaged cross-attention map (ccx_attn_head_mean), probs (B,H,Tq,Tk):
+        over="heads":     alphas[b, t, :] = mean over layers and heads  (greedy, transformerDecoderAttVis.py:223-226)
+        over="positions": alphas[h, b, :] = mean over layers and target positions — what the reference's teacher-forced
+                          path really computes: (L,B,H,T,P).mean(dim=(0,3)).permute(1,0,2), :163-165."""
+        H, L = self.num_heads, self.num_layers
+        if over == "heads":
+            args = (H * Tq * Tk, Tq * Tk, Tk, ptr(prob_mask), ptr(row_active), alphas, a_sb, a_st, B, H, Tq, Tk,
+                    1.0 / (H * L))
+        else:      # summed axis = positions (stride Tk), kept axis = heads (stride Tq*Tk)
+            args = (H * Tq * Tk, Tk, Tq * Tk, ptr(prob_mask), ptr(row_active), alphas, a_sb, a_st, B, Tq, H, Tk,
+                    1.0 / (Tq * L))
+        _lib.check(_lib.lib().ccx_attn_head_mean(ptr(probs), *args, 1 if layer > 0 else 0, _lib.stream_ptr()),
+                   "attn_head_mean")
+
+    def _run_layers(self, Pw, x_plain, x_op, mem, B, T, Pn, causal, kpm, alphas=None):
+        """The 6 post-norm layers on batch-first rows (eval-mode math): torch/nn/modules/transformer.py:1089-1199.
+        alphas (H, B, Pn), optional: receives the AttVis teacher-forcing map (see _head_mean over="positions")."""
         D = self.embed_dim
         dev = x_plain.device
         kvs = self._cross_kv(Pw, mem)
-        for lw, kv in zip(Pw["layers"], kvs):
+        probs = None
+        if alphas is not None:
+            probs = torch.empty((B, self.num_heads, T, Pn), dtype=torch.float32, device=dev)
+        for li, (lw, kv) in enumerate(zip(Pw["layers"], kvs)):
             qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
             ctx = self._mha(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
                             qkv.data_ptr() + 8 * D, B, T, T, causal, 0, kpm, None, 1, dev)
@@ -230,7 +250,9 @@ class TransformerDecoder(nn.Module):
             x_plain, x_op = self._ln(y, lw["n"][0], B * T)
             q = _lib.linear(x_op, lw["ca_q"], bias=lw["ca_q_b"])
             ctx = self._mha(ptr(q), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, B, T, Pn, 0, 0,
-                            None, None, 1, dev)
+                            None, None, 1, dev, probs_out=probs)
+            if alphas is not None:
+                self._head_mean(probs, None, ptr(alphas), Pn, B * Pn, B, T, Pn, li, over="positions")
             y = _lib.linear(ctx, lw["ca_out"], bias=lw["ca_out_b"], residual=x_plain)
             x_plain, x_op = self._ln(y, lw["n"][1], B * T)
             h = self._linear_op(x_op, lw["l1"], lw["l1_b"], act=_lib.ACT_RELU)
@@ -280,9 +302,12 @@ class TransformerDecoder(nn.Module):
         kpm = None
         if tgt_key_padding_mask is not None:
             kpm = tgt_key_padding_mask.to(torch.uint8).contiguous()
-        x_plain, x_op = self._run_layers(Pw, x_plain, x_op, mem, B, T, Pn, 1, kpm)
+        alphas = (torch.empty((self.num_heads, B, Pn), dtype=torch.float32, device=dev) if self._want_alphas
+                  else None)
+        x_plain, x_op = self._run_layers(Pw, x_plain, x_op, mem, B, T, Pn, 1, kpm, alphas=alphas)
         predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)
         _lib.linear(x_op, Pw["fc"], bias=Pw["fc_b"], out=predictions.view(B * T, V))
+        self._last_alphas = alphas
         return predictions, encoded_captions, decode_lengths
 
     @torch.no_grad()
@@ -314,6 +339,14 @@ class TransformerDecoder(nn.Module):
                 # head slice is staged once instead of being re-read by every beam
                 ctx = self._mha(ptr(q), g * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows // g, g, Pn,
                                 0, 0, None, None, 1, dev)
+            elif state.get("alphas") is not None:
+                # attention-map variant: the staged kernel can also write the probabilities of the new token
+                probs = state["probs"]
+                ctx = self._mha(ptr(q), D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows, 1, Pn, 0, 0,
+                                None, None, 1, dev, probs_out=probs)
+                al = state["alphas"]
+                self._head_mean(probs, None, al.data_ptr() + 4 * t * Pn, al.stride(0), 0, rows, 1, Pn,
+                                state["layer_index"][id(cache)], row_active=state["active"])
             else:
                 ctx = self._mha_decode(ptr(q), D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, rows, Pn, None,
                                        1, dev)
@@ -359,6 +392,13 @@ class TransformerDecoder(nn.Module):
         predictions = torch.zeros((B, T, V), dtype=torch.float32, device=dev)
         sequences = torch.zeros((B, T), dtype=torch.long, device=dev)
         active = torch.ones(B, dtype=torch.float32, device=dev)
+        self._last_alphas = None
+        if self._want_alphas:
+            Pn = state["Pn"]
+            state["alphas"] = self._last_alphas = torch.zeros((B, T, Pn), dtype=torch.float32, device=dev)
+            state["probs"] = torch.empty((B, self.num_heads, 1, Pn), dtype=torch.float32, device=dev)
+            state["active"] = active
+            state["layer_index"] = {id(c): i for i, c in enumerate(state["cache"])}
         for t in range(T):
             x_op = self.decode_step_cached(Pw, state, t, B)
             p_t = predictions[:, t]
@@ -372,6 +412,62 @@ class TransformerDecoder(nn.Module):
     def forward(self, teacherForcing, encoder_out, encoded_captions=None, caption_lengths=None,
                 tgt_key_padding_mask=None, wordMap=None, maxDecodeLen=None):
         """models/transformerDecoder.py:162-168."""
+        if teacherForcing is True:
+            return self.forwardWithTeacherForcing(encoder_out, encoded_captions, caption_lengths,
+                                                  tgt_key_padding_mask)
+        return self.forwardWithoutTeacherForcing(encoder_out, wordMap, maxDecodeLen)
+
+
+class TransformerDecoderForAttentionViz(TransformerDecoder):
+    """models/transformerDecoderAttVis.py:105-236: the TransformerDecoder that also returns ``alphas`` for
+    attention-map visualisation — greedy: the new token's cross-attention weights averaged over the 6 layers and 8
+    heads, (B, maxDecodeLen, num_pixels); teacher forcing: what the reference computes there, the average over layers
+    and target positions, (num_heads, B, num_pixels).  Same arithmetic as TransformerDecoder (its CustomTransformerDecoderLayer restates the post-norm
+    nn.TransformerDecoderLayer, :63-97); the maps come out of the fused attention kernel's optional probability
+    output and one head/layer-mean kernel per layer.  state_dict keys follow the reference class
+    (``decoder_layers.{i}.…``).  The maps are returned detached (the reference only plots them; its alpha
+    regulariser for this decoder is commented out, trainMultiGPU.py:377,458)."""
+
+    def __init__(self, embed_dim, decoder_dim, vocab_size, maxLen, device, dropout=0.5, encoder_dim=1024, num_heads=8,
+                 num_layers=6, compute_dtype=torch.float32):
+        super().__init__(embed_dim, decoder_dim, vocab_size, maxLen, device, None, None, True, dropout=dropout,
+                         encoder_dim=encoder_dim, num_heads=num_heads, num_layers=num_layers,
+                         compute_dtype=compute_dtype)
+        self._want_alphas = True
+        self._register_state_dict_hook(self._rename_out)
+        self._register_load_state_dict_pre_hook(self._rename_in)
+
+    _OURS, _THEIRS = "transformer_decoder.layers.", "decoder_layers."
+
+    @property
+    def decoder_layers(self):
+        return self.transformer_decoder.layers
+
+    @staticmethod
+    def _rename_out(module, state_dict, prefix, local_metadata):
+        a, b = prefix + module._OURS, prefix + module._THEIRS
+        for k in [k for k in state_dict if k.startswith(a)]:
+            state_dict[b + k[len(a):]] = state_dict.pop(k)
+        return state_dict
+
+    def _rename_in(self, state_dict, prefix, *args):
+        a, b = prefix + self._THEIRS, prefix + self._OURS
+        for k in [k for k in state_dict if k.startswith(a)]:
+            state_dict[b + k[len(a):]] = state_dict.pop(k)
+
+    def forwardWithTeacherForcing(self, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
+        """models/transformerDecoderAttVis.py:133-167 -> (predictions, encoded_captions, decode_lengths, alphas)."""
+        out = super().forwardWithTeacherForcing(encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask)
+        return out + (self._last_alphas,)
+
+    def forwardWithoutTeacherForcing(self, encoder_out, wordMap, maxDecodeLen):
+        """models/transformerDecoderAttVis.py:170-228 -> (predictions, sequences, alphas)."""
+        out = super().forwardWithoutTeacherForcing(encoder_out, wordMap, maxDecodeLen)
+        return out + (self._last_alphas,)
+
+    def forward(self, teacherForcing, encoder_out, encoded_captions=None, caption_lengths=None,
+                tgt_key_padding_mask=None, wordMap=None, maxDecodeLen=None):
+        """models/transformerDecoderAttVis.py:231-236."""
         if teacherForcing is True:
             return self.forwardWithTeacherForcing(encoder_out, encoded_captions, caption_lengths,
                                                   tgt_key_padding_mask)

@@ -70,6 +70,7 @@ def _forward_body(dec, encoder_out, caps, kpm):
                                     ptr(x_plain), T * D, D, ptr(x_op.hi), x_op.lo_ptr, code, T * D, D, B, T, st),
                    "embed_rows")
         saved = []
+        alphas = torch.empty((H, B, Pn), dtype=torch.float32, device=dev) if dec._want_alphas else None
         for li, lw in enumerate(Pw["layers"]):
             S = {"x0_op": x_op}
             qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
@@ -83,6 +84,8 @@ def _forward_body(dec, encoder_out, caps, kpm):
             probs2 = torch.empty((B, H, T, Pn), dtype=torch.float32, device=dev)
             ctx2 = dec._mha(ptr(q2), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, B, T, Pn, 0, 0,
                             None, mk((li, "ca_p")), 1, dev, probs_out=probs2)
+            if alphas is not None:          # what need_weights=True returns in train mode: dropped-out weights
+                dec._head_mean(probs2, mk((li, "ca_p")), ptr(alphas), Pn, B * Pn, B, T, Pn, li, over="positions")
             y2 = _lib.linear(ctx2, lw["ca_out"], bias=lw["ca_out_b"], residual=x1_plain, emask=mk((li, "d2")))
             x2_plain, x2_op = dec._ln(y2, lw["n"][1], B * T)
             h_plain = _lib.linear(x2_op, lw["l1"], bias=lw["l1_b"], act=_lib.ACT_RELU, emask=mk((li, "ff")))
@@ -98,6 +101,7 @@ def _forward_body(dec, encoder_out, caps, kpm):
         ctx.x_last_op, ctx.mem, ctx.enc_op, ctx.caps = x_op, mem, enc_op, caps
         ctx.dims = (B, T, Pn, E)
         ctx.enc_shape = encoder_out.shape
+        ctx.alphas = alphas
         return predictions, ctx
 
 
@@ -206,6 +210,7 @@ class _Token:
 
 def _graph_key(dec, encoder_out, caps, kpm):
     return (tuple(encoder_out.shape), tuple(caps.shape), kpm is not None, dec.training, encoder_out.requires_grad,
+            dec._want_alphas,
             dec.compute_dtype, encoder_out.device, dec._cache.storage_key(),
             tuple(p.requires_grad for p in dec.parameters()))
 
@@ -233,6 +238,7 @@ class _TransformerTF(torch.autograd.Function):
         ctx.gstate = st
         if st is None:
             predictions, ctx.payload = _forward_body(dec, encoder_out, caps, kpm)
+            dec._last_alphas = ctx.payload.alphas
             return predictions
         if st.fwd is None:
             st.enc_in, st.caps_in = encoder_out.detach().clone(), caps.clone()
@@ -250,6 +256,7 @@ class _TransformerTF(torch.autograd.Function):
         ctx.token = _Token()
         st.owner = weakref.ref(ctx.token)
         ctx.payload = st.payload
+        dec._last_alphas = st.payload.alphas
         return st.predictions.detach()          # fresh alias: autograd attaches this call's node to it
 
     @staticmethod
@@ -297,9 +304,11 @@ def transformer_free_running_with_grad(dec, encoder_out, wordMap, maxDecodeLen):
     from .decoder_train import generated_captions
     T = int(maxDecodeLen)
     _, sequences = dec._greedy(encoder_out.detach(), wordMap, T, dropout_free=True)
+    greedy_alphas = dec._last_alphas          # attention-map variant: maps of the generation pass (zero once finished)
     caps, lens = generated_captions(sequences, wordMap['<start>'], wordMap['<end>'], T)
     params = [p for _, p in dec.named_parameters()]
     preds = _TransformerTF.apply(dec, encoder_out, caps[:, :T].contiguous(), None, True, *params)
+    dec._last_alphas = greedy_alphas
     valid = torch.arange(T, device=preds.device).unsqueeze(0) < (lens - 1)
     return preds * valid.unsqueeze(-1).to(preds.dtype), sequences
 

@@ -232,6 +232,19 @@ CCX_API int ccx_mha_small(const float* q, int64_t q_sb, int64_t q_st, const floa
                           int32_t hd, int32_t causal, int32_t q_pos0, float scale, int32_t kv_group,
                           void* stream);
 
+/* Attention maps for visualisation (models/transformerDecoderAttVis.py:223-226 greedy: the new token's
+ * cross-attention weights averaged over layers and heads; :163-165 teacher forcing: averaged over layers and target
+ * positions).  A strided reduction over ONE axis of the probabilities written by ccx_mha_small (probs_out, element
+ * (b, h, t, j) at ((b*H + h)*Tq + t)*Tk + j):
+ *   alphas[b*a_sb + t*a_st + j] (+)= scale * row_active[b] * sum_{h < H} probs[b*p_sb + h*p_sh + t*p_st + j]
+ *                                                                (* prob_mask at the same offset, optional)
+ * "h" is the summed axis and "t" the kept one — pass the head stride as p_sh to average heads, or the position
+ * stride to average positions.  accumulate != 0 adds to alphas (one call per layer, scale = 1/(layers * |axis|));
+ * row_active (B floats, optional) zeroes finished rows like the reference's active_indices scatter. */
+CCX_API int ccx_attn_head_mean(const float* probs, int64_t p_sb, int64_t p_sh, int64_t p_st, const float* prob_mask,
+                               const float* row_active, float* alphas, int64_t a_sb, int64_t a_st, int32_t B,
+                               int32_t H, int32_t Tq, int32_t Tk, float scale, int32_t accumulate, void* stream);
+
 /* Single-query attention for KV-cache decoding (one warp per (row, head), no staging): q row r attends to Tk
  * cached positions.  kv_rows [rows, ld_map] (optional): physical cache row that holds position j of logical row
  * r — beam search re-orders beams by rewriting this map instead of copying caches; without it rows read cache

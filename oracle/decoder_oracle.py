@@ -217,7 +217,7 @@ def positional_encoding(embed_dim, max_len, dtype=torch.float32):
     return pe.to(dtype)
 
 
-def _mha(x_q, x_kv, w_in, b_in, w_out, b_out, nheads, add_mask=None, prob_mask=None):
+def _mha(x_q, x_kv, w_in, b_in, w_out, b_out, nheads, add_mask=None, prob_mask=None, probs_sink=None):
     """F.multi_head_attention_forward restated, batch-first: x_q (B,Tq,D), x_kv (B,Tk,D);
     add_mask broadcastable to (B,H,Tq,Tk) with 0 / -inf entries; prob_mask = attention-dropout multiplier."""
     B, Tq, D = x_q.shape
@@ -235,11 +235,13 @@ def _mha(x_q, x_kv, w_in, b_in, w_out, b_out, nheads, add_mask=None, prob_mask=N
     p = F.softmax(s, dim=-1)
     if prob_mask is not None:
         p = p * prob_mask
+    if probs_sink is not None:
+        probs_sink.append(p)          # what need_weights=True, average_attn_weights=False returns: (B, H, Tq, Tk)
     ctx = (p @ v).transpose(1, 2).reshape(B, Tq, D)
     return F.linear(ctx, w_out, b_out)
 
 
-def transformer_layers(sd, x, mem, nheads, nlayers, self_mask, drop=None):
+def transformer_layers(sd, x, mem, nheads, nlayers, self_mask, drop=None, cross_probs=None):
     """nn.TransformerDecoder of post-norm ReLU layers (torch/nn/modules/transformer.py:1089-1199), batch-first.
     drop: optional dict of injected dropout multipliers keyed (layer, name), names: 'sa_p','ca_p' (attention
     probabilities), 'd1','d2','d3' (residual dropouts), 'ff' (FFN hidden)."""
@@ -254,7 +256,7 @@ def transformer_layers(sd, x, mem, nheads, nlayers, self_mask, drop=None):
         x = F.layer_norm(x + sa, (x.shape[-1],), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
         ca = _mha(x, mem, sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"],
                   sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"], nheads, None,
-                  drop.get((l, "ca_p")))
+                  drop.get((l, "ca_p")), probs_sink=cross_probs)
         if (l, "d2") in drop:
             ca = ca * drop[(l, "d2")]
         x = F.layer_norm(x + ca, (x.shape[-1],), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
@@ -280,9 +282,11 @@ def transformer_memory(sd, encoder_out):
     return enc
 
 
-def transformer_teacher_forcing(sd, encoder_out, caps, caplens, key_padding_mask, nheads=8, drop=None):
+def transformer_teacher_forcing(sd, encoder_out, caps, caplens, key_padding_mask, nheads=8, drop=None,
+                                return_alphas=False):
     """models/transformerDecoder.py:88-108.  key_padding_mask (B,T) bool, True = pad.
-    drop: injected dropout multipliers; additionally key 'emb' (B,T,D) for the embedding dropout of :98."""
+    drop: injected dropout multipliers; additionally key 'emb' (B,T,D) for the embedding dropout of :98.
+    return_alphas: also return the AttVis variant's fourth output (models/transformerDecoderAttVis.py:163-165)."""
     drop = drop or {}
     dl = (caplens.squeeze(1) - 1).tolist()
     mem = transformer_memory(sd, encoder_out)
@@ -296,33 +300,48 @@ def transformer_teacher_forcing(sd, encoder_out, caps, caplens, key_padding_mask
     if key_padding_mask is not None:
         kp = torch.zeros(key_padding_mask.shape, dtype=x.dtype).masked_fill(key_padding_mask, float("-inf"))
         mask = mask + kp.view(-1, 1, 1, T)
-    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), mask, drop)
-    return F.linear(y, sd["fc_out.weight"], sd["fc_out.bias"]), caps, dl
+    cross = [] if return_alphas else None
+    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), mask, drop, cross_probs=cross)
+    preds = F.linear(y, sd["fc_out.weight"], sd["fc_out.bias"])
+    if return_alphas:
+        # (L,B,H,T,P).mean(dim=(0,3)).permute(1,0,2): the reference averages over layers and TARGET POSITIONS and
+        # returns (H, B, P) — not the (B, T, P) its comment promises; reproduced as is
+        return preds, caps, dl, torch.stack(cross, 0).mean(dim=(0, 3)).permute(1, 0, 2)
+    return preds, caps, dl
 
 
-def transformer_last_logits(sd, mem, tokens, nheads=8):
-    """Re-run the whole prefix (no KV cache, as the reference does) and return fc_out of the last position."""
+def transformer_last_logits(sd, mem, tokens, nheads=8, alpha_out=None):
+    """Re-run the whole prefix (no KV cache, as the reference does) and return fc_out of the last position.
+    alpha_out (list): receives the last position's cross-attention map averaged over layers and heads
+    (models/transformerDecoderAttVis.py:223-226)."""
     T = tokens.shape[1]
     x = sd["embedding.weight"][tokens] + sd["pos_encoding.pe"][0, :T].to(mem.dtype)
     causal = torch.full((T, T), float("-inf"), dtype=x.dtype).triu(1).view(1, 1, T, T)
-    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), causal)
+    cross = [] if alpha_out is not None else None
+    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), causal, cross_probs=cross)
+    if alpha_out is not None:
+        alpha_out.append(torch.stack(cross, 0)[:, :, :, -1, :].mean(dim=(0, 2)))
     return F.linear(y[:, -1], sd["fc_out.weight"], sd["fc_out.bias"])
 
 
-def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nheads=8):
-    """models/transformerDecoder.py:110-160 (eval mode)."""
+def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nheads=8, return_alphas=False):
+    """models/transformerDecoder.py:110-160 (eval mode); return_alphas: the AttVis variant's third output."""
     B = encoder_out.size(0)
     mem = transformer_memory(sd, encoder_out)
     V = sd["fc_out.weight"].shape[0]
     inputs = torch.full((B, 1), start_tok, dtype=torch.long)
     preds = torch.zeros(B, max_len, V, dtype=mem.dtype)
     seqs = torch.zeros(B, max_len, dtype=torch.long)
+    alphas = torch.zeros(B, max_len, mem.size(1), dtype=mem.dtype)
     finished = torch.zeros(B, dtype=torch.bool)
     for t in range(max_len):
         act = (~finished).nonzero(as_tuple=False).squeeze(1)
         if len(act) == 0:
             break
-        p = transformer_last_logits(sd, mem[act], inputs[act], nheads)
+        a_out = [] if return_alphas else None
+        p = transformer_last_logits(sd, mem[act], inputs[act], nheads, alpha_out=a_out)
+        if return_alphas:
+            alphas[act, t] = a_out[0]
         preds[act, t] = p
         ids = p.argmax(dim=-1)
         seqs[act, t] = ids
@@ -331,6 +350,8 @@ def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nh
         new[:, :t + 1] = inputs
         new[act, t + 1] = ids
         inputs = new
+    if return_alphas:
+        return preds, seqs, alphas
     return preds, seqs
 
 

@@ -185,6 +185,30 @@ def golden_free_running():
     torch.save(out, os.path.join(HERE, "free_running.pt"))
 
 
+def golden_attvis():
+    """Reference TransformerDecoderForAttentionViz (models/transformerDecoderAttVis.py): teacher forcing and greedy,
+    eval mode, same weights as the TransformerDecoder golden under the reference class's key names."""
+    from models.transformerDecoderAttVis import TransformerDecoderForAttentionViz
+    from oracle import decoder_oracle as do
+
+    sd = do.random_transformer_decoder_state(0, V, end_bias=3.2)
+    ref = TransformerDecoderForAttentionViz(512, 512, V, 52, torch.device("cpu")).eval()
+    ref.load_state_dict({k.replace("transformer_decoder.layers.", "decoder_layers."): v for k, v in sd.items()})
+    B = 4
+    enc = do.synthetic_features(B, 200)
+    caps, lens = do.synthetic_captions(B, 201, V)
+    with torch.no_grad():
+        preds, _, dl, alphas = ref(teacherForcing=True, encoder_out=enc, encoded_captions=caps, caption_lengths=lens,
+                                   tgt_key_padding_mask=caps == 0)
+        gp, gs, ga = ref(teacherForcing=False, encoder_out=enc, wordMap=WORDMAP, maxDecodeLen=51)
+    out = {"B": B, "feat_seed": 200, "cap_seed": 201, "weight_seed": 0, "end_bias": 3.2,
+           "state_dict_keys": sorted(ref.state_dict().keys()),
+           "tf": {"preds": _sub(preds), "alphas": alphas, "decode_lengths": dl},
+           "greedy": {"preds": _sub(gp), "sequences": gs, "alphas": ga}}
+    print("attvis alphas", tuple(alphas.shape), float(alphas.sum(-1).mean()), tuple(ga.shape))
+    torch.save(out, os.path.join(HERE, "attvis.pt"))
+
+
 def golden_beam():
     """Reference caption.py beam search (k=5), full pipeline image file -> Encoder -> decoder, both decoders."""
     import numpy as np

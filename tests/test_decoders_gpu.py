@@ -196,3 +196,47 @@ def test_poked_transformer_submodules_run_on_libccx():
     logits = m.fc_out(out[-1])
     ref = do.transformer_last_logits(sd, do.transformer_memory(sd, enc), toks)
     assert rel_err(logits, ref) < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_viz_decoder_vs_oracle_and_golden(golden_dir, dtype):
+    """TransformerDecoderForAttentionViz: reference key names, 4-/3-tuple outputs, attention
+    maps from the fused attention kernel against the oracle and the reference-run golden."""
+    from oracle import decoder_oracle as do
+    from imagecaptioningconvnext_b200 import TransformerDecoderForAttentionViz
+    g = torch.load(os.path.join(golden_dir, "attvis.pt"))
+    sd = do.random_transformer_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    m = TransformerDecoderForAttentionViz(512, 512, V, 52, torch.device("cuda"), compute_dtype=dtype)
+    assert sorted(m.state_dict().keys()) == g["state_dict_keys"]
+    m.load_state_dict({k.replace("transformer_decoder.layers.", "decoder_layers."): v for k, v in sd.items()})
+    m = m.cuda().eval()
+    enc = do.synthetic_features(g["B"], g["feat_seed"])
+    caps, lens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    with torch.no_grad():
+        preds, caps_o, dl, alphas = m(teacherForcing=True, encoder_out=enc.cuda(), encoded_captions=caps.cuda(),
+                                      caption_lengths=lens.cuda(), tgt_key_padding_mask=(caps == 0).cuda())
+        rp, _, _, ra = do.transformer_teacher_forcing(sd, enc, caps, lens, caps == 0, return_alphas=True)
+    assert dl == g["tf"]["decode_lengths"]
+    assert rel_err(preds, rp) < TOL[dtype]
+    assert alphas.shape == (8, g["B"], 49)
+    assert rel_err(alphas, ra) < TOL[dtype] and rel_err(alphas, g["tf"]["alphas"]) < TOL[dtype]
+    gp, gs, ga = m(teacherForcing=False, encoder_out=enc.cuda(), wordMap=WORDMAP, maxDecodeLen=51)
+    with torch.no_grad():
+        op, os_, oa = do.transformer_greedy(sd, enc, V - 2, V - 1, 0, 51, return_alphas=True)
+    _greedy_tokens_agree(gs.cpu(), os_, op)
+    if torch.equal(gs.cpu(), os_):
+        assert rel_err(ga, oa) < TOL[dtype] and rel_err(ga, g["greedy"]["alphas"]) < TOL[dtype]
+        assert torch.equal(ga.cpu() == 0, oa == 0)           # maps stay zero after a row's <end>
+    else:
+        assert dtype == torch.bfloat16
+    # rows of an active step are probability distributions (mean of softmaxes)
+    live = ga.sum(-1)
+    assert bool(((live - 1).abs() < 1e-3)[live > 0].all())
+    # training forward (autograd) returns the maps too, detached
+    m.train()
+    m.dropout_p = 0.0
+    preds_t, _, _, al_t = m(teacherForcing=True, encoder_out=enc.cuda().requires_grad_(True),
+                            encoded_captions=caps.cuda(), caption_lengths=lens.cuda(),
+                            tgt_key_padding_mask=(caps == 0).cuda())
+    assert preds_t.requires_grad and not al_t.requires_grad
+    assert rel_err(al_t, ra) < TOL[dtype]

@@ -154,3 +154,25 @@ def test_free_running_training_oracle_matches_reference_golden(golden_dir):
             assert abs(float(grads[k].norm()) - ref_n) <= 1e-4 * ref_n + 1e-9, (kind, k)
             if ref_n > 0:
                 assert rel_err(grads[k].reshape(-1)[::499], d["sub"]) < 1e-3, (kind, k)
+
+
+def test_attention_viz_oracle_matches_reference_golden(golden_dir):
+    """transformerDecoderAttVis.py outputs: same logits as the plain TransformerDecoder plus the attention maps —
+    teacher forcing (H, B, P) = mean over layers and target positions (what the reference's reduction really does),
+    greedy (B, 51, P) = mean over layers and heads of the newest token, zero once a row has finished."""
+    from oracle import decoder_oracle as do
+    V = 9490
+    g = torch.load(os.path.join(golden_dir, "attvis.pt"))
+    sd = do.random_transformer_decoder_state(g["weight_seed"], V, end_bias=g["end_bias"])
+    enc = do.synthetic_features(g["B"], g["feat_seed"])
+    caps, lens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    with torch.no_grad():
+        preds, _, dl, alphas = do.transformer_teacher_forcing(sd, enc, caps, lens, caps == 0, return_alphas=True)
+        gp, gs, ga = do.transformer_greedy(sd, enc, V - 2, V - 1, 0, 51, return_alphas=True)
+    assert dl == g["tf"]["decode_lengths"]
+    _check_sub(preds, g["tf"]["preds"], 1e-4)
+    assert alphas.shape == g["tf"]["alphas"].shape == (8, g["B"], 49)
+    assert rel_err(alphas, g["tf"]["alphas"]) < 1e-4
+    assert torch.equal(gs, g["greedy"]["sequences"])
+    assert rel_err(ga, g["greedy"]["alphas"]) < 1e-4
+    assert torch.equal(ga == 0, g["greedy"]["alphas"] == 0)
