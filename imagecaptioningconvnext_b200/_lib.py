@@ -91,7 +91,7 @@ SIGNATURES = {
                                  _i32, _i32, _i32, _i32, _f32, _vp]),
     "ccx_beam_topk": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "ccx_beam_update": (C.c_int, [_i32, _i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                  _vp, _vp, _vp, _i64, _vp]),
+                                  _vp, _vp, _vp, _i64, _vp, _vp]),
     "ccx_gather_rows": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _vp]),
     "ccx_convert_operand": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i32, _i64, _i32, _i32,
                                       _i32, _i32, _vp]),

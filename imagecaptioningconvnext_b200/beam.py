@@ -33,6 +33,10 @@ class _BeamState:
         self.cand_p = torch.empty((NI, k), dtype=i32, device=dev)
         self.cand_w = torch.empty((NI, k), dtype=i32, device=dev)
         self.cur = 0
+        # attention-map tracking (beam_search_lstm(return_alphas=True)): per step the maps of every row and the
+        # parent of every surviving row; a completed sequence records the row it grew from
+        self.done_parent = None
+        self.alpha_hist = self.parent_hist = None
 
     def advance(self, logits, V, step, end_tok, next_tok_ptr, ld_next, trace):
         """top-k + bookkeeping for one decode step (`step` = tokens per sequence so far, 1 at the first step)."""
@@ -46,8 +50,44 @@ class _BeamState:
                                      ptr(self.cand_w), ptr(self.seqs[self.cur]), ptr(self.seqs[1 - self.cur]),
                                      ptr(self.top), ptr(self.k_rem), ptr(self.done_seqs), ptr(self.done_scores),
                                      ptr(self.done_len), ptr(self.n_done), ptr(self.src_row), next_tok_ptr, ld_next,
-                                     st), "beam_update")
+                                     ptr(self.done_parent), st), "beam_update")
+        if self.parent_hist is not None:
+            self.parent_hist[step - 1].copy_(self.src_row)
         self.cur = 1 - self.cur
+
+    def track_alphas(self, steps, Pn):
+        dev = self.top.device
+        self.done_parent = torch.zeros((self.NI, self.k), dtype=torch.int32, device=dev)
+        self.alpha_hist = torch.zeros((steps, self.NI * self.k, Pn), dtype=torch.float32, device=dev)
+        self.parent_hist = torch.zeros((steps, self.NI * self.k), dtype=torch.int32, device=dev)
+
+    def results_with_alphas(self, return_all=False):
+        """caption.py:151-155 per image: (best completed sequence, its alphas (len(seq), s, s)) or None.  alphas[0]
+        is the all-ones map the reference starts seqsAlpha with (caption.py:85); alphas[t] is the attention of the
+        step that produced token t, followed back through the beam re-orderings.  return_all: additionally, per
+        image, the (seq, alphas) of every completed sequence in completion order."""
+        n_done = self.n_done.cpu()
+        scores, lens, seqs = self.done_scores.cpu(), self.done_len.cpu(), self.done_seqs.cpu()
+        parent, ahist, phist = self.done_parent.cpu(), self.alpha_hist.cpu(), self.parent_hist.cpu()
+        Pn = ahist.shape[-1]
+        side = int(round(Pn ** 0.5))
+
+        def chain(i, j):
+            L = int(lens[i, j])
+            row, back = int(parent[i, j]), []
+            for s in range(L - 1, 0, -1):            # decode steps s = L-1 .. 1 (1-based)
+                back.append(ahist[s - 1, row])
+                if s > 1:
+                    row = int(phist[s - 2, row])
+            maps = [torch.ones(Pn)] + back[::-1]
+            return seqs[i, j, :L].tolist(), torch.stack(maps).view(L, side, side)
+
+        best, every = [], []
+        for i in range(self.NI):
+            n = int(n_done[i])
+            every.append([chain(i, j) for j in range(n)] if return_all else None)
+            best.append(chain(i, int(torch.argmax(scores[i, :n]))) if n else None)
+        return (best, every) if return_all else best
 
     def all_done(self):
         """Per image: (list of completed sequences in completion order, list of their scores)."""
@@ -81,8 +121,9 @@ def _gather(src, dst, src_row, rows):
 
 @torch.no_grad()
 def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, trace=None, return_all=False,
-                     _state_only=False):
-    """caption.py:39-155 for a batch of images.  encoder_out (NI, s, s, E) from ``Encoder``; eval-mode decoder."""
+                     _state_only=False, return_alphas=False):
+    """caption.py:39-155 for a batch of images.  encoder_out (NI, s, s, E) from ``Encoder``; eval-mode decoder.
+    return_alphas: per image (seq, alphas) like the reference's ``return seq, alphas`` (caption.py:155)."""
     _lib.require_cuda(encoder_out, "encoder_out")
     NI, E = encoder_out.size(0), encoder_out.size(-1)
     k, V, D, A = int(beamSize), decoder.vocab_size, decoder.decoder_dim, decoder.attention_dim
@@ -107,6 +148,8 @@ def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, tr
                                          ptr(expand), D * es, rows, st), "gather_rows")
     _gather(C0[0], Cs[0], expand, rows)
     bs = _BeamState(NI, k, Tcap, wordMap['<start>'], dev)
+    if return_alphas:
+        bs.track_alphas(max_steps + 1, Pn)
     tokens = torch.full((rows, 1), wordMap['<start>'], dtype=torch.long, device=dev)
     HG = torch.empty((rows, A + E), dtype=torch.float32, device=dev)
     G = torch.empty((rows, 4 * D), dtype=torch.float32, device=dev)
@@ -121,9 +164,10 @@ def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, tr
         h_prev = x.map(lambda t: t[:, hoff:])
         _lib.linear(h_prev, Pw["w_h"], bias=Pw["b_h"], out=HG)
         awe = x.map(lambda t: t[:, decoder.embed_dim:hoff])
+        a_out = None if bs.alpha_hist is None else bs.alpha_hist[step - 1]
         _lib.check(L.ccx_bahdanau_attention(ptr(att1), ptr(HG), A + E, ptr(Pw["w_f"]), ptr(Pw["b_f"]), ptr(enc), None,
-                                            None, 0, ptr(awe.hi), awe.lo_ptr, code, K, rows, Pn, A, E, 1, k, st),
-                   "attention")
+                                            ptr(a_out), Pn, ptr(awe.hi), awe.lo_ptr, code, K, rows, Pn, A, E, 1, k,
+                                            st), "attention")
         _lib.linear(x, Pw["w_lstm"], bias=Pw["b_lstm"], out=G)
         _lib.check(L.ccx_lstm_pointwise(ptr(G), 4 * D, ptr(Cs[cur]), ptr(c_new), None, None, 0, ptr(h_new.hi),
                                         h_new.lo_ptr, D, code, None, 0, None, 0, rows, D, st), "lstm_pointwise")
@@ -140,6 +184,8 @@ def beam_search_lstm(decoder, encoder_out, wordMap, beamSize=3, max_steps=50, tr
             break
     if _state_only:
         return bs
+    if return_alphas:
+        return bs.results_with_alphas(return_all)
     return (bs.results(), bs.all_done()) if return_all else bs.results()
 
 

@@ -147,7 +147,8 @@ beam_update_kernel(int k, int Tcap, int step, long long end_token, const float* 
                    long long* __restrict__ done_seqs, float* __restrict__ done_scores, int* __restrict__ done_len,
                    int* __restrict__ n_done,   // [NI, k, Tcap], [NI, k], [NI, k], [NI]
                    int* __restrict__ src_row,  // [NI * k] global parent row of each surviving beam
-                   long long* __restrict__ next_tok, long long ld_next) {
+                   long long* __restrict__ next_tok, long long ld_next,
+                   int* __restrict__ done_parent) {  // [NI, k] optional: global parent row of each completed sequence
   const int img = blockIdx.x;
   const int kr = k_rem[img];
   __shared__ int s_slot[BEAM_KMAX];   // destination: >= 0 alive slot, < 0: -(done index + 1)
@@ -159,6 +160,7 @@ beam_update_kernel(int k, int Tcap, int step, long long end_token, const float* 
         s_slot[c] = -(nd + 1);
         done_scores[img * k + nd] = cand_score[img * k + c];
         done_len[img * k + nd] = step + 1;   // tokens incl. <start> and <end>
+        if (done_parent != nullptr) done_parent[img * k + nd] = img * k + cand_prev[img * k + c];
         ++nd;
       } else {
         s_slot[c] = alive;
@@ -188,13 +190,13 @@ beam_update_kernel(int k, int Tcap, int step, long long end_token, const float* 
 int beam_update(int NI, int k, int Tcap, int step, long long end_token, const float* cand_score,
                 const int* cand_prev, const int* cand_word, const long long* seqs_in, long long* seqs_out,
                 float* top_scores, int* k_rem, long long* done_seqs, float* done_scores, int* done_len, int* n_done,
-                int* src_row, long long* next_tok, long long ld_next, cudaStream_t stream) {
+                int* src_row, long long* next_tok, long long ld_next, int* done_parent, cudaStream_t stream) {
   if (NI <= 0) return CCX_OK;
   if (k <= 0 || k > BEAM_KMAX || step < 1 || step >= Tcap) return CCX_ERR_SHAPE;
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)NI * k * Tcap * 16.0);
   beam_update_kernel<<<NI, 64, 0, stream>>>(k, Tcap, step, end_token, cand_score, cand_prev, cand_word, seqs_in,
                                             seqs_out, top_scores, k_rem, done_seqs, done_scores, done_len, n_done,
-                                            src_row, next_tok, ld_next);
+                                            src_row, next_tok, ld_next, done_parent);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

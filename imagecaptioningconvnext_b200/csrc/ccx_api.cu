@@ -158,11 +158,12 @@ int ccx_beam_topk(const float* logits, int64_t ld, int32_t NI, int32_t k, int32_
 int ccx_beam_update(int32_t NI, int32_t k, int32_t Tcap, int32_t step, int64_t end_token, const float* cand_score,
                     const int32_t* cand_prev, const int32_t* cand_word, const int64_t* seqs_in, int64_t* seqs_out,
                     float* top_scores, int32_t* k_rem, int64_t* done_seqs, float* done_scores, int32_t* done_len,
-                    int32_t* n_done, int32_t* src_row, int64_t* next_tok, int64_t ld_next, void* stream) {
+                    int32_t* n_done, int32_t* src_row, int64_t* next_tok, int64_t ld_next, int32_t* done_parent,
+                    void* stream) {
   return beam_update(NI, k, Tcap, step, end_token, cand_score, cand_prev, cand_word,
                      reinterpret_cast<const long long*>(seqs_in), reinterpret_cast<long long*>(seqs_out), top_scores,
                      k_rem, reinterpret_cast<long long*>(done_seqs), done_scores, done_len, n_done, src_row,
-                     reinterpret_cast<long long*>(next_tok), ld_next, as_stream(stream));
+                     reinterpret_cast<long long*>(next_tok), ld_next, done_parent, as_stream(stream));
 }
 
 int ccx_gather_rows(const void* src, int64_t src_stride_bytes, void* dst, int64_t dst_stride_bytes,

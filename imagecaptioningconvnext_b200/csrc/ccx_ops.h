@@ -55,7 +55,7 @@ int beam_topk(const float* logits, long long ld, int NI, int k, int V, const flo
 int beam_update(int NI, int k, int Tcap, int step, long long end_token, const float* cand_score,
                 const int* cand_prev, const int* cand_word, const long long* seqs_in, long long* seqs_out,
                 float* top_scores, int* k_rem, long long* done_seqs, float* done_scores, int* done_len, int* n_done,
-                int* src_row, long long* next_tok, long long ld_next, cudaStream_t stream);
+                int* src_row, long long* next_tok, long long ld_next, int* done_parent, cudaStream_t stream);
 int gather_rows(const void* src, long long src_stride, void* dst, long long dst_stride, const int* src_row,
                 long long row_bytes, int rows, cudaStream_t stream);
 

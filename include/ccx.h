@@ -268,12 +268,15 @@ CCX_API int ccx_beam_topk(const float* logits, int64_t ld, int32_t NI, int32_t k
 /* Bookkeeping of caption.py:121-145: seqs_out[slot] = seqs_in[prev] + word; candidates ending in <end> are moved
  * to done_seqs/done_scores/done_len (in candidate order), k_rem shrinks; src_row[row] = parent row of each survivor
  * (identity for dead slots) for ccx_gather_rows; next_tok[row*ld_next] = the survivor's new word.
- * step = tokens per sequence before this step (1 at the first step: just <start>). */
+ * step = tokens per sequence before this step (1 at the first step: just <start>).
+ * done_parent [NI,k] (optional): global parent row of each completed sequence, from which the caller walks the
+ * per-step src_row records back to recover its attention maps (caption.py:122,129 seqsAlpha / completeSeqsAlpha). */
 CCX_API int ccx_beam_update(int32_t NI, int32_t k, int32_t Tcap, int32_t step, int64_t end_token,
                             const float* cand_score, const int32_t* cand_prev, const int32_t* cand_word,
                             const int64_t* seqs_in, int64_t* seqs_out, float* top_scores, int32_t* k_rem,
                             int64_t* done_seqs, float* done_scores, int32_t* done_len, int32_t* n_done,
-                            int32_t* src_row, int64_t* next_tok, int64_t ld_next, void* stream);
+                            int32_t* src_row, int64_t* next_tok, int64_t ld_next, int32_t* done_parent,
+                            void* stream);
 
 /* dst[r, 0:row_bytes) = src[src_row[r], 0:row_bytes) — beam re-ordering of h/c (caption.py:140-141) and of the
  * KV caches; src_row NULL = identity.  16-byte granules; strides in bytes. */

@@ -358,14 +358,18 @@ def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nh
 # ------------------------------------------------------------------------------------------------
 # beam search (caption.py:39-155 and :160-255) — one image, beams as batch
 # ------------------------------------------------------------------------------------------------
-def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=50, nheads=8, trace=None):
+def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=50, nheads=8, trace=None,
+                alphas_out=None):
     """Returns (best_seq or None if nothing completed, complete_seqs, complete_scores).
-    ``trace`` (a list) receives per step: (top-k scores, prev beam indices, next words) — the per-step contract."""
+    ``trace`` (a list) receives per step: (top-k scores, prev beam indices, next words) — the per-step contract.
+    ``alphas_out`` (a list, LSTM only) receives [the best sequence's attention maps (len(seq), P) — the reference's
+    second return value (caption.py:85,122,129,153), first entry all ones —, the maps of all completed sequences]."""
     E = encoder_out.size(-1)
     enc1 = encoder_out.reshape(1, -1, E)
     seqs = torch.full((k, 1), start_tok, dtype=torch.long)
     top = torch.zeros(k, 1, dtype=enc1.dtype)
-    done_seqs, done_scores = [], []
+    done_seqs, done_scores, done_alpha = [], [], []
+    seqs_alpha = torch.ones(k, 1, enc1.size(1), dtype=enc1.dtype)
     if kind == "lstm":
         enc = enc1.expand(k, -1, -1)
         h, c = init_hidden_state(sd, enc)
@@ -375,7 +379,7 @@ def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=5
     step = 1
     while True:
         if kind == "lstm":
-            h, c, _ = lstm_step(sd, enc, sd["embedding.weight"][prev_words], h, c)
+            h, c, alpha = lstm_step(sd, enc, sd["embedding.weight"][prev_words], h, c)
             logits = F.linear(h, sd["fc.weight"], sd["fc.bias"])
         else:
             logits = transformer_last_logits(sd, mem[:seqs.shape[0]], seqs, nheads)
@@ -389,16 +393,21 @@ def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=5
         if trace is not None:
             trace.append((top_s.clone(), prev.clone(), nxt.clone()))
         seqs = torch.cat([seqs[prev], nxt.unsqueeze(1)], dim=1)
+        if kind == "lstm":
+            seqs_alpha = torch.cat([seqs_alpha[prev], alpha[prev].unsqueeze(1)], dim=1)
         inc = [i for i, w in enumerate(nxt.tolist()) if w != end_tok]
         com = [i for i in range(len(nxt)) if i not in inc]
         if com:
             done_seqs.extend(seqs[com].tolist())
             done_scores.extend(top_s[com].tolist())
+            if kind == "lstm":
+                done_alpha.extend(seqs_alpha[com])
         k -= len(com)
         if k == 0:
             break
         seqs = seqs[inc]
         if kind == "lstm":
+            seqs_alpha = seqs_alpha[inc]
             h, c, enc = h[prev[inc]], c[prev[inc]], enc[prev[inc]]
             prev_words = nxt[inc]
         top = top_s[inc].unsqueeze(1)
@@ -409,7 +418,11 @@ def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=5
         step += 1
     if not done_scores:
         return None, done_seqs, done_scores
-    return done_seqs[done_scores.index(max(done_scores))], done_seqs, done_scores
+    best = done_scores.index(max(done_scores))
+    if alphas_out is not None and kind == "lstm":
+        alphas_out.append(done_alpha[best])
+        alphas_out.append(done_alpha)           # every completed sequence's maps, in completion order
+    return done_seqs[best], done_seqs, done_scores
 
 
 # ------------------------------------------------------------------------------------------------

@@ -227,22 +227,39 @@ def golden_beam():
     lstm.load_state_dict(do.random_lstm_decoder_state(0, V, end_bias=0.5))
     tr = TransformerDecoder(512, 512, V, 52, torch.device("cpu"), None, None, True).eval()
     tr.load_state_dict(do.random_transformer_decoder_state(0, V, end_bias=3.6))
-    out = {"image_seeds": [11, 12], "k": 5, "lstm_end_bias": 0.5, "transformer_end_bias": 3.6, "lstm": [], "transformer": [], "features": []}
+    out = {"image_seeds": [11, 12], "k": 5, "lstm_end_bias": 0.5, "transformer_end_bias": 3.6, "lstm": [], "transformer": [], "features": [],
+           "lstm_alphas": []}
     for seed in out["image_seeds"]:
         img = np.random.RandomState(seed).randint(0, 256, size=(256, 256, 3), dtype=np.uint8)
         path = f"/tmp/golden_beam_{seed}.png"
         Image.fromarray(img).save(path)
         with torch.no_grad():
-            seq, _ = cap.caption_image_beam_search(enc, lstm, path, WORDMAP, 5)
+            seq, alphas = cap.caption_image_beam_search(enc, lstm, path, WORDMAP, 5)
             seq_t, _ = cap.caption_image_beam_search_transformer(enc, tr, path, WORDMAP, 5)
             x = torch.from_numpy(img.transpose(2, 0, 1) / 255.).float()
             mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
             std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
             feats = enc(((x - mean) / std).unsqueeze(0)).contiguous()
         out["lstm"].append(seq)
+        out["lstm_alphas"].append(torch.tensor(alphas))        # (len(seq), 7, 7), caption.py:153
         out["transformer"].append(seq_t)
         out["features"].append(feats[0, ::3, ::3, ::64].clone())   # spot-check values of the encoder output
         print("beam", seed, seq, seq_t)
+    # longer LSTM captions so the attention-map chain has several steps: random-init decoders either emit <end> at
+    # once or never, so <end> is re-mapped (wordMap is an input of caption.py) to word 351, which these weights emit
+    # at step 3 — captions of 4 tokens with beam re-ordering at step 2
+    end_word = 351
+    wm = dict(WORDMAP)
+    wm["<end>"], wm[f"w{end_word}"] = end_word, V - 1
+    out["lstm_long"] = {"end_bias": 0.0, "end_word": end_word, "image_seeds": [11, 12], "seqs": [], "alphas": []}
+    lstm.load_state_dict(do.random_lstm_decoder_state(0, V, end_bias=0.0))
+    for seed in out["lstm_long"]["image_seeds"]:
+        path = f"/tmp/golden_beam_{seed}.png"
+        with torch.no_grad():
+            seq, alphas = cap.caption_image_beam_search(enc, lstm, path, wm, 5)
+        out["lstm_long"]["seqs"].append(seq)
+        out["lstm_long"]["alphas"].append(torch.tensor(alphas))
+        print("beam long", seed, seq)
     torch.save(out, os.path.join(HERE, "beam.pt"))
 
 

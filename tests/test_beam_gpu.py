@@ -49,6 +49,35 @@ def test_lstm_beam_vs_oracle():
     assert _compare("lstm", sd, _lstm(sd, torch.float32), feats, 5, beam_search_lstm) >= 3
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_lstm_beam_attention_maps_vs_oracle(dtype):
+    """beam_search_lstm(return_alphas=True) (caption.py:85,122,129,153): the maps of every
+    completed caption, followed back through the beam re-orderings, equal the oracle's seqsAlpha bookkeeping."""
+    from imagecaptioningconvnext_b200.beam import beam_search_lstm
+    from oracle import decoder_oracle as do
+    sd = do.random_lstm_decoder_state(0, V, end_bias=0.21)
+    feats = do.synthetic_features(4, 300)
+    m = _lstm(sd, dtype)
+    best, every = beam_search_lstm(m, feats.cuda(), WORDMAP, beamSize=5, return_all=True, return_alphas=True)
+    plain = beam_search_lstm(m, feats.cuda(), WORDMAP, beamSize=5)
+    checked = longest = 0
+    for i in range(feats.shape[0]):
+        al = []
+        obest, odone, _ = do.beam_search(sd, feats[i:i + 1], "lstm", 5, V - 2, V - 1, V, alphas_out=al)
+        assert (best[i] is None) == (obest is None) and (best[i] is None or best[i][0] == plain[i])
+        if [s for s, _ in every[i]] != odone:
+            assert dtype == torch.bfloat16          # a near-tie resolved differently in bf16
+            continue
+        for (seq, maps), omaps in zip(every[i], al[1]):
+            assert maps.shape == (len(seq), 7, 7) and torch.equal(maps[0], torch.ones(7, 7))
+            assert rel_err(maps.view(len(seq), 49), omaps) < (1e-3 if dtype == torch.float32 else 2e-2)
+            checked += 1
+            longest = max(longest, len(seq))
+        if obest is not None:
+            assert best[i][0] == obest and rel_err(best[i][1].view(len(obest), 49), al[0]) < 2e-2
+    assert checked >= 5 and longest >= 4, (checked, longest)
+
+
 def test_transformer_beam_vs_oracle():
     from imagecaptioningconvnext_b200.beam import beam_search_transformer
     from oracle import decoder_oracle as do

@@ -113,6 +113,17 @@ def test_beam_oracle_matches_reference_caption_py_golden(golden_dir):
         assert rel_err(f[0, ::3, ::3, ::64], gold["features"][i]) < 1e-5
         assert do.beam_search(lsd, f, "lstm", gold["k"], V - 2, V - 1, V)[0] == gold["lstm"][i]
         assert do.beam_search(tsd, f, "transformer", gold["k"], V - 2, V - 1, V)[0] == gold["transformer"][i]
+    # attention maps of the winning caption (caption.py:85,122,129,153) on 4-token captions: <end> re-mapped to a
+    # word these random weights emit at step 3 (see make_golden.py)
+    long = gold["lstm_long"]
+    lsd = do.random_lstm_decoder_state(0, V, end_bias=long["end_bias"])
+    for i, f in enumerate(feats):
+        al = []
+        best = do.beam_search(lsd, f, "lstm", gold["k"], V - 2, long["end_word"], V, alphas_out=al)[0]
+        assert best == long["seqs"][i] and len(best) == 4
+        ref = long["alphas"][i]
+        assert al[0].shape == (4, 49) and torch.equal(al[0][0], torch.ones(49))
+        assert rel_err(al[0].view(4, 7, 7), ref) < 1e-4
 
 
 def _oracle_free_running(kind, g, V=9490):
