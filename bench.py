@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the captioning hot path (contract: see DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|encoder]
 
-Workload (BASELINE.json configs[1]): ``Encoder.forward`` on a batch of 64 synthetic 256x256 images per GPU.
-One "step" = one Encoder.forward over one batch.  N > 1 (launched by torchrun, one rank per GPU): every rank runs
-its own batch (weak scaling, no data-path collective — inference shards by sample).
+Headline workload = the configuration BASELINE.json's metric ("train images/sec ... at 1/2/4/8 B200") is quoted on,
+configs[3]: the trainMultiGPU.py step — Encoder fine-tuned from startingLayer=7 + LSTM-attention decoder, teacher
+forcing, bf16 compute, batch 32 per GPU, 256x256 synthetic images, 52-token synthetic captions, packed cross-entropy
++ attention regulariser, clamp +-5, Adam.  One "step" = one such train step.  N > 1 (launched by torchrun, one rank
+per GPU): DistributedDataParallel over NCCL, disjoint per-rank batches (weak scaling), gradient all-reduce
+overlapped with the explicit backward.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event time, live, vs MEASURED_PEAKS.json
-  kernels       per-kernel-kind breakdown from the same instrumented pass (ms share, achieved TFLOP/s or GB/s)
-  cpu_baseline  the oracle (CPU restatement of the reference's torchvision/torch arithmetic) on the host cores
-  e2e           same metric through the public nn.Module call with pinned HOST input and a D2H read of the result
+  roofline      dominant kernel of the step (the tcgen05 GEMM, ~50 % of the kernel time): algorithmic FLOPs /
+                CUDA-event time summed over its launches, live, vs MEASURED_PEAKS.json
+  kernels       per-kernel-kind breakdown from the same instrumented pass
+  cpu_baseline  the oracle (CPU restatement of the reference's step) on the host cores, bounded sample
+  e2e           same metric through the public call with pinned HOST inputs and a D2H read of the loss every step
+  extra         the other BASELINE.json configs: encoder_forward (configs[1], with its own roofline / e2e),
+                Transformer train step (configs[2]), batched beam search (configs[4]), torch-eager encoder on B200
+``--workload encoder`` makes configs[1] (Encoder.forward, batch 64) the headline line instead.
 ``--impl reference`` times the reference's CPU implementation of the same path (the oracle port: the reference
 itself is pure Python on torchvision and /root/reference does not exist on the GPU box) with all host threads.
 """
@@ -29,6 +36,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENCODER_GFLOP_PER_IMAGE = 40.11   # 20.054 GMAC per 256x256 image
+TRAIN_BATCH = 32                  # BASELINE.json configs[3]: per-GPU batch of the trainMultiGPU.py step
+V = 9490
+WORDMAP = {"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1}
 L2_BYTES = 126 * 2 ** 20
 
 
@@ -42,38 +52,80 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every 250 ms while the timed region runs.  NVML in a thread (a polling
+    nvidia-smi process costs a launch-bound step several ms: its queries contend with the kernel launches);
+    nvidia-smi is only the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self._stop = index, [], None, None, threading.Event()
+        self.period = float(os.environ.get("BENCH_CLOCK_PERIOD", "0.25"))
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self):
+        n = self.nvml
+        bits = [(n.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                (n.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (n.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")]
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                flags = ["Active" if mask & b else "Not Active" for b, _ in bits]
+                self.rows.append((time.time(), [str(sm), str(self.max_sm), "0"] + flags))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t_begin=None, t_end=None):
-        if self.proc is None:
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, r in self.rows:
             if len(r) < 7 or (t_begin is not None and not (t_begin <= ts <= t_end + 0.15)):
                 continue
@@ -82,12 +134,12 @@ class ClockSampler:
                 mx = float(r[1])
             except ValueError:
                 continue
-            for n, v in zip(names, r[3:7]):
+            for n, v in zip(self.NAMES, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def max_over_ranks(ms_local, dev, world):
@@ -130,25 +182,93 @@ def cpu_encoder_throughput(sample_images, steps, warmup):
     return sample_images * steps / dt, cores, dt / steps
 
 
+def cpu_train_throughput(sample_images, steps, warmup):
+    """images/s of the oracle's restatement of the trainMultiGPU.py:357-394 step (configs[3]) on the host cores:
+    frozen children 0-6 + trainable child 7, LSTM-attention decoder teacher forcing, loss, backward, clamp, Adam;
+    fp32, train-mode dropout via the injected-mask path, all host threads."""
+    from oracle import decoder_oracle as do
+    from oracle import encoder_oracle as eo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_flush_denormal(True)
+    esd = eo.random_encoder_state(seed=0, layer_scale=1.0)
+    dsd = do.random_lstm_decoder_state(0, V)
+    e_leaf = {k: v.clone().requires_grad_(k.startswith("convnext.7.")) for k, v in esd.items()}
+    d_leaf = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in dsd.items()}
+    tr_e = [v for v in e_leaf.values() if v.requires_grad]
+    tr_d = [v for v in d_leaf.values() if v.requires_grad]
+    opt_e, opt_d = torch.optim.Adam(tr_e, lr=1e-4), torch.optim.Adam(tr_d, lr=1e-4)
+    imgs = synthetic_images(sample_images, 1234)
+    caps, lens = do.synthetic_captions(sample_images, 7, V)
+    T = int(lens.max()) - 1
+
+    def step():
+        mask = (torch.rand(sample_images, T, 512) > 0.5).float() * 2.0
+        feats = eo.encoder_forward(e_leaf, imgs, 7)
+        p, cs, dl, al, _ = do.lstm_teacher_forcing(d_leaf, feats, caps, lens, dropmask=mask)
+        loss = do.train_loss_lstm(p, cs, dl, al)
+        opt_e.zero_grad()
+        opt_d.zero_grad()
+        loss.backward()
+        for prm in tr_e + tr_d:
+            prm.grad.clamp_(-5.0, 5.0)
+        opt_e.step()
+        opt_d.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample_images * steps / dt, cores, dt / steps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 4
     steps = max(1, min(args.steps, 5))
     warmup = max(1, min(args.warmup, 1))
-    ips, cores, spstep = cpu_encoder_throughput(sample, steps, warmup)
+    if args.workload == "encoder":
+        sample = 4
+        ips, cores, spstep = cpu_encoder_throughput(sample, steps, warmup)
+        metric, cfg = "encoder_forward_images_per_sec", workload_config(
+            args, sample_note=f"CPU arm: each step = {sample} of the 64 images")
+        what = f"{sample} synthetic 256x256 images per step (Encoder.forward)"
+    else:
+        sample = 8
+        ips, cores, spstep = cpu_train_throughput(sample, steps, warmup)
+        metric, cfg = "train_images_per_sec", train_config(args, 1, sample_note=f"CPU arm: each step = one train "
+                                                           f"step on {sample} of the 32 images of a batch")
+        what = f"one full train step (fwd, loss, bwd, clamp, Adam) on {sample} synthetic images per step"
     line = {
-        "impl": "reference", "metric": "encoder_forward_images_per_sec", "value": ips, "unit": "images/s",
+        "impl": "reference", "metric": metric, "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spstep * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args, sample_note=f"CPU arm: each step = {sample} of the 64 images"),
+        "config": cfg,
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} synthetic 256x256 images per step, {steps} steps, fp32, "
-                                   f"torch {torch.__version__} CPU ops, flush-denormal on"},
+                         "sample": f"{what}, {steps} steps, fp32, torch {torch.__version__} CPU ops, "
+                                   f"flush-denormal on"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+def train_config(args, world, sample_note=None):
+    c = {"workload": "trainMultiGPU.py train step (BASELINE.json configs[3]): Encoder.fine_tune(True, startingLayer=7) "
+                     "+ DecoderWithAttention, teacher forcing, batch 32 per GPU, 256x256 synthetic images, 52-token "
+                     "caption rows (lengths uniform 7..52), packed CE + alpha regulariser, clamp +-5, Adam",
+         "batch_per_gpu": TRAIN_BATCH, "image": "3x256x256", "caption_tokens": 52, "vocab": V,
+         "weights": "random init (reference initialisers, seed 0), layer_scale=1.0; dropout 0.5 and stochastic depth on",
+         "parallelism": f"dp{world}" + (" (DistributedDataParallel, NCCL all-reduce overlapped with backward)"
+                                        if world > 1 else ""),
+         "l2_policy": "4 input batches rotated; one step touches > 1 GB of activations / weights / Adam state "
+                      "(L2 = 126 MB), so nothing survives in L2 between steps"}
+    if sample_note:
+        c["note"] = sample_note
+    return c
 
 
 def workload_config(args, sample_note=None):
@@ -166,21 +286,76 @@ def workload_config(args, sample_note=None):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-group / device context of one bench process."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torchrun (one rank per GPU)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
 def run_ours(args):
+    ctx = Ctx(args)
+    if args.workload == "encoder":
+        line = encoder_line(args, ctx, with_cpu=not args.no_cpu_baseline)
+        if line is not None and not args.no_extras:
+            line["extra"] = _guard(lambda: run_extras(args, ctx))
+    else:
+        line = train_line(args, ctx)
+        extra = None
+        if not args.no_extras:
+            torch.cuda.empty_cache()
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.warmup, sub.spans = 50, 5, None
+            extra = {}
+            enc_line = _guard(lambda: encoder_line(sub, ctx, with_cpu=False))
+            if ctx.rank == 0:
+                keep = ("metric", "value", "unit", "ms_per_step", "dtype", "config", "e2e", "gpu_launches_per_step",
+                        "roofline", "kernels", "model_tflops", "error")
+                extra["encoder_forward_configs1"] = {k: enc_line[k] for k in keep if k in enc_line}
+            torch.cuda.empty_cache()
+            more = _guard(lambda: run_extras(args, ctx))
+            extra.update(more or {})
+        if line is not None:
+            line["extra"] = extra
+    if ctx.rank == 0:
+        emit(line)
+    ctx.close()
+
+
+def _guard(fn):
+    """The headline line must survive a failing secondary workload."""
+    try:
+        return fn()
+    except Exception as ex:  # noqa: BLE001
+        return {"error": f"{type(ex).__name__}: {ex}"}
+
+
+def encoder_line(args, ctx, with_cpu):
+    """BASELINE.json configs[1]: Encoder.forward, batch 64 per GPU -> the JSON line (rank 0) / None (other ranks)."""
     import torch.distributed as dist
     from imagecaptioningconvnext_b200 import Encoder, _lib
     from oracle.encoder_oracle import random_encoder_state
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("bench.py --gpus N>1 must be launched with torchrun (one rank per GPU)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev, barrier = ctx.world, ctx.rank, ctx.local, ctx.dev, ctx.barrier
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     enc = Encoder(encoded_image_size=7, compute_dtype=dtype)
@@ -193,11 +368,6 @@ def run_ours(args):
     nbuf = 4
     host = [synthetic_images(B, 1234 + rank * 16 + i).pin_memory() for i in range(nbuf)]
     devbuf = [h.to(dev) for h in host]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---- device-resident throughput -------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -295,19 +465,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
-    extra = None
-    if not args.no_extras:
-        try:
-            del enc
-            torch.cuda.empty_cache()
-            extra = run_extras(args, dev, world, rank, local)
-        except Exception as ex:  # the headline line must survive a failing secondary workload
-            extra = {"error": f"{type(ex).__name__}: {ex}"}
-
+    del enc
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = measured_peaks()
     tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -335,7 +495,7 @@ def run_ours(args):
     launches = sum(v["launches"] for v in prof.values()) // args.steps
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and with_cpu:
         sample, csteps = 4, 3
         ips, cores, _ = cpu_encoder_throughput(sample, csteps, 1)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
@@ -355,20 +515,165 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches),
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
         "model_tflops": value / world * ENCODER_GFLOP_PER_IMAGE / 1e3,
-        "extra": extra,
     }
-    emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+def train_line(args, ctx):
+    """BASELINE.json configs[3] — the trainMultiGPU.py step — as the headline JSON line (rank 0) / None."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from imagecaptioningconvnext_b200 import DecoderWithAttention, Encoder, _lib
+    from imagecaptioningconvnext_b200.train_step import caption_train_step, make_optimizers
+    from oracle.decoder_oracle import random_lstm_decoder_state, synthetic_captions
+    from oracle.encoder_oracle import random_encoder_state
+    world, rank, local, dev, barrier = ctx.world, ctx.rank, ctx.local, ctx.dev, ctx.barrier
+    B, bf16 = TRAIN_BATCH, torch.bfloat16
+    torch.manual_seed(42 + rank)                      # trainMultiGPU.py:8: per-rank dropout / stochastic-depth streams
+    enc = Encoder(compute_dtype=bf16)
+    enc.load_state_dict(random_encoder_state(seed=0, layer_scale=1.0))
+    enc = enc.to(dev).train()
+    enc.fine_tune(True, 7)                            # trainMultiGPU.py:68,223: startingLayer=7
+    dec = DecoderWithAttention(512, 512, 512, V, dev, compute_dtype=bf16)
+    dec.load_state_dict(random_lstm_decoder_state(0, V))
+    dec = dec.to(dev).train()
+    d_opt, e_opt = make_optimizers(enc, dec)
+    enc_w = DDP(enc, device_ids=[local]) if world > 1 else enc      # trainMultiGPU.py:233-236
+    dec_w = DDP(dec, device_ids=[local]) if world > 1 else dec
+
+    nbuf = 4
+    host = []
+    for i in range(nbuf):
+        caps, lens = synthetic_captions(B, 7 + rank * 16 + i, V)
+        host.append((synthetic_images(B, 1234 + rank * 16 + i).pin_memory(), caps.pin_memory(), lens.pin_memory()))
+    devbuf = [tuple(t.to(dev) for t in h) for h in host]
+
+    def step(batch):
+        return caption_train_step(enc_w, dec_w, batch[0], batch[1], batch[2], d_opt, e_opt)
+
+    warmup = max(args.warmup, 10)                     # allocator / cuBLAS-free but lazy-init heavy: settle first
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident throughput -------------------------------------------------------------
+    for i in range(warmup):
+        step(devbuf[i % nbuf])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(devbuf[i % nbuf])
+    e1.record()
+    barrier()
+    t_end = time.time()
+    ms_total = max_over_ranks(e0.elapsed_time(e1), dev, world)
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    value = aggregate_throughput(B, args.steps, world, ms_total)
+    last_loss = float(loss)
+
+    # ---- end to end: host-pinned batches in, loss out, every step ---------------------------------
+    # the next batch is uploaded on a copy stream while the current step computes (a DataLoader with pin_memory and
+    # non_blocking copies, train.py:152-155,257-259, does the same); the loss is read back to pinned memory per step
+    main, copy_s = torch.cuda.current_stream(), torch.cuda.Stream()
+    stages = [tuple(torch.empty_like(t) for t in devbuf[0]) for _ in range(2)]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(slot, i):
+        for d, h in zip(stages[slot], host[i % nbuf]):
+            d.copy_(h, non_blocking=True)
+
+    barrier()
+    e0.record()
+    with torch.cuda.stream(copy_s):
+        copy_s.wait_event(e0)
+        upload(0, 0)
+        ready[0].record(copy_s)
+    for i in range(args.steps):
+        cur, nxt = i % 2, (i + 1) % 2
+        if i + 1 < args.steps:
+            with torch.cuda.stream(copy_s):
+                if i >= 1:
+                    copy_s.wait_event(consumed[nxt])
+                upload(nxt, i + 1)
+                ready[nxt].record(copy_s)
+        main.wait_event(ready[cur])
+        loss = step(stages[cur])
+        consumed[cur].record(main)
+        loss_host[cur:cur + 1].copy_(loss.reshape(1), non_blocking=True)        # D2H of this step's loss
+    e1.record()
+    barrier()
+    e2e_value = aggregate_throughput(B, args.steps, world, max_over_ranks(e0.elapsed_time(e1), dev, world))
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- instrumented pass: per-kernel CUDA events over the same steps -----------------------------
+    n_inst = min(args.steps, 10)
+    torch.cuda.synchronize()
+    _lib.prof_begin()
+    for i in range(n_inst):
+        step(devbuf[i % nbuf])
+    spans = _lib.prof_spans() if args.spans else None
+    prof = _lib.prof_end()
+    if spans is not None and rank == 0:
+        per = len(spans) // n_inst
+        with open(args.spans, "w") as f:
+            f.write("# launch index within the first instrumented step, kind, ms, work (FLOPs for gemm, bytes otherwise)\n")
+            for i, (k, ms_i, wk) in enumerate(spans[:per]):
+                f.write(f"{i:4d} {k:12s} {ms_i * 1e3:9.1f} us  work={wk:.4g}\n")
+    barrier()
+    del enc_w, dec_w, d_opt, e_opt, enc, dec, devbuf, stages
+    if rank != 0:
+        return None
+
+    peaks = measured_peaks()
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    kernels = {}
+    for k, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        rate = v["work"] / (v["ms"] * 1e-3) if v["ms"] > 0 else 0.0
+        kernels[k] = {"launches_per_step": v["launches"] / n_inst, "ms_per_step": v["ms"] / n_inst,
+                      "share": v["ms"] / tot_ms,
+                      ("tflops" if k == "gemm" else "gbs"): rate / (1e12 if k == "gemm" else 1e9)}
+    g = prof["gemm"]
+    achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"kernel": "gemm_tn_kernel (tcgen05): every GEMM of the step — encoder pointwise/downsample forward, "
+                          "stage-4 dgrad/wgrad, per-time-step LSTM / attention projections (M <= 32), vocabulary "
+                          "projection and the batched weight gradients",
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                "flops_per_launch": g["work"] / max(g["launches"], 1),
+                "us_per_launch": g["ms"] * 1e3 / max(g["launches"], 1),
+                "share_of_step_kernel_time": g["ms"] / tot_ms,
+                "note": "aggregate over ~310 launches per step, two thirds of them latency-bound M<=32 recurrent "
+                        "GEMMs; the large-GEMM roofline is extra.encoder_forward_configs1.roofline"}
+    launches = sum(v["launches"] for v in prof.values()) // n_inst
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample, csteps = 4, 2
+        ips, cores, _ = cpu_train_throughput(sample, csteps, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"oracle train step (fwd, loss, bwd, clamp, Adam) on {sample} of the {B} images x {csteps} "
+                         f"steps, fp32, all host threads"}
+    return {
+        "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": train_config(args, world),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "how": "caption_train_step per step on host-pinned images / captions / lengths (upload of batch i+1 "
+                       "on a copy stream during step i) and a D2H read of every step's loss"},
+        "gpu_launches": int(launches * args.steps), "gpu_launches_per_step": int(launches),
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+        "last_loss": last_loss,
+    }
 
 
 # ------------------------------------------------------------------------------------------------
 # secondary workloads (BASELINE.json configs[2..4]) reported under "extra" in the same JSON line
 # ------------------------------------------------------------------------------------------------
-V = 9490
-WORDMAP = {"<pad>": 0, "<unk>": V - 3, "<start>": V - 2, "<end>": V - 1}
-
-
 def _timed(fn, steps, warmup, dev, world):
     import torch.distributed as dist
     for _ in range(warmup):
@@ -390,8 +695,10 @@ def _timed(fn, steps, warmup, dev, world):
     return float(t.item()) / steps
 
 
-def run_extras(args, dev, world, rank, local):
-    """train images/s (configs[2], configs[3]) and beam-search captions/s (configs[4]); device-resident inputs."""
+def run_extras(args, ctx):
+    """Transformer train images/s (configs[2]) and beam-search captions/s (configs[4]); device-resident inputs.
+    With --workload encoder also the LSTM train step (configs[3], otherwise the headline)."""
+    dev, world, rank, local = ctx.dev, ctx.world, ctx.rank, ctx.local
     from torch.nn.parallel import DistributedDataParallel as DDP
     from imagecaptioningconvnext_b200 import DecoderWithAttention, Encoder, TransformerDecoder
     from imagecaptioningconvnext_b200.beam import CapturedBeamSearch
@@ -410,23 +717,24 @@ def run_extras(args, dev, world, rank, local):
     def wrap(m):
         return DDP(m, device_ids=[local]) if world > 1 and any(p.requires_grad for p in m.parameters()) else m
 
-    # configs[3]: encoder fine-tuned from child 7 + LSTM-attention decoder, bf16, DDP
-    enc = Encoder(compute_dtype=bf16)
-    enc.load_state_dict(esd)
-    enc = enc.to(dev).train()
-    enc.fine_tune(True, 7)
-    dec = DecoderWithAttention(512, 512, 512, V, dev, compute_dtype=bf16)
-    dec.load_state_dict(random_lstm_decoder_state(0, V))
-    dec = dec.to(dev).train()
-    d_opt, e_opt = make_optimizers(enc, dec)
-    enc_w, dec_w = wrap(enc), wrap(dec)
-    ms = _timed(lambda: caption_train_step(enc_w, dec_w, imgs, caps, lens, d_opt, e_opt), 20, 10, dev, world)
-    out["train_lstm_finetune7_bf16"] = {"images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms,
-                                        "batch_per_gpu": B, "config": "BASELINE.json configs[3]: encoder "
-                                        "fine_tune(True,7) + DecoderWithAttention, teacher forcing, captions uniform "
-                                        "7..52 tokens, dropout/stochastic depth on, clamp+Adam"
-                                        + (", DDP/NCCL" if world > 1 else "")}
-    del enc_w, dec_w, d_opt, e_opt, dec
+    # configs[3]: encoder fine-tuned from child 7 + LSTM-attention decoder, bf16, DDP (the headline unless --workload encoder)
+    if args.workload == "encoder":
+        enc = Encoder(compute_dtype=bf16)
+        enc.load_state_dict(esd)
+        enc = enc.to(dev).train()
+        enc.fine_tune(True, 7)
+        dec = DecoderWithAttention(512, 512, 512, V, dev, compute_dtype=bf16)
+        dec.load_state_dict(random_lstm_decoder_state(0, V))
+        dec = dec.to(dev).train()
+        d_opt, e_opt = make_optimizers(enc, dec)
+        enc_w, dec_w = wrap(enc), wrap(dec)
+        ms = _timed(lambda: caption_train_step(enc_w, dec_w, imgs, caps, lens, d_opt, e_opt), 20, 10, dev, world)
+        out["train_lstm_finetune7_bf16"] = {"images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms,
+                                            "batch_per_gpu": B, "config": "BASELINE.json configs[3]: encoder "
+                                            "fine_tune(True,7) + DecoderWithAttention, teacher forcing, captions uniform "
+                                            "7..52 tokens, dropout/stochastic depth on, clamp+Adam"
+                                            + (", DDP/NCCL" if world > 1 else "")}
+        del enc_w, dec_w, d_opt, e_opt, dec
     # configs[2]: frozen encoder + TransformerDecoder teacher forcing
     for name, cd in (("bf16", bf16), ("fp32", torch.float32)):
         enc2 = Encoder(compute_dtype=cd)
@@ -468,7 +776,46 @@ def run_extras(args, dev, world, rank, local):
                                               "config": "BASELINE.json configs[4]: Encoder + TransformerDecoder beam "
                                                         "search (KV cache, decode loop replayed as one CUDA graph), "
                                                         "captions read back to the host, replicas only, no collective"}
+    # "reported beside torch-eager-on-B200" — the stock torchvision ConvNeXt-base feature stack (what
+    # models/encoder.py:18-20 wraps) + AdaptiveAvgPool2d + permute, run by PyTorch's own kernels on this GPU.  Library
+    # comparison only; rank 0, same B=64 batch shape as the headline.
+    if rank == 0:
+        try:
+            out["torch_eager_encoder_b200"] = _torch_eager_encoder(dev)
+        except Exception as ex:  # noqa: BLE001  (torchvision missing / OOM: report, do not fail the bench)
+            out["torch_eager_encoder_b200"] = {"error": f"{type(ex).__name__}: {ex}"}
     return out
+
+
+def _torch_eager_encoder(dev, B=64):
+    import torchvision
+    net = torchvision.models.convnext_base(weights=None).features.to(dev).eval()
+    pool = torch.nn.AdaptiveAvgPool2d((7, 7))
+    x = torch.randn(B, 3, 256, 256, device=dev)
+    res = {"batch": B, "what": "torchvision convnext_base().features + AdaptiveAvgPool2d(7) + permute, eval, "
+                               "torch " + torch.__version__ + " eager kernels (cuDNN/cuBLAS), random weights"}
+
+    def run(fn):
+        with torch.no_grad():
+            ms = _timed(fn, 10, 3, dev, 1)
+        return {"images_per_sec": B / (ms * 1e-3), "ms_per_step": ms}
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    res["fp32"] = run(lambda: pool(net(x)).permute(0, 2, 3, 1))
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    res["tf32"] = run(lambda: pool(net(x)).permute(0, 2, 3, 1))
+    xc = x.contiguous(memory_format=torch.channels_last)
+    netc = net.to(memory_format=torch.channels_last)
+
+    def amp():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return pool(netc(xc)).permute(0, 2, 3, 1)
+    res["bf16_autocast_channels_last"] = run(amp)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return res
 
 
 _REAL_STDOUT = None
@@ -486,7 +833,9 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="train", choices=["train", "encoder"],
+                    help="headline line: the train step (BASELINE.json configs[3]) or Encoder.forward (configs[1])")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"], help="--workload encoder only")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")

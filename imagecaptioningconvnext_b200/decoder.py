@@ -25,6 +25,17 @@ from ._host import CcxEmbedding, CcxLinear, PreparedCache
 from ._lib import Operand, ptr
 
 
+_INT_ARRAYS = {}
+
+
+def _int_array_type(n):
+    """ctypes array types are cached: creating `c_int32 * n` per call leaves a new (cyclic) type object behind."""
+    t = _INT_ARRAYS.get(n)
+    if t is None:
+        t = _INT_ARRAYS[n] = ctypes.c_int32 * n
+    return t
+
+
 class Attention(nn.Module):
     """models/decoder.py:16-31."""
 
@@ -199,7 +210,7 @@ class DecoderWithAttention(nn.Module):
         d.w_h, d.w_h_lo, d.b_h = ptr(Pw["w_h"].hi), Pw["w_h"].lo_ptr, ptr(Pw["b_h"])
         d.w_f, d.b_f = ptr(Pw["w_f"]), ptr(Pw["b_f"])
         d.w_lstm, d.w_lstm_lo, d.b_lstm = ptr(Pw["w_lstm"].hi), Pw["w_lstm"].lo_ptr, ptr(Pw["b_lstm"])
-        arr = (ctypes.c_int32 * max(len(bts), 1))(*bts)
+        arr = _int_array_type(max(len(bts), 1))(*bts)
         d.bts_host = arr
         d._keep = arr                                   # ctypes does not keep the array alive by itself
         d.B, d.T, d.P, d.E = enc.shape[0], len(bts), enc.shape[1], enc.shape[2]
@@ -266,7 +277,9 @@ class DecoderWithAttention(nn.Module):
                     rows_per_group=1, out=predictions.view(B * T, V))
         saved = dict(enc=enc, att1=att1, XH=XH, C_all=C_all, HG=HG, G=G, H_all=H_all, dm=dm, valid=valid, bts=bts,
                      sort_ind=sort_ind, caps=encoded_captions, Pw=Pw, m_op=self._setup_extras[0],
-                     enc_op=self._setup_extras[1], alphas=alphas, T=T)
+                     enc_op=self._setup_extras[1], alphas=alphas.detach(), T=T)   # an alias: the returned
+        # tensor becomes an autograd OUTPUT (grad_fn -> node -> saved -> tensor would be a reference cycle that keeps
+        # every activation of the step alive until the cyclic GC runs)
         self._setup_extras = None
         return predictions, encoded_captions, decode_lengths, alphas, sort_ind, saved
 
