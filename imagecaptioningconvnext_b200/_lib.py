@@ -55,7 +55,8 @@ class LstmTFBwd(C.Structure):
     _fields_ = [("dH_all", _vp), ("dalphas", _vp), ("dG_all", _vp), ("dHG_all", _vp), ("dXH_all", _vp),
                 ("dh", _vp), ("dc", _vp), ("d_att1", _vp), ("d_enc", _vp), ("d_wf", _vp),
                 ("w_lstm_t", _vp), ("w_lstm_t_lo", _vp), ("w_h_t", _vp), ("w_h_t_lo", _vp),
-                ("scratch_hi", _vp), ("scratch_lo", _vp), ("scratch2_hi", _vp), ("scratch2_lo", _vp)]
+                ("scratch_hi", _vp), ("scratch_lo", _vp), ("scratch2_hi", _vp), ("scratch2_lo", _vp),
+                ("dawe_all", _vp), ("dalpha_all", _vp), ("de_all", _vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/ccx.h declares (tests/test_abi.py checks it)

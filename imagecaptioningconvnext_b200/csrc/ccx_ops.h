@@ -84,12 +84,17 @@ int lstm_pointwise_bwd(const float* gates, long long ldg, const float* c_prev, c
                        const float* dh_carry, float* dc_carry, float* dgates, long long lddg, int bt, int D,
                        cudaStream_t stream, void* dg_op_hi = nullptr, float* dg_op_lo = nullptr, int dg_op_dtype = 0,
                        long long ld_op = 0, float* zero_rows = nullptr, long long ld_zero = 0, int n_zero = 0);
+int attention_bwd_finish(const float* alphas, long long a_sb, long long a_st, const float* dawe_all,
+                         const float* de_all, const float* att1, const float* hg_all, long long ldhg,
+                         const float* w_f, float* d_att1, float* d_enc, int B, int T, int P, int A, int E,
+                         cudaStream_t stream);
 int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* enc,
                            const float* alpha, long long alpha_ld, const float* d_out, long long ld_dout,
                            const float* d_alpha_ext, long long dalpha_ld, float* d_hg, long long ld_dhg,
                            float* d_att1, float* d_enc, float* d_wf, int bt, int P, int A, int E,
                            cudaStream_t stream, void* op_hi = nullptr, float* op_lo = nullptr, int op_dtype = 0,
-                           long long ld_op = 0, int scratch_zeroed = 0);
+                           long long ld_op = 0, int scratch_zeroed = 0, float* dawe_out = nullptr,
+                           float* dalpha_acc = nullptr, float* de_out = nullptr);
 int bcast_add_rows(float* out, const float* v, float scale, int B, int P, int E, cudaStream_t stream);
 int adam_clamp(const void* table, const int* block_entry, const long long* block_offset, int n_blocks, float lr,
                float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip, int chunk,

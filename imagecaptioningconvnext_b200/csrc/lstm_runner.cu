@@ -76,6 +76,9 @@ int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* s
   const int cd = s->compute_dtype;
   const bool f32 = (cd == CCX_F32);
   int rc;
+  // deferred mode: the per-step kernels only record d_awe_raw / d e; the d_enc and d_att1 sums over time are done
+  // once after the loop instead of as a read-modify-write pass over both tensors at every step
+  const bool deferred = b->dawe_all != nullptr && b->dalpha_all != nullptr && b->de_all != nullptr;
   for (int t = T - 1; t >= 0; --t) {
     const int bt = s->bts_host[t];
     if (bt <= 0) continue;
@@ -106,7 +109,10 @@ int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* s
                                      s->alphas + static_cast<long long>(t) * P, static_cast<long long>(T) * P, dXH + Emb,
                                      K, b->dalphas ? b->dalphas + static_cast<long long>(t) * P : nullptr,
                                      static_cast<long long>(T) * P, dHG, AE, b->d_att1, b->d_enc, b->d_wf, bt, P, A, E,
-                                     st, b->scratch2_hi, f32 ? b->scratch2_lo : nullptr, cd, AE, 1)))
+                                     st, b->scratch2_hi, f32 ? b->scratch2_lo : nullptr, cd, AE, 1,
+                                     deferred ? b->dawe_all + static_cast<long long>(t) * B * E : nullptr,
+                                     deferred ? b->dalpha_all + static_cast<long long>(t) * B * P : nullptr,
+                                     deferred ? b->de_all + static_cast<long long>(t) * B * P : nullptr)))
       return rc;
     // (5) d h_{t-1} = d h_prev (from the gates GEMM) + dHG . [decoder_att ; f_beta]
     GemmDesc g2;
@@ -118,6 +124,9 @@ int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* s
     g2.in_dtype = cd; g2.out_dtype = CCX_F32;
     if ((rc = gemm_tn(g2, st))) return rc;
   }
+  if (deferred)
+    return attention_bwd_finish(s->alphas, static_cast<long long>(T) * P, P, b->dawe_all, b->de_all, s->att1, s->HG,
+                                AE, s->w_f, b->d_att1, b->d_enc, B, T, P, A, E, st);
   return CCX_OK;
 }
 

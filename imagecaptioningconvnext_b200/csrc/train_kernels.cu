@@ -555,7 +555,9 @@ __global__ void __launch_bounds__(128)
 attention_bwd_enc_kernel(const float* __restrict__ hg, long long ldhg, const float* __restrict__ enc,
                          const float* __restrict__ alpha, long long alpha_ld, const float* __restrict__ d_out,
                          long long ld_dout, float* __restrict__ d_hg, long long ld_dhg, float* __restrict__ d_enc,
-                         OpDst dhg_op, long long ld_op, int P, int A, int E) {
+                         OpDst dhg_op, long long ld_op, int P, int A, int E,
+                         float* __restrict__ dawe_out,      // deferred mode: [bt, E] d_awe_raw of this step
+                         float* __restrict__ dalpha_acc) {  // deferred mode: [bt, P] d alpha accumulator (zeroed)
   __shared__ float s_a[PMAX];
   const int b = blockIdx.x;
   const int e = blockIdx.y * 128 + threadIdx.x;
@@ -578,14 +580,152 @@ attention_bwd_enc_kernel(const float* __restrict__ hg, long long ldhg, const flo
     d_hg[b * ld_dhg + A + e] = dgp;
     if (dhg_op.hi != nullptr) put(dhg_op, b * ld_op + A + e, dgp);
     draw = dout * gate;
+    if (dawe_out != nullptr) dawe_out[static_cast<long long>(b) * E + e] = draw;
   }
+  float* acc = dalpha_acc != nullptr ? dalpha_acc + static_cast<long long>(b) * P : d_hg + b * ld_dhg;
+  const bool rmw = ok && d_enc != nullptr && dawe_out == nullptr;
 #pragma unroll
   for (int p = 0; p < PMAX; ++p) {
     if (p >= P) break;
     const float part = warp_sum(draw * x[p]);
-    if (lane == 0) atomicAdd(d_hg + b * ld_dhg + p, part);          // d alpha_p accumulator (scratch)
-    if (ok && d_enc != nullptr) d_enc[(static_cast<long long>(b) * P + p) * E + e] += s_a[p] * draw;
+    if (lane == 0) atomicAdd(acc + p, part);          // d alpha_p accumulator (d_hg[b, 0:P] as scratch, or dalpha_acc)
+    if (rmw) d_enc[(static_cast<long long>(b) * P + p) * E + e] += s_a[p] * draw;
   }
+}
+
+// Deferred mode of K2: grid (bt, A/128), one thread per attention unit; every CTA re-derives the 49 softmax-backward
+// values (cheap) so a step with <= 32 active rows still spreads over 4x as many SMs; no d_att1 read-modify-write.
+__global__ void __launch_bounds__(128)
+attention_bwd_att_split_kernel(const float* __restrict__ att1, const float* __restrict__ hg, long long ldhg,
+                               const float* __restrict__ w_f, const float* __restrict__ alpha, long long alpha_ld,
+                               const float* __restrict__ d_alpha_ext, long long dalpha_ld,
+                               const float* __restrict__ dalpha_acc, float* __restrict__ de_out,
+                               float* __restrict__ d_hg, long long ld_dhg, float* __restrict__ d_wf, OpDst dhg_op,
+                               long long ld_op, int P, int A) {
+  __shared__ float s_de[ATT_MAX_P_BWD];
+  __shared__ float s_red[4];
+  const int b = blockIdx.x;
+  float dot = 0.f;
+  for (int p = threadIdx.x; p < P; p += 128) {
+    const float a_p = alpha[b * alpha_ld + p];
+    const float da_p = dalpha_acc[static_cast<long long>(b) * P + p] +
+                       (d_alpha_ext ? d_alpha_ext[b * dalpha_ld + p] : 0.f);
+    s_de[p] = da_p;
+    dot = fmaf(a_p, da_p, dot);
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  dot = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+  for (int p = threadIdx.x; p < P; p += 128) {
+    const float de = alpha[b * alpha_ld + p] * (s_de[p] - dot);      // each p is owned by one thread: no hazard
+    s_de[p] = de;
+    if (blockIdx.y == 0) de_out[static_cast<long long>(b) * P + p] = de;
+  }
+  __syncthreads();
+  const int a = blockIdx.y * 128 + threadIdx.x;
+  if (a >= A) return;
+  float datt2 = 0.f, dwf = 0.f;
+  const float h2 = hg[b * ldhg + a], wf = __ldg(w_f + a);
+  const float* a1 = att1 + static_cast<long long>(b) * P * A + a;
+#pragma unroll 7
+  for (int p = 0; p < P; ++p) {
+    const float pre = __ldg(a1 + static_cast<long long>(p) * A) + h2;
+    if (pre > 0.f) {
+      const float de = s_de[p];
+      datt2 = fmaf(de, wf, datt2);
+      dwf = fmaf(de, pre, dwf);
+    }
+  }
+  d_hg[b * ld_dhg + a] = datt2;
+  if (dhg_op.hi != nullptr) put(dhg_op, b * ld_op + a, datt2);
+  atomicAdd(d_wf + a, dwf);
+}
+
+// After the time loop (deferred mode): the two accumulations that the per-step kernels would otherwise do as
+// read-modify-write passes over d_enc [B,P,E] and d_att1 [B,P,A] at every step.
+//   d_enc[b,p,e]  += sum_t alpha[b,t,p] * dawe[t,b,e]
+//   d_att1[b,p,a] += w_f[a] * sum_t de[t,b,p] * [att1[b,p,a] + att2[t,b,a] > 0]
+// grid (B, channels/128, ceil(P/32)); 32 pixels per CTA live in registers; rows / steps that never ran hold zeros.
+static constexpr int FIN_P = 32;
+
+__global__ void __launch_bounds__(128)
+attention_bwd_finish_enc_kernel(const float* __restrict__ alphas, long long a_sb, long long a_st,
+                                const float* __restrict__ dawe, float* __restrict__ d_enc, int B, int T, int P,
+                                int E) {
+  extern __shared__ float s_al[];           // [T][FIN_P]
+  const int b = blockIdx.x, e = blockIdx.y * 128 + threadIdx.x, p0 = blockIdx.z * FIN_P;
+  for (int i = threadIdx.x; i < T * FIN_P; i += 128) {
+    const int t = i / FIN_P, p = p0 + i % FIN_P;
+    s_al[i] = p < P ? alphas[b * a_sb + t * a_st + p] : 0.f;
+  }
+  __syncthreads();
+  if (e >= E) return;
+  float acc[FIN_P];
+#pragma unroll
+  for (int p = 0; p < FIN_P; ++p) acc[p] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float x = __ldg(dawe + (static_cast<long long>(t) * B + b) * E + e);
+#pragma unroll
+    for (int p = 0; p < FIN_P; ++p) acc[p] = fmaf(s_al[t * FIN_P + p], x, acc[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < FIN_P; ++p)
+    if (p0 + p < P) d_enc[(static_cast<long long>(b) * P + p0 + p) * E + e] += acc[p];
+}
+
+__global__ void __launch_bounds__(128)
+attention_bwd_finish_att_kernel(const float* __restrict__ att1, const float* __restrict__ hg_all, long long ldhg,
+                                const float* __restrict__ w_f, const float* __restrict__ de_all,
+                                float* __restrict__ d_att1, int B, int T, int P, int A) {
+  extern __shared__ float s_de[];           // [T][FIN_P]
+  const int b = blockIdx.x, a = blockIdx.y * 128 + threadIdx.x, p0 = blockIdx.z * FIN_P;
+  for (int i = threadIdx.x; i < T * FIN_P; i += 128) {
+    const int t = i / FIN_P, p = p0 + i % FIN_P;
+    s_de[i] = p < P ? de_all[(static_cast<long long>(t) * B + b) * P + p] : 0.f;
+  }
+  __syncthreads();
+  if (a >= A) return;
+  float x[FIN_P], acc[FIN_P];
+#pragma unroll
+  for (int p = 0; p < FIN_P; ++p) {
+    x[p] = (p0 + p < P) ? __ldg(att1 + (static_cast<long long>(b) * P + p0 + p) * A + a) : -INFINITY;
+    acc[p] = 0.f;
+  }
+  for (int t = 0; t < T; ++t) {
+    const float h2 = __ldg(hg_all + (static_cast<long long>(t) * B + b) * ldhg + a);
+#pragma unroll
+    for (int p = 0; p < FIN_P; ++p)
+      if (x[p] + h2 > 0.f) acc[p] += s_de[t * FIN_P + p];
+  }
+  const float wf = __ldg(w_f + a);
+#pragma unroll
+  for (int p = 0; p < FIN_P; ++p)
+    if (p0 + p < P) d_att1[(static_cast<long long>(b) * P + p0 + p) * A + a] += wf * acc[p];
+}
+
+int attention_bwd_finish(const float* alphas, long long a_sb, long long a_st, const float* dawe_all,
+                         const float* de_all, const float* att1, const float* hg_all, long long ldhg,
+                         const float* w_f, float* d_att1, float* d_enc, int B, int T, int P, int A, int E,
+                         cudaStream_t stream) {
+  if (B <= 0 || T <= 0) return CCX_OK;
+  if (P <= 0 || T * FIN_P * 4 > 200 * 1024) return CCX_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(T) * FIN_P * sizeof(float);
+  const unsigned pz = static_cast<unsigned>((P + FIN_P - 1) / FIN_P);
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(attention_bwd_finish_enc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess ||
+        cudaFuncSetAttribute(attention_bwd_finish_att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return CCX_ERR_CUDA;
+  }
+  ProfScope prof(PROF_ATTENTION, stream, (double)B * T * (E + A) * 4.0 + (double)B * P * (2.0 * E + 3.0 * A) * 4.0);
+  if (d_enc != nullptr)
+    attention_bwd_finish_enc_kernel<<<dim3(B, (E + 127) / 128, pz), 128, smem, stream>>>(alphas, a_sb, a_st, dawe_all,
+                                                                                         d_enc, B, T, P, E);
+  attention_bwd_finish_att_kernel<<<dim3(B, (A + 127) / 128, pz), 128, smem, stream>>>(att1, hg_all, ldhg, w_f, de_all,
+                                                                                       d_att1, B, T, P, A);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
 __global__ void __launch_bounds__(512)
@@ -636,23 +776,32 @@ int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, c
                            const float* d_alpha_ext, long long dalpha_ld, float* d_hg, long long ld_dhg,
                            float* d_att1, float* d_enc, float* d_wf, int bt, int P, int A, int E,
                            cudaStream_t stream, void* op_hi, float* op_lo, int op_dtype, long long ld_op,
-                           int scratch_zeroed) {
+                           int scratch_zeroed, float* dawe_out, float* dalpha_acc, float* de_out) {
   if (bt <= 0) return CCX_OK;
   if (P <= 0 || P > ATT_MAX_P_BWD || P > A || bt > 65535) return CCX_ERR_SHAPE;
   OpDst dhg_op{op_hi, op_lo, op_dtype};
   ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (2.0 * A + 3.0 * E) * 4.0);
-  if (!scratch_zeroed &&
+  const bool deferred = dawe_out != nullptr && dalpha_acc != nullptr && de_out != nullptr;
+  if (!deferred) dawe_out = dalpha_acc = de_out = nullptr;
+  if (!deferred && !scratch_zeroed &&
       cudaMemset2DAsync(d_hg, ld_dhg * sizeof(float), 0, P * sizeof(float), bt, stream) != cudaSuccess)
     return CCX_ERR_CUDA;
   dim3 g1(bt, (E + 127) / 128);
   if (P <= ATTB_P)
     attention_bwd_enc_kernel<ATTB_P><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout, d_hg,
-                                                             ld_dhg, d_enc, dhg_op, ld_op, P, A, E);
+                                                             ld_dhg, d_enc, dhg_op, ld_op, P, A, E, dawe_out,
+                                                             dalpha_acc);
   else
     attention_bwd_enc_kernel<ATT_MAX_P_BWD><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout,
-                                                                    d_hg, ld_dhg, d_enc, dhg_op, ld_op, P, A, E);
-  attention_bwd_att_kernel<<<bt, 512, 0, stream>>>(att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld, d_hg,
-                                                   ld_dhg, d_att1, d_wf, dhg_op, ld_op, P, A);
+                                                                    d_hg, ld_dhg, d_enc, dhg_op, ld_op, P, A, E,
+                                                                    dawe_out, dalpha_acc);
+  if (deferred)
+    attention_bwd_att_split_kernel<<<dim3(bt, (A + 127) / 128), 128, 0, stream>>>(
+        att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld, dalpha_acc, de_out, d_hg, ld_dhg, d_wf, dhg_op,
+        ld_op, P, A);
+  else
+    attention_bwd_att_kernel<<<bt, 512, 0, stream>>>(att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld,
+                                                     d_hg, ld_dhg, d_att1, d_wf, dhg_op, ld_op, P, A);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -72,6 +72,10 @@ class _LstmTF(torch.autograd.Function):
         bd.w_h_t, bd.w_h_t_lo = ptr(w_h_t.hi), w_h_t.lo_ptr
         bd.scratch_hi, bd.scratch_lo = ptr(scratch.hi), scratch.lo_ptr
         bd.scratch2_hi, bd.scratch2_lo = ptr(scratch2.hi), scratch2.lo_ptr
+        # deferred accumulation (see ccx_lstm_tf_bwd): per-step records, summed over time once after the loop
+        dawe_all = torch.zeros((T, B, E), **f32)
+        dalpha_all = torch.zeros((2, T, B, Pn), **f32)
+        bd.dawe_all, bd.dalpha_all, bd.de_all = ptr(dawe_all), ptr(dalpha_all[0]), ptr(dalpha_all[1])
         _lib.check(L.ccx_lstm_tf_backward(ctypes.byref(fwd), ctypes.byref(bd), st), "lstm_tf_backward")
         # ---- weight gradients, batched over time -------------------------------------------------------------
         TB = T * B

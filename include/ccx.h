@@ -420,6 +420,12 @@ typedef struct ccx_lstm_tf_bwd {
   float* scratch_lo;
   void* scratch2_hi; /* [B, A+E] operand staging of d[att2 | gate] */
   float* scratch2_lo;
+  /* optional (all three or none), zero-initialised by the caller: with them the per-step attention backward only
+   * records d_awe_raw [T][B][E] and d e [T][B][P] (d alpha accumulates in dalpha_all [T][B][P]) and the sums over
+   * time into d_enc / d_att1 run once after the loop, not as a read-modify-write pass at every step */
+  float* dawe_all;
+  float* dalpha_all;
+  float* de_all;
 } ccx_lstm_tf_bwd;
 CCX_API int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* stream);
 
