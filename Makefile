@@ -15,8 +15,9 @@ build/%.o: $(PKG)/csrc/%.cu $(HDR)
 $(PKG)/libccx.so: $(OBJ)
 	$(NVCC) -shared -o $@ $(OBJ) -lcudart -Wno-deprecated-gpu-targets
 
-tools/gemm_selftest: tools/gemm_selftest.cu $(PKG)/csrc/gemm_tcgen05.cu $(HDR)
-	$(NVCC) $(NVFLAGS) -o $@ tools/gemm_selftest.cu $(PKG)/csrc/gemm_tcgen05.cu
+GEMM_SRC := $(PKG)/csrc/gemm_tcgen05.cu $(PKG)/csrc/gemm_tcgen05_2cta.cu $(PKG)/csrc/gemm_skinny.cu $(PKG)/csrc/prof.cu
+tools/gemm_selftest: tools/gemm_selftest.cu $(GEMM_SRC) $(HDR)
+	$(NVCC) $(NVFLAGS) -I$(PKG)/csrc -Iinclude -o $@ tools/gemm_selftest.cu $(GEMM_SRC)
 
 clean:
 	rm -rf build $(PKG)/libccx.so

@@ -29,6 +29,9 @@ struct GemmDesc {
 };
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream);
+// M <= 32 bf16 -> fp32 GEMMs (the recurrent ones): mma.sync kernel spread over N, see gemm_skinny.cu
+bool gemm_skinny_eligible(const GemmDesc& g);
+int gemm_skinny(const GemmDesc& g, cudaStream_t stream);
 void set_gemm_pair_mode(int mode);
 
 // driver entry point for building TMA descriptors (resolved through the runtime; no -lcuda needed)

@@ -263,6 +263,7 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (!tf32 && g.out_dtype == CCX_F32 && g.split) return CCX_ERR_DTYPE;
   if (tf32 && g.out_dtype != CCX_F32) return CCX_ERR_DTYPE;
   (void)BK;
+  if (gemm_skinny_eligible(g)) return gemm_skinny(g, stream);
   // tile-N choice: widest tile that still gives every SM work
   int bn = g.force_bn;
   if (bn == 0) {

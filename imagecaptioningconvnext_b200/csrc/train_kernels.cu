@@ -841,16 +841,42 @@ adam_clamp_kernel(const AdamEntry* __restrict__ table, const int* __restrict__ b
   const long long begin = block_offset[blockIdx.x];
   const long long end = min(e.n, begin + chunk);
   const float step = lr / bc1;
-  for (long long i = begin + threadIdx.x; i < end; i += 256) {
-    float g = e.g[i];
+  auto update = [&](float& p, float& g, float& m, float& v) {
     if (clip > 0.f) g = fminf(fmaxf(g, -clip), clip);     // utils/utils.py:189-192
+    m = beta1 * m + (1.f - beta1) * g;                    // torch/optim/adam.py _single_tensor_adam
+    v = beta2 * v + (1.f - beta2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= step * (m / denom);
+  };
+  // 16-byte path: 7 x 128-bit transactions per 4 elements (the clamped gradient is written back only if it changed)
+  const bool vec = (((reinterpret_cast<uintptr_t>(e.p) | reinterpret_cast<uintptr_t>(e.g) |
+                      reinterpret_cast<uintptr_t>(e.m) | reinterpret_cast<uintptr_t>(e.v)) & 15) == 0) &&
+                   ((begin & 3) == 0);
+  long long scalar_from = begin;
+  if (vec) {
+    const long long q0 = begin >> 2, q1 = end >> 2;
+    for (long long q = q0 + threadIdx.x; q < q1; q += 256) {
+      float4 p4 = reinterpret_cast<float4*>(e.p)[q], g4 = reinterpret_cast<float4*>(e.g)[q];
+      float4 m4 = reinterpret_cast<float4*>(e.m)[q], v4 = reinterpret_cast<float4*>(e.v)[q];
+      const float4 g0 = g4;
+      update(p4.x, g4.x, m4.x, v4.x);
+      update(p4.y, g4.y, m4.y, v4.y);
+      update(p4.z, g4.z, m4.z, v4.z);
+      update(p4.w, g4.w, m4.w, v4.w);
+      reinterpret_cast<float4*>(e.p)[q] = p4;
+      reinterpret_cast<float4*>(e.m)[q] = m4;
+      reinterpret_cast<float4*>(e.v)[q] = v4;
+      if (g0.x != g4.x || g0.y != g4.y || g0.z != g4.z || g0.w != g4.w) reinterpret_cast<float4*>(e.g)[q] = g4;
+    }
+    scalar_from = q1 << 2;
+  }
+  for (long long i = scalar_from + threadIdx.x; i < end; i += 256) {
+    float p = e.p[i], g = e.g[i], m = e.m[i], v = e.v[i];
+    update(p, g, m, v);
     e.g[i] = g;
-    const float m = beta1 * e.m[i] + (1.f - beta1) * g;   // torch/optim/adam.py _single_tensor_adam
-    const float v = beta2 * e.v[i] + (1.f - beta2) * g * g;
     e.m[i] = m;
     e.v[i] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    e.p[i] -= step * (m / denom);
+    e.p[i] = p;
   }
 }
 

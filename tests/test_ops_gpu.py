@@ -147,3 +147,27 @@ def _linear_epilogue_checks(M, N, K, dtype):
     else:
         y = _lib.linear(A, Wt, bias=bias.cuda(), out_dtype=torch.bfloat16)
         assert y.dtype == torch.bfloat16 and rel_err(y.float(), a @ w.t() + bias) < tol
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 2048, 2048), (17, 2048, 2048), (1, 1536, 512), (32, 512, 1536), (9, 72, 64),
+                                   (32, 9490, 512)])
+def test_skinny_gemm_matches_exact_bf16_product(M, N, K):
+    """M <= 32 bf16 GEMMs take the mma.sync kernel (csrc/gemm_skinny.cu).  Against the exact product of the
+    bf16-rounded operands (fp64), with bias, with a strided residual and a strided output: the tolerance only
+    leaves room for fp32 summation order — a wrong fragment / k-permutation mapping fails by O(1)."""
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import Operand
+    g = _g(M * 7 + N)
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    A, Wt = Operand.prepare(a.cuda(), torch.bfloat16), Operand.prepare(w.cuda(), torch.bfloat16)
+    exact = (a.bfloat16().double() @ w.bfloat16().double().t())
+    y = _lib.linear(A, Wt, bias=bias.cuda())
+    assert y.shape == (M, N) and rel_err(y.double(), exact + bias.double()) < 2e-5
+    # residual read with a leading dimension, output written into a column slice of a wider buffer
+    wide_res = torch.randn(M, N + 24, generator=g).cuda()
+    wide_out = torch.full((M, N + 40), 7.0, device="cuda")
+    _lib.linear(A, Wt, residual=wide_res[:, 8:8 + N], out=wide_out[:, 16:16 + N])
+    assert rel_err(wide_out[:, 16:16 + N].double(), exact + wide_res[:, 8:8 + N].cpu().double()) < 2e-5
+    assert bool((wide_out[:, :16] == 7.0).all()) and bool((wide_out[:, 16 + N:] == 7.0).all())
