@@ -127,11 +127,16 @@ int mean_pixels(const float* enc, int B, int P, int E, void* op_hi, float* op_lo
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bahdanau attention step: one CTA per sample
+// Bahdanau attention step: one CTA of 1024 threads per sample.  The kernel sits on the recurrence's critical path
+// ~50 times per caption batch with only bt <= 32 CTAs, so it is latency- not bandwidth-bound: 32 warps take two
+// pixels each for the scores (instead of 8 warps x 7 dependent round trips), and the weighted pixel sum is split
+// four ways over P with a shared-memory combine.
 // ---------------------------------------------------------------------------------------------
 static constexpr int ATT_MAX_P = 256;
+static constexpr int ATT_THREADS = 1024;
+static constexpr int ATT_PSPLIT = 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(ATT_THREADS)
 bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
                           const float* __restrict__ hg, long long ldhg,  // [bt, >= A+E]: att2 | gate pre-activation
                           const float* __restrict__ w_f, const float* __restrict__ b_f,
@@ -140,20 +145,21 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
                           float* __restrict__ alpha_out, long long alpha_ld,  // row b at alpha_out + b*alpha_ld
                           OpOut awe, long long ld_awe,     // row b at b*ld_awe (column offset folded into pointers)
                           int P, int A, int E, int apply_gate, int enc_group) {
-  extern __shared__ float att_sm[];
-  float* s_att2 = att_sm;        // [A]
-  float* s_wf = att_sm + A;      // [A]
+  extern __shared__ __align__(16) float att_sm[];
+  float* s_att2 = att_sm;            // [A]
+  float* s_wf = att_sm + A;          // [A]
+  float* s_part = att_sm + 2 * A;    // [ATT_PSPLIT][E] partial weighted sums
   __shared__ float s_e[ATT_MAX_P];
   const int b = blockIdx.x;
   const int be = b / enc_group;  // row of att1 / enc this decode row reads (beam search: beams share the image)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < A; i += 256) {
+  for (int i = threadIdx.x; i < A; i += ATT_THREADS) {
     s_att2[i] = hg[b * ldhg + i];
     s_wf[i] = __ldg(w_f + i);
   }
   __syncthreads();
   const float bf = b_f ? __ldg(b_f) : 0.f;
-  for (int p = warp; p < P; p += 8) {
+  for (int p = warp; p < P; p += ATT_THREADS / 32) {
     const float4* a1 = reinterpret_cast<const float4*>(att1 + (static_cast<long long>(be) * P + p) * A);
     float acc = 0.f;
     for (int i = lane; i < A / 4; i += 32) {
@@ -189,23 +195,43 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
     }
   }
   __syncthreads();
-  for (int e4 = threadIdx.x; e4 < E / 4; e4 += 256) {
+  // awe[e] = sum_p alpha_p enc[p, e]: thread group q (of ATT_PSPLIT) sums pixels [q*pp, (q+1)*pp) in pixel order,
+  // group 0 then adds the partials in group order (a fixed summation order: results do not depend on timing)
+  constexpr int GT = ATT_THREADS / ATT_PSPLIT;
+  const int q = threadIdx.x / GT, tq = threadIdx.x % GT;
+  const int pp = (P + ATT_PSPLIT - 1) / ATT_PSPLIT;
+  const int pa = q * pp, pb = min(P, pa + pp);
+  for (int e4 = tq; e4 < E / 4; e4 += GT) {
     const float4* src = reinterpret_cast<const float4*>(enc + static_cast<long long>(be) * P * E) + e4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < P; ++p) {
+    for (int p = pa; p < pb; ++p) {
       const float4 v = __ldg(src + static_cast<long long>(p) * (E / 4));
       const float a = s_e[p];
       acc.x = fmaf(v.x, a, acc.x); acc.y = fmaf(v.y, a, acc.y);
       acc.z = fmaf(v.z, a, acc.z); acc.w = fmaf(v.w, a, acc.w);
     }
-    if (apply_gate) {
-      const float4 gp = *reinterpret_cast<const float4*>(hg + b * ldhg + A + e4 * 4);
-      acc.x *= 1.0f / (1.0f + expf(-gp.x));
-      acc.y *= 1.0f / (1.0f + expf(-gp.y));
-      acc.z *= 1.0f / (1.0f + expf(-gp.z));
-      acc.w *= 1.0f / (1.0f + expf(-gp.w));
+    // partial of group q -> slot q-1; group 0 parks its own in the last slot
+    const int slot = q > 0 ? q - 1 : ATT_PSPLIT - 1;
+    *reinterpret_cast<float4*>(s_part + static_cast<long long>(slot) * E + e4 * 4) = acc;
+  }
+  __syncthreads();
+  if (q == 0) {
+    for (int e4 = tq; e4 < E / 4; e4 += GT) {
+      float4 acc = *reinterpret_cast<const float4*>(s_part + static_cast<long long>(ATT_PSPLIT - 1) * E + e4 * 4);
+#pragma unroll
+      for (int g = 0; g < ATT_PSPLIT - 1; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(s_part + static_cast<long long>(g) * E + e4 * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (apply_gate) {
+        const float4 gp = *reinterpret_cast<const float4*>(hg + b * ldhg + A + e4 * 4);
+        acc.x *= 1.0f / (1.0f + expf(-gp.x));
+        acc.y *= 1.0f / (1.0f + expf(-gp.y));
+        acc.z *= 1.0f / (1.0f + expf(-gp.z));
+        acc.w *= 1.0f / (1.0f + expf(-gp.w));
+      }
+      store_op4(awe, b * ld_awe + e4 * 4, acc);
     }
-    store_op4(awe, b * ld_awe + e4 * 4, acc);
   }
 }
 
@@ -217,9 +243,20 @@ int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const
   if (P <= 0 || P > ATT_MAX_P || A % 4 != 0 || E % 4 != 0 || (ldhg % 4) != 0) return CCX_ERR_SHAPE;
   OpOut awe{awe_hi, awe_lo, awe_dtype};
   ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (A + E) * 4.0);
-  bahdanau_attention_kernel<<<bt, 256, 2 * A * sizeof(float), stream>>>(att1, hg, ldhg, w_f, b_f, enc, active,
-                                                                        alpha_out, alpha_ld, awe, ld_awe, P, A, E,
-                                                                        apply_gate, enc_group > 0 ? enc_group : 1);
+  const size_t smem = (2 * static_cast<size_t>(A) + ATT_PSPLIT * static_cast<size_t>(E)) * sizeof(float);
+  if (smem > 48 * 1024) {
+    if (smem > 200 * 1024) return CCX_ERR_SHAPE;
+    static size_t configured = 0;
+    if (smem > configured) {
+      if (cudaFuncSetAttribute(bahdanau_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem)) != cudaSuccess)
+        return CCX_ERR_CUDA;
+      configured = smem;
+    }
+  }
+  bahdanau_attention_kernel<<<bt, ATT_THREADS, smem, stream>>>(att1, hg, ldhg, w_f, b_f, enc, active, alpha_out,
+                                                              alpha_ld, awe, ld_awe, P, A, E, apply_gate,
+                                                              enc_group > 0 ? enc_group : 1);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import Operand, ptr
-from .train_ops import linear_bwd, to_operand, weight_t
+from .train_ops import linear_bwd, to_operand, weight_t, zero_grads_like, zeros_many
 
 
 class _LstmTF(torch.autograd.Function):
@@ -40,7 +40,7 @@ class _LstmTF(torch.autograd.Function):
         f32 = dict(dtype=torch.float32, device=dev)
         names = [n for n, _ in dec.named_parameters()]
         params = dict(dec.named_parameters())
-        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in params.items() if p.requires_grad}
+        grads = zero_grads_like(params.items())
         g = lambda n: grads.get(n)
         need_enc = ctx.enc_needs_grad
 
@@ -50,14 +50,11 @@ class _LstmTF(torch.autograd.Function):
                             g("fc.weight"), g("fc.bias"))
         w_lstm_t = weight_t(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd)
         w_h_t = weight_t(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd)
-        dG_all = torch.zeros((T, B, 4 * D), **f32)
-        dHG_all = torch.zeros((T, B, A + E), **f32)
-        dXH_all = torch.zeros((T, B, K), **f32)
-        d_att1 = torch.zeros((B * Pn, A), **f32)
-        d_enc = torch.zeros((B, Pn, E), **f32) if need_enc else None
-        d_wf = torch.zeros((A,), **f32)
-        dc = torch.zeros((B, D), **f32)
-        dh = torch.zeros((B, D), **f32)
+        (dG_all, dHG_all, dXH_all, d_att1, d_enc, d_wf, dc, dh, dawe_all, dalpha_all) = zeros_many(
+            [(T, B, 4 * D), (T, B, A + E), (T, B, K), (B * Pn, A), (B, Pn, E), (A,), (B, D), (B, D), (T, B, E),
+             (2, T, B, Pn)], dev)
+        if not need_enc:
+            d_enc = None
         dal = None if dalphas is None else dalphas.contiguous()
         # the whole BPTT loop in ONE FFI call (csrc/lstm_runner.cu): per step LSTM point-wise backward, dgrad GEMM
         # through [W_ih | W_hh], attention backward, dgrad GEMM through [decoder_att ; f_beta]
@@ -73,8 +70,6 @@ class _LstmTF(torch.autograd.Function):
         bd.scratch_hi, bd.scratch_lo = ptr(scratch.hi), scratch.lo_ptr
         bd.scratch2_hi, bd.scratch2_lo = ptr(scratch2.hi), scratch2.lo_ptr
         # deferred accumulation (see ccx_lstm_tf_bwd): per-step records, summed over time once after the loop
-        dawe_all = torch.zeros((T, B, E), **f32)
-        dalpha_all = torch.zeros((2, T, B, Pn), **f32)
         bd.dawe_all, bd.dalpha_all, bd.de_all = ptr(dawe_all), ptr(dalpha_all[0]), ptr(dalpha_all[1])
         _lib.check(L.ccx_lstm_tf_backward(ctypes.byref(fwd), ctypes.byref(bd), st), "lstm_tf_backward")
         # ---- weight gradients, batched over time -------------------------------------------------------------

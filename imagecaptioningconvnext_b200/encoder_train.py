@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import Operand, ptr
 from .encoder import DIMS
-from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t
+from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
 
 def _first_trainable_child(enc):
@@ -83,7 +83,9 @@ class _EncoderTail(torch.autograd.Function):
         dev = dpooled.device
         f32 = dict(dtype=torch.float32, device=dev)
         tail = [(f"{c}.{n}", p) for c in range(ctx.first, 8) for n, p in enc.convnext[c].named_parameters()]
-        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in tail}
+        grads = zero_grads_like(tail)
+        for n, p in tail:                      # frozen parameters inside the tail (not a reference use case)
+            grads.setdefault(n, torch.zeros_like(p, dtype=torch.float32))
         B, H, W, C = ctx.feat_shape
         dout = torch.empty((B * H * W, C), **f32)
         _lib.check(L.ccx_avgpool_nhwc_bwd(ptr(dpooled.contiguous()), ptr(dout), B, H, W, C, enc.enc_image_size, st),

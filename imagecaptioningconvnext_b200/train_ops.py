@@ -13,6 +13,27 @@ from . import _lib
 from ._lib import Operand, ptr
 
 
+def zeros_many(shapes, device):
+    """fp32 zero tensors of the given shapes carved out of ONE allocation and ONE fill kernel (a backward pass
+    otherwise issues ~100 tiny memset launches).  Views start on 256-byte boundaries."""
+    sizes = [max(1, int(torch.Size(sh).numel())) for sh in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 63) // 64 * 64
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    return [flat[o:o + torch.Size(sh).numel()].view(sh) for o, sh in zip(offs, shapes)]
+
+
+def zero_grads_like(named_params):
+    """{name: zero fp32 gradient buffer} for the parameters that require grad (one allocation, see zeros_many)."""
+    items = [(n, p) for n, p in named_params if p.requires_grad]
+    if not items:
+        return {}
+    bufs = zeros_many([tuple(p.shape) for _, p in items], items[0][1].device)
+    return {n: b for (n, _), b in zip(items, bufs)}
+
+
 def _pad8(n):
     return (n + 7) // 8 * 8
 

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import Operand, ptr
-from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t
+from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
 _SITES = ("sa_p", "d1", "ca_p", "d2", "ff", "d3")
 
@@ -121,7 +121,7 @@ def _backward_body(ctx, dpred, enc_needs_grad):
         scale = 1.0 / math.sqrt(D // H)
         names = [n for n, _ in dec.named_parameters()]
         params = dict(dec.named_parameters())
-        grads = {n: torch.zeros_like(p, dtype=torch.float32) for n, p in params.items() if p.requires_grad}
+        grads = zero_grads_like(params.items())
         g = lambda n: grads.get(n)
         M = B * T
 
