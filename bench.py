@@ -755,6 +755,29 @@ def run_extras(args, ctx):
             "config": "BASELINE.json configs[2]: frozen encoder + TransformerDecoder, teacher forcing, 52-token "
                       "rows (captions uniform 7..52), dropout on, clamp+Adam" + (", DDP/NCCL" if world > 1 else "")}
         del tr_w, d_opt
+    # trainWithoutTeacherForcing (trainMultiGPU.py:423-498): greedy generation + one
+    # differentiable pass over the generated ids; random-init decoders never emit <end>, i.e. all 51 steps run
+    for kind in ("lstm", "transformer"):
+        encf = Encoder(compute_dtype=bf16)
+        encf.load_state_dict(esd)
+        encf = encf.to(dev).train()
+        encf.fine_tune(False)
+        if kind == "lstm":
+            decf = DecoderWithAttention(512, 512, 512, V, dev, compute_dtype=bf16)
+            decf.load_state_dict(random_lstm_decoder_state(0, V))
+        else:
+            decf = TransformerDecoder(512, 512, V, 52, dev, None, None, True, compute_dtype=bf16)
+            decf.load_state_dict(random_transformer_decoder_state(0, V))
+        decf = decf.to(dev).train()
+        d_opt, _ = make_optimizers(encf, decf)
+        dec_w = wrap(decf)
+        ms = _timed(lambda: caption_train_step(encf, dec_w, imgs, caps, lens, d_opt, None, teacher_forcing=False,
+                                               wordMap=WORDMAP), 10, 5, dev, world)
+        out[f"train_free_running_{kind}_frozen_encoder_bf16"] = {
+            "images_per_sec": world * B / (ms * 1e-3), "ms_per_step": ms, "batch_per_gpu": B,
+            "config": "trainWithoutTeacherForcing step: frozen encoder, 51 free-running steps (KV cache for the "
+                      "Transformer), loss on the generated positions, clamp+Adam" + (", DDP/NCCL" if world > 1 else "")}
+        del dec_w, d_opt, decf, encf
     # configs[4]: batched beam search k=5, 128 images per GPU, TransformerDecoder (encoder included)
     NI = 128
     enc3 = Encoder(compute_dtype=bf16)
