@@ -90,41 +90,68 @@ int cnblock_param_grads(const float* G, const float* W2, const float* b2, const 
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
-// dw[tap][c] += sum_{b,h,w} du[b,h,w,c] * x[b,h+kh-3,w+kw-3,c];  one CTA = 128 channels of one image
-__global__ void __launch_bounds__(128)
+// dw[tap][c] += sum_{b,h,w} du[b,h,w,c] * x[b,h+kh-3,w+kw-3,c]
+// one CTA = 64 channels x one 8x8 output patch of one image: the 14x14 halo of x (zero padded) and the 8x8 patch of
+// du are staged in shared memory once, then thread (c, q) accumulates the 49 taps over output rows 2q, 2q+1 from
+// shared memory (the first version re-read x through L1 49 times per pixel with bounds checks: 128 us per launch)
+static constexpr int WG_C = 64;
+__global__ void __launch_bounds__(256)
 dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ dw, int H, int W,
-                     int C) {
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  const int b = blockIdx.y;
-  if (c >= C) return;
+                     int C, int tiles_w) {
+  extern __shared__ __align__(16) float wg_sm[];
+  float* xs = wg_sm;                     // [14][14][WG_C]
+  float* ds = wg_sm + 14 * 14 * WG_C;    // [8][8][WG_C]
+  const int c0 = blockIdx.x * WG_C, b = blockIdx.y;
+  const int th0 = (blockIdx.z / tiles_w) * 8, tw0 = (blockIdx.z % tiles_w) * 8;
+  const float* xb = x + static_cast<long long>(b) * H * W * C;
+  const float* db = du + static_cast<long long>(b) * H * W * C;
+  for (int i = threadIdx.x; i < 14 * 14 * WG_C; i += 256) {
+    const int cc = i % WG_C, pix = i / WG_C;
+    const int ih = th0 + pix / 14 - 3, iw = tw0 + pix % 14 - 3;
+    xs[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W && c0 + cc < C)
+                ? __ldg(xb + (static_cast<long long>(ih) * W + iw) * C + c0 + cc) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 8 * 8 * WG_C; i += 256) {
+    const int cc = i % WG_C, pix = i / WG_C;
+    const int h = th0 + pix / 8, w = tw0 + pix % 8;
+    ds[i] = (h < H && w < W && c0 + cc < C) ? __ldg(db + (static_cast<long long>(h) * W + w) * C + c0 + cc) : 0.f;
+  }
+  __syncthreads();
+  const int c = threadIdx.x % WG_C, q = threadIdx.x / WG_C;
   float acc[49];
 #pragma unroll
   for (int t = 0; t < 49; ++t) acc[t] = 0.f;
-  const float* xb = x + static_cast<long long>(b) * H * W * C + c;
-  const float* db = du + static_cast<long long>(b) * H * W * C + c;
-  for (int h = 0; h < H; ++h)
-    for (int w = 0; w < W; ++w) {
-      const float d = db[(static_cast<long long>(h) * W + w) * C];
 #pragma unroll
-      for (int kh = 0; kh < 7; ++kh) {
-        const int ih = h + kh - 3;
-        if (ih < 0 || ih >= H) continue;
+  for (int hh = 0; hh < 2; ++hh) {
+    const int h = q * 2 + hh;
+    for (int w = 0; w < 8; ++w) {
+      const float d = ds[(h * 8 + w) * WG_C + c];
 #pragma unroll
-        for (int kw = 0; kw < 7; ++kw) {
-          const int iw = w + kw - 3;
-          if (iw < 0 || iw >= W) continue;
-          acc[kh * 7 + kw] = fmaf(d, xb[(static_cast<long long>(ih) * W + iw) * C], acc[kh * 7 + kw]);
-        }
-      }
+      for (int kh = 0; kh < 7; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw)
+          acc[kh * 7 + kw] = fmaf(d, xs[((h + kh) * 14 + (w + kw)) * WG_C + c], acc[kh * 7 + kw]);
     }
+  }
+  if (c0 + c < C) {
 #pragma unroll
-  for (int t = 0; t < 49; ++t) atomicAdd(dw + static_cast<long long>(t) * C + c, acc[t]);
+    for (int t = 0; t < 49; ++t) atomicAdd(dw + static_cast<long long>(t) * C + c0 + c, acc[t]);
+  }
 }
 int dwconv7_wgrad(const float* x, const float* du, float* dw49c, int B, int H, int W, int C, cudaStream_t stream) {
   if (B <= 0) return CCX_OK;
-  if (B > 65535) return CCX_ERR_SHAPE;
+  const int tiles_h = (H + 7) / 8, tiles_w = (W + 7) / 8;
+  if (B > 65535 || tiles_h * tiles_w > 65535) return CCX_ERR_SHAPE;
+  constexpr int smem = (14 * 14 + 8 * 8) * WG_C * static_cast<int>(sizeof(float));
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return CCX_ERR_CUDA;
+    configured = true;
+  }
   ProfScope prof(PROF_DWCONV_LN, stream, (double)B * H * W * C * 8.0);
-  dwconv7_wgrad_kernel<<<dim3((C + 127) / 128, B), 128, 0, stream>>>(x, du, dw49c, H, W, C);
+  dwconv7_wgrad_kernel<<<dim3((C + WG_C - 1) / WG_C, B, tiles_h * tiles_w), 256, smem, stream>>>(x, du, dw49c, H, W,
+                                                                                                C, tiles_w);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
