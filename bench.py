@@ -478,7 +478,7 @@ def encoder_line(args, ctx, with_cpu):
         rate = v["work"] / (v["ms"] * 1e-3) if v["ms"] > 0 else 0.0
         kernels[k] = {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps,
                       "share": v["ms"] / tot_ms,
-                      ("tflops" if k == "gemm" else "gbs"): rate / (1e12 if k == "gemm" else 1e9)}
+                      ("tflops" if k.startswith("gemm") else "gbs"): rate / (1e12 if k.startswith("gemm") else 1e9)}
     g = prof["gemm"]
     achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"] if dtype == torch.bfloat16 else peaks["bf16_tflops_sustained"] / 6.0
@@ -635,20 +635,24 @@ def train_line(args, ctx):
         rate = v["work"] / (v["ms"] * 1e-3) if v["ms"] > 0 else 0.0
         kernels[k] = {"launches_per_step": v["launches"] / n_inst, "ms_per_step": v["ms"] / n_inst,
                       "share": v["ms"] / tot_ms,
-                      ("tflops" if k == "gemm" else "gbs"): rate / (1e12 if k == "gemm" else 1e9)}
+                      ("tflops" if k.startswith("gemm") else "gbs"): rate / (1e12 if k.startswith("gemm") else 1e9)}
     g = prof["gemm"]
     achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
-    roofline = {"kernel": "gemm_tn_kernel (tcgen05): every GEMM of the step — encoder pointwise/downsample forward, "
-                          "stage-4 dgrad/wgrad, per-time-step LSTM / attention projections (M <= 32), vocabulary "
-                          "projection and the batched weight gradients",
+    sk = prof.get("gemm_skinny", {"ms": 0.0, "work": 0.0, "launches": 0})
+    roofline = {"kernel": "gemm_tn_kernel (tcgen05/TMEM, TMA-fed): the M >= 33 GEMMs of the step — encoder pointwise / "
+                          "downsample forward at B=32, stage-4 dgrad / wgrad, hoisted attention and vocabulary "
+                          "projections, time-batched weight gradients",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
                 "flops_per_launch": g["work"] / max(g["launches"], 1),
                 "us_per_launch": g["ms"] * 1e3 / max(g["launches"], 1),
                 "share_of_step_kernel_time": g["ms"] / tot_ms,
-                "note": "aggregate over ~310 launches per step, two thirds of them latency-bound M<=32 recurrent "
-                        "GEMMs; the large-GEMM roofline is extra.encoder_forward_configs1.roofline"}
+                "note": "largest kernel by time share; traffic: see extra.encoder_forward_configs1.roofline (ncu capture "
+                        "of the same kernel on the B=64 shapes).  The M <= 32 recurrent GEMMs run on gemm_skinny_kernel "
+                        "(mma.sync, latency-bound, no roofline claim): "
+                        f"{sk['launches'] / n_inst:.0f} launches/step, {sk['ms'] / n_inst:.2f} ms/step, "
+                        f"{sk['ms'] * 1e3 / max(sk['launches'], 1):.1f} us each"}
     launches = sum(v["launches"] for v in prof.values()) // n_inst
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

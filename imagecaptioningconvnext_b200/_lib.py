@@ -123,7 +123,8 @@ SIGNATURES = {
     "ccx_prof_spans": (C.c_int, [C.POINTER(_i32), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "ccx_prof_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
 }
-PROF_KINDS = ("gemm", "dwconv_ln", "stem", "ln_rows", "pool", "elementwise", "attention", "lstm", "loss", "optimizer")
+PROF_KINDS = ("gemm", "dwconv_ln", "stem", "ln_rows", "pool", "elementwise", "attention", "lstm", "loss", "optimizer",
+              "gemm_skinny")
 
 _lib = None
 

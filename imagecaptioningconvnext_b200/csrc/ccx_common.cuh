@@ -331,4 +331,30 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
+// Programmatic dependent launch for chains of short dependent kernels (the decoder recurrences: ~460 launches per
+// train step, each waiting on the previous one).  A kernel launched with launch_pdl() may be scheduled while its
+// predecessor is still running; it must call grid_dep_sync() before touching anything the predecessor wrote.
+// grid_dep_sync() = wait for the predecessors to complete and flush, then let the NEXT kernel of the stream be
+// pre-staged behind this one.  Both instructions are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void grid_dep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace ccx

@@ -17,7 +17,8 @@ enum ProfKind : int {
   PROF_LSTM = 7,
   PROF_LOSS = 8,
   PROF_OPTIM = 9,
-  PROF_NUM_KINDS = 10
+  PROF_GEMM_SKINNY = 10,   // M <= 32 recurrent GEMMs (gemm_skinny.cu): latency-bound, kept apart from the tcgen05 roofline
+  PROF_NUM_KINDS = 11
 };
 
 extern bool g_prof_on;

@@ -9,9 +9,13 @@
 //   mha_small           scaled-dot-product attention for T<=~200 keys          torch/nn/functional.py multi_head_attention_forward
 //
 // "Operand" outputs feed the next tcgen05 GEMM: bf16, or an fp32 (tf32-hi, lo) pair for the 3xTF32 path.
+#include <cooperative_groups.h>
+
 #include "ccx_common.cuh"
 #include "ccx_ops.h"
 #include "ccx_prof.h"
+
+namespace cg = cooperative_groups;
 
 namespace ccx {
 
@@ -235,6 +239,111 @@ bahdanau_attention_kernel(const float* __restrict__ att1,  // [B, P, A]
   }
 }
 
+// Cluster version (the default when E % 16 == 0): the sample is spread over a cluster of 4 CTAs, i.e. 4x as many SMs
+// for the <= 32 rows of a recurrent step.  Rank r scores pixels r, r+4, ... and publishes each e_p into the shared
+// memory of all four CTAs (DSMEM stores), one cluster barrier, every CTA runs the 49-element softmax redundantly
+// (same arithmetic -> same bits), then rank r produces channels [r*E/4, (r+1)*E/4) of the gated context vector.
+static constexpr int ATC = 4;
+
+__global__ void __cluster_dims__(ATC, 1, 1) __launch_bounds__(256)
+bahdanau_attention_cluster_kernel(const float* __restrict__ att1, const float* __restrict__ hg, long long ldhg,
+                                  const float* __restrict__ w_f, const float* __restrict__ b_f,
+                                  const float* __restrict__ enc, const float* __restrict__ active,
+                                  float* __restrict__ alpha_out, long long alpha_ld, OpOut awe, long long ld_awe,
+                                  int P, int A, int E, int apply_gate, int enc_group) {
+  cg::cluster_group cluster = cg::this_cluster();
+  grid_dep_sync();
+  extern __shared__ __align__(16) float att_sm[];
+  float* s_att2 = att_sm;            // [A]
+  float* s_wf = att_sm + A;          // [A]
+  float* s_part = att_sm + 2 * A;    // [4][E / ATC] partial weighted sums of this CTA's channel slice
+  __shared__ float s_e[ATT_MAX_P];
+  const int r = static_cast<int>(cluster.block_rank());
+  const int b = blockIdx.x / ATC;
+  const int be = b / enc_group;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < A; i += 256) {
+    s_att2[i] = hg[b * ldhg + i];
+    s_wf[i] = __ldg(w_f + i);
+  }
+  __syncthreads();
+  const float bf = b_f ? __ldg(b_f) : 0.f;
+  float* s_e_remote = cluster.map_shared_rank(s_e, lane < ATC ? lane : 0);   // lane q addresses CTA q's copy
+  for (int p = r + ATC * warp; p < P; p += ATC * 8) {
+    const float4* a1 = reinterpret_cast<const float4*>(att1 + (static_cast<long long>(be) * P + p) * A);
+    float acc = 0.f;
+    for (int i = lane; i < A / 4; i += 32) {
+      const float4 v = __ldg(a1 + i);
+      const float4 h = *reinterpret_cast<const float4*>(s_att2 + i * 4);
+      const float4 w = *reinterpret_cast<const float4*>(s_wf + i * 4);
+      acc = fmaf(fmaxf(v.x + h.x, 0.f), w.x, acc);
+      acc = fmaf(fmaxf(v.y + h.y, 0.f), w.y, acc);
+      acc = fmaf(fmaxf(v.z + h.z, 0.f), w.z, acc);
+      acc = fmaf(fmaxf(v.w + h.w, 0.f), w.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane < ATC) s_e_remote[p] = acc + bf;
+  }
+  cluster.sync();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int p = lane; p < P; p += 32) mx = fmaxf(mx, s_e[p]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int p = lane; p < P; p += 32) {
+      const float ex = expf(s_e[p] - mx);
+      s_e[p] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    const bool wr = (r == 0) && (alpha_out != nullptr) && (active == nullptr || active[b] != 0.f);
+    for (int p = lane; p < P; p += 32) {
+      const float a = s_e[p] * inv;
+      s_e[p] = a;
+      if (wr) alpha_out[b * alpha_ld + p] = a;
+    }
+  }
+  __syncthreads();
+  const int slice4 = E / 4 / ATC;                 // float4 lanes of this CTA's channel slice
+  constexpr int PS = 4, GT = 256 / PS;
+  const int q = threadIdx.x / GT, tq = threadIdx.x % GT;
+  const int pp = (P + PS - 1) / PS;
+  const int pa = q * pp, pb = min(P, pa + pp);
+  for (int l4 = tq; l4 < slice4; l4 += GT) {
+    const int e4 = r * slice4 + l4;
+    const float4* src = reinterpret_cast<const float4*>(enc + static_cast<long long>(be) * P * E) + e4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = pa; p < pb; ++p) {
+      const float4 v = __ldg(src + static_cast<long long>(p) * (E / 4));
+      const float a = s_e[p];
+      acc.x = fmaf(v.x, a, acc.x); acc.y = fmaf(v.y, a, acc.y);
+      acc.z = fmaf(v.z, a, acc.z); acc.w = fmaf(v.w, a, acc.w);
+    }
+    *reinterpret_cast<float4*>(s_part + (static_cast<long long>(q) * slice4 + l4) * 4) = acc;
+  }
+  __syncthreads();
+  if (q == 0) {
+    for (int l4 = tq; l4 < slice4; l4 += GT) {
+      const int e4 = r * slice4 + l4;
+      float4 acc = *reinterpret_cast<const float4*>(s_part + static_cast<long long>(l4) * 4);
+#pragma unroll
+      for (int g = 1; g < PS; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(s_part + (static_cast<long long>(g) * slice4 + l4) * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (apply_gate) {
+        const float4 gp = *reinterpret_cast<const float4*>(hg + b * ldhg + A + e4 * 4);
+        acc.x *= 1.0f / (1.0f + expf(-gp.x));
+        acc.y *= 1.0f / (1.0f + expf(-gp.y));
+        acc.z *= 1.0f / (1.0f + expf(-gp.z));
+        acc.w *= 1.0f / (1.0f + expf(-gp.w));
+      }
+      store_op4(awe, b * ld_awe + e4 * 4, acc);
+    }
+  }
+}
+
 int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const float* w_f, const float* b_f,
                        const float* enc, const float* active, float* alpha_out, long long alpha_ld, void* awe_hi,
                        float* awe_lo, int awe_dtype, long long ld_awe, int bt, int P, int A, int E,
@@ -243,6 +352,16 @@ int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const
   if (P <= 0 || P > ATT_MAX_P || A % 4 != 0 || E % 4 != 0 || (ldhg % 4) != 0) return CCX_ERR_SHAPE;
   OpOut awe{awe_hi, awe_lo, awe_dtype};
   ProfScope prof(PROF_ATTENTION, stream, (double)bt * P * (A + E) * 4.0);
+  static int use_cluster = -1;
+  if (use_cluster < 0) use_cluster = getenv("CCX_ATT_CLUSTER") ? atoi(getenv("CCX_ATT_CLUSTER")) : 1;
+  if (use_cluster && (E % (4 * ATC)) == 0 && static_cast<long long>(bt) * ATC <= 0x7fffffffLL) {
+    const size_t csm = (2 * static_cast<size_t>(A) + static_cast<size_t>(E)) * sizeof(float);
+    if (csm <= 48 * 1024) {
+      return launch_pdl(bahdanau_attention_cluster_kernel, dim3(bt * ATC), dim3(256), csm, stream, att1, hg, ldhg,
+                        w_f, b_f, enc, active, alpha_out, alpha_ld, awe, ld_awe, P, A, E, apply_gate,
+                        enc_group > 0 ? enc_group : 1) == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+    }
+  }
   const size_t smem = (2 * static_cast<size_t>(A) + ATT_PSPLIT * static_cast<size_t>(E)) * sizeof(float);
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) return CCX_ERR_SHAPE;
@@ -268,6 +387,7 @@ lstm_pointwise_kernel(const float* __restrict__ gates, long long ldg, const floa
                       float* __restrict__ c_new, OpOut h_next, long long ld_hn, OpOut h_all, long long ld_ha,
                       const float* __restrict__ dropmask, long long ld_dm, float* __restrict__ h_plain,
                       long long ld_hp, int bt, int D) {
+  grid_dep_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(bt) * D) return;
   const int b = static_cast<int>(i / D), j = static_cast<int>(i % D);
@@ -294,9 +414,9 @@ int lstm_pointwise(const float* gates, long long ldg, const float* c_prev, float
   OpOut hn{hn_hi, hn_lo, op_dtype}, ha{ha_hi, ha_lo, op_dtype};
   const long long n = static_cast<long long>(bt) * D;
   ProfScope prof(PROF_LSTM, stream, (double)n * 36.0);
-  lstm_pointwise_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      gates, ldg, c_prev, c_new, hn, ld_hn, ha, ld_ha, dropmask, ld_dm, h_plain, ld_hp, bt, D);
-  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  return launch_pdl(lstm_pointwise_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream, gates,
+                    ldg, c_prev, c_new, hn, ld_hn, ha, ld_ha, dropmask, ld_dm, h_plain, ld_hp, bt, D) == cudaSuccess
+             ? CCX_OK : CCX_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------

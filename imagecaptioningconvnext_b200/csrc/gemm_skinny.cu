@@ -34,6 +34,7 @@ gemm_skinny_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __n
                    const float* __restrict__ residual, long long ldr, int M, int N, int K) {
   constexpr int BN = 8 * NT;
   __shared__ float red[SK_WARPS][32][BN + 1];
+  grid_dep_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int n0 = blockIdx.x * BN;
   float acc[2][NT][4];
@@ -108,18 +109,20 @@ bool gemm_skinny_eligible(const GemmDesc& g) {
 }
 
 int gemm_skinny(const GemmDesc& g, cudaStream_t stream) {
-  ProfScope prof(PROF_GEMM, stream, 2.0 * g.M * (double)g.N * g.K);
+  ProfScope prof(PROF_GEMM_SKINNY, stream, 2.0 * g.M * (double)g.N * g.K);
   const auto* A = static_cast<const __nv_bfloat16*>(g.A);
   const auto* B = static_cast<const __nv_bfloat16*>(g.B);
   auto* C = static_cast<float*>(g.C);
   const auto* R = static_cast<const float*>(g.residual);
   // 16 columns per CTA when that still gives ~one CTA per SM, else 8
+  cudaError_t e;
   if ((g.N + 15) / 16 >= num_sms() * 3 / 4)
-    gemm_skinny_kernel<2><<<(g.N + 15) / 16, SK_WARPS * 32, 0, stream>>>(A, g.lda, B, g.ldb, C, g.ldc, g.bias, R, g.ldr,
-                                                                        g.M, g.N, g.K);
+    e = launch_pdl(gemm_skinny_kernel<2>, dim3((g.N + 15) / 16), dim3(SK_WARPS * 32), 0, stream, A, g.lda, B, g.ldb, C,
+                   g.ldc, g.bias, R, g.ldr, g.M, g.N, g.K);
   else
-    gemm_skinny_kernel<1><<<(g.N + 7) / 8, SK_WARPS * 32, 0, stream>>>(A, g.lda, B, g.ldb, C, g.ldc, g.bias, R, g.ldr,
-                                                                      g.M, g.N, g.K);
+    e = launch_pdl(gemm_skinny_kernel<1>, dim3((g.N + 7) / 8), dim3(SK_WARPS * 32), 0, stream, A, g.lda, B, g.ldb, C,
+                   g.ldc, g.bias, R, g.ldr, g.M, g.N, g.K);
+  if (e != cudaSuccess) return CCX_ERR_CUDA;
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

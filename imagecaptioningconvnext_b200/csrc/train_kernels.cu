@@ -498,6 +498,7 @@ lstm_pointwise_bwd_kernel(const float* __restrict__ gates, long long ldg, const 
                           float* __restrict__ dc_carry,  // in: dL/dc_new, out: dL/dc_prev   [bt, D]
                           float* __restrict__ dgates, long long lddg, OpDst dg_op, long long ld_op,
                           float* __restrict__ zero_rows, long long ld_zero, int n_zero, int bt, int D) {
+  grid_dep_sync();
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<long long>(bt) * D) return;
   const int b = static_cast<int>(idx / D), j = static_cast<int>(idx % D);
@@ -534,10 +535,9 @@ int lstm_pointwise_bwd(const float* gates, long long ldg, const float* c_prev, c
   OpDst dg_op{dg_op_hi, dg_op_lo, dg_op_dtype};
   const long long n = static_cast<long long>(bt) * D;
   ProfScope prof(PROF_LSTM, stream, (double)n * 48.0);
-  lstm_pointwise_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-      gates, ldg, c_prev, c_new, dh_fc, ld_fc, dropmask, ld_dm, dh_carry, dc_carry, dgates, lddg, dg_op, ld_op,
-      zero_rows, ld_zero, n_zero, bt, D);
-  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  return launch_pdl(lstm_pointwise_bwd_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, stream,
+                    gates, ldg, c_prev, c_new, dh_fc, ld_fc, dropmask, ld_dm, dh_carry, dc_carry, dgates, lddg, dg_op,
+                    ld_op, zero_rows, ld_zero, n_zero, bt, D) == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -559,6 +559,7 @@ attention_bwd_enc_kernel(const float* __restrict__ hg, long long ldhg, const flo
                          float* __restrict__ dawe_out,      // deferred mode: [bt, E] d_awe_raw of this step
                          float* __restrict__ dalpha_acc) {  // deferred mode: [bt, P] d alpha accumulator (zeroed)
   __shared__ float s_a[PMAX];
+  grid_dep_sync();
   const int b = blockIdx.x;
   const int e = blockIdx.y * 128 + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -604,6 +605,7 @@ attention_bwd_att_split_kernel(const float* __restrict__ att1, const float* __re
                                long long ld_op, int P, int A) {
   __shared__ float s_de[ATT_MAX_P_BWD];
   __shared__ float s_red[4];
+  grid_dep_sync();
   const int b = blockIdx.x;
   float dot = 0.f;
   for (int p = threadIdx.x; p < P; p += 128) {
@@ -787,19 +789,21 @@ int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, c
       cudaMemset2DAsync(d_hg, ld_dhg * sizeof(float), 0, P * sizeof(float), bt, stream) != cudaSuccess)
     return CCX_ERR_CUDA;
   dim3 g1(bt, (E + 127) / 128);
-  if (P <= ATTB_P)
-    attention_bwd_enc_kernel<ATTB_P><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout, d_hg,
-                                                             ld_dhg, d_enc, dhg_op, ld_op, P, A, E, dawe_out,
-                                                             dalpha_acc);
+  if (P <= ATTB_P) {
+    if (launch_pdl(attention_bwd_enc_kernel<ATTB_P>, g1, dim3(128), 0, stream, hg, ldhg, enc, alpha, alpha_ld, d_out,
+                   ld_dout, d_hg, ld_dhg, d_enc, dhg_op, ld_op, P, A, E, dawe_out, dalpha_acc) != cudaSuccess)
+      return CCX_ERR_CUDA;
+  }
   else
     attention_bwd_enc_kernel<ATT_MAX_P_BWD><<<g1, 128, 0, stream>>>(hg, ldhg, enc, alpha, alpha_ld, d_out, ld_dout,
                                                                     d_hg, ld_dhg, d_enc, dhg_op, ld_op, P, A, E,
                                                                     dawe_out, dalpha_acc);
-  if (deferred)
-    attention_bwd_att_split_kernel<<<dim3(bt, (A + 127) / 128), 128, 0, stream>>>(
-        att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld, dalpha_acc, de_out, d_hg, ld_dhg, d_wf, dhg_op,
-        ld_op, P, A);
-  else
+  if (deferred) {
+    if (launch_pdl(attention_bwd_att_split_kernel, dim3(bt, (A + 127) / 128), dim3(128), 0, stream, att1, hg, ldhg,
+                   w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld, dalpha_acc, de_out, d_hg, ld_dhg, d_wf, dhg_op,
+                   ld_op, P, A) != cudaSuccess)
+      return CCX_ERR_CUDA;
+  } else
     attention_bwd_att_kernel<<<bt, 512, 0, stream>>>(att1, hg, ldhg, w_f, alpha, alpha_ld, d_alpha_ext, dalpha_ld,
                                                      d_hg, ld_dhg, d_att1, d_wf, dhg_op, ld_op, P, A);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;

@@ -439,10 +439,10 @@ CCX_API int ccx_adam_clamp(const void* table, const int32_t* block_entry, const 
 /* ------------------------------------------------------------------------------------------------
  * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the
  * library is bracketed by two events on its stream; end() synchronises the device and returns, per kernel kind
- * (0 gemm, 1 dwconv+ln, 2 stem, 3 ln_rows, 4 pool, 5 elementwise, 6 attention, 7 lstm, 8 loss, 9 optimizer),
+ * (0 gemm, 1 dwconv+ln, 2 stem, 3 ln_rows, 4 pool, 5 elementwise, 6 attention, 7 lstm, 8 loss, 9 optimizer, 10 skinny (M <= 32) gemm),
  * the summed milliseconds, the summed algorithmic work (FLOPs for kind 0, bytes otherwise) and the launch count.
  * ------------------------------------------------------------------------------------------------ */
-#define CCX_PROF_KINDS 10
+#define CCX_PROF_KINDS 11
 CCX_API int ccx_prof_begin(void);
 CCX_API int ccx_prof_spans(int32_t* kind_host, double* ms_host, double* work_host, int32_t max);
 CCX_API int ccx_prof_end(double* ms_per_kind_host, double* work_per_kind_host, int64_t* launches_per_kind_host,
