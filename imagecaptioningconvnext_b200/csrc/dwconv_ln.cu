@@ -256,6 +256,7 @@ dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
     mbar_fence_init();
   }
   __syncthreads();
+  grid_dep_sync();          // PDL: everything above overlaps the previous kernel's tail
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bar, TILE_BYTES);
     tma_load_4d(tile, &tmX, &bar, crank * CH, w0 - 3, h0 - 3, b);
@@ -432,13 +433,15 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   cfg.blockDim = dim3(use_v1 ? DW_THREADS : CH, 1, 1);
   cfg.dynamicSmemBytes = (CH == 64) ? DW_SMEM64 : DW_SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = nc;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // v2 kernels call grid_dep_sync()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_v1 ? 1 : 2;
   const double bytes = (double)B * H * W * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0)));
   ProfScope prof(PROF_DWCONV_LN, stream, bytes);
   if (use_v1) {

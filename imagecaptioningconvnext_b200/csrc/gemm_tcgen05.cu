@@ -116,6 +116,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();          // PDL: barrier init / TMEM allocation / descriptor prefetch overlap the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -246,8 +247,9 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtens
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid < 1) return CCX_OK;
-  kfn<<<grid, NUM_THREADS, S::TOTAL, stream>>>(a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep);
-  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  return launch_pdl(kfn, dim3(grid), dim3(NUM_THREADS), S::TOTAL, stream, a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep) ==
+                 cudaSuccess
+             ? CCX_OK : CCX_ERR_CUDA;
 }
 
 int gemm_tn_2cta(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
