@@ -107,3 +107,27 @@ class PreparedCache:
 
     def invalidate(self):
         self._key = None
+
+
+# ---- host copies of small device tensors --------------------------------------------------------------------------
+# The reference reads the caption lengths back in the middle of the step (`.tolist()`, models/decoder.py:91,
+# models/transformerDecoder.py:92): the host then waits for the encoder forward before it can enqueue the decoder.
+# A caller that knows the lengths early (train_step.caption_train_step) stashes a host copy BEFORE launching the
+# encoder; the decoders pick it up and the mid-step synchronisation disappears.
+_HOST_COPIES = {}
+
+
+def _key(t):
+    return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
+
+
+def stash_host_copy(t):
+    if len(_HOST_COPIES) >= 8:
+        _HOST_COPIES.clear()
+    _HOST_COPIES[_key(t)] = t.detach().cpu()
+
+
+def host_copy(t):
+    """Host copy of a device tensor: the stashed one if `t` is unchanged since stash_host_copy(t), else a D2H read."""
+    h = _HOST_COPIES.get(_key(t)) if t.is_cuda else t
+    return h if h is not None else t.detach().cpu()

@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache
+from ._host import CcxEmbedding, CcxLinear, PreparedCache, host_copy
 from ._lib import Operand, ptr
 
 
@@ -244,10 +244,11 @@ class DecoderWithAttention(nn.Module):
         dev = encoder_out.device
         enc = encoder_out.reshape(B, -1, E)
         Pn = enc.size(1)
+        host_lengths = host_copy(caption_lengths).reshape(-1)
         caption_lengths, sort_ind = caption_lengths.squeeze(1).sort(dim=0, descending=True)
         enc = enc[sort_ind].float().contiguous()
         encoded_captions = encoded_captions[sort_ind].contiguous()
-        decode_lengths = (caption_lengths - 1).tolist()
+        decode_lengths = sorted((host_lengths - 1).tolist(), reverse=True)      # = (sorted lengths - 1).tolist()
         T = max(decode_lengths)
         L, st, cd = _lib.lib(), _lib.stream_ptr(), self.compute_dtype
         code = _lib.dt_code(cd)

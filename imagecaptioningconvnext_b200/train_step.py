@@ -6,6 +6,7 @@ gradient all-reduce over NCCL overlaps with the explicit backward.
 """
 import torch
 
+from ._host import stash_host_copy
 from .decoder import DecoderWithAttention
 from .losses import free_running_cross_entropy, packed_cross_entropy
 from .optim import ClampAdam
@@ -28,6 +29,8 @@ def caption_train_step(encoder, decoder, imgs, caps, caplens, decoder_optimizer,
     """Returns the loss tensor (no host sync).  imgs (B,3,256,256) fp32, caps (B,52) int64, caplens (B,1) int64.
     teacher_forcing=False: the free-running step of trainWithoutTeacherForcing (trainMultiGPU.py:423-460; needs
     wordMap for <start>/<end>)."""
+    if teacher_forcing:
+        stash_host_copy(caplens)      # the decoders need the lengths on the host: read them before the encoder is queued
     feats = encoder(imgs)                                                              # trainMultiGPU.py:361
     if not teacher_forcing:
         out = decoder(teacherForcing=False, encoder_out=feats, wordMap=wordMap, maxDecodeLen=max_decode_len)  # :445,:451

@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache
+from ._host import CcxEmbedding, CcxLinear, PreparedCache, host_copy
 from ._lib import Operand, ptr
 
 
@@ -286,7 +286,7 @@ class TransformerDecoder(nn.Module):
                                "for inference or enable grad for training")
         _lib.require_cuda(encoder_out, "encoder_out")
         B = encoder_out.size(0)
-        decode_lengths = (caption_lengths.squeeze(1) - 1).tolist()
+        decode_lengths = (host_copy(caption_lengths).reshape(-1) - 1).tolist()
         dev = encoder_out.device
         D, V, cd = self.embed_dim, self.vocab_size, self.compute_dtype
         T = encoded_captions.size(1)
