@@ -238,32 +238,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf): one MUFU.EX2 + one MUFU.RCP
-// and ~10 FMA-pipe instructions instead of erff's ~30.  Used where the result is rounded to bf16 anyway.
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);                 // erf(|x|/sqrt2)
-  const float half_x = 0.5f * x;
-  return fmaf(fabsf(half_x), erf_abs, half_x);             // 0.5x + 0.5|x| erf(|x|/sqrt2) = 0.5x(1+erf(x/sqrt2))
-}
-
 // GELU for bf16 OUTPUTS: 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715 x^3))) with MUFU.TANH — 5 FMA-pipe instructions and
 // one MUFU per element instead of the 12 + 2 of the erf form, which makes the Linear(C->4C)+GELU epilogue MUFU/issue
 // bound above the MMA time.  |tanh form - erf form| <= 4.7e-4 absolute; after rounding to bf16 the RMS error against

@@ -1,0 +1,61 @@
+"""Host-side logic that needs no GPU: caption bookkeeping of the free-running training path, buffer carving,
+state_dict key mapping of the attention-map decoder, the host-copy stash."""
+import os
+
+import torch
+
+
+def test_generated_captions_lengths_follow_first_end_token():
+    """utils/utils.py:270-276: decode length = index of the first <end> + 1, or maxDecodeLen."""
+    from imagecaptioningconvnext_b200.decoder_train import generated_captions
+    start, end, T = 98, 99, 6
+    seqs = torch.tensor([[5, 6, end, 0, 0, 0],        # finished at step 2
+                         [end, 0, 0, 0, 0, 0],        # finished at once
+                         [1, 2, 3, 4, 5, 6],          # never finished
+                         [7, end, 8, end, 0, 0]])     # first <end> counts
+    caps, lens = generated_captions(seqs, start, end, T)
+    assert caps.shape == (4, T + 1) and bool((caps[:, 0] == start).all()) and torch.equal(caps[:, 1:], seqs)
+    assert lens.view(-1).tolist() == [3 + 1, 1 + 1, 6 + 1, 2 + 1]          # caption_lengths = decode length + 1
+
+
+def test_zeros_many_is_one_allocation_of_aligned_zero_views():
+    from imagecaptioningconvnext_b200.train_ops import zero_grads_like, zeros_many
+    shapes = [(3, 5), (7,), (2, 2, 2), (130,)]
+    bufs = zeros_many(shapes, torch.device("cpu"))
+    assert [tuple(b.shape) for b in bufs] == shapes
+    assert len({b.untyped_storage().data_ptr() for b in bufs}) == 1
+    offs = [b.storage_offset() for b in bufs]
+    assert all(o % 64 == 0 for o in offs) and offs == sorted(offs)
+    for b in bufs:
+        assert b.is_contiguous() and float(b.abs().sum()) == 0.0
+    bufs[0].fill_(1.0)
+    assert float(bufs[1].abs().sum()) == 0.0                              # no overlap
+    p = [("a", torch.nn.Parameter(torch.ones(4, 4))), ("b", torch.nn.Parameter(torch.ones(3), requires_grad=False))]
+    g = zero_grads_like(p)
+    assert set(g) == {"a"} and g["a"].shape == (4, 4)
+
+
+def test_attention_viz_decoder_uses_the_reference_key_names(golden_dir):
+    from imagecaptioningconvnext_b200 import TransformerDecoder, TransformerDecoderForAttentionViz
+    keys = torch.load(os.path.join(golden_dir, "attvis.pt"))["state_dict_keys"]
+    m = TransformerDecoderForAttentionViz(512, 512, 9490, 52, torch.device("cpu"))
+    assert sorted(m.state_dict().keys()) == keys
+    # round trip through the plain decoder's naming
+    plain = TransformerDecoder(512, 512, 9490, 52, torch.device("cpu"), None, None, True)
+    renamed = {k.replace("transformer_decoder.layers.", "decoder_layers."): v for k, v in plain.state_dict().items()}
+    m.load_state_dict(renamed)
+    for (ka, a), (kb, b) in zip(sorted(m.state_dict().items()), sorted(renamed.items())):
+        assert ka == kb and torch.equal(a, b)
+    assert len(m.decoder_layers) == 6
+
+
+def test_host_copy_stash_is_keyed_on_tensor_identity_and_version():
+    from imagecaptioningconvnext_b200 import _host
+    t = torch.arange(4)
+    assert _host.host_copy(t) is t                                        # CPU tensors pass through
+    _host._HOST_COPIES.clear()
+    _host.stash_host_copy(t)
+    assert len(_host._HOST_COPIES) == 1
+    key = next(iter(_host._HOST_COPIES))
+    t.add_(1)                                                              # version bump -> stale key
+    assert _host._key(t) != key
