@@ -537,8 +537,9 @@ def train_line(args, ctx):
     dec.load_state_dict(random_lstm_decoder_state(0, V))
     dec = dec.to(dev).train()
     d_opt, e_opt = make_optimizers(enc, dec)
-    enc_w = DDP(enc, device_ids=[local]) if world > 1 else enc      # trainMultiGPU.py:233-236
-    dec_w = DDP(dec, device_ids=[local]) if world > 1 else dec
+    ddp_kw = json.loads(os.environ.get("BENCH_DDP_KW", "{}"))         # experiments only; default = the reference's call
+    enc_w = DDP(enc, device_ids=[local], **ddp_kw) if world > 1 else enc      # trainMultiGPU.py:233-236
+    dec_w = DDP(dec, device_ids=[local], **ddp_kw) if world > 1 else dec
 
     nbuf = 4
     host = []
