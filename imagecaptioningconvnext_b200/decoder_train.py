@@ -50,9 +50,10 @@ class _LstmTF(torch.autograd.Function):
                             g("fc.weight"), g("fc.bias"))
         w_lstm_t = weight_t(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd)
         w_h_t = weight_t(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd)
-        (dG_all, dHG_all, dXH_all, d_att1, d_enc, d_wf, dc, dh, dawe_all, dalpha_all) = zeros_many(
+        (dG_all, dHG_all, dXH_all, d_att1, d_enc, d_wf, dc, dh, dawe_all, dalpha_all, gw_lstm, gb_lstm, gw_h,
+         gb_h) = zeros_many(
             [(T, B, 4 * D), (T, B, A + E), (T, B, K), (B * Pn, A), (B, Pn, E), (A,), (B, D), (B, D), (T, B, E),
-             (2, T, B, Pn)], dev)
+             (2, T, B, Pn), (4 * D, K), (4 * D,), (A + E, D), (A + E,)], dev)
         if not need_enc:
             d_enc = None
         dal = None if dalphas is None else dalphas.contiguous()
@@ -76,14 +77,12 @@ class _LstmTF(torch.autograd.Function):
         TB = T * B
         x_all = XH.map(lambda x: x[:T].view(TB, K))
         if g("decode_step.weight_ih") is not None:
-            gw = torch.zeros((4 * D, K), **f32)
-            gb = torch.zeros((4 * D,), **f32)
+            gw, gb = gw_lstm, gb_lstm
             linear_bwd(dG_all.view(TB, 4 * D), x_all, None, cd, gw, gb, need_dx=False)
             grads["decode_step.weight_ih"], grads["decode_step.weight_hh"] = gw[:, :hoff].contiguous(), gw[:, hoff:].contiguous()
             grads["decode_step.bias_ih"], grads["decode_step.bias_hh"] = gb, gb.clone()
         if g("f_beta.weight") is not None:
-            gw = torch.zeros((A + E, D), **f32)
-            gb = torch.zeros((A + E,), **f32)
+            gw, gb = gw_h, gb_h
             h_prev_all = XH.map(lambda x: x[:T].view(TB, K)[:, hoff:])
             linear_bwd(dHG_all.view(TB, A + E), h_prev_all, None, cd, gw, gb, need_dx=False)
             grads["attention.decoder_att.weight"], grads["f_beta.weight"] = gw[:A].contiguous(), gw[A:].contiguous()

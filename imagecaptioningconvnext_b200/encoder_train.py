@@ -78,7 +78,7 @@ class _BlockFn(torch.autograd.Function):
         blk = enc.convnext[child][i]
         ops = enc._block_ops[gi]
         named = _named(blk)
-        grads = zero_grads_like(named)
+        grads, (s, dw) = zero_grads_like(named, extra_shapes=[(C,), (49, C)])
         for n, p in named:                     # frozen parameters inside the tail (not a reference use case)
             grads.setdefault(n, torch.zeros_like(p, dtype=torch.float32))
         dout = dout.contiguous().view(M, C)
@@ -95,7 +95,6 @@ class _BlockFn(torch.autograd.Function):
         # second Linear: dgrad, un-scaled wgrad G, and the layer_scale / W2 / b2 gradients from it
         dh = _lib.linear(to_operand(dz, cd), weight_t(W2, cd), k=C)                       # [M, 4C]
         G = _lib.linear(to_operand(doutp, cd, transpose=True), to_operand(h_op, cd, transpose=True))  # [C, 4C]
-        s = torch.zeros((C,), **f32)
         colsum_acc(doutp, s)
         _lib.check(L.ccx_cnblock_param_grads(ptr(G), ptr(W2), ptr(blk.block[5].bias.detach()), ptr(gamma), ptr(s),
                                              ptr(grads["block.5.weight"]), ptr(grads["layer_scale"]),
@@ -112,7 +111,6 @@ class _BlockFn(torch.autograd.Function):
         du = ln_bwd(dy, u, blk.block[2].weight.detach(), grads["block.2.weight"], grads["block.2.bias"], 1e-6)
         # depthwise conv: bias, filter and data gradients; residual add fused into the data-gradient launch
         colsum_acc(du, grads["block.0.bias"])
-        dw = torch.zeros((49, C), **f32)
         _lib.check(L.ccx_dwconv7_wgrad(ptr(x_in), ptr(du), ptr(dw), B, H, W, C, st), "dwconv7_wgrad")
         grads["block.0.weight"] = dw.t().reshape(C, 1, 7, 7).contiguous()     # tap-major -> (C,1,7,7)
         dprev = None

@@ -16,7 +16,9 @@ _CHUNK = 16384
 
 class ClampAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_clip=None):
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_clip=grad_clip))
+        # foreach=True: Optimizer.zero_grad(set_to_none=False) then clears all gradients with multi-tensor launches
+        # instead of one fill kernel per parameter (40 launches per step for the fine-tuned encoder + LSTM decoder)
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_clip=grad_clip, foreach=True))
         self._tables = {}
 
     def _table(self, gi, ps):

@@ -25,13 +25,16 @@ def zeros_many(shapes, device):
     return [flat[o:o + torch.Size(sh).numel()].view(sh) for o, sh in zip(offs, shapes)]
 
 
-def zero_grads_like(named_params):
-    """{name: zero fp32 gradient buffer} for the parameters that require grad (one allocation, see zeros_many)."""
+def zero_grads_like(named_params, extra_shapes=None):
+    """{name: zero fp32 gradient buffer} for the parameters that require grad (one allocation, see zeros_many).
+    extra_shapes: further zero buffers carved from the same allocation -> returns (dict, [extras])."""
     items = [(n, p) for n, p in named_params if p.requires_grad]
     if not items:
-        return {}
-    bufs = zeros_many([tuple(p.shape) for _, p in items], items[0][1].device)
-    return {n: b for (n, _), b in zip(items, bufs)}
+        return {} if extra_shapes is None else ({}, zeros_many(list(extra_shapes), named_params[0][1].device))
+    shapes = [tuple(p.shape) for _, p in items] + list(extra_shapes or ())
+    bufs = zeros_many(shapes, items[0][1].device)
+    grads = {n: b for (n, _), b in zip(items, bufs)}
+    return grads if extra_shapes is None else (grads, bufs[len(items):])
 
 
 def _pad8(n):
