@@ -1,5 +1,7 @@
 """Host-side helpers shared by the decoder modules: parameter holders whose ``forward`` runs on libccx, and the
 prepared-weight cache (bf16 / tf32-split copies of the fp32 master weights, rebuilt when a parameter changes)."""
+import weakref
+
 import torch
 from torch import nn
 
@@ -113,21 +115,28 @@ class PreparedCache:
 # The reference reads the caption lengths back in the middle of the step (`.tolist()`, models/decoder.py:91,
 # models/transformerDecoder.py:92): the host then waits for the encoder forward before it can enqueue the decoder.
 # A caller that knows the lengths early (train_step.caption_train_step) stashes a host copy BEFORE launching the
-# encoder; the decoders pick it up and the mid-step synchronisation disappears.
+# encoder — or hands over the host tensor it still has from the data loader, in which case the step has no
+# host<->device synchronisation at all and the host can run ahead of the GPU across steps.
+# Entries are bound to the tensor OBJECT (weak reference) and its version counter, so a recycled address or an
+# in-place update can never produce a stale answer.
 _HOST_COPIES = {}
 
 
-def _key(t):
-    return (t.data_ptr(), t._version, tuple(t.shape), t.dtype)
-
-
-def stash_host_copy(t):
+def stash_host_copy(t, host=None):
+    """Remember a host copy of device tensor `t` (made now, synchronising, unless `host` is supplied)."""
     if len(_HOST_COPIES) >= 8:
         _HOST_COPIES.clear()
-    _HOST_COPIES[_key(t)] = t.detach().cpu()
+    h = t.detach().cpu() if host is None else host.detach()
+    if tuple(h.shape) != tuple(t.shape):
+        raise ValueError("host copy has a different shape")
+    _HOST_COPIES[id(t)] = (weakref.ref(t), t._version, h)
 
 
 def host_copy(t):
-    """Host copy of a device tensor: the stashed one if `t` is unchanged since stash_host_copy(t), else a D2H read."""
-    h = _HOST_COPIES.get(_key(t)) if t.is_cuda else t
-    return h if h is not None else t.detach().cpu()
+    """Host copy of a device tensor: the stashed one if `t` is that very tensor, unmodified; else a D2H read."""
+    if not t.is_cuda:
+        return t
+    e = _HOST_COPIES.get(id(t))
+    if e is not None and e[0]() is t and e[1] == t._version:
+        return e[2]
+    return t.detach().cpu()

@@ -25,12 +25,15 @@ def make_optimizers(encoder, decoder, decoder_lr=1e-4, encoder_lr=1e-4, grad_cli
 
 
 def caption_train_step(encoder, decoder, imgs, caps, caplens, decoder_optimizer, encoder_optimizer=None, pad_token=0,
-                       alpha_c=1.0, teacher_forcing=True, wordMap=None, max_decode_len=51):
+                       alpha_c=1.0, teacher_forcing=True, wordMap=None, max_decode_len=51, caplens_host=None):
     """Returns the loss tensor (no host sync).  imgs (B,3,256,256) fp32, caps (B,52) int64, caplens (B,1) int64.
     teacher_forcing=False: the free-running step of trainWithoutTeacherForcing (trainMultiGPU.py:423-460; needs
-    wordMap for <start>/<end>)."""
+    wordMap for <start>/<end>).  caplens_host: optional host copy of caplens (what the DataLoader yielded before
+    `.to(device)`, trainMultiGPU.py:355-359) — saves the step's only device-to-host read."""
     if teacher_forcing:
-        stash_host_copy(caplens)      # the decoders need the lengths on the host: read them before the encoder is queued
+        # the decoders need the lengths on the host: read them before the encoder is queued — or not at all when the
+        # caller still has the data loader's host tensor (caplens_host), which leaves the step free of host syncs
+        stash_host_copy(caplens, caplens_host)
     feats = encoder(imgs)                                                              # trainMultiGPU.py:361
     if not teacher_forcing:
         out = decoder(teacherForcing=False, encoder_out=feats, wordMap=wordMap, maxDecodeLen=max_decode_len)  # :445,:451

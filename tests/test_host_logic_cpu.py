@@ -49,13 +49,26 @@ def test_attention_viz_decoder_uses_the_reference_key_names(golden_dir):
     assert len(m.decoder_layers) == 6
 
 
-def test_host_copy_stash_is_keyed_on_tensor_identity_and_version():
+def test_host_copy_stash_is_bound_to_the_tensor_object_and_version():
     from imagecaptioningconvnext_b200 import _host
-    t = torch.arange(4)
-    assert _host.host_copy(t) is t                                        # CPU tensors pass through
+
+    class FakeCuda(torch.Tensor):            # a CPU tensor that claims to live on the GPU (no GPU in this suite)
+        @property
+        def is_cuda(self):
+            return True
+
+    t = torch.arange(4).as_subclass(FakeCuda)
+    assert _host.host_copy(torch.arange(4)) is not None                    # CPU tensors pass through
     _host._HOST_COPIES.clear()
-    _host.stash_host_copy(t)
-    assert len(_host._HOST_COPIES) == 1
-    key = next(iter(_host._HOST_COPIES))
-    t.add_(1)                                                              # version bump -> stale key
-    assert _host._key(t) != key
+    h = torch.tensor([9, 9, 9, 9])
+    _host.stash_host_copy(t, h)
+    assert _host.host_copy(t).data_ptr() == h.data_ptr()                   # same object, same version
+    t.add_(1)                                                              # in-place update -> stale
+    assert _host.host_copy(t).data_ptr() != h.data_ptr()
+    u = torch.arange(4).as_subclass(FakeCuda)                              # another tensor, equal content
+    assert _host.host_copy(u).data_ptr() != h.data_ptr()
+    try:
+        _host.stash_host_copy(t, torch.zeros(3))
+        raise AssertionError("shape mismatch accepted")
+    except ValueError:
+        pass
