@@ -88,7 +88,7 @@ class PreparedCache:
 
     def get(self):
         owner = self._owner[0]
-        params = list(owner.parameters())
+        params = params_of(owner)
         key = (owner.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(),
                sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params))
         if key != self._key:
@@ -140,3 +140,39 @@ def host_copy(t):
     if e is not None and e[0]() is t and e[1] == t._version:
         return e[2]
     return t.detach().cpu()
+
+
+# ---- cached parameter lists ------------------------------------------------------------------------------------------
+# nn.Module.named_parameters() walks the module tree (named_modules + a dedup set) on every call; the train step asked
+# for it ~1,500 times per step (requires_grad checks, gradient dicts), about a quarter of the host time of a step that
+# is host-bound.  The list is cached on the module and re-validated by resolving its first and last entry.
+def _resolve(module, dotted):
+    obj = module
+    for part in dotted.split("."):
+        obj = obj._modules[part] if part in obj._modules else obj._parameters[part]
+    return obj
+
+
+def named_params(module):
+    """[(name, parameter)] of `module`, cached."""
+    c = module.__dict__.get("_ccx_named_params")
+    if c is not None:
+        try:
+            if not c or (_resolve(module, c[0][0]) is c[0][1] and _resolve(module, c[-1][0]) is c[-1][1]):
+                return c
+        except (KeyError, AttributeError):
+            pass
+    c = list(module.named_parameters())
+    module.__dict__["_ccx_named_params"] = c
+    return c
+
+
+def params_of(module):
+    return [p for _, p in named_params(module)]
+
+
+def any_requires_grad(module):
+    for _, p in named_params(module):
+        if p.requires_grad:
+            return True
+    return False

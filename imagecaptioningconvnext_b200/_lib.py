@@ -181,7 +181,9 @@ def ptr(t):
 
 
 def stream_ptr():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream on the current device (the raw getter: torch.cuda.current_stream()
+    costs ~15 us of Python per call, and a train step asks ~130 times)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def dt_code(dtype):

@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache, host_copy
+from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy
 from ._lib import Operand, ptr
 
 
@@ -230,7 +230,7 @@ class DecoderWithAttention(nn.Module):
     # ---- reference API -----------------------------------------------------------------------------------------
     def forwardWithTeacherForcing(self, encoder_out, encoded_captions, caption_lengths):
         """models/decoder.py:69-113."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and any_requires_grad(self):
             from .decoder_train import lstm_teacher_forcing_with_grad
             return lstm_teacher_forcing_with_grad(self, encoder_out, encoded_captions, caption_lengths)
         return self._tf_forward(encoder_out, encoded_captions, caption_lengths)[:5]
@@ -287,7 +287,7 @@ class DecoderWithAttention(nn.Module):
     def forwardWithoutTeacherForcing(self, encoder_out, wordMap, maxDecodeLen):
         """models/decoder.py:119-163 (greedy).  With autograd enabled (trainWithoutTeacherForcing,
         trainMultiGPU.py:444-460) the outputs carry gradients to every parameter and to encoder_out."""
-        if torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (encoder_out.requires_grad or any_requires_grad(self)):
             from .decoder_train import lstm_free_running_with_grad
             return lstm_free_running_with_grad(self, encoder_out, wordMap, maxDecodeLen)
         return self._greedy(encoder_out, wordMap, maxDecodeLen)

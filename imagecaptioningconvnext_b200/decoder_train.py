@@ -11,6 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
+from ._host import named_params, params_of
 from ._lib import Operand, ptr
 from .train_ops import linear_bwd, to_operand, weight_t, zero_grads_like, zeros_many
 
@@ -38,8 +39,8 @@ class _LstmTF(torch.autograd.Function):
         K, hoff = Emb + E + D, Emb + E
         dev = enc.device
         f32 = dict(dtype=torch.float32, device=dev)
-        names = [n for n, _ in dec.named_parameters()]
-        params = dict(dec.named_parameters())
+        names = [n for n, _ in named_params(dec)]
+        params = dict(named_params(dec))
         grads = zero_grads_like(params.items())
         g = lambda n: grads.get(n)
         need_enc = ctx.enc_needs_grad
@@ -119,7 +120,7 @@ class _LstmTF(torch.autograd.Function):
 
 def lstm_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, dropmask_unsorted=None):
     holder = {"dropmask_unsorted": dropmask_unsorted}
-    params = [p for _, p in dec.named_parameters()]
+    params = params_of(dec)
     preds, alphas = _LstmTF.apply(dec, holder, encoder_out, encoded_captions, caption_lengths, *params)
     return preds, holder["caps_sorted"], holder["decode_lengths"], alphas, holder["sort_ind"]
 

@@ -18,6 +18,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from ._host import any_requires_grad, params_of
 from ._lib import Operand
 
 DEPTHS = (3, 3, 27, 3)
@@ -115,7 +116,7 @@ class Encoder(nn.Module):
         if H % 32 or W % 32:
             raise ValueError("image height/width must be multiples of 32 (ConvNeXt total stride)")
         images = images.contiguous()
-        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.convnext.parameters())
+        needs_grad = torch.is_grad_enabled() and any_requires_grad(self.convnext)
         noise = self._stochastic_depth_noise(B, images.device)
         if self._graphs is not None and not needs_grad and noise is None:
             return self._forward_graphed(images)
@@ -198,7 +199,7 @@ class Encoder(nn.Module):
         Built once; afterwards a changed parameter (optimizer step, load_state_dict) is re-converted IN PLACE into
         its existing buffer, so the table's pointers never change (fine-tuning touches 3 of the 36 blocks per step;
         rebuilding the table or re-casting all 88 M weights every step costs more than those blocks' forward)."""
-        params = list(self.convnext.parameters())
+        params = params_of(self.convnext)
         vsum = sum(p._version + getattr(p, "_ccx_epoch", 0) for p in params)
         key = (self.compute_dtype, params[0].data_ptr(), params[-1].data_ptr(), vsum)
         if self._prep_key == key:

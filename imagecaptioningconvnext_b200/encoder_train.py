@@ -14,6 +14,7 @@ only):
 import torch
 
 from . import _lib
+from ._host import any_requires_grad, named_params
 from ._lib import Operand, ptr
 from .encoder import DIMS
 from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
@@ -21,7 +22,7 @@ from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zer
 
 def _first_trainable_child(enc):
     for i, c in enumerate(enc.convnext.children()):
-        if any(p.requires_grad for p in c.parameters()):
+        if any_requires_grad(c):
             return i
     return 8
 
@@ -32,7 +33,7 @@ def _block_index0(enc, child):
 
 
 def _named(mod):
-    return [(n, p) for n, p in mod.named_parameters()]
+    return named_params(mod)
 
 
 class _BlockFn(torch.autograd.Function):

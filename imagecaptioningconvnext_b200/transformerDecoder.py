@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache, host_copy
+from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy
 from ._lib import Operand, ptr
 
 
@@ -277,7 +277,7 @@ class TransformerDecoder(nn.Module):
     # ---- reference API ------------------------------------------------------------------------------------------
     def forwardWithTeacherForcing(self, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
         """models/transformerDecoder.py:88-108."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and any_requires_grad(self):
             from .transformer_train import transformer_teacher_forcing_with_grad
             return transformer_teacher_forcing_with_grad(self, encoder_out, encoded_captions, caption_lengths,
                                                          tgt_key_padding_mask)
@@ -370,7 +370,7 @@ class TransformerDecoder(nn.Module):
     def forwardWithoutTeacherForcing(self, encoder_out, wordMap, maxDecodeLen):
         """models/transformerDecoder.py:110-160 (greedy), with a KV cache instead of prefix recomputation.  With
         autograd enabled (trainWithoutTeacherForcing, trainMultiGPU.py:444-460) the predictions carry gradients."""
-        if torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (encoder_out.requires_grad or any_requires_grad(self)):
             from .transformer_train import transformer_free_running_with_grad
             return transformer_free_running_with_grad(self, encoder_out, wordMap, maxDecodeLen)
         return self._greedy(encoder_out, wordMap, maxDecodeLen)

@@ -11,7 +11,7 @@ import weakref
 import torch
 
 from . import _lib
-from ._host import host_copy
+from ._host import host_copy, named_params, params_of
 from ._lib import Operand, ptr
 from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
@@ -120,8 +120,8 @@ def _backward_body(ctx, dpred, enc_needs_grad):
         mode = 0 if masks is None else 1
         keep_scale = 1.0 if masks is None else 1.0 / (1.0 - dec.dropout_p)
         scale = 1.0 / math.sqrt(D // H)
-        names = [n for n, _ in dec.named_parameters()]
-        params = dict(dec.named_parameters())
+        names = [n for n, _ in named_params(dec)]
+        params = dict(named_params(dec))
         grads = zero_grads_like(params.items())
         g = lambda n: grads.get(n)
         M = B * T
@@ -213,7 +213,7 @@ def _graph_key(dec, encoder_out, caps, kpm):
     return (tuple(encoder_out.shape), tuple(caps.shape), kpm is not None, dec.training, encoder_out.requires_grad,
             dec._want_alphas,
             dec.compute_dtype, encoder_out.device, dec._cache.storage_key(),
-            tuple(p.requires_grad for p in dec.parameters()))
+            tuple(p.requires_grad for p in params_of(dec)))
 
 
 class _TransformerTF(torch.autograd.Function):
@@ -224,7 +224,7 @@ class _TransformerTF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dec, encoder_out, caps, kpm, use_graph, *params):
         ctx.enc_needs_grad = encoder_out.requires_grad
-        ctx.names = [n for n, _ in dec.named_parameters()]
+        ctx.names = [n for n, _ in named_params(dec)]
         graphs = getattr(dec, "_train_graphs", None)
         st = None
         if graphs is not None and use_graph:
@@ -285,7 +285,7 @@ def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, ca
     decode_lengths = (host_copy(caption_lengths).reshape(-1) - 1).tolist()
     caps = encoded_captions.contiguous()
     kpm = None if tgt_key_padding_mask is None else tgt_key_padding_mask.to(torch.uint8).contiguous()
-    params = [p for _, p in dec.named_parameters()]
+    params = params_of(dec)
     use_graph = torch.is_grad_enabled() and (encoder_out.requires_grad or any(p.requires_grad for p in params))
     predictions = _TransformerTF.apply(dec, encoder_out, caps, kpm, use_graph, *params)
     return predictions, encoded_captions, decode_lengths
@@ -307,7 +307,7 @@ def transformer_free_running_with_grad(dec, encoder_out, wordMap, maxDecodeLen):
     _, sequences = dec._greedy(encoder_out.detach(), wordMap, T, dropout_free=True)
     greedy_alphas = dec._last_alphas          # attention-map variant: maps of the generation pass (zero once finished)
     caps, lens = generated_captions(sequences, wordMap['<start>'], wordMap['<end>'], T)
-    params = [p for _, p in dec.named_parameters()]
+    params = params_of(dec)
     preds = _TransformerTF.apply(dec, encoder_out, caps[:, :T].contiguous(), None, True, *params)
     dec._last_alphas = greedy_alphas
     valid = torch.arange(T, device=preds.device).unsqueeze(0) < (lens - 1)
