@@ -176,3 +176,27 @@ def any_requires_grad(module):
         if p.requires_grad:
             return True
     return False
+
+
+# ---- device twins of small host lists --------------------------------------------------------------------------------
+# The reference API hands `decode_lengths` around as a Python list (models/decoder.py:91).  Turning such a list into a
+# device tensor with torch.tensor(list, device="cuda") is a BLOCKING copy — it drains the stream, twice per train
+# step.  Whoever produced the list from a device tensor registers that tensor here; consumers ask for it back.
+_DEVICE_TWINS = {}
+
+
+def stash_device_twin(lst, tensor):
+    if len(_DEVICE_TWINS) >= 8:
+        _DEVICE_TWINS.clear()
+    _DEVICE_TWINS[id(lst)] = (lst, tensor)
+
+
+def device_twin(lst, device, dtype=torch.int64):
+    """Device tensor holding `lst`: the registered twin if `lst` is that very list, else an asynchronous upload
+    from pinned memory (never a blocking copy)."""
+    e = _DEVICE_TWINS.get(id(lst))
+    if e is not None and e[0] is lst and e[1].device == torch.device(device):
+        return e[1].to(dtype)
+    if isinstance(lst, torch.Tensor):
+        return lst.to(device=device, dtype=dtype)
+    return torch.tensor(lst, dtype=dtype).pin_memory().to(device, non_blocking=True)

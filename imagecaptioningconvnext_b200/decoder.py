@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy
+from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy, stash_device_twin
 from ._lib import Operand, ptr
 
 
@@ -249,6 +249,8 @@ class DecoderWithAttention(nn.Module):
         enc = enc[sort_ind].float().contiguous()
         encoded_captions = encoded_captions[sort_ind].contiguous()
         decode_lengths = sorted((host_lengths - 1).tolist(), reverse=True)      # = (sorted lengths - 1).tolist()
+        decode_lengths_dev = caption_lengths - 1                                # the same values, on the device
+        stash_device_twin(decode_lengths, decode_lengths_dev)
         T = max(decode_lengths)
         L, st, cd = _lib.lib(), _lib.stream_ptr(), self.compute_dtype
         code = _lib.dt_code(cd)
@@ -272,7 +274,7 @@ class DecoderWithAttention(nn.Module):
         desc = self._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
         _lib.check(L.ccx_lstm_tf_forward(ctypes.byref(desc), st), "lstm_tf_forward")
         valid = (torch.arange(T, device=dev).unsqueeze(0) <
-                 torch.tensor(decode_lengths, device=dev).unsqueeze(1)).to(torch.float32).reshape(-1).contiguous()
+                 decode_lengths_dev.unsqueeze(1)).to(torch.float32).reshape(-1).contiguous()
         predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)
         _lib.linear(H_all.map(lambda x: x.view(B * T, D)), Pw["w_fc"], bias=self.fc.bias.detach(), rowscale=valid,
                     rows_per_group=1, out=predictions.view(B * T, V))

@@ -138,8 +138,10 @@ class Encoder(nn.Module):
             return None
         if self.sd_noise is not None:
             return self.sd_noise.to(device=device, dtype=torch.float32).contiguous()
-        p = torch.tensor(stochastic_depth_probs(), device=device, dtype=torch.float32).view(-1, 1)
-        keep = 1.0 - p
+        if getattr(self, "_sd_keep", None) is None or self._sd_keep.device != device:
+            p = torch.tensor(stochastic_depth_probs(), device=device, dtype=torch.float32).view(-1, 1)
+            self._sd_keep = 1.0 - p          # built once: torch.tensor(..., device=cuda) is a blocking copy
+        keep = self._sd_keep
         return (torch.bernoulli(keep.expand(-1, B)) / keep).contiguous()
 
     def _forward_eager_nograd(self, images):

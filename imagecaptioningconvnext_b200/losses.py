@@ -3,6 +3,7 @@
 import torch
 
 from . import _lib
+from ._host import device_twin
 from ._lib import ptr
 
 
@@ -29,7 +30,7 @@ def packed_cross_entropy(scores, captions, decode_lengths):
     restricted to the first decode_lengths[b] positions of row b (the reference's pack_padded_sequence + CE)."""
     B, T, V = scores.shape
     dev = scores.device
-    dl = torch.as_tensor(decode_lengths, device=dev)
+    dl = device_twin(decode_lengths, dev)
     tgt = captions[:, 1:T + 1].to(torch.long)
     if tgt.shape[1] < T:                                   # Transformer: T = 52 positions, targets exist for 51
         tgt = torch.nn.functional.pad(tgt, (0, T - tgt.shape[1]), value=0)
@@ -41,7 +42,7 @@ def packed_cross_entropy(scores, captions, decode_lengths):
 def packed_targets(captions, decode_lengths, T):
     """int64 (B*T,) targets for ``ccx_softmax_ce``: captions[b, 1+t] for t < decode_lengths[b], else -1."""
     dev = captions.device
-    dl = torch.as_tensor(decode_lengths, device=dev)
+    dl = device_twin(decode_lengths, dev)
     tgt = captions[:, 1:T + 1].to(torch.long)
     if tgt.shape[1] < T:
         tgt = torch.nn.functional.pad(tgt, (0, T - tgt.shape[1]), value=0)

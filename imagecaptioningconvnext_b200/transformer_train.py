@@ -11,7 +11,7 @@ import weakref
 import torch
 
 from . import _lib
-from ._host import host_copy, named_params, params_of
+from ._host import host_copy, named_params, params_of, stash_device_twin
 from ._lib import Operand, ptr
 from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
@@ -283,6 +283,8 @@ class _TransformerTF(torch.autograd.Function):
 def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
     _lib.require_cuda(encoder_out, "encoder_out")
     decode_lengths = (host_copy(caption_lengths).reshape(-1) - 1).tolist()
+    if caption_lengths.is_cuda:
+        stash_device_twin(decode_lengths, caption_lengths.reshape(-1) - 1)
     caps = encoded_captions.contiguous()
     kpm = None if tgt_key_padding_mask is None else tgt_key_padding_mask.to(torch.uint8).contiguous()
     params = params_of(dec)
