@@ -152,7 +152,6 @@ beam_update_kernel(int k, int Tcap, int step, long long end_token, const float* 
   const int img = blockIdx.x;
   const int kr = k_rem[img];
   __shared__ int s_slot[BEAM_KMAX];   // destination: >= 0 alive slot, < 0: -(done index + 1)
-  __shared__ int s_alive;
   if (threadIdx.x == 0) {
     int alive = 0, nd = n_done[img];
     for (int c = 0; c < kr; ++c) {
@@ -173,7 +172,6 @@ beam_update_kernel(int k, int Tcap, int step, long long end_token, const float* 
     for (int a = alive; a < k; ++a) src_row[img * k + a] = img * k + a;
     n_done[img] = nd;
     k_rem[img] = alive;
-    s_alive = alive;
   }
   __syncthreads();
   // sequences: seq_new[c] = seqs_in[prev[c]][0..step) + word   (step tokens so far incl. <start>)
