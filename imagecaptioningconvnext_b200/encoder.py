@@ -122,9 +122,10 @@ class Encoder(nn.Module):
             return self._forward_graphed(images)
         if images.dtype == torch.uint8:
             # raw dataset pixels: /255 and Normalize(mean, std) (dataLoader.py:43-45) are fused into the stem kernel
-            if needs_grad:
-                raise NotImplementedError("uint8 input with encoder fine-tuning: normalise on the host side instead")
             x1 = self._stem_u8(images)
+            if needs_grad:    # the stem (child 0) is never trainable (encoder_train.py), so it runs frozen here too
+                from .encoder_train import encoder_features_with_grad
+                return encoder_features_with_grad(self, x1, noise, begin_child=1, image_hw=(H, W))
             return self._pool(self.run_children(x1, 1, 8, noise, image_hw=(H, W)))
         if needs_grad:
             from .encoder_train import encoder_features_with_grad  # backward kernels live there

@@ -183,14 +183,15 @@ class _PoolFn(torch.autograd.Function):
         return None, dx
 
 
-def encoder_features_with_grad(enc, images, noise):
-    """Returns the POOLED features (B,s,s,C); Encoder.forward must not pool again."""
+def encoder_features_with_grad(enc, images, noise, begin_child=0, image_hw=None):
+    """Returns the POOLED features (B,s,s,C); Encoder.forward must not pool again.
+    begin_child=1: `images` is already the stem's NHWC output (uint8 input path), image_hw the original size."""
     first = _first_trainable_child(enc)
     if first < 1:
         raise NotImplementedError("fine-tuning the stem (startingLayer=0) is not built: its backward kernel is missing; "
                                   "startingLayer 1..7 are supported (reference defaults: 7 and 5)")
     with torch.no_grad():
-        x = enc.run_children(images, 0, first, noise)
+        x = images if begin_child >= first else enc.run_children(images, begin_child, first, noise, image_hw=image_hw)
     enc.prepared()
     for child in range(first, 8):
         if child % 2 == 0:

@@ -430,3 +430,28 @@ def test_free_running_train_step_runs_with_dropout(kind):
         assert torch.isfinite(loss)
     moved = [n for n, p in dec.named_parameters() if not torch.equal(p, before[n])]
     assert len(moved) >= len(before) - 1, set(before) - set(moved)       # full_att.bias has an identically-zero grad
+
+
+def test_encoder_fine_tune_accepts_uint8_images():
+    """uint8 pixels + fine-tuning: the normalising stem runs frozen, the trainable stage gets the same gradients as
+    with host-normalised fp32 input."""
+    from oracle import encoder_oracle as eo
+    from imagecaptioningconvnext_b200 import Encoder
+    enc = Encoder()
+    enc.load_state_dict(eo.random_encoder_state(seed=0, layer_scale=1.0))
+    enc = enc.cuda().eval()
+    enc.fine_tune(True, 7)
+    u8 = torch.randint(0, 256, (2, 3, 64, 64), generator=torch.Generator().manual_seed(4), dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    x = ((u8.float() / 255.0) - mean) / std
+    grads = []
+    for inp in (u8.cuda(), x.cuda()):
+        enc.zero_grad(set_to_none=True)
+        out = enc(inp)
+        assert out.requires_grad
+        (out * torch.linspace(-1, 1, out.numel(), device="cuda").view_as(out)).sum().backward()
+        grads.append({n: p.grad.clone() for n, p in enc.named_parameters() if p.grad is not None})
+    assert len(grads[0]) == 27 and set(grads[0]) == set(grads[1])
+    for n in grads[0]:
+        assert rel_err(grads[0][n], grads[1][n]) < 1e-4, n
