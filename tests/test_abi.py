@@ -66,3 +66,20 @@ def test_encoder_refuses_cpu_tensors():
     from imagecaptioningconvnext_b200 import Encoder
     with pytest.raises(ValueError):
         Encoder()(torch.zeros(1, 3, 64, 64))
+
+
+def test_integration_md_binding_example_matches_the_abi():
+    """The ctypes struct shown to maintainers in INTEGRATION.md is the one the library expects."""
+    import ctypes
+    import os
+    import re
+    from imagecaptioningconvnext_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"class LinearDesc\(ctypes.Structure\):.*?\n\n", src, re.S)
+    assert m, "INTEGRATION.md lost its LinearDesc example"
+    ns = {"ctypes": ctypes}
+    exec(m.group(0), ns)
+    doc = ns["LinearDesc"]
+    assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.LinearDesc._fields_]
+    assert ctypes.sizeof(doc) == ctypes.sizeof(_lib.LinearDesc)
