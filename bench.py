@@ -643,16 +643,20 @@ def train_line(args, ctx):
     achieved = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
     sk = prof.get("gemm_skinny", {"ms": 0.0, "work": 0.0, "launches": 0})
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):      # committed ncu --set full capture of this kernel inside this bench command
+        traffic = json.load(open(tpath)).get("gemm_tn_kernel_train", {}).get("dram_bytes_per_launch")
     roofline = {"kernel": "gemm_tn_kernel (tcgen05/TMEM, TMA-fed): the M >= 33 GEMMs of the step — encoder pointwise / "
                           "downsample forward at B=32, stage-4 dgrad / wgrad, hoisted attention and vocabulary "
                           "projections, time-batched weight gradients",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
+                "traffic": traffic, "peak_source": peaks["source"] + " bf16 sustained",
                 "flops_per_launch": g["work"] / max(g["launches"], 1),
                 "us_per_launch": g["ms"] * 1e3 / max(g["launches"], 1),
                 "share_of_step_kernel_time": g["ms"] / tot_ms,
-                "note": "largest kernel by time share; traffic: see extra.encoder_forward_configs1.roofline (ncu capture "
-                        "of the same kernel on the B=64 shapes).  The M <= 32 recurrent GEMMs run on gemm_skinny_kernel "
+                "note": "largest kernel by time share; traffic = DRAM bytes per launch of two sampled stage-3 launches "
+                        "(profiles/ncu_traffic.json; algorithmic bytes of the same launches: 56.6 MB).  The M <= 32 recurrent GEMMs run on gemm_skinny_kernel "
                         "(mma.sync, latency-bound, no roofline claim): "
                         f"{sk['launches'] / n_inst:.0f} launches/step, {sk['ms'] / n_inst:.2f} ms/step, "
                         f"{sk['ms'] * 1e3 / max(sk['launches'], 1):.1f} us each"}
