@@ -134,9 +134,9 @@ def golden_transformer():
     torch.save(out, os.path.join(HERE, "transformer_decoder.pt"))
 
 
-def _grad_digest(named_grads):
-    """Small fingerprint of a gradient set: per tensor its norm and every 499th element."""
-    return {k: {"norm": g.norm(), "sub": g.reshape(-1)[::499].clone()} for k, g in named_grads}
+def _grad_digest(named_grads, stride=499):
+    """Small fingerprint of a tensor set: per tensor its norm and every stride-th element."""
+    return {k: {"norm": g.norm(), "sub": g.reshape(-1)[::stride].clone()} for k, g in named_grads}
 
 
 def golden_free_running():
@@ -207,6 +207,78 @@ def golden_attvis():
            "greedy": {"preds": _sub(gp), "sequences": gs, "alphas": ga}}
     print("attvis alphas", tuple(alphas.shape), float(alphas.sum(-1).mean()), tuple(ga.shape))
     torch.save(out, os.path.join(HERE, "attvis.pt"))
+
+
+def golden_train_step():
+    """The reference's train-step body, statement by statement (trainMultiGPU.py:361-394 = train.py:261-291) on the
+    reference modules: Encoder.fine_tune(True, 7) + each decoder, pack_padded_sequence + CrossEntropyLoss (+ alpha
+    regulariser), zero_grad, backward, utils.clip_gradient (exec'd from the source text: utils/utils.py imports
+    h5py), torch.optim.Adam.  Two steps in eval mode (dropout / stochastic depth are random in train mode); stored:
+    the losses and a digest of every trainable tensor after the second step."""
+    import torch.nn as nn
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from models.decoder import DecoderWithAttention
+    from models.encoder import Encoder
+    from models.transformerDecoder import TransformerDecoder
+    from oracle import decoder_oracle as do
+    from oracle.encoder_oracle import random_encoder_state
+
+    src = open(os.path.join(REF, "utils", "utils.py")).read()
+    a = src.index("def clip_gradient")
+    b = src.index("def save_checkpoint")
+    ns = {"torch": torch}
+    exec(src[a:b], ns)
+    clip_gradient = ns["clip_gradient"]
+    criterion = nn.CrossEntropyLoss()
+    out = {"B": 3, "image_seed": 1, "cap_seed": 2, "encoder_seed": 0, "decoder_seed": 7, "lr": 1e-3, "grad_clip": 5.0,
+           "image_hw": 64}
+    B = out["B"]
+    imgs = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(out["image_seed"]))
+    caps, lens = do.synthetic_captions(B, out["cap_seed"], V)
+    for kind in ("lstm", "transformer"):
+        enc = Encoder().eval()
+        enc.load_state_dict(random_encoder_state(seed=0, layer_scale=1.0))
+        enc.fine_tune(True, 7)
+        if kind == "lstm":
+            dec = DecoderWithAttention(512, 512, 512, V, torch.device("cpu")).eval()
+            dec.load_state_dict(do.random_lstm_decoder_state(7, V))
+        else:
+            dec = TransformerDecoder(512, 512, V, 52, torch.device("cpu"), None, None, True).eval()
+            dec.load_state_dict(do.random_transformer_decoder_state(7, V))
+        dec_opt = torch.optim.Adam(params=filter(lambda p: p.requires_grad, dec.parameters()), lr=out["lr"])
+        enc_opt = torch.optim.Adam(params=filter(lambda p: p.requires_grad, enc.parameters()), lr=out["lr"])
+        losses = []
+        for _ in range(2):
+            feats = enc(imgs)
+            if kind == "lstm":
+                scores, caps_sorted, dl, alphas, _ = dec(teacherForcing=True, encoder_out=feats, encoded_captions=caps,
+                                                         caption_lengths=lens)
+                targets = caps_sorted[:, 1:]
+                scores = pack_padded_sequence(scores, dl, batch_first=True).data
+                targets = pack_padded_sequence(targets, dl, batch_first=True).data
+                loss = criterion(scores, targets)
+                loss += 1.0 * ((1. - alphas.sum(dim=1)) ** 2).mean()
+            else:
+                kpm = caps == WORDMAP["<pad>"]
+                scores, caps_sorted, dl = dec(teacherForcing=True, encoder_out=feats, encoded_captions=caps,
+                                              caption_lengths=lens, tgt_key_padding_mask=kpm)
+                targets = caps_sorted[:, 1:]
+                scores = pack_padded_sequence(scores, dl, batch_first=True, enforce_sorted=False).data
+                targets = pack_padded_sequence(targets, dl, batch_first=True, enforce_sorted=False).data
+                loss = criterion(scores, targets)
+            enc_opt.zero_grad()
+            dec_opt.zero_grad()
+            loss.backward()
+            clip_gradient(dec_opt, out["grad_clip"])
+            clip_gradient(enc_opt, out["grad_clip"])
+            enc_opt.step()
+            dec_opt.step()
+            losses.append(float(loss))
+        tr = [("decoder." + k, p.detach()) for k, p in dec.named_parameters() if p.requires_grad]
+        tr += [("encoder." + k, p.detach()) for k, p in enc.named_parameters() if p.requires_grad]
+        out[kind] = {"losses": losses, "weights": _grad_digest(tr, stride=1999)}
+        print(kind, "train-step losses", losses, "trainable tensors", len(tr))
+    torch.save(out, os.path.join(HERE, "train_step.pt"))
 
 
 def golden_beam():

@@ -187,3 +187,59 @@ def test_attention_viz_oracle_matches_reference_golden(golden_dir):
     assert torch.equal(gs, g["greedy"]["sequences"])
     assert rel_err(ga, g["greedy"]["alphas"]) < 1e-4
     assert torch.equal(ga == 0, g["greedy"]["alphas"] == 0)
+
+
+def _oracle_train_steps(kind, g, n_steps=2):
+    """The oracle's restatement of the train-step body (the CPU baseline bench.py times): functional encoder /
+    decoder on leaf tensors, packed CE (+ alpha term), clamp, torch.optim.Adam."""
+    from oracle import decoder_oracle as do
+    from oracle import encoder_oracle as eo
+    V = 9490
+    esd = eo.random_encoder_state(seed=g["encoder_seed"], layer_scale=1.0)
+    dsd = (do.random_lstm_decoder_state(g["decoder_seed"], V) if kind == "lstm"
+           else do.random_transformer_decoder_state(g["decoder_seed"], V))
+    e_leaf = {k: v.clone().requires_grad_(k.startswith("convnext.7.")) for k, v in esd.items()}
+    d_leaf = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_encoding.pe") for k, v in dsd.items()}
+    tr_e = [v for v in e_leaf.values() if v.requires_grad]
+    tr_d = [v for v in d_leaf.values() if v.requires_grad]
+    opt_e, opt_d = torch.optim.Adam(tr_e, lr=g["lr"]), torch.optim.Adam(tr_d, lr=g["lr"])
+    imgs = torch.randn(g["B"], 3, g["image_hw"], g["image_hw"], generator=torch.Generator().manual_seed(g["image_seed"]))
+    caps, lens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    losses = []
+    for _ in range(n_steps):
+        feats = eo.encoder_forward(e_leaf, imgs, 7)
+        if kind == "lstm":
+            p, cs, dl, al, _ = do.lstm_teacher_forcing(d_leaf, feats, caps, lens)
+            loss = do.train_loss_lstm(p, cs, dl, al)
+        else:
+            p, _, dl = do.transformer_teacher_forcing(d_leaf, feats, caps, lens, caps == 0)
+            loss = do.train_loss_transformer(p, caps, dl)
+        opt_e.zero_grad()
+        opt_d.zero_grad()
+        loss.backward()
+        for prm in tr_e + tr_d:
+            prm.grad.clamp_(-g["grad_clip"], g["grad_clip"])
+        opt_e.step()
+        opt_d.step()
+        losses.append(float(loss))
+    weights = {"decoder." + k: v.detach() for k, v in d_leaf.items() if v.requires_grad}
+    weights.update({"encoder." + k: v.detach() for k, v in e_leaf.items() if v.requires_grad})
+    return losses, weights
+
+
+def test_train_step_oracle_matches_reference_step_body_golden(golden_dir):
+    """Two optimizer steps of the reference's own loop body (pack_padded_sequence + CrossEntropyLoss, utils.clip_gradient,
+    torch.optim.Adam on the reference modules) against the oracle's restatement: losses and every updated tensor."""
+    g = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    for kind in ("lstm", "transformer"):
+        losses, weights = _oracle_train_steps(kind, g)
+        ref = g[kind]
+        assert max(abs(a - b) / abs(b) for a, b in zip(losses, ref["losses"])) < 2e-5, (losses, ref["losses"])
+        assert set(weights) == set(ref["weights"]), set(weights) ^ set(ref["weights"])
+        for k, d in ref["weights"].items():
+            w = weights[k]
+            assert abs(float(w.norm()) - float(d["norm"])) <= 1e-4 * float(d["norm"]) + 1e-9, (kind, k)
+            # an Adam step moves an element by ~lr whatever its gradient: elements with a noise-level gradient
+            # may move the other way, so compare the fraction that differs by more than a fifth of a step
+            off = ((w.reshape(-1)[::1999] - d["sub"]).abs() > 0.2 * g["lr"]).float().mean()
+            assert float(off) < 0.02, (kind, k, float(off))
