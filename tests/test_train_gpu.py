@@ -455,3 +455,42 @@ def test_encoder_fine_tune_accepts_uint8_images():
     assert len(grads[0]) == 27 and set(grads[0]) == set(grads[1])
     for n in grads[0]:
         assert rel_err(grads[0][n], grads[1][n]) < 1e-4, n
+
+
+@pytest.mark.parametrize("kind", ["lstm", "transformer"])
+def test_train_step_matches_reference_golden(golden_dir, kind):
+    """caption_train_step (fp32) against the committed output of the REFERENCE's own loop body
+    (tests/golden/train_step.pt: pack_padded_sequence + CrossEntropyLoss, utils.clip_gradient, torch.optim.Adam on
+    the reference modules): both losses and every updated tensor."""
+    import os
+    from imagecaptioningconvnext_b200 import Encoder
+    from imagecaptioningconvnext_b200.train_step import caption_train_step, make_optimizers
+    from oracle import decoder_oracle as do
+    from oracle import encoder_oracle as eo
+    g = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    imgs = torch.randn(g["B"], 3, g["image_hw"], g["image_hw"], generator=torch.Generator().manual_seed(g["image_seed"]))
+    caps, lens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    enc = Encoder()
+    enc.load_state_dict(eo.random_encoder_state(seed=g["encoder_seed"], layer_scale=1.0))
+    enc = enc.cuda().eval()
+    enc.fine_tune(True, 7)
+    dsd = (do.random_lstm_decoder_state(g["decoder_seed"], V) if kind == "lstm"
+           else do.random_transformer_decoder_state(g["decoder_seed"], V))
+    dec = (_lstm if kind == "lstm" else _transformer)(dsd, torch.float32)
+    dec.dropout_p = 0.0            # the golden was produced in eval mode
+    dec.train()
+    d_opt, e_opt = make_optimizers(enc, dec, decoder_lr=g["lr"], encoder_lr=g["lr"], grad_clip=g["grad_clip"])
+    losses = [float(caption_train_step(enc, dec, imgs.cuda(), caps.cuda(), lens.cuda(), d_opt, e_opt))
+              for _ in range(2)]
+    ref = g[kind]
+    assert abs(losses[0] - ref["losses"][0]) < 1e-3 and abs(losses[1] - ref["losses"][1]) < 2e-3, (losses, ref["losses"])
+    ours = {"decoder." + n: p for n, p in dec.named_parameters() if p.requires_grad}
+    ours.update({"encoder." + n: p for n, p in enc.named_parameters() if p.requires_grad})
+    assert set(ours) == set(ref["weights"])
+    worst = 0.0
+    for k, d in ref["weights"].items():
+        if k == "decoder.attention.full_att.bias":      # identically-zero gradient: Adam moves it on rounding noise
+            continue
+        w = ours[k].detach().cpu().reshape(-1)[::1999]
+        worst = max(worst, float(((w - d["sub"]).abs() > 0.2 * g["lr"]).float().mean()))
+    assert worst < 0.02, worst
