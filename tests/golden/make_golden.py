@@ -281,6 +281,23 @@ def golden_train_step():
     torch.save(out, os.path.join(HERE, "train_step.pt"))
 
 
+def golden_fine_tune():
+    """Which parameters the reference's Encoder.fine_tune (models/encoder.py:29-34) leaves trainable, for every
+    startingLayer, and the constructor default."""
+    from models.encoder import Encoder
+    enc = Encoder()
+    out = {"default": sorted(n for n, p in enc.named_parameters() if p.requires_grad),
+           "n_params": sum(p.numel() for p in enc.parameters()), "keys": sorted(enc.state_dict().keys())}
+    for L in range(0, 9):
+        enc.fine_tune(True, L)
+        out[L] = sorted(n for n, p in enc.named_parameters() if p.requires_grad)
+    enc.fine_tune(False)
+    out["off"] = sorted(n for n, p in enc.named_parameters() if p.requires_grad)
+    print("fine_tune: default trainable", len(out["default"]), "params", out["n_params"],
+          {L: len(out[L]) for L in range(9)})
+    torch.save(out, os.path.join(HERE, "fine_tune.pt"))
+
+
 def golden_beam():
     """Reference caption.py beam search (k=5), full pipeline image file -> Encoder -> decoder, both decoders."""
     import numpy as np

@@ -72,3 +72,19 @@ def test_host_copy_stash_is_bound_to_the_tensor_object_and_version():
         raise AssertionError("shape mismatch accepted")
     except ValueError:
         pass
+
+
+def test_encoder_fine_tune_marks_the_same_parameters_as_the_reference(golden_dir):
+    """models/encoder.py:15-21,29-34: constructor default (only child 7 trainable) and every startingLayer."""
+    from imagecaptioningconvnext_b200 import Encoder
+    g = torch.load(os.path.join(golden_dir, "fine_tune.pt"))
+    enc = Encoder()
+    trainable = lambda: sorted(n for n, p in enc.named_parameters() if p.requires_grad)
+    assert sorted(enc.state_dict().keys()) == g["keys"]
+    assert sum(p.numel() for p in enc.parameters()) == g["n_params"] == 87564416
+    assert trainable() == g["default"]
+    for L in range(0, 9):
+        enc.fine_tune(True, L)
+        assert trainable() == g[L], L
+    enc.fine_tune(False)
+    assert trainable() == g["off"] == []
