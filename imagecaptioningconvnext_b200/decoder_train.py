@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._host import named_params, params_of
 from ._lib import Operand, ptr
-from .train_ops import linear_bwd, to_operand, weight_t, zero_grads_like, zeros_many
+from .train_ops import linear_bwd, weight_t, zero_grads_like, zeros_many
 
 
 class _LstmTF(torch.autograd.Function):

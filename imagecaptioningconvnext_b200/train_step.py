@@ -4,7 +4,6 @@ LSTM decoder) -> zero_grad -> backward -> clip_gradient(+-5) -> Adam.  Everythin
 modules in ``torch.nn.parallel.DistributedDataParallel`` (as the reference does, trainMultiGPU.py:233-235) and the
 gradient all-reduce over NCCL overlaps with the explicit backward.
 """
-import torch
 
 from ._host import stash_host_copy
 from .decoder import DecoderWithAttention

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._host import host_copy, named_params, params_of, stash_device_twin
 from ._lib import Operand, ptr
-from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
+from .train_ops import linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
 _SITES = ("sa_p", "d1", "ca_p", "d2", "ff", "d3")
 
