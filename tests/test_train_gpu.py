@@ -494,3 +494,69 @@ def test_train_step_matches_reference_golden(golden_dir, kind):
         w = ours[k].detach().cpu().reshape(-1)[::1999]
         worst = max(worst, float(((w - d["sub"]).abs() > 0.2 * g["lr"]).float().mean()))
     assert worst < 0.02, worst
+
+
+@pytest.mark.parametrize("kind", ["lstm", "transformer"])
+def test_unmodified_reference_loop_body_runs_on_the_drop_in_modules(golden_dir, kind):
+    """The reference's loop body as written (trainMultiGPU.py:361-394): torch's pack_padded_sequence,
+    nn.CrossEntropyLoss, clip_gradient and torch.optim.Adam around the drop-in modules.  The second step's loss only
+    matches the reference golden if the weights torch's optimizer updated in place are picked up by the kernel-side
+    weight copies."""
+    import os
+    import torch.nn as nn
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from imagecaptioningconvnext_b200 import Encoder
+    from oracle import decoder_oracle as do
+    from oracle import encoder_oracle as eo
+    g = torch.load(os.path.join(golden_dir, "train_step.pt"))
+    imgs = torch.randn(g["B"], 3, g["image_hw"], g["image_hw"],
+                       generator=torch.Generator().manual_seed(g["image_seed"])).cuda()
+    caps, caplens = do.synthetic_captions(g["B"], g["cap_seed"], V)
+    caps, caplens = caps.cuda(), caplens.cuda()
+    encoder = Encoder()
+    encoder.load_state_dict(eo.random_encoder_state(seed=g["encoder_seed"], layer_scale=1.0))
+    encoder = encoder.cuda().eval()
+    encoder.fine_tune(True, 7)
+    dsd = (do.random_lstm_decoder_state(g["decoder_seed"], V) if kind == "lstm"
+           else do.random_transformer_decoder_state(g["decoder_seed"], V))
+    decoder = (_lstm if kind == "lstm" else _transformer)(dsd, torch.float32)      # eval mode, like the golden
+    decoderOptimizer = torch.optim.Adam(params=filter(lambda p: p.requires_grad, decoder.parameters()), lr=g["lr"])
+    encoderOptimizer = torch.optim.Adam(params=filter(lambda p: p.requires_grad, encoder.parameters()), lr=g["lr"])
+    criterion = nn.CrossEntropyLoss().cuda()
+
+    def clip_gradient(optimizer, gradClip):            # utils/utils.py:183-192
+        for group in optimizer.param_groups:
+            for param in group['params']:
+                if param.grad is not None:
+                    param.grad.data.clamp_(-gradClip, gradClip)
+
+    losses = []
+    for _ in range(2):
+        feats = encoder(imgs)
+        if kind == "lstm":
+            scores, capsSorted, decodeLengths, alphas, sortInd = decoder(teacherForcing=True, encoder_out=feats,
+                                                                        encoded_captions=caps, caption_lengths=caplens)
+            targets = capsSorted[:, 1:]
+            scores = pack_padded_sequence(scores, decodeLengths, batch_first=True).data
+            targets = pack_padded_sequence(targets, decodeLengths, batch_first=True).data
+            loss = criterion(scores, targets)
+            loss += 1.0 * ((1. - alphas.sum(dim=1)) ** 2).mean()
+        else:
+            tgt_key_padding_mask = (caps == 0)
+            scores, capsSorted, decodeLengths = decoder(teacherForcing=True, encoder_out=feats, encoded_captions=caps,
+                                                        caption_lengths=caplens,
+                                                        tgt_key_padding_mask=tgt_key_padding_mask)
+            targets = capsSorted[:, 1:]
+            scores = pack_padded_sequence(scores, decodeLengths, batch_first=True, enforce_sorted=False).data
+            targets = pack_padded_sequence(targets, decodeLengths, batch_first=True, enforce_sorted=False).data
+            loss = criterion(scores, targets)
+        encoderOptimizer.zero_grad()
+        decoderOptimizer.zero_grad()
+        loss.backward()
+        clip_gradient(decoderOptimizer, g["grad_clip"])
+        clip_gradient(encoderOptimizer, g["grad_clip"])
+        encoderOptimizer.step()
+        decoderOptimizer.step()
+        losses.append(float(loss))
+    ref = g[kind]["losses"]
+    assert abs(losses[0] - ref[0]) < 1e-3 and abs(losses[1] - ref[1]) < 2e-3, (losses, ref)
