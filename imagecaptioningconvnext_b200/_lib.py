@@ -59,6 +59,16 @@ class LstmTFBwd(C.Structure):
                 ("dawe_all", _vp), ("dalpha_all", _vp), ("de_all", _vp)]
 
 
+class LstmPersist(C.Structure):
+    _fields_ = [("E_all", _vp), ("w2p", _vp), ("att1_bf", _vp), ("enc_bf", _vp), ("decode_len", _vp),
+                ("counters", _vp), ("scratch", _vp), ("awe_all", _vp), ("dbg", _vp)]
+
+
+class LstmPersistBwd(C.Structure):
+    _fields_ = [("wx", _vp), ("wht", _vp), ("dG_bf", _vp), ("scratch", _vp), ("Xp", _vp), ("awe_all", _vp),
+                ("att1_bf", _vp), ("enc_bf", _vp), ("decode_len", _vp), ("counters", _vp), ("dbg", _vp)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ccx.h declares (tests/test_abi.py checks it)
 SIGNATURES = {
     "ccx_version": (C.c_int, []),
@@ -117,6 +127,10 @@ SIGNATURES = {
     "ccx_avgpool_nhwc_bwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "ccx_lstm_tf_forward": (C.c_int, [C.POINTER(LstmTF), _vp]),
     "ccx_lstm_tf_backward": (C.c_int, [C.POINTER(LstmTF), C.POINTER(LstmTFBwd), _vp]),
+    "ccx_lstm_persist_supported": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _i32, _i32]),
+    "ccx_lstm_tf_forward_persist": (C.c_int, [C.POINTER(LstmTF), C.POINTER(LstmPersist), _vp]),
+    "ccx_lstm_tf_backward_persist": (C.c_int, [C.POINTER(LstmTF), C.POINTER(LstmTFBwd), C.POINTER(LstmPersistBwd),
+                                                _vp]),
     "ccx_adam_clamp": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_double,
                                  _vp]),
     "ccx_prof_begin": (C.c_int, []),

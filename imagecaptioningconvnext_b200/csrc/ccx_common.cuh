@@ -305,6 +305,18 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return d;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE, not to the process: a process
+// that drives a second GPU must configure each kernel there too (one flag / value per device ordinal).
+template <typename T>
+struct PerDevice {
+  T v[64] = {};
+  T& ref() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return v[(d >= 0 && d < 64) ? d : 0];
+  }
+};
+
 // Programmatic dependent launch for chains of short dependent kernels (the decoder recurrences: ~460 launches per
 // train step, each waiting on the previous one).  A kernel launched with launch_pdl() may be scheduled while its
 // predecessor is still running; it must call grid_dep_sync() before touching anything the predecessor wrote.

@@ -365,7 +365,8 @@ int bahdanau_attention(const float* att1, const float* hg, long long ldhg, const
   const size_t smem = (2 * static_cast<size_t>(A) + ATT_PSPLIT * static_cast<size_t>(E)) * sizeof(float);
   if (smem > 48 * 1024) {
     if (smem > 200 * 1024) return CCX_ERR_SHAPE;
-    static size_t configured = 0;
+    static PerDevice<size_t> configured_dev;
+    size_t& configured = configured_dev.ref();
     if (smem > configured) {
       if (cudaFuncSetAttribute(bahdanau_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                static_cast<int>(smem)) != cudaSuccess)
@@ -578,7 +579,8 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
   const size_t smem = (static_cast<size_t>(2) * Tk * (hd + 1) + static_cast<size_t>(rows_per_cta) * hd + 4 * Tk) *
                       sizeof(float);
   if (smem > 200 * 1024) return CCX_ERR_SHAPE;
-  static size_t configured = 0;
+  static PerDevice<size_t> configured_dev;
+    size_t& configured = configured_dev.ref();
   if (smem > 48 * 1024 && smem > configured) {
     if (cudaFuncSetAttribute(mha_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess)

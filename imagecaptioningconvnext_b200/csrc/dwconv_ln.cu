@@ -407,7 +407,8 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return CCX_ERR_TMA;
 
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.ref();
   if (!configured) {
     if (cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
             cudaSuccess ||

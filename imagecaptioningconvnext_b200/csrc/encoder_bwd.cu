@@ -143,7 +143,8 @@ int dwconv7_wgrad(const float* x, const float* du, float* dw49c, int B, int H, i
   const int tiles_h = (H + 7) / 8, tiles_w = (W + 7) / 8;
   if (B > 65535 || tiles_h * tiles_w > 65535) return CCX_ERR_SHAPE;
   constexpr int smem = (14 * 14 + 8 * 8) * WG_C * static_cast<int>(sizeof(float));
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.ref();
   if (!configured) {
     if (cudaFuncSetAttribute(dwconv7_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return CCX_ERR_CUDA;

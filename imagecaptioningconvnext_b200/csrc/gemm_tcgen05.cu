@@ -223,7 +223,8 @@ static int make_map_2d(CUtensorMap* map, const void* ptr, int is_f32, long long 
 }
 
 int num_sms() {
-  static int n = 0;
+  static PerDevice<int> cache;
+  int& n = cache.ref();
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -237,7 +238,8 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtens
                   const CUtensorMap& b_lo, int M, int N, int K, int nseg, const EpiArgs& ep,
                   cudaStream_t stream) {
   using S = GemmSmem<BN>;
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.ref();
   auto kfn = gemm_tn_kernel<BN, IS_TF32>;
   if (!configured) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)

@@ -240,7 +240,8 @@ template <int BN, bool IS_TF32>
 static int launch2(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
                    int M, int N, int K, int nseg, const EpiArgs& ep, cudaStream_t stream) {
   using S = Gemm2Smem<BN>;
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.ref();
   auto kfn = gemm_tn_2cta_kernel<BN, IS_TF32>;
   if (!configured) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)

@@ -341,7 +341,8 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
   if ((hd & 3) || ((q_sb | q_st | k_sb | k_st | v_sb | v_st | d_sb | d_st) & 3) || Tk > 256) return CCX_ERR_SHAPE;
   const size_t smem = (static_cast<size_t>(2) * (Tq + Tk) * (hd + 1) + 2 * static_cast<size_t>(Tq) * Tk) * 4;
   if (smem > 200 * 1024) return CCX_ERR_SHAPE;
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.ref();
   if (!configured) {
     if (cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return CCX_ERR_CUDA;

@@ -16,6 +16,7 @@ What runs underneath (all libccx kernels, no torch compute on the path):
 Extra ctor kwarg: ``compute_dtype`` (float32 = 3xTF32, bfloat16).  There is no CPU path.
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -116,6 +117,8 @@ class DecoderWithAttention(nn.Module):
         self.init_weights()
         self.device = device
         self._cache = PreparedCache(self)
+        self.use_persist = os.environ.get("CCX_LSTM_PERSIST", "1") != "0"
+        self._persist_dbg = None
         self.inject_dropmask = None   # tests: (B, T, decoder_dim) multiplier used instead of a fresh Bernoulli draw
 
     def init_weights(self):
@@ -142,7 +145,31 @@ class DecoderWithAttention(nn.Module):
         P["w_lstm"] = Operand.prepare(torch.cat([d(ds.weight_ih), d(ds.weight_hh)], dim=1), cd)
         P["b_lstm"] = (d(ds.bias_ih) + d(ds.bias_hh)).contiguous()
         P["w_fc"] = Operand.prepare(d(self.fc.weight), cd)
+        if self._persist_dims_ok():
+            # persistent recurrence kernel (csrc/lstm_persist.cu): gate rows re-ordered so that each CTA's 32 rows are
+            # {i,f,g,o} x 8 hidden units: new row 32*(j//8) + 8*gate + j%8  <-  torch row gate*D + j
+            D, Emb = self.decoder_dim, self.embed_dim
+            perm = torch.arange(4 * D, device=ds.weight_ih.device).view(4, D // 8, 8).permute(1, 0, 2).reshape(-1)
+            P["w2p"] = Operand.prepare(torch.cat([d(ds.weight_hh), d(ds.weight_ih)[:, Emb:]], dim=1)[perm], cd)
+            P["w2p_emb"] = Operand.prepare(d(ds.weight_ih)[:, :Emb][perm], cd)
+            P["b_perm"] = P["b_lstm"][perm].contiguous()
+            # backward kernel: W^T with the contraction (gate) index innermost
+            P["wx"] = Operand.prepare(torch.cat([d(ds.weight_ih)[:, Emb:], d(ds.weight_hh)], dim=1).t().contiguous(), cd)
+            P["wht"] = Operand.prepare(torch.cat([d(att.decoder_att.weight), d(self.f_beta.weight)], dim=0)
+                                       .t().contiguous(), cd)
+            P["w_emb_t"] = Operand.prepare(d(ds.weight_ih)[:, :Emb].t().contiguous(), cd)      # [Emb, 4D]
         return P
+
+    def _persist_dims_ok(self):
+        return (self.compute_dtype == torch.bfloat16 and self.decoder_dim == 512 and self.attention_dim == 512 and
+                self.embed_dim == 512 and self.encoder_dim == 1024)
+
+    def _persist_ok(self, B, Pn):
+        """The one-kernel recurrence (ccx_lstm_tf_forward_persist) serves this call?  Otherwise the per-step launch
+        loop of the same library runs (fp32 / 3xTF32 mode, B > 32, 14x14 feature maps)."""
+        return (self.use_persist and self._persist_dims_ok() and bool(_lib.lib().ccx_lstm_persist_supported(
+            B, Pn, self.encoder_dim, self.attention_dim, self.decoder_dim, self.embed_dim,
+            _lib.dt_code(self.compute_dtype))))
 
     def init_hidden_state(self, encoder_out):
         """models/decoder.py:63-67 (external callers: caption.py:94)."""
@@ -272,7 +299,27 @@ class DecoderWithAttention(nn.Module):
         bts = [sum(l > t for l in decode_lengths) for t in range(T)]
         # the whole time loop in ONE FFI call (csrc/lstm_runner.cu): same kernels/order as self._step per step
         desc = self._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
-        _lib.check(L.ccx_lstm_tf_forward(ctypes.byref(desc), st), "lstm_tf_forward")
+        if self._persist_ok(B, Pn):
+            # ONE cooperative kernel for all T steps (csrc/lstm_persist.cu).  Hoisted out of it: the embedding part of
+            # the gate GEMM for every (t, b) at once, bias included, columns in the kernel's permuted gate order.
+            E_all = _lib.linear(XH.map(lambda x: x[:T].view(T * B, K)[:, :self.embed_dim]), Pw["w2p_emb"],
+                                bias=Pw["b_perm"])
+            pd = _lib.LstmPersist()
+            att1_bf = _lib.cast_bf16(att1)
+            counters = torch.empty(4 * (T + 1), dtype=torch.int32, device=dev)
+            pd.E_all, pd.w2p, pd.att1_bf, pd.enc_bf = ptr(E_all), ptr(Pw["w2p"].hi), ptr(att1_bf), ptr(
+                self._setup_extras[1].hi)
+            pd.decode_len, pd.counters = ptr(decode_lengths_dev), ptr(counters)
+            awe_all = torch.empty((T, B, E), dtype=torch.float32, device=dev)
+            scratch = torch.empty((T + 1) * 32768 + T * 65536 + 2 * 4 * 32 * 1536 * 4, dtype=torch.uint8, device=dev)
+            pd.awe_all, pd.scratch = ptr(awe_all), ptr(scratch)
+            if self._persist_dbg is not None:          # tools/bench_lstm_persist.py: in-kernel clock64 stamps
+                self._persist_dbg = torch.zeros((3, T, 8), dtype=torch.int64, device=dev)
+                pd.dbg = ptr(self._persist_dbg)
+            _lib.check(L.ccx_lstm_tf_forward_persist(ctypes.byref(desc), ctypes.byref(pd), st), "lstm_tf_forward_persist")
+        else:
+            awe_all = att1_bf = None
+            _lib.check(L.ccx_lstm_tf_forward(ctypes.byref(desc), st), "lstm_tf_forward")
         valid = (torch.arange(T, device=dev).unsqueeze(0) <
                  decode_lengths_dev.unsqueeze(1)).to(torch.float32).reshape(-1).contiguous()
         predictions = torch.empty((B, T, V), dtype=torch.float32, device=dev)
@@ -280,7 +327,8 @@ class DecoderWithAttention(nn.Module):
                     rows_per_group=1, out=predictions.view(B * T, V))
         saved = dict(enc=enc, att1=att1, XH=XH, C_all=C_all, HG=HG, G=G, H_all=H_all, dm=dm, valid=valid, bts=bts,
                      sort_ind=sort_ind, caps=encoded_captions, Pw=Pw, m_op=self._setup_extras[0],
-                     enc_op=self._setup_extras[1], alphas=alphas.detach(), T=T)   # an alias: the returned
+                     enc_op=self._setup_extras[1], alphas=alphas.detach(), T=T, awe_all=awe_all, att1_bf=att1_bf,
+                     decode_lengths_dev=decode_lengths_dev)   # an alias: the returned
         # tensor becomes an autograd OUTPUT (grad_fn -> node -> saved -> tensor would be a reference cycle that keeps
         # every activation of the step alive until the cyclic GC runs)
         self._setup_extras = None

@@ -16,6 +16,40 @@ from ._lib import Operand, ptr
 from .train_ops import linear_bwd, weight_t, zero_grads_like, zeros_many
 
 
+def _bptt_launch_loop(dec, S, dH_all, dalphas, need_enc, cd, dev):
+    """BPTT as the per-step launch loop (csrc/lstm_runner.cu: 5 launches per step): fp32 / 3xTF32 mode, B > 32 or
+    feature maps that do not fit the persistent kernel.  Returns the same pieces as the persistent path."""
+    L, st = _lib.lib(), _lib.stream_ptr()
+    enc, att1, XH, C_all, HG, G, H_all = S["enc"], S["att1"], S["XH"], S["C_all"], S["HG"], S["G"], S["H_all"]
+    dm, bts, T, alphas, Pw = S["dm"], S["bts"], S["T"], S["alphas"], S["Pw"]
+    B, Pn, E = enc.shape
+    D, A, Emb = dec.decoder_dim, dec.attention_dim, dec.embed_dim
+    K = Emb + E + D
+    w_lstm_t = weight_t(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd)
+    w_h_t = weight_t(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd)
+    (dG_all, dHG_all, dXH_all, d_att1, d_enc, d_wf, dc, dh, dawe_all, dalpha_all) = zeros_many(
+        [(T, B, 4 * D), (T, B, A + E), (T, B, K), (B * Pn, A), (B, Pn, E), (A,), (B, D), (B, D), (T, B, E),
+         (2, T, B, Pn)], dev)
+    if not need_enc:
+        d_enc = None
+    dal = None if dalphas is None else dalphas.contiguous()
+    scratch = Operand.empty((B, 4 * D), cd, dev)
+    scratch2 = Operand.empty((B, A + E), cd, dev)
+    fwd = dec._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
+    bd = _lib.LstmTFBwd()
+    bd.dH_all, bd.dalphas = ptr(dH_all), ptr(dal)
+    bd.dG_all, bd.dHG_all, bd.dXH_all = ptr(dG_all), ptr(dHG_all), ptr(dXH_all)
+    bd.dh, bd.dc, bd.d_att1, bd.d_enc, bd.d_wf = ptr(dh), ptr(dc), ptr(d_att1), ptr(d_enc), ptr(d_wf)
+    bd.w_lstm_t, bd.w_lstm_t_lo = ptr(w_lstm_t.hi), w_lstm_t.lo_ptr
+    bd.w_h_t, bd.w_h_t_lo = ptr(w_h_t.hi), w_h_t.lo_ptr
+    bd.scratch_hi, bd.scratch_lo = ptr(scratch.hi), scratch.lo_ptr
+    bd.scratch2_hi, bd.scratch2_lo = ptr(scratch2.hi), scratch2.lo_ptr
+    # deferred accumulation (see ccx_lstm_tf_bwd): per-step records, summed over time once after the loop
+    bd.dawe_all, bd.dalpha_all, bd.de_all = ptr(dawe_all), ptr(dalpha_all[0]), ptr(dalpha_all[1])
+    _lib.check(L.ccx_lstm_tf_backward(ctypes.byref(fwd), ctypes.byref(bd), st), "lstm_tf_backward")
+    return dG_all, dHG_all, d_att1, d_enc, d_wf, dc, dh, (dXH_all, K, B * K)
+
+
 class _LstmTF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dec, holder, encoder_out, caps, lens, *params):
@@ -49,32 +83,43 @@ class _LstmTF(torch.autograd.Function):
         dpred = dpred.contiguous().view(B * T, V)
         dH_all = linear_bwd(dpred, H_all.map(lambda x: x.view(B * T, D)), weight_t(dec.fc.weight, cd), cd,
                             g("fc.weight"), g("fc.bias"))
-        w_lstm_t = weight_t(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd)
-        w_h_t = weight_t(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd)
-        (dG_all, dHG_all, dXH_all, d_att1, d_enc, d_wf, dc, dh, dawe_all, dalpha_all, gw_lstm, gb_lstm, gw_h,
-         gb_h) = zeros_many(
-            [(T, B, 4 * D), (T, B, A + E), (T, B, K), (B * Pn, A), (B, Pn, E), (A,), (B, D), (B, D), (T, B, E),
-             (2, T, B, Pn), (4 * D, K), (4 * D,), (A + E, D), (A + E,)], dev)
-        if not need_enc:
-            d_enc = None
-        dal = None if dalphas is None else dalphas.contiguous()
-        # the whole BPTT loop in ONE FFI call (csrc/lstm_runner.cu): per step LSTM point-wise backward, dgrad GEMM
-        # through [W_ih | W_hh], attention backward, dgrad GEMM through [decoder_att ; f_beta]
-        scratch = Operand.empty((B, 4 * D), cd, dev)
-        scratch2 = Operand.empty((B, A + E), cd, dev)
-        fwd = dec._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
-        bd = _lib.LstmTFBwd()
-        bd.dH_all, bd.dalphas = ptr(dH_all), ptr(dal)
-        bd.dG_all, bd.dHG_all, bd.dXH_all = ptr(dG_all), ptr(dHG_all), ptr(dXH_all)
-        bd.dh, bd.dc, bd.d_att1, bd.d_enc, bd.d_wf = ptr(dh), ptr(dc), ptr(d_att1), ptr(d_enc), ptr(d_wf)
-        bd.w_lstm_t, bd.w_lstm_t_lo = ptr(w_lstm_t.hi), w_lstm_t.lo_ptr
-        bd.w_h_t, bd.w_h_t_lo = ptr(w_h_t.hi), w_h_t.lo_ptr
-        bd.scratch_hi, bd.scratch_lo = ptr(scratch.hi), scratch.lo_ptr
-        bd.scratch2_hi, bd.scratch2_lo = ptr(scratch2.hi), scratch2.lo_ptr
-        # deferred accumulation (see ccx_lstm_tf_bwd): per-step records, summed over time once after the loop
-        bd.dawe_all, bd.dalpha_all, bd.de_all = ptr(dawe_all), ptr(dalpha_all[0]), ptr(dalpha_all[1])
-        _lib.check(L.ccx_lstm_tf_backward(ctypes.byref(fwd), ctypes.byref(bd), st), "lstm_tf_backward")
+        persist = S.get("awe_all") is not None
+        if persist:
+            # BPTT as ONE cooperative kernel (csrc/lstm_persist.cu) + the two deferred attention sums
+            (dG_all, dHG_all, d_att1, d_enc, d_wf, dawe_all, de_all) = zeros_many(
+                [(T, B, 4 * D), (T, B, A + E), (B * Pn, A), (B, Pn, E), (A,), (T, B, E), (T, B, Pn)], dev)
+            dc, dh = torch.empty((B, D), **f32), torch.empty((B, D), **f32)
+            dG_bf = torch.zeros((T, B, 4 * D), dtype=torch.bfloat16, device=dev)
+            scratch = torch.empty(T * 229376, dtype=torch.uint8, device=dev)
+            Xp = torch.empty(2 * 8 * B * E + 2 * 4 * B * D, **f32)
+            counters = torch.empty(4 * (T + 1), dtype=torch.int32, device=dev)
+            if not need_enc:
+                d_enc = None
+            dal = None if dalphas is None else dalphas.contiguous()
+            fwd = dec._loop_desc(Pw, enc, att1, XH, C_all, HG, G, alphas, H_all, dm, bts)
+            bd = _lib.LstmTFBwd()
+            bd.dH_all, bd.dalphas = ptr(dH_all), ptr(dal)
+            bd.dG_all, bd.dHG_all = ptr(dG_all), ptr(dHG_all)
+            bd.dh, bd.dc, bd.d_att1, bd.d_enc, bd.d_wf = ptr(dh), ptr(dc), ptr(d_att1), ptr(d_enc), ptr(d_wf)
+            bd.dawe_all, bd.de_all = ptr(dawe_all), ptr(de_all)
+            pb = _lib.LstmPersistBwd()
+            pb.wx, pb.wht, pb.dG_bf, pb.scratch, pb.Xp = ptr(Pw["wx"].hi), ptr(Pw["wht"].hi), ptr(dG_bf), ptr(
+                scratch), ptr(Xp)
+            pb.awe_all, pb.att1_bf, pb.enc_bf = ptr(S["awe_all"]), ptr(S["att1_bf"]), ptr(S["enc_op"].hi)
+            pb.decode_len, pb.counters = ptr(S["decode_lengths_dev"]), ptr(counters)
+            if dec._persist_dbg is not None:
+                dec._persist_dbg = torch.zeros((3, T, 8), dtype=torch.int64, device=dev)
+                pb.dbg = ptr(dec._persist_dbg)
+            _lib.check(L.ccx_lstm_tf_backward_persist(ctypes.byref(fwd), ctypes.byref(bd), ctypes.byref(pb), st),
+                       "lstm_tf_backward_persist")
+            # d emb_t = dgates_t . W_ih[:, :Emb], all steps in one GEMM
+            d_emb = _lib.linear(Operand(dG_bf.view(T * B, 4 * D), None, torch.bfloat16), Pw["w_emb_t"])
+            emb_grad_src = (d_emb, Emb, B * Emb)
+        else:
+            dG_all, dHG_all, d_att1, d_enc, d_wf, dc, dh, emb_grad_src = _bptt_launch_loop(
+                dec, S, dH_all, dalphas, need_enc, cd, dev)
         # ---- weight gradients, batched over time -------------------------------------------------------------
+        gw_lstm, gb_lstm, gw_h, gb_h = zeros_many([(4 * D, K), (4 * D,), (A + E, D), (A + E,)], dev)
         TB = T * B
         x_all = XH.map(lambda x: x[:T].view(TB, K))
         if g("decode_step.weight_ih") is not None:
@@ -94,7 +139,8 @@ class _LstmTF(torch.autograd.Function):
         ge = g("embedding.weight")
         if ge is not None:
             caps = S["caps"]
-            _lib.check(L.ccx_embedding_bwd(ptr(caps), caps.stride(0), 0, ptr(dXH_all), K, B * K, None, ptr(ge), V,
+            dx, sb, stt = emb_grad_src
+            _lib.check(L.ccx_embedding_bwd(ptr(caps), caps.stride(0), 0, ptr(dx), sb, stt, None, ptr(ge), V,
                                            Emb, B, T, st), "embedding_bwd")
         # ---- initial state and hoisted encoder_att -------------------------------------------------------------
         dmean = linear_bwd(dh, S["m_op"], weight_t(dec.init_h.weight, cd), cd, g("init_h.weight"), g("init_h.bias"),

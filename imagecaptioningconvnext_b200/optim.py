@@ -2,7 +2,9 @@
 update (trainMultiGPU.py:387-394) in ONE multi-tensor kernel launch per parameter group (``ccx_adam_clamp``).
 
 State layout and ``state_dict`` keys equal torch.optim.Adam's (``step``, ``exp_avg``, ``exp_avg_sq``), so optimizer
-states from reference checkpoints load unchanged.  No weight decay / amsgrad (the reference uses neither).
+states from reference checkpoints (``torch.optim.Adam.state_dict()``, trainMultiGPU.py:218,223) load unchanged:
+``load_state_dict`` fills in the ``grad_clip`` key those lack and refuses ``weight_decay`` / ``amsgrad`` states, which
+this kernel does not implement (the reference uses neither).
 """
 import math
 
@@ -21,8 +23,32 @@ class ClampAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_clip=grad_clip, foreach=True))
         self._tables = {}
 
+    # ---- checkpoint compatibility ------------------------------------------------------------------------------
+    def _normalise_groups(self):
+        """A torch.optim.Adam state_dict carries no 'grad_clip' and may carry options this kernel does not have."""
+        for group in self.param_groups:
+            group.setdefault("grad_clip", self.defaults["grad_clip"])
+            group.setdefault("foreach", True)
+            if group.get("weight_decay", 0) not in (0, 0.0, None):
+                raise ValueError("ClampAdam: weight_decay is not implemented (the reference trains without it)")
+            if group.get("amsgrad", False):
+                raise ValueError("ClampAdam: amsgrad is not implemented (the reference trains without it)")
+            if group.get("maximize", False):
+                raise ValueError("ClampAdam: maximize is not implemented")
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._normalise_groups()
+        self._tables = {}            # the moment tensors were replaced: cached device pointers are stale
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}            # Optimizer.__getstate__ only keeps defaults / state / param_groups
+        self._normalise_groups()
+
     def _table(self, gi, ps):
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p in ps)
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == key:
             return cached[1:]
@@ -46,10 +72,10 @@ class ClampAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         for gi, group in enumerate(self.param_groups):
-            ps = [p for p in group["params"] if p.grad is not None]
-            if not ps:
+            all_ps = [p for p in group["params"] if p.grad is not None]
+            if not all_ps:
                 continue
-            for p in ps:
+            for p in all_ps:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
                     raise ValueError("ClampAdam needs contiguous float32 CUDA parameters and gradients")
                 stt = self.state[p]
@@ -57,14 +83,22 @@ class ClampAdam(torch.optim.Optimizer):
                     stt["step"] = torch.tensor(0.0)
                     stt["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     stt["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if not torch.is_tensor(stt["step"]):           # very old checkpoints store a python int
+                    stt["step"] = torch.tensor(float(stt["step"]))
                 stt["step"] += 1
-            step = int(self.state[ps[0]]["step"])
+            # torch.optim.Adam keeps one step count per parameter (bias correction): parameters whose first gradient
+            # came later (fine_tune() switched on mid-run) are launched apart, one launch per distinct step value
+            by_step = {}
+            for p in all_ps:
+                by_step.setdefault(int(self.state[p]["step"]), []).append(p)
             b1, b2 = group["betas"]
-            table, be, bo, nblk, total = self._table(gi, ps)
-            clip = group["grad_clip"] if group["grad_clip"] is not None else 0.0
-            _lib.check(_lib.lib().ccx_adam_clamp(ptr(table), ptr(be), ptr(bo), nblk, group["lr"], b1, b2, group["eps"],
-                                                 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step), clip, _CHUNK, total,
-                                                 _lib.stream_ptr()), "adam_clamp")
-            for p in ps:          # the weights changed behind torch's back: invalidate kernel-side copies
+            clip = group.get("grad_clip")
+            clip = clip if clip is not None else 0.0
+            for step, ps in by_step.items():
+                table, be, bo, nblk, total = self._table((gi, step if len(by_step) > 1 else -1), ps)
+                _lib.check(_lib.lib().ccx_adam_clamp(ptr(table), ptr(be), ptr(bo), nblk, group["lr"], b1, b2,
+                                                     group["eps"], 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step), clip,
+                                                     _CHUNK, total, _lib.stream_ptr()), "adam_clamp")
+            for p in all_ps:      # the weights changed behind torch's back: invalidate kernel-side copies
                 p._ccx_epoch = getattr(p, "_ccx_epoch", 0) + 1
         return loss

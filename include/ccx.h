@@ -429,6 +429,52 @@ typedef struct ccx_lstm_tf_bwd {
 } ccx_lstm_tf_bwd;
 CCX_API int ccx_lstm_tf_backward(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, void* stream);
 
+/* Persistent form of the two loops above (bf16 compute, B <= 32, P*(A+E)*2 bytes of one sample resident in one
+ * CTA's shared memory, A = D = Emb = 512, E = 1024 — ccx_lstm_persist_supported() tells): ONE cooperative kernel per
+ * direction; the recurrent weights stay in shared memory, every GEMM is a swap-AB tcgen05.mma (weights = M side,
+ * batch = N = 32, accumulator in TMEM) and the CTA roles hand over through release/acquire counters instead of
+ * kernel boundaries (csrc/lstm_persist.cu).  Replaces models/decoder.py:100-111 (and its autograd graph) exactly like
+ * ccx_lstm_tf_forward / _backward and fills the same buffers.  Extra inputs:
+ *   E_all   [T][B][4D] fp32: hoisted emb_t . W_ih[:, :Emb]^T + b_ih + b_hh with columns in the PERMUTED gate order
+ *           col = 32*(j/8) + 8*gate + j%8  for hidden unit j (the row order of w2p),
+ *   w2p     [4D][D+E] bf16: rows in that permuted order, columns [W_hh | W_ih[:, Emb:]],
+ *   att1_bf [B*P][A], enc_bf [B*P][E] bf16; decode_len [B] (sorted descending, = caption length - 1),
+ *   counters: >= 4*(T+1) int32 of scratch (cleared by the call). */
+typedef struct ccx_lstm_persist {
+  const float* E_all;
+  const void* w2p;
+  const void* att1_bf;
+  const void* enc_bf;
+  const int64_t* decode_len;
+  int32_t* counters;
+  void* scratch;  /* (T+1)*32 KB + T*64 KB + 1.5 MB, 128-byte aligned: per-step operand images (h, gated awe) and the K-quarter partial sums of the attention projections; no init needed */
+  float* awe_all; /* [T][B][E] out: un-gated context vectors (what the backward kernel needs), or NULL */
+  int64_t* dbg;   /* optional [3][T][8] clock64 stamps of one CTA per role (tools/bench_lstm_persist.py), or NULL */
+} ccx_lstm_persist;
+CCX_API int ccx_lstm_persist_supported(int32_t B, int32_t P, int32_t E, int32_t A, int32_t D, int32_t Emb,
+                                       int32_t compute_dtype);
+CCX_API int ccx_lstm_tf_forward_persist(const ccx_lstm_tf* s, const ccx_lstm_persist* p, void* stream);
+
+/* BPTT as one cooperative kernel (+ the two deferred d_enc / d_att1 sums): fills dG_all, dHG_all, dawe_all, de_all,
+ * d_wf (+=), dh / dc (dL/dh_0, dL/dc_0), d_att1 / d_enc (+=) of ccx_lstm_tf_bwd exactly like ccx_lstm_tf_backward;
+ * dXH_all, the w_*_t operands and the scratch operands of that struct are not used (the embedding gradient comes
+ * from dG_bf . W_ih[:, :Emb] as one GEMM after the call).  awe_all / att1_bf / enc_bf / decode_len as in the forward. */
+typedef struct ccx_lstm_persist_bwd {
+  const void* wx;   /* [E+D][4D] bf16: rows = [W_ih[:, Emb:]^T ; W_hh^T] */
+  const void* wht;  /* [D][A+E] bf16: [decoder_att ; f_beta]^T */
+  void* dG_bf;      /* [T][B][4D] bf16 out (dgates as a row-major GEMM operand); zero-initialised by the caller */
+  void* scratch;    /* T*224 KB, 128-byte aligned: per-step operand images (dgates, d[att2|gate]); no init needed */
+  float* Xp;        /* 2*8*B*E + 2*4*B*D fp32 of scratch (K-slice partial sums) */
+  const float* awe_all;
+  const void* att1_bf;
+  const void* enc_bf;
+  const int64_t* decode_len;
+  int32_t* counters; /* >= 4*(T+1) int32, cleared by the call */
+  int64_t* dbg;
+} ccx_lstm_persist_bwd;
+CCX_API int ccx_lstm_tf_backward_persist(const ccx_lstm_tf* s, const ccx_lstm_tf_bwd* b, const ccx_lstm_persist_bwd* p,
+                                         void* stream);
+
 /* clip_gradient (grad.clamp_(-clip, clip), utils/utils.py:189-192) fused with torch.optim.Adam's single-tensor
  * update (no weight decay / amsgrad), over a device table of {param, grad, exp_avg, exp_avg_sq, n} entries;
  * block i handles elements [block_offset[i], +chunk) of entry block_entry[i]. */

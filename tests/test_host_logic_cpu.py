@@ -88,3 +88,39 @@ def test_encoder_fine_tune_marks_the_same_parameters_as_the_reference(golden_dir
         assert trainable() == g[L], L
     enc.fine_tune(False)
     assert trainable() == g["off"] == []
+
+
+def test_clamp_adam_loads_a_reference_adam_state_dict_and_survives_pickling():
+    """The reference resumes with optimizer.load_state_dict(checkpoint[...]) of a torch.optim.Adam state
+    (trainMultiGPU.py:218,223): no 'grad_clip' key there; pickled ClampAdam objects (torch.save of the optimizer)
+    must come back with their pointer-table cache; weight decay / amsgrad states are refused, not silently ignored."""
+    import copy
+    import pickle
+
+    import pytest
+
+    from imagecaptioningconvnext_b200.optim import ClampAdam
+    w = [torch.nn.Parameter(torch.ones(4, 3)), torch.nn.Parameter(torch.ones(5))]
+    ref = torch.optim.Adam(w, lr=1e-4)
+    for p in w:
+        p.grad = torch.ones_like(p)
+    ref.step()
+    sd = copy.deepcopy(ref.state_dict())
+    assert "grad_clip" not in sd["param_groups"][0]
+    opt = ClampAdam(w, lr=3e-4, grad_clip=5.0)
+    opt._tables[0] = ("stale",)
+    opt.load_state_dict(sd)
+    g = opt.param_groups[0]
+    assert g["grad_clip"] == 5.0 and g["lr"] == 1e-4 and opt._tables == {}
+    assert torch.equal(opt.state[w[0]]["exp_avg"], ref.state[w[0]]["exp_avg"])
+    assert float(opt.state[w[1]]["step"]) == 1.0
+    clone = pickle.loads(pickle.dumps(opt))
+    assert clone._tables == {} and clone.param_groups[0]["grad_clip"] == 5.0
+    bad = copy.deepcopy(sd)
+    bad["param_groups"][0]["weight_decay"] = 0.01
+    with pytest.raises(ValueError):
+        ClampAdam(w, lr=1e-4).load_state_dict(bad)
+    bad = copy.deepcopy(sd)
+    bad["param_groups"][0]["amsgrad"] = True
+    with pytest.raises(ValueError):
+        ClampAdam(w, lr=1e-4).load_state_dict(bad)

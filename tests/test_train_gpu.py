@@ -215,6 +215,47 @@ def test_clamp_adam_matches_clip_gradient_plus_torch_adam():
     assert set(our_opt.state_dict()["state"][0]) == set(ref_opt.state_dict()["state"][0])
 
 
+def test_clamp_adam_resumes_from_a_torch_adam_checkpoint_and_tracks_per_parameter_steps():
+    """Resume flow of the reference (trainMultiGPU.py:218,223: optimizer.load_state_dict of a torch.optim.Adam state),
+    then keep stepping: the loaded moments must be the ones updated (not stale buffers), and a parameter whose first
+    gradient arrives later (Encoder.fine_tune switched on mid-run) gets its own bias correction like torch's."""
+    import copy
+
+    from imagecaptioningconvnext_b200.optim import ClampAdam
+    g = torch.Generator().manual_seed(1)
+    shapes = [(64, 33), (700,), (20000,)]
+    ref_p = [torch.randn(*s, generator=g).requires_grad_(True) for s in shapes]
+    our_p = [p.detach().clone().cuda().requires_grad_(True) for p in ref_p]
+    ref_opt = torch.optim.Adam(ref_p, lr=1e-2)
+    our_opt = ClampAdam(our_p, lr=1e-2, grad_clip=5.0)
+
+    def step(active):
+        for i, (rp, op) in enumerate(zip(ref_p, our_p)):
+            if i in active:
+                grad = torch.randn(rp.shape, generator=g) * 4.0
+                rp.grad, op.grad = grad.clone().clamp_(-5.0, 5.0), grad.cuda()
+            else:
+                rp.grad, op.grad = None, None
+        ref_opt.step()
+        our_opt.step()
+
+    step({0, 1})                        # parameter 2 joins two steps late
+    step({0, 1})
+    step({0, 1, 2})
+    # checkpoint the torch optimizer, resume ours from it (after it has already stepped: its cached table is live)
+    sd = copy.deepcopy(ref_opt.state_dict())
+    sd["state"] = {k: {n: (v.cuda() if torch.is_tensor(v) and v.dim() > 0 else v) for n, v in st.items()}
+                   for k, st in sd["state"].items()}
+    our_opt.load_state_dict(sd)
+    step({0, 1, 2})
+    step({0, 1, 2})
+    for rp, op in zip(ref_p, our_p):
+        assert rel_err(op, rp) < 1e-6
+    for i, (rp, op) in enumerate(zip(ref_p, our_p)):
+        assert rel_err(our_opt.state[op]["exp_avg"], ref_opt.state[rp]["exp_avg"]) < 1e-6
+        assert float(our_opt.state[op]["step"]) == float(ref_opt.state[rp]["step"])
+
+
 @pytest.mark.parametrize("dtype,train_mode,start", [(torch.float32, False, 7), (torch.float32, True, 7),
                                                     (torch.bfloat16, False, 7), (torch.bfloat16, True, 7),
                                                     (torch.float32, True, 5), (torch.float32, False, 2),
