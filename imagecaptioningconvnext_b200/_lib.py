@@ -112,6 +112,7 @@ SIGNATURES = {
                               _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
                               _f32, _vp]),
     "ccx_softmax_ce": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "ccx_softmax_ce_dev": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
     "ccx_free_running_targets": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp]),
     "ccx_embedding_bwd": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "ccx_lstm_pointwise_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i32, _i32,
@@ -133,6 +134,7 @@ SIGNATURES = {
                                                 _vp]),
     "ccx_adam_clamp": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _i32, C.c_double,
                                  _vp]),
+    "ccx_adam_clamp_dev": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _f32, _f32, _f32, _vp, _f32, _i32, C.c_double, _vp]),
     "ccx_prof_begin": (C.c_int, []),
     "ccx_prof_spans": (C.c_int, [C.POINTER(_i32), C.POINTER(C.c_double), C.POINTER(C.c_double), _i32]),
     "ccx_prof_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64), _i32]),

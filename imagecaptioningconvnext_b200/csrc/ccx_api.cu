@@ -199,6 +199,13 @@ int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int6
   return softmax_ce(logits, ld, reinterpret_cast<const long long*>(targets), R, V, inv_n, loss_sum, dlogits, ldd,
                     stats, topk, as_stream(stream));
 }
+int ccx_softmax_ce_dev(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V,
+                       const float* n_valid_dev, float* loss_sum, float* dlogits, int64_t ldd, float* stats,
+                       int32_t topk, void* stream) {
+  if (n_valid_dev == nullptr) return CCX_ERR_SHAPE;
+  return softmax_ce(logits, ld, reinterpret_cast<const long long*>(targets), R, V, 1.0f, loss_sum, dlogits, ldd,
+                    stats, topk, as_stream(stream), n_valid_dev);
+}
 int ccx_free_running_targets(const int64_t* sequences, const int64_t* caps, int64_t cap_ld, int64_t* targets,
                              int32_t* decode_len, int32_t B, int32_t T, int32_t cap_T, int64_t end_tok,
                              int64_t pad_tok, void* stream) {
@@ -235,6 +242,14 @@ int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t*
                    int32_t chunk, double total_params, void* stream) {
   return adam_clamp(table, block_entry, reinterpret_cast<const long long*>(block_offset), n_blocks, lr, beta1, beta2,
                     eps, bc1, bc2_sqrt, clip, chunk, total_params, as_stream(stream));
+}
+
+int ccx_adam_clamp_dev(const void* table, const int32_t* block_entry, const int64_t* block_offset, int32_t n_blocks,
+                       float lr, float beta1, float beta2, float eps, const float* step_dev, float clip,
+                       int32_t chunk, double total_params, void* stream) {
+  if (step_dev == nullptr) return CCX_ERR_SHAPE;
+  return adam_clamp(table, block_entry, reinterpret_cast<const long long*>(block_offset), n_blocks, lr, beta1, beta2,
+                    eps, 1.f, 1.f, clip, chunk, total_params, as_stream(stream), step_dev);
 }
 
 int ccx_attn_head_mean(const float* probs, int64_t p_sb, int64_t p_sh, int64_t p_st, const float* prob_mask,

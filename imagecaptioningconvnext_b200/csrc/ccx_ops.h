@@ -73,7 +73,8 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
             long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
             int Tk, int hd, float scale, cudaStream_t stream);
 int softmax_ce(const float* logits, long long ld, const long long* targets, long long R, int V, float inv_n,
-               float* loss_sum, float* dlogits, long long ldd, float* stats, int topk, cudaStream_t stream);
+               float* loss_sum, float* dlogits, long long ldd, float* stats, int topk, cudaStream_t stream,
+               const float* n_valid_dev = nullptr);
 int free_running_targets(const long long* sequences, const long long* caps, long long cap_ld, long long* targets,
                          int* decode_len, int B, int T, int cap_T, long long end_tok, long long pad_tok,
                          cudaStream_t stream);
@@ -98,7 +99,7 @@ int bahdanau_attention_bwd(const float* att1, const float* hg, long long ldhg, c
 int bcast_add_rows(float* out, const float* v, float scale, int B, int P, int E, cudaStream_t stream);
 int adam_clamp(const void* table, const int* block_entry, const long long* block_offset, int n_blocks, float lr,
                float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip, int chunk,
-               double total_params, cudaStream_t stream);
+               double total_params, cudaStream_t stream, const float* step_dev = nullptr);
 
 // encoder_bwd.cu
 int scale_rows_cols(const float* x, const float* colscale, const float* rowscale, int rows_per_group, float* out,

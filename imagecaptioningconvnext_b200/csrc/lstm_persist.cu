@@ -116,6 +116,12 @@ __device__ __forceinline__ void wait_counter(const int* p, int target, int tag) 
   [[maybe_unused]] int v;      // the acquire that pairs with the producers' red.release (cheaper than a full fence.acq_rel.gpu)
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 }
+// Time steps the recurrence really has: T is the extent of the step buffers (the longest caption the CALLER allows for,
+// e.g. always 51 under CUDA-graph replay), the rows are sorted by length, so row 0 holds the longest decode length.
+__device__ __forceinline__ int steps_to_run(int T, const long long* decode_len) {
+  const long long d0 = decode_len[0];
+  return d0 < T ? static_cast<int>(d0 < 0 ? 0 : d0) : T;
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -268,9 +274,10 @@ __device__ void fwd_role_g1(const FwdArgs& a, const CUtensorMap* tm_wh, int idx,
   const int row = rt * 128 + threadIdx.x;
   const float bias = kq == 0 ? __ldg(a.b_h + row) : 0.f;
   const long long dl = lane < a.B ? a.decode_len[lane] : 0;
+  const int Tn = steps_to_run(a.T, a.decode_len);
   long long* dbg = idx == 0 && threadIdx.x == 0 ? a.dbg : nullptr;
   const uint32_t wlo = desc_lo(smem_w), blo = desc_lo(smem_b);
-  for (int t = 0; t < a.T; ++t) {
+  for (int t = 0; t < Tn; ++t) {
     const int bt = __popc(__ballot_sync(0xffffffffu, dl > t));
     if (threadIdx.x == 0) {
       dbg_stamp(dbg, smem, t, 0);
@@ -343,6 +350,7 @@ __device__ void fwd_role_g2(const FwdArgs& a, const CUtensorMap* tm_w2, int tile
   const int jj = tid & 7, b = tid >> 3;            // this thread's (hidden unit, batch row)
   const int unit = tile * 8 + jj;
   const long long dl = lane < a.B ? a.decode_len[lane] : 0;
+  const int Tn = steps_to_run(a.T, a.decode_len);
   float c = b < a.B ? a.C_all[static_cast<long long>(b) * D + unit] : 0.f;
   const uint32_t hoff_img = img_off(b, unit);
   // h_0 (written row-major by the init_h GEMM) -> operand image 0
@@ -353,7 +361,7 @@ __device__ void fwd_role_g2(const FwdArgs& a, const CUtensorMap* tm_w2, int tile
   mbar_wait(bar_w, 0);
   long long* dbg = tile == 0 && tid == 0 ? a.dbg : nullptr;
   const uint32_t sw = smem_u32(smem_w), sb = smem_u32(smem_b);
-  for (int t = 0; t < a.T; ++t) {
+  for (int t = 0; t < Tn; ++t) {
     const int bt = __popc(__ballot_sync(0xffffffffu, dl > t));
     const bool live = b < bt;
     // what does not depend on the recurrence is fetched first: hoisted emb-part gates and the dropout multiplier
@@ -706,9 +714,10 @@ __device__ void bwd_role_x(const BwdArgs& a, const CUtensorMap* tm_wx, int row0,
     mbar_wait(bar_w, 0);
   }
   long long* dbg = dbg_on && threadIdx.x == 0 ? a.dbg : nullptr;
+  const int Tn = steps_to_run(a.T, a.decode_len);
   const uint32_t wlo = desc_lo(smem_w), blo = desc_lo(smem_b);
-  for (int it = 0; it < a.T; ++it) {
-    const int t = a.T - 1 - it;
+  for (int it = 0; it < Tn; ++it) {
+    const int t = Tn - 1 - it;
     if (threadIdx.x == 0) {
       dbg_stamp(dbg, smem, t, 0);
       wait_counter(a.cnt_dg + t, N_HP, 40);
@@ -828,12 +837,13 @@ __device__ void bwd_role_hp(const BwdArgs& a, const CUtensorMap* tm_wht, int til
   const int u = tid & 15, bq = tid >> 4;            // unit within the tile; batch rows bq, bq+8, bq+16, bq+24
   const int j = tile * 16 + u;
   const long long dl = lane < a.B ? a.decode_len[lane] : 0;
+  const int Tn = steps_to_run(a.T, a.decode_len);
   float dc[4] = {0.f, 0.f, 0.f, 0.f};
   long long* dbg = tile == 0 && tid == 0 ? a.dbg : nullptr;
   const uint32_t sw = smem_u32(smem_w), sb = smem_u32(smem_b);
   // prologue: point-wise backward of the last step (no recurrent gradient yet)
   {
-    const int tp = a.T - 1;
+    const int tp = Tn - 1;
     const int btp = __popc(__ballot_sync(0xffffffffu, dl > tp));
     PwOut po[4];
 #pragma unroll
@@ -850,8 +860,8 @@ __device__ void bwd_role_hp(const BwdArgs& a, const CUtensorMap* tm_wht, int til
     }
   }
   mbar_wait(bar_w, 0);
-  for (int it = 0; it < a.T; ++it) {
-    const int t = a.T - 1 - it;
+  for (int it = 0; it < Tn; ++it) {
+    const int t = Tn - 1 - it;
     const int bt = __popc(__ballot_sync(0xffffffffu, dl > t));
     const int btp = t > 0 ? __popc(__ballot_sync(0xffffffffu, dl > t - 1)) : 0;
     // forward-pass factors of step t-1 do not depend on the recurrence: compute them before waiting

@@ -364,10 +364,11 @@ int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ targets, int V,
-                  float inv_n, float* __restrict__ loss_sum, float* __restrict__ dlogits, long long ldd,
-                  float* __restrict__ stats, int topk) {
+                  float inv_n, const float* __restrict__ n_valid_dev, float* __restrict__ loss_sum,
+                  float* __restrict__ dlogits, long long ldd, float* __restrict__ stats, int topk) {
   __shared__ float red[8], red2[8];
   __shared__ float s_b, s_c;
+  if (n_valid_dev != nullptr) inv_n = 1.0f / fmaxf(__ldg(n_valid_dev), 1.0f);   // row count known only on the device
   const long long r = blockIdx.x;
   const long long tgt = targets[r];
   float* drow = dlogits ? dlogits + r * ldd : nullptr;
@@ -419,11 +420,12 @@ softmax_ce_kernel(const float* __restrict__ logits, long long ld, const long lon
 }
 
 int softmax_ce(const float* logits, long long ld, const long long* targets, long long R, int V, float inv_n,
-               float* loss_sum, float* dlogits, long long ldd, float* stats, int topk, cudaStream_t stream) {
+               float* loss_sum, float* dlogits, long long ldd, float* stats, int topk, cudaStream_t stream,
+               const float* n_valid_dev) {
   if (R <= 0) return CCX_OK;
   ProfScope prof(PROF_LOSS, stream, (double)R * V * (dlogits ? 8.0 : 4.0));
-  softmax_ce_kernel<<<static_cast<unsigned>(R), 256, 0, stream>>>(logits, ld, targets, V, inv_n, loss_sum, dlogits,
-                                                                 ldd, stats, topk);
+  softmax_ce_kernel<<<static_cast<unsigned>(R), 256, 0, stream>>>(logits, ld, targets, V, inv_n, n_valid_dev, loss_sum,
+                                                                 dlogits, ldd, stats, topk);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
@@ -841,7 +843,12 @@ struct AdamEntry {
 __global__ void __launch_bounds__(256)
 adam_clamp_kernel(const AdamEntry* __restrict__ table, const int* __restrict__ block_entry,
                   const long long* __restrict__ block_offset, float lr, float beta1, float beta2, float eps,
-                  float bc1, float bc2_sqrt, float clip, int chunk) {
+                  float bc1, float bc2_sqrt, float clip, int chunk, const float* __restrict__ step_dev) {
+  if (step_dev != nullptr) {       // step count kept on the device (CUDA-graph replay: no host value can be baked in)
+    const float t = __ldg(step_dev);
+    bc1 = 1.f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, t));
+  }
   const AdamEntry e = table[block_entry[blockIdx.x]];
   const long long begin = block_offset[blockIdx.x];
   const long long end = min(e.n, begin + chunk);
@@ -887,11 +894,12 @@ adam_clamp_kernel(const AdamEntry* __restrict__ table, const int* __restrict__ b
 
 int adam_clamp(const void* table, const int* block_entry, const long long* block_offset, int n_blocks, float lr,
                float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float clip, int chunk,
-               double total_params, cudaStream_t stream) {
+               double total_params, cudaStream_t stream, const float* step_dev) {
   if (n_blocks <= 0) return CCX_OK;
   ProfScope prof(PROF_OPTIM, stream, total_params * 28.0);
   adam_clamp_kernel<<<n_blocks, 256, 0, stream>>>(reinterpret_cast<const AdamEntry*>(table), block_entry,
-                                                  block_offset, lr, beta1, beta2, eps, bc1, bc2_sqrt, clip, chunk);
+                                                  block_offset, lr, beta1, beta2, eps, bc1, bc2_sqrt, clip, chunk,
+                                                  step_dev);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

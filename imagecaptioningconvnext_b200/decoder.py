@@ -119,6 +119,7 @@ class DecoderWithAttention(nn.Module):
         self._cache = PreparedCache(self)
         self.use_persist = os.environ.get("CCX_LSTM_PERSIST", "1") != "0"
         self._persist_dbg = None
+        self.fixed_T = False          # True: step buffers always span captions.shape[1] - 1 steps (CUDA-graph replay)
         self.inject_dropmask = None   # tests: (B, T, decoder_dim) multiplier used instead of a fresh Bernoulli draw
 
     def init_weights(self):
@@ -279,6 +280,12 @@ class DecoderWithAttention(nn.Module):
         decode_lengths_dev = caption_lengths - 1                                # the same values, on the device
         stash_device_twin(decode_lengths, decode_lengths_dev)
         T = max(decode_lengths)
+        if self.fixed_T:
+            # static shapes for CUDA-graph replay: buffers span every possible step; the kernels stop at the longest
+            # caption of the batch (read from the device) and rows / steps past a caption's length stay zero
+            if not self._persist_ok(B, Pn):
+                raise ValueError("fixed_T needs the persistent recurrence kernel (bf16, B <= 32, 7x7 features)")
+            T = encoded_captions.shape[1] - 1
         L, st, cd = _lib.lib(), _lib.stream_ptr(), self.compute_dtype
         code = _lib.dt_code(cd)
 

@@ -9,25 +9,36 @@ from ._lib import ptr
 
 class _PackedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, scores, targets, n_valid):
+    def forward(ctx, scores, targets, n_valid, unit_grad):
+        """n_valid: number of scored rows — a python number, or a float32 DEVICE tensor (then nothing about the
+        caption lengths is needed on the host: CUDA-graph replay).  unit_grad: the caller guarantees that the loss
+        enters ``backward()`` with gradient 1 (``(ce + regulariser).backward()`` as in trainMultiGPU.py:367-384), so
+        the stored d logits are returned as they are instead of being multiplied by the incoming gradient (a full
+        extra pass over the B x T x V tensor)."""
         B, T, V = scores.shape
         s2 = scores.contiguous().view(B * T, V)
         loss = torch.zeros(1, dtype=torch.float32, device=scores.device)
         need_grad = scores.requires_grad
         dlogits = torch.empty_like(s2) if need_grad else None
-        _lib.check(_lib.lib().ccx_softmax_ce(ptr(s2), V, ptr(targets), B * T, V, 1.0 / n_valid, ptr(loss),
-                                             ptr(dlogits), V, None, 0, _lib.stream_ptr()), "softmax_ce")
-        ctx.dlogits, ctx.shape = dlogits, scores.shape
+        if torch.is_tensor(n_valid):
+            _lib.check(_lib.lib().ccx_softmax_ce_dev(ptr(s2), V, ptr(targets), B * T, V, ptr(n_valid), ptr(loss),
+                                                     ptr(dlogits), V, None, 0, _lib.stream_ptr()), "softmax_ce_dev")
+        else:
+            _lib.check(_lib.lib().ccx_softmax_ce(ptr(s2), V, ptr(targets), B * T, V, 1.0 / n_valid, ptr(loss),
+                                                 ptr(dlogits), V, None, 0, _lib.stream_ptr()), "softmax_ce")
+        ctx.dlogits, ctx.shape, ctx.unit_grad = dlogits, scores.shape, unit_grad
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        return ctx.dlogits.view(ctx.shape) * g, None, None
+        d = ctx.dlogits.view(ctx.shape)
+        return (d if ctx.unit_grad else d * g), None, None, None
 
 
-def packed_cross_entropy(scores, captions, decode_lengths):
+def packed_cross_entropy(scores, captions, decode_lengths, n_valid_dev=None, unit_grad=False):
     """scores (B, T, V) logits; captions (B, Tc) token ids aligned with `scores` rows; targets are captions[:, 1:]
-    restricted to the first decode_lengths[b] positions of row b (the reference's pack_padded_sequence + CE)."""
+    restricted to the first decode_lengths[b] positions of row b (the reference's pack_padded_sequence + CE).
+    n_valid_dev / unit_grad: see _PackedCE.forward."""
     B, T, V = scores.shape
     dev = scores.device
     dl = device_twin(decode_lengths, dev)
@@ -36,7 +47,8 @@ def packed_cross_entropy(scores, captions, decode_lengths):
         tgt = torch.nn.functional.pad(tgt, (0, T - tgt.shape[1]), value=0)
     valid = torch.arange(T, device=dev).unsqueeze(0) < dl.unsqueeze(1)
     targets = torch.where(valid, tgt, torch.full_like(tgt, -1)).contiguous().view(-1)
-    return _PackedCE.apply(scores, targets, float(sum(decode_lengths)))
+    return _PackedCE.apply(scores, targets, float(sum(decode_lengths)) if n_valid_dev is None else n_valid_dev,
+                           unit_grad)
 
 
 def packed_targets(captions, decode_lengths, T):
@@ -85,4 +97,4 @@ def free_running_cross_entropy(scores, sequences, captions, end_token, pad_token
     ground-truth token is not <pad>.  Returns (loss with autograd, targets (B*T,) with -1 = ignored, token count)."""
     targets, _ = free_running_targets(sequences, captions, end_token, pad_token)
     n_valid = int((targets >= 0).sum())                  # the reference syncs here too (totalValidTokenCount)
-    return _PackedCE.apply(scores, targets, float(max(n_valid, 1))), targets, n_valid
+    return _PackedCE.apply(scores, targets, float(max(n_valid, 1)), False), targets, n_valid

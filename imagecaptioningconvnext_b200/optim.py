@@ -22,6 +22,37 @@ class ClampAdam(torch.optim.Optimizer):
         # instead of one fill kernel per parameter (40 launches per step for the fine-tuned encoder + LSTM decoder)
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, grad_clip=grad_clip, foreach=True))
         self._tables = {}
+        self._dev_steps = None     # capturable mode: {group index: float32 [1] device tensor holding the step count}
+
+    def make_capturable(self):
+        """Keep the step count on the DEVICE (like torch.optim.Adam(capturable=True)) so that ``step()`` can be
+        recorded into a CUDA graph: the bias corrections are then computed inside the kernel from that tensor and
+        nothing host-side is baked into the launch.  All parameters of a group must share one step count.  The
+        per-parameter ``state['step']`` entries are brought up to date by ``sync_step_counts()`` (state_dict() calls
+        it), since a graph replay does not run this Python code."""
+        self._dev_steps = {}
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.requires_grad]
+            steps = {int(self.state[p]["step"]) for p in ps if len(self.state[p])}
+            if len(steps) > 1:
+                raise ValueError("ClampAdam.make_capturable: parameters of one group have different step counts")
+            dev = ps[0].device if ps else torch.device("cuda")
+            self._dev_steps[gi] = torch.full((1,), float(steps.pop() if steps else 0), dtype=torch.float32, device=dev)
+        return self
+
+    def sync_step_counts(self):
+        """capturable mode: copy the device step counts into the torch.optim.Adam-style per-parameter state."""
+        if self._dev_steps is None:
+            return
+        for gi, group in enumerate(self.param_groups):
+            t = float(self._dev_steps[gi].item())
+            for p in group["params"]:
+                if len(self.state[p]):
+                    self.state[p]["step"] = torch.tensor(t)
+
+    def state_dict(self):
+        self.sync_step_counts()
+        return super().state_dict()
 
     # ---- checkpoint compatibility ------------------------------------------------------------------------------
     def _normalise_groups(self):
@@ -40,10 +71,13 @@ class ClampAdam(torch.optim.Optimizer):
         super().load_state_dict(state_dict)
         self._normalise_groups()
         self._tables = {}            # the moment tensors were replaced: cached device pointers are stale
+        if self._dev_steps is not None:
+            self.make_capturable()
 
     def __setstate__(self, state):
         super().__setstate__(state)
         self._tables = {}            # Optimizer.__getstate__ only keeps defaults / state / param_groups
+        self._dev_steps = None
         self._normalise_groups()
 
     def _table(self, gi, ps):
@@ -85,7 +119,22 @@ class ClampAdam(torch.optim.Optimizer):
                     stt["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 if not torch.is_tensor(stt["step"]):           # very old checkpoints store a python int
                     stt["step"] = torch.tensor(float(stt["step"]))
-                stt["step"] += 1
+                if self._dev_steps is None:
+                    stt["step"] += 1
+            b1, b2 = group["betas"]
+            clip = group.get("grad_clip")
+            clip = clip if clip is not None else 0.0
+            if self._dev_steps is not None:
+                # capturable: count on the device, bias corrections in the kernel (see make_capturable)
+                dstep = self._dev_steps[gi]
+                dstep += 1
+                table, be, bo, nblk, total = self._table((gi, -1), all_ps)
+                _lib.check(_lib.lib().ccx_adam_clamp_dev(ptr(table), ptr(be), ptr(bo), nblk, group["lr"], b1, b2,
+                                                         group["eps"], ptr(dstep), clip, _CHUNK, total,
+                                                         _lib.stream_ptr()), "adam_clamp_dev")
+                for p in all_ps:
+                    p._ccx_epoch = getattr(p, "_ccx_epoch", 0) + 1
+                continue
             # torch.optim.Adam keeps one step count per parameter (bias correction): parameters whose first gradient
             # came later (fine_tune() switched on mid-run) are launched apart, one launch per distinct step value
             by_step = {}

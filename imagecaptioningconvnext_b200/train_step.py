@@ -5,7 +5,9 @@ modules in ``torch.nn.parallel.DistributedDataParallel`` (as the reference does,
 gradient all-reduce over NCCL overlaps with the explicit backward.
 """
 
-from ._host import stash_host_copy
+import torch
+
+from ._host import device_twin, named_params, stash_host_copy
 from .decoder import DecoderWithAttention
 from .losses import free_running_cross_entropy, packed_cross_entropy
 from .optim import ClampAdam
@@ -43,13 +45,13 @@ def caption_train_step(encoder, decoder, imgs, caps, caplens, decoder_optimizer,
     elif isinstance(_unwrap(decoder), DecoderWithAttention):
         scores, caps_sorted, decode_lengths, alphas, _ = decoder(teacherForcing=True, encoder_out=feats,
                                                                  encoded_captions=caps, caption_lengths=caplens)
-        loss = packed_cross_entropy(scores, caps_sorted, decode_lengths)              # :364-367
+        loss = packed_cross_entropy(scores, caps_sorted, decode_lengths, unit_grad=True)   # :364-367
         loss = loss + alpha_c * ((1.0 - alphas.sum(dim=1)) ** 2).mean()               # :369
     else:
         kpm = caps == pad_token                                                        # :371
         scores, caps_out, decode_lengths = decoder(teacherForcing=True, encoder_out=feats, encoded_captions=caps,
                                                    caption_lengths=caplens, tgt_key_padding_mask=kpm)
-        loss = packed_cross_entropy(scores, caps_out, decode_lengths)                 # :373-377
+        loss = packed_cross_entropy(scores, caps_out, decode_lengths, unit_grad=True)  # :373-377
     if encoder_optimizer is not None:
         encoder_optimizer.zero_grad(set_to_none=False)
     decoder_optimizer.zero_grad(set_to_none=False)                                     # :381-383
@@ -58,3 +60,137 @@ def caption_train_step(encoder, decoder, imgs, caps, caplens, decoder_optimizer,
         encoder_optimizer.step()                                                       # :387-394 (clamp fused)
     decoder_optimizer.step()
     return loss.detach()
+
+
+class CapturedTrainStep:
+    """The teacher-forced train step (``caption_train_step``: trainMultiGPU.py:357-394) recorded ONCE into a CUDA
+    graph and replayed — encoder forward, decoder forward, loss, backward, gradient all-reduce, clamp + Adam — so
+    that neither Python nor the ~500 launch calls of a step sit between the GPU and its work (the eager step is
+    host-bound: 7.4 ms of enqueue time for ~6 ms of kernels).  An addition: the reference call sites keep working
+    through ``caption_train_step``.
+
+        step = CapturedTrainStep(encoder, decoder, decoder_optimizer, encoder_optimizer)
+        for imgs, caps, caplens in loader:                 # device tensors of a FIXED shape
+            loss = step(imgs, caps, caplens)               # device scalar, valid until the next call
+
+    What makes the step replayable:
+      * shapes never depend on the batch: the step buffers span all ``caps.shape[1] - 1`` time steps
+        (``decoder.fixed_T``); the recurrence kernels read the longest caption of the batch from the device and stop
+        there, rows / steps past a caption's length stay zero, the loss normaliser (number of scored tokens) is a
+        device scalar — nothing about the caption lengths is needed on the host;
+      * the optimizers count their steps on the device (``ClampAdam.make_capturable``);
+      * the kernel-side bf16 copies of the weights are refreshed inside the graph at the top of every step.
+    Multi-GPU (``torch.distributed`` initialised, one process per GPU): gradients live in two flat fp32 buckets
+    (decoder, fine-tuned encoder stage).  The decoder bucket is all-reduced (NCCL, average) as soon as the decoder's
+    backward is done, while the encoder stage still back-propagates; each optimizer waits only for its own bucket.
+    This replaces DistributedDataParallel's reducer (trainMultiGPU.py:233-236) and is part of the same graph.
+    Parameters are broadcast from rank 0 at construction, as DDP does.
+    """
+
+    def __init__(self, encoder, decoder, decoder_optimizer, encoder_optimizer=None, pad_token=0, alpha_c=1.0,
+                 warmup_steps=3, process_group=None):
+        import torch.distributed as dist
+        self.encoder, self.decoder = encoder, decoder
+        self.d_opt, self.e_opt = decoder_optimizer, encoder_optimizer
+        self.pad_token, self.alpha_c = pad_token, alpha_c
+        self.warmup_left = max(int(warmup_steps), 2)     # the first eager steps also build every lazily created cache
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.lstm = isinstance(decoder, DecoderWithAttention)
+        self.graph, self.static, self.loss = None, None, None
+        self._shape_key = None
+        if self.lstm:
+            decoder.fixed_T = True
+        self._trainable = [p for _, p in named_params(decoder) if p.requires_grad] + \
+                          [p for _, p in named_params(encoder) if p.requires_grad]
+        self._buckets = []
+        for opt in (decoder_optimizer, encoder_optimizer):
+            if opt is None:
+                continue
+            ps = [p for g in opt.param_groups for p in g["params"] if p.requires_grad]
+            if not ps:
+                continue
+            flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+            off = 0
+            for p in ps:                       # gradients are views of one flat bucket: one all-reduce, no copies
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            opt.make_capturable()
+            self._buckets.append(flat)
+        if self.world > 1:
+            with torch.no_grad():
+                for p in list(decoder.parameters()) + list(encoder.parameters()):
+                    dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group else 0,
+                                   group=process_group)
+
+    def eager_step(self, imgs, caps, caplens):
+        """The same step without the graph (debugging, per-kernel timing through the library's event hooks)."""
+        if self._shape_key is None:
+            return self(imgs, caps, caplens)
+        loss = self._body(imgs, caps, caplens)
+        for p in self._trainable:
+            p._ccx_epoch = getattr(p, "_ccx_epoch", 0) + 1
+        return loss
+
+    # ---- one step, eagerly; also the body that is captured ----------------------------------------------------
+    def _body(self, imgs, caps, caplens):
+        import torch.distributed as dist
+        # the only use of the lengths on the host is to size the step buffers; they always span every step here
+        fake = self._fake_lens
+        stash_host_copy(caplens, fake)
+        feats = self.encoder(imgs)                                                         # trainMultiGPU.py:361
+        enc_trains = feats.requires_grad
+        feats_in = feats.detach().requires_grad_() if enc_trains else feats
+        if self.lstm:
+            scores, caps_s, decode_lengths, alphas, _ = self.decoder(
+                teacherForcing=True, encoder_out=feats_in, encoded_captions=caps, caption_lengths=caplens)
+        else:
+            scores, caps_s, decode_lengths = self.decoder(
+                teacherForcing=True, encoder_out=feats_in, encoded_captions=caps, caption_lengths=caplens,
+                tgt_key_padding_mask=(caps == self.pad_token))
+        n_valid = device_twin(decode_lengths, scores.device).sum().to(torch.float32).reshape(1)
+        loss = packed_cross_entropy(scores, caps_s, decode_lengths, n_valid_dev=n_valid, unit_grad=True)
+        if self.lstm:
+            loss = loss + self.alpha_c * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+        for flat in self._buckets:
+            flat.zero_()
+        loss.backward()                                   # decoder part: parameter gradients + d features
+        works = []
+        if self.world > 1:
+            works.append(dist.all_reduce(self._buckets[0], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        if enc_trains:
+            feats.backward(feats_in.grad)                 # fine-tuned encoder stage; overlaps the decoder all-reduce
+            if self.world > 1 and len(self._buckets) > 1:
+                works.append(dist.all_reduce(self._buckets[1], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        if works:
+            works[0].wait()
+        self.d_opt.step()
+        if self.e_opt is not None:
+            if len(works) > 1:
+                works[1].wait()
+            self.e_opt.step()
+        return loss.detach()
+
+    def __call__(self, imgs, caps, caplens):
+        key = (tuple(imgs.shape), imgs.dtype, tuple(caps.shape), tuple(caplens.shape))
+        if self._shape_key is None:
+            self._shape_key = key
+            self._fake_lens = torch.full(tuple(caplens.shape), caps.shape[1], dtype=caplens.dtype)
+        elif key != self._shape_key:
+            raise ValueError(f"CapturedTrainStep was built for inputs {self._shape_key}, got {key}: shapes must not "
+                             "change (pad the last batch or use caption_train_step for it)")
+        if self.warmup_left > 0:
+            self.warmup_left -= 1
+            return self._body(imgs, caps, caplens)
+        if self.graph is None:
+            self.static = (imgs.clone(), caps.clone(), caplens.clone())
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):          # records the step; nothing runs yet
+                self.loss = self._body(*self.static)
+        for dst, src in zip(self.static, (imgs, caps, caplens)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for p in self._trainable:          # the masters moved without this Python code running: kernel-side copies
+            p._ccx_epoch = getattr(p, "_ccx_epoch", 0) + 1     # are stale for any eager call that follows
+        return self.loss

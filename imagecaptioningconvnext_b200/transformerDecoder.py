@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy
+from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy, stash_device_twin
 from ._lib import Operand, ptr
 
 
@@ -287,6 +287,7 @@ class TransformerDecoder(nn.Module):
         _lib.require_cuda(encoder_out, "encoder_out")
         B = encoder_out.size(0)
         decode_lengths = (host_copy(caption_lengths).reshape(-1) - 1).tolist()
+        stash_device_twin(decode_lengths, caption_lengths.reshape(-1) - 1)     # the same values, on the device
         dev = encoder_out.device
         D, V, cd = self.embed_dim, self.vocab_size, self.compute_dtype
         T = encoded_captions.size(1)

@@ -317,6 +317,11 @@ CCX_API int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float*
  * pass; a hit = fewer than topk logits strictly larger than the target's. */
 CCX_API int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V, float inv_n,
                            float* loss_sum, float* dlogits, int64_t ldd, float* stats, int32_t topk, void* stream);
+/* Same kernel with the number of scored rows read from DEVICE memory (inv_n = 1 / max(*n_valid_dev, 1)): the caption
+ * lengths then never have to be known on the host (CUDA-graph replay of the train step). */
+CCX_API int ccx_softmax_ce_dev(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V,
+                               const float* n_valid_dev, float* loss_sum, float* dlogits, int64_t ldd, float* stats,
+                               int32_t topk, void* stream);
 /* Targets of the free-running evaluation (utils/utils.py:261-295 preprocessDecoderOutputForMetrics) on the device:
  * targets[i,t] = caps[i,1+t] for t < L_i (L_i = first <end> in sequences[i] + 1, else T) and != <pad>, else -1;
  * decode_len[i] = L_i (may be NULL).  Feed targets to ccx_softmax_ce. */
@@ -481,6 +486,11 @@ CCX_API int ccx_lstm_tf_backward_persist(const ccx_lstm_tf* s, const ccx_lstm_tf
 CCX_API int ccx_adam_clamp(const void* table, const int32_t* block_entry, const int64_t* block_offset,
                            int32_t n_blocks, float lr, float beta1, float beta2, float eps, float bc1,
                            float bc2_sqrt, float clip, int32_t chunk, double total_params, void* stream);
+/* Same update with the step count t read from DEVICE memory (bias corrections 1 - beta^t computed in the kernel): the
+ * form a CUDA-graph replay of the train step needs, where no host-side value may be baked into the launch. */
+CCX_API int ccx_adam_clamp_dev(const void* table, const int32_t* block_entry, const int64_t* block_offset,
+                               int32_t n_blocks, float lr, float beta1, float beta2, float eps,
+                               const float* step_dev, float clip, int32_t chunk, double total_params, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-launch CUDA-event timing (bench.py's roofline).  Between begin and end every kernel launch made by the

@@ -21,97 +21,10 @@ import torch
 import torch.nn.functional as F
 
 
-# ------------------------------------------------------------------------------------------------
-# deterministic random-init weights in the reference's state_dict layout
-# ------------------------------------------------------------------------------------------------
-def _perturb(sd, seed, scale):
-    """Add small noise to every tensor so that zero-initialised biases / identical cloned layers do not hide
-    indexing bugs.  Deterministic in (seed, key order)."""
-    g = torch.Generator().manual_seed(seed + 7919)
-    for k in sd:
-        if sd[k].is_floating_point() and k != "pos_encoding.pe":
-            sd[k] = sd[k] + scale * sd[k].abs().mean().clamp_min(0.02) * torch.randn(sd[k].shape, generator=g)
-    return sd
-
-
-def random_lstm_decoder_state(seed=0, vocab=9490, attention_dim=512, embed_dim=512, decoder_dim=512,
-                              encoder_dim=1024, end_bias=None, perturb=0.5):
-    """Same module-construction order as models/decoder.py:35-61, so under the same seed the tensors equal
-    ``DecoderWithAttention(...).state_dict()`` bit for bit (checked by tests/golden/make_golden.py) before the
-    optional perturbation.  end_bias: value written to fc.bias[<end> = vocab-1]."""
-    from torch import nn
-    rng = torch.random.get_rng_state()
-    torch.manual_seed(seed)
-    mods = {}
-    mods["attention.encoder_att"] = nn.Linear(encoder_dim, attention_dim)
-    mods["attention.decoder_att"] = nn.Linear(decoder_dim, attention_dim)
-    mods["attention.full_att"] = nn.Linear(attention_dim, 1)
-    mods["embedding"] = nn.Embedding(vocab, embed_dim)
-    mods["decode_step"] = nn.LSTMCell(embed_dim + encoder_dim, decoder_dim, bias=True)
-    mods["init_h"] = nn.Linear(encoder_dim, decoder_dim)
-    mods["init_c"] = nn.Linear(encoder_dim, decoder_dim)
-    mods["f_beta"] = nn.Linear(decoder_dim, encoder_dim)
-    mods["fc"] = nn.Linear(decoder_dim, vocab)
-    mods["embedding"].weight.data.uniform_(-0.1, 0.1)
-    mods["fc"].bias.data.fill_(0)
-    mods["fc"].weight.data.uniform_(-0.1, 0.1)
-    torch.random.set_rng_state(rng)
-    sd = {}
-    for name, m in mods.items():
-        for k, v in m.state_dict().items():
-            sd[f"{name}.{k}"] = v.detach().clone()
-    if perturb:
-        _perturb(sd, seed, perturb)
-    if end_bias is not None:
-        sd["fc.bias"][vocab - 1] = end_bias
-    return sd
-
-
-def random_transformer_decoder_state(seed=0, vocab=9490, embed_dim=512, decoder_dim=512, max_len=52,
-                                     encoder_dim=1024, nheads=8, nlayers=6, end_bias=None, perturb=0.5):
-    """Same construction order as models/transformerDecoder.py:54-86 (random embeddings branch)."""
-    from torch import nn
-    rng = torch.random.get_rng_state()
-    torch.manual_seed(seed)
-    emb = nn.Embedding(vocab, embed_dim)
-    layer = nn.TransformerDecoderLayer(d_model=embed_dim, nhead=nheads, dim_feedforward=decoder_dim, dropout=0.5)
-    dec = nn.TransformerDecoder(layer, num_layers=nlayers)
-    fc_out = nn.Linear(embed_dim, vocab)
-    proj = nn.Linear(encoder_dim, embed_dim)
-    torch.random.set_rng_state(rng)
-    sd = {"embedding.weight": emb.weight.detach().clone(),
-          "pos_encoding.pe": positional_encoding(embed_dim, max_len).unsqueeze(0)}
-    for k, v in dec.state_dict().items():
-        sd["transformer_decoder." + k] = v.detach().clone()
-    for k, v in fc_out.state_dict().items():
-        sd["fc_out." + k] = v.detach().clone()
-    for k, v in proj.state_dict().items():
-        sd["encoder_proj." + k] = v.detach().clone()
-    if perturb:
-        _perturb(sd, seed, perturb)
-    if end_bias is not None:
-        sd["fc_out.bias"][vocab - 1] = end_bias
-    return sd
-
-
-def synthetic_features(B, seed, P=49, E=1024):
-    """Encoder-output-like features (B, 7, 7, E): non-negative-ish, O(1) scale."""
-    g = torch.Generator().manual_seed(seed)
-    s = int(round(P ** 0.5))
-    return torch.randn(B, s, s, E, generator=g) * 0.7
-
-
-def synthetic_captions(B, seed, vocab=9490, T=52, min_len=7):
-    """<start>, len-2 tokens in [1, V-4], <end>, then <pad>=0; lengths uniform in [min_len, T]."""
-    g = torch.Generator().manual_seed(seed)
-    lens = torch.randint(min_len, T + 1, (B, 1), generator=g)
-    caps = torch.zeros(B, T, dtype=torch.long)
-    for b in range(B):
-        L = int(lens[b])
-        caps[b, 0] = vocab - 2
-        caps[b, 1:L - 1] = torch.randint(1, vocab - 3, (L - 2,), generator=g)
-        caps[b, L - 1] = vocab - 1
-    return caps, lens
+# deterministic random-init weights / synthetic inputs live in the neutral ``synthetic`` module (bench.py's own arm
+# uses them too and must not import the oracle); re-exported here for the tests
+from synthetic import (random_lstm_decoder_state, random_transformer_decoder_state, synthetic_captions,  # noqa: F401,E402
+                       synthetic_features)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -163,8 +76,8 @@ def lstm_teacher_forcing(sd, encoder_out, caps, caplens, dropmask=None):
     h, c = init_hidden_state(sd, enc)
     dl = (lens - 1).tolist()
     V = sd["fc.weight"].shape[0]
-    preds = torch.zeros(B, max(dl), V, dtype=enc.dtype)
-    alphas = torch.zeros(B, max(dl), enc.size(1), dtype=enc.dtype)
+    preds = torch.zeros(B, max(dl), V, dtype=enc.dtype, device=enc.device)
+    alphas = torch.zeros(B, max(dl), enc.size(1), dtype=enc.dtype, device=enc.device)
     for t in range(max(dl)):
         bt = sum(l > t for l in dl)
         h, c, alpha = lstm_step(sd, enc[:bt], emb[:bt, t], h[:bt], c[:bt])
@@ -182,11 +95,12 @@ def lstm_greedy(sd, encoder_out, start_tok, end_tok, max_len, dropmask=None):
     enc = encoder_out.reshape(B, -1, E)
     h, c = init_hidden_state(sd, enc)
     V = sd["fc.weight"].shape[0]
-    inputs = sd["embedding.weight"][torch.full((B,), start_tok, dtype=torch.long)].clone()
-    preds = torch.zeros(B, max_len, V, dtype=enc.dtype)
-    alphas = torch.zeros(B, max_len, enc.size(1), dtype=enc.dtype)
-    seqs = torch.zeros(B, max_len, dtype=torch.long)
-    finished = torch.zeros(B, dtype=torch.bool)
+    dev = enc.device
+    inputs = sd["embedding.weight"][torch.full((B,), start_tok, dtype=torch.long, device=dev)].clone()
+    preds = torch.zeros(B, max_len, V, dtype=enc.dtype, device=dev)
+    alphas = torch.zeros(B, max_len, enc.size(1), dtype=enc.dtype, device=dev)
+    seqs = torch.zeros(B, max_len, dtype=torch.long, device=dev)
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
     for t in range(max_len):
         act = (~finished).nonzero(as_tuple=False).squeeze(1)
         if len(act) == 0:
@@ -295,10 +209,10 @@ def transformer_teacher_forcing(sd, encoder_out, caps, caplens, key_padding_mask
         emb = emb * drop["emb"]
     T = caps.shape[1]
     x = emb + sd["pos_encoding.pe"][0, :T].to(emb.dtype)
-    causal = torch.full((T, T), float("-inf"), dtype=x.dtype).triu(1)
+    causal = torch.full((T, T), float("-inf"), dtype=x.dtype, device=x.device).triu(1)
     mask = causal.view(1, 1, T, T)
     if key_padding_mask is not None:
-        kp = torch.zeros(key_padding_mask.shape, dtype=x.dtype).masked_fill(key_padding_mask, float("-inf"))
+        kp = torch.zeros(key_padding_mask.shape, dtype=x.dtype, device=x.device).masked_fill(key_padding_mask, float("-inf"))
         mask = mask + kp.view(-1, 1, 1, T)
     cross = [] if return_alphas else None
     y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), mask, drop, cross_probs=cross)
@@ -316,7 +230,7 @@ def transformer_last_logits(sd, mem, tokens, nheads=8, alpha_out=None):
     (models/transformerDecoderAttVis.py:223-226)."""
     T = tokens.shape[1]
     x = sd["embedding.weight"][tokens] + sd["pos_encoding.pe"][0, :T].to(mem.dtype)
-    causal = torch.full((T, T), float("-inf"), dtype=x.dtype).triu(1).view(1, 1, T, T)
+    causal = torch.full((T, T), float("-inf"), dtype=x.dtype, device=x.device).triu(1).view(1, 1, T, T)
     cross = [] if alpha_out is not None else None
     y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), causal, cross_probs=cross)
     if alpha_out is not None:
@@ -329,11 +243,12 @@ def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nh
     B = encoder_out.size(0)
     mem = transformer_memory(sd, encoder_out)
     V = sd["fc_out.weight"].shape[0]
-    inputs = torch.full((B, 1), start_tok, dtype=torch.long)
-    preds = torch.zeros(B, max_len, V, dtype=mem.dtype)
-    seqs = torch.zeros(B, max_len, dtype=torch.long)
-    alphas = torch.zeros(B, max_len, mem.size(1), dtype=mem.dtype)
-    finished = torch.zeros(B, dtype=torch.bool)
+    dev = mem.device
+    inputs = torch.full((B, 1), start_tok, dtype=torch.long, device=dev)
+    preds = torch.zeros(B, max_len, V, dtype=mem.dtype, device=dev)
+    seqs = torch.zeros(B, max_len, dtype=torch.long, device=dev)
+    alphas = torch.zeros(B, max_len, mem.size(1), dtype=mem.dtype, device=dev)
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
     for t in range(max_len):
         act = (~finished).nonzero(as_tuple=False).squeeze(1)
         if len(act) == 0:
@@ -346,7 +261,7 @@ def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nh
         ids = p.argmax(dim=-1)
         seqs[act, t] = ids
         finished[act] |= ids == end_tok
-        new = torch.full((B, t + 2), pad_tok, dtype=torch.long)
+        new = torch.full((B, t + 2), pad_tok, dtype=torch.long, device=dev)
         new[:, :t + 1] = inputs
         new[act, t + 1] = ids
         inputs = new
@@ -366,10 +281,11 @@ def beam_search(sd, encoder_out, kind, k, start_tok, end_tok, vocab, max_steps=5
     second return value (caption.py:85,122,129,153), first entry all ones —, the maps of all completed sequences]."""
     E = encoder_out.size(-1)
     enc1 = encoder_out.reshape(1, -1, E)
-    seqs = torch.full((k, 1), start_tok, dtype=torch.long)
-    top = torch.zeros(k, 1, dtype=enc1.dtype)
+    dev = enc1.device          # device-agnostic: bench.py also runs this loop with torch's eager CUDA kernels
+    seqs = torch.full((k, 1), start_tok, dtype=torch.long, device=dev)
+    top = torch.zeros(k, 1, dtype=enc1.dtype, device=dev)
     done_seqs, done_scores, done_alpha = [], [], []
-    seqs_alpha = torch.ones(k, 1, enc1.size(1), dtype=enc1.dtype)
+    seqs_alpha = torch.ones(k, 1, enc1.size(1), dtype=enc1.dtype, device=dev)
     if kind == "lstm":
         enc = enc1.expand(k, -1, -1)
         h, c = init_hidden_state(sd, enc)

@@ -74,18 +74,4 @@ def encoder_forward(sd, images, encoded_image_size=7, noise=None, return_pre_poo
     return x.permute(0, 2, 3, 1)
 
 
-def random_encoder_state(seed=0, layer_scale=1.0, dtype=torch.float32):
-    """Random-init ConvNeXt-Base weights in the reference's key layout (``convnext.*``), with layer_scale
-    overwritten (the default 1e-6 hides CNBlock bugs).  Uses torchvision's own initialiser so
-    the statistics match what ``Encoder()`` would hold before loading ImageNet weights."""
-    import torchvision
-
-    g = torch.random.get_rng_state()
-    torch.manual_seed(seed)
-    feats = torchvision.models.convnext_base(weights=None).features
-    torch.random.set_rng_state(g)
-    sd = {"convnext." + k: v.detach().clone().to(dtype) for k, v in feats.state_dict().items()}
-    for k in sd:
-        if k.endswith("layer_scale"):
-            sd[k].fill_(layer_scale)
-    return sd
+from synthetic import random_encoder_state  # noqa: F401,E402  (neutral module; re-exported for the tests)
