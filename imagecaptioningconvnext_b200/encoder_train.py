@@ -193,12 +193,23 @@ def encoder_features_with_grad(enc, images, noise, begin_child=0, image_hw=None)
     with torch.no_grad():
         x = images if begin_child >= first else enc.run_children(images, begin_child, first, noise, image_hw=image_hw)
     enc.prepared()
+    # optional callback hook(child, i): the gradients of block i of child `child` (i = None: a downsample child) are
+    # complete — fired from a tensor hook on the unit's INPUT, i.e. when its backward node has run and (AccumulateGrad
+    # nodes have the highest priority in the autograd engine) its parameter gradients have been accumulated.
+    # CapturedTrainStep uses it to all-reduce a unit's gradient slice while the previous unit still back-propagates.
+    hook = getattr(enc, "_unit_grads_ready", None)
+
+    def watch(x, child, i):
+        if hook is not None and x.requires_grad:
+            x.register_hook(lambda g, child=child, i=i: hook(child, i))
     for child in range(first, 8):
         if child % 2 == 0:
+            watch(x, child, None)
             x = _DownFn.apply(enc, child, x, *[p for _, p in _named(enc.convnext[child])])
             continue
         nb0 = _block_index0(enc, child)
         for i, blk in enumerate(enc.convnext[child]):
             rs = None if noise is None else noise[nb0 + i]
+            watch(x, child, i)
             x = _BlockFn.apply(enc, child, i, nb0 + i, x, rs, *[p for _, p in _named(blk)])
     return _PoolFn.apply(enc, x)

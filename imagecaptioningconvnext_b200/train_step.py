@@ -82,7 +82,8 @@ class CapturedTrainStep:
       * the kernel-side bf16 copies of the weights are refreshed inside the graph at the top of every step.
     Multi-GPU (``torch.distributed`` initialised, one process per GPU): gradients live in two flat fp32 buckets
     (decoder, fine-tuned encoder stage).  The decoder bucket is all-reduced (NCCL, average) as soon as the decoder's
-    backward is done, while the encoder stage still back-propagates; each optimizer waits only for its own bucket.
+    backward is done, and each CNBlock's slice of the encoder bucket as soon as that block's backward is done, while
+    the blocks before it still back-propagate; each optimizer waits only for its own bucket.
     This replaces DistributedDataParallel's reducer (trainMultiGPU.py:233-236) and is part of the same graph.
     Parameters are broadcast from rank 0 at construction, as DDP does.
     """
@@ -117,6 +118,20 @@ class CapturedTrainStep:
                 off += p.numel()
             opt.make_capturable()
             self._buckets.append(flat)
+            if opt is encoder_optimizer:
+                # gradient slice of every trainable unit of the encoder (a CNBlock or a downsample child): contiguous
+                # inside the bucket because the bucket follows the module order
+                where, off = {}, 0
+                for p in ps:
+                    where[id(p)] = (off, off + p.numel())
+                    off += p.numel()
+                self._enc_units = {}
+                for child, mod in enumerate(encoder.convnext.children()):
+                    units = [(None, mod)] if child % 2 == 0 else list(enumerate(mod))
+                    for i, unit in units:
+                        spans = [where[id(p)] for p in unit.parameters() if id(p) in where]
+                        if spans:
+                            self._enc_units[(child, i)] = (min(a for a, _ in spans), max(b for _, b in spans))
         if self.world > 1:
             with torch.no_grad():
                 for p in list(decoder.parameters()) + list(encoder.parameters()):
@@ -155,19 +170,34 @@ class CapturedTrainStep:
         for flat in self._buckets:
             flat.zero_()
         loss.backward()                                   # decoder part: parameter gradients + d features
-        works = []
-        if self.world > 1:
-            works.append(dist.all_reduce(self._buckets[0], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        dec_work, enc_works, reduced = None, [], set()
+        multi = self.world > 1
+
+        def reduce_slice(flat, a, b):
+            return dist.all_reduce(flat[a:b], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        if multi:
+            dec_work = reduce_slice(self._buckets[0], 0, self._buckets[0].numel())
         if enc_trains:
+            if multi and len(self._buckets) > 1:
+                # a unit's slice goes on the wire as soon as its backward is done, under the backward of the units
+                # before it (same overlap DDP gets from one autograd node per CNBlock, without its reducer)
+                def ready(child, i):
+                    if (child, i) in self._enc_units and (child, i) not in reduced:
+                        reduced.add((child, i))
+                        enc_works.append(reduce_slice(self._buckets[1], *self._enc_units[(child, i)]))
+                self.encoder._unit_grads_ready = ready
             feats.backward(feats_in.grad)                 # fine-tuned encoder stage; overlaps the decoder all-reduce
-            if self.world > 1 and len(self._buckets) > 1:
-                works.append(dist.all_reduce(self._buckets[1], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
-        if works:
-            works[0].wait()
+            self.encoder._unit_grads_ready = None
+            if multi and len(self._buckets) > 1:
+                for key, (a, b) in self._enc_units.items():       # the first trainable unit (its input has no gradient)
+                    if key not in reduced:
+                        enc_works.append(reduce_slice(self._buckets[1], a, b))
+        if dec_work is not None:
+            dec_work.wait()
         self.d_opt.step()
         if self.e_opt is not None:
-            if len(works) > 1:
-                works[1].wait()
+            for w in enc_works:
+                w.wait()
             self.e_opt.step()
         return loss.detach()
 

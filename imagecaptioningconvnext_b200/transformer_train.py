@@ -297,13 +297,22 @@ def transformer_free_running_with_grad(dec, encoder_out, wordMap, maxDecodeLen):
     """Free-running TRAINING forward (models/transformerDecoder.py:110-160 with autograd).
 
     The reference re-runs the whole prefix at every step and keeps all 51 graphs (O(T^2) forward and backward).
-    Under the causal mask the step-t logits depend only on tokens 0..t, a finished row is never computed again and
-    an active row's prefix holds no <pad>, so — no gradient passing through argmax — the same loss gradient comes
-    from (1) the KV-cached greedy pass that fixes the generated ids and (2) ONE causal teacher-forced pass over
-    [<start>, generated ids] with autograd, its logits zeroed past each row's finish step.  Exact for dropout-free
-    modules (eval mode, dropout=0; parity-tested against the reference's gradients).  DEVIATION with live dropout:
-    the ids are generated dropout-free and pass (2) draws one mask set per sequence, where the reference draws fresh
-    masks at every step's prefix recomputation (a different estimator of the same expectation)."""
+
+    Dropout-free modules (eval mode, dropout = 0): under the causal mask the step-t logits depend only on tokens 0..t,
+    a finished row is never computed again and an active row's prefix holds no <pad>, so — no gradient passing through
+    argmax — the same loss gradient comes from (1) the KV-cached greedy pass that fixes the generated ids and (2) ONE
+    causal teacher-forced pass over [<start>, generated ids] with autograd, its logits zeroed past each row's finish
+    step (parity-tested against the reference's gradients).
+
+    Live dropout (decoder.train(), trainMultiGPU.py:425-426): the reference draws a FRESH dropout realisation at every
+    step's prefix recomputation (models/transformerDecoder.py:129-130 and the layers' own dropouts), which both picks
+    the generated ids and defines the gradient; a KV cache cannot reproduce that (the keys / values of earlier
+    positions change with every realisation).  ``_free_running_exact`` therefore does what the reference does — one
+    differentiable causal pass over the prefix per step, 51 autograd nodes — on the libccx kernels.
+    ``dec.free_running_fast = True`` opts into the cheap estimator instead (ids generated dropout-free, one mask set
+    for the single differentiable pass): same expectation, ~12x faster, not the reference's sampling."""
+    if dec.training and dec.dropout_p > 0 and not getattr(dec, "free_running_fast", False):
+        return _free_running_exact(dec, encoder_out, wordMap, maxDecodeLen)
     from .decoder_train import generated_captions
     T = int(maxDecodeLen)
     _, sequences = dec._greedy(encoder_out.detach(), wordMap, T, dropout_free=True)
@@ -314,6 +323,47 @@ def transformer_free_running_with_grad(dec, encoder_out, wordMap, maxDecodeLen):
     dec._last_alphas = greedy_alphas
     valid = torch.arange(T, device=preds.device).unsqueeze(0) < (lens - 1)
     return preds * valid.unsqueeze(-1).to(preds.dtype), sequences
+
+
+def _free_running_exact(dec, encoder_out, wordMap, maxDecodeLen):
+    """models/transformerDecoder.py:124-158 step by step under autograd: at step t the whole prefix (t + 1 tokens, the
+    finished rows padded with <pad>) goes through the decoder with that step's own dropout masks; the last position's
+    logits give the step's predictions (kept in the autograd graph) and, by argmax, the next token.
+    ``dec.inject_dropout_steps`` (tests): list over t of mask dicts in ``_masks``' format for T = t + 1."""
+    T = int(maxDecodeLen)
+    B = encoder_out.size(0)
+    dev = encoder_out.device
+    start, end, pad = wordMap['<start>'], wordMap['<end>'], wordMap['<pad>']
+    params = params_of(dec)
+    inputs = torch.full((B, T), pad, dtype=torch.long, device=dev)
+    inputs[:, 0] = start
+    finished = torch.zeros(B, dtype=torch.bool, device=dev)
+    sequences = torch.zeros((B, T), dtype=torch.long, device=dev)
+    steps = getattr(dec, "inject_dropout_steps", None)
+    saved_inject = dec.inject_dropout
+    preds = []
+    try:
+        for t in range(T):
+            if steps is not None:
+                dec.inject_dropout = steps[t]
+            active = ~finished
+            p_all = _TransformerTF.apply(dec, encoder_out, inputs[:, :t + 1].contiguous(), None, False, *params)
+            p_t = p_all[:, t] * active.unsqueeze(1).to(p_all.dtype)      # finished rows stay zero (:119-121)
+            ids = p_t.detach().argmax(dim=1)
+            sequences[:, t] = torch.where(active, ids, sequences[:, t])
+            finished = finished | (active & (ids == end))
+            if t + 1 < T:
+                inputs[:, t + 1] = torch.where(active, ids, torch.full_like(ids, pad))   # :150-158
+            preds.append(p_t)
+            if t % 8 == 7 and bool(finished.all()):                      # the reference breaks when all rows finished
+                break
+    finally:
+        dec.inject_dropout = saved_inject
+    out = torch.stack(preds, dim=1)
+    if out.size(1) < T:
+        out = torch.nn.functional.pad(out, (0, 0, 0, T - out.size(1)))
+    dec._last_alphas = None
+    return out, sequences
 
 
 def enable_cuda_graph(dec, enabled=True):

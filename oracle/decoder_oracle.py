@@ -224,22 +224,32 @@ def transformer_teacher_forcing(sd, encoder_out, caps, caplens, key_padding_mask
     return preds, caps, dl
 
 
-def transformer_last_logits(sd, mem, tokens, nheads=8, alpha_out=None):
+def transformer_last_logits(sd, mem, tokens, nheads=8, alpha_out=None, drop=None):
     """Re-run the whole prefix (no KV cache, as the reference does) and return fc_out of the last position.
     alpha_out (list): receives the last position's cross-attention map averaged over layers and heads
-    (models/transformerDecoderAttVis.py:223-226)."""
+    (models/transformerDecoderAttVis.py:223-226).  drop: injected dropout multipliers of THIS prefix pass (train mode:
+    models/transformerDecoder.py:129-130 applies self.dropout to the re-embedded prefix and the layers run with their
+    dropouts live, a fresh realisation at every step), keys as in transformer_teacher_forcing."""
+    drop = drop or {}
     T = tokens.shape[1]
-    x = sd["embedding.weight"][tokens] + sd["pos_encoding.pe"][0, :T].to(mem.dtype)
+    emb = sd["embedding.weight"][tokens]
+    if "emb" in drop:
+        emb = emb * drop["emb"]
+    x = emb + sd["pos_encoding.pe"][0, :T].to(mem.dtype)
     causal = torch.full((T, T), float("-inf"), dtype=x.dtype, device=x.device).triu(1).view(1, 1, T, T)
     cross = [] if alpha_out is not None else None
-    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), causal, cross_probs=cross)
+    y = transformer_layers(sd, x, mem, nheads, _num_layers(sd), causal, drop, cross_probs=cross)
     if alpha_out is not None:
         alpha_out.append(torch.stack(cross, 0)[:, :, :, -1, :].mean(dim=(0, 2)))
     return F.linear(y[:, -1], sd["fc_out.weight"], sd["fc_out.bias"])
 
 
-def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nheads=8, return_alphas=False):
-    """models/transformerDecoder.py:110-160 (eval mode); return_alphas: the AttVis variant's third output."""
+def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nheads=8, return_alphas=False,
+                       drops=None):
+    """models/transformerDecoder.py:110-160; return_alphas: the AttVis variant's third output.
+    drops: None = eval mode; else a list over steps t of injected dropout multipliers for step t's prefix pass
+    (full-batch shapes with T = t + 1; the rows of the still-active samples are used) — the train-mode behaviour of
+    trainWithoutTeacherForcing (trainMultiGPU.py:425-452)."""
     B = encoder_out.size(0)
     mem = transformer_memory(sd, encoder_out)
     V = sd["fc_out.weight"].shape[0]
@@ -254,7 +264,8 @@ def transformer_greedy(sd, encoder_out, start_tok, end_tok, pad_tok, max_len, nh
         if len(act) == 0:
             break
         a_out = [] if return_alphas else None
-        p = transformer_last_logits(sd, mem[act], inputs[act], nheads, alpha_out=a_out)
+        drop_t = None if drops is None else {k: v[act] for k, v in drops[t].items()}
+        p = transformer_last_logits(sd, mem[act], inputs[act], nheads, alpha_out=a_out, drop=drop_t)
         if return_alphas:
             alphas[act, t] = a_out[0]
         preds[act, t] = p
