@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._host import named_params, params_of
 from ._lib import Operand, ptr
-from .train_ops import linear_bwd, weight_t, zero_grads_like, zeros_many
+from .train_ops import deliver, grads_out, linear_bwd, weight_t, zero_grads_like, zeros_many
 
 
 def _bptt_launch_loop(dec, S, dH_all, dalphas, need_enc, cd, dev):
@@ -125,16 +125,21 @@ class _LstmTF(torch.autograd.Function):
         if g("decode_step.weight_ih") is not None:
             gw, gb = gw_lstm, gb_lstm
             linear_bwd(dG_all.view(TB, 4 * D), x_all, None, cd, gw, gb, need_dx=False)
-            grads["decode_step.weight_ih"], grads["decode_step.weight_hh"] = gw[:, :hoff].contiguous(), gw[:, hoff:].contiguous()
-            grads["decode_step.bias_ih"], grads["decode_step.bias_hh"] = gb, gb.clone()
+            ds = dec.decode_step
+            deliver(grads, "decode_step.weight_ih", ds.weight_ih, gw[:, :hoff])
+            deliver(grads, "decode_step.weight_hh", ds.weight_hh, gw[:, hoff:])
+            deliver(grads, "decode_step.bias_ih", ds.bias_ih, gb)
+            deliver(grads, "decode_step.bias_hh", ds.bias_hh, gb.clone() if grads.get("decode_step.bias_ih") is gb else gb)
         if g("f_beta.weight") is not None:
             gw, gb = gw_h, gb_h
             h_prev_all = XH.map(lambda x: x[:T].view(TB, K)[:, hoff:])
             linear_bwd(dHG_all.view(TB, A + E), h_prev_all, None, cd, gw, gb, need_dx=False)
-            grads["attention.decoder_att.weight"], grads["f_beta.weight"] = gw[:A].contiguous(), gw[A:].contiguous()
-            grads["attention.decoder_att.bias"], grads["f_beta.bias"] = gb[:A].contiguous(), gb[A:].contiguous()
+            deliver(grads, "attention.decoder_att.weight", dec.attention.decoder_att.weight, gw[:A])
+            deliver(grads, "f_beta.weight", dec.f_beta.weight, gw[A:])
+            deliver(grads, "attention.decoder_att.bias", dec.attention.decoder_att.bias, gb[:A])
+            deliver(grads, "f_beta.bias", dec.f_beta.bias, gb[A:])
         if g("attention.full_att.weight") is not None:
-            grads["attention.full_att.weight"] = d_wf.view(1, A)
+            deliver(grads, "attention.full_att.weight", dec.attention.full_att.weight, d_wf.view(1, A))
             # d/d b_f of softmax(e + b_f) is identically zero (softmax is shift invariant)
         ge = g("embedding.weight")
         if ge is not None:
@@ -161,7 +166,7 @@ class _LstmTF(torch.autograd.Function):
             _lib.check(L.ccx_gather_rows(ptr(d_enc_flat), Pn * E * 4, ptr(d_unsorted), Pn * E * 4, ptr(inv32),
                                          Pn * E * 4, B, st), "gather_rows")
             d_encoder_out = d_unsorted.view(ctx.enc_shape)
-        return (None, None, d_encoder_out, None, None) + tuple(grads.get(n) for n in names)
+        return (None, None, d_encoder_out, None, None) + grads_out(grads, named_params(dec))
 
 
 def lstm_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, dropmask_unsorted=None):

@@ -17,7 +17,7 @@ from . import _lib
 from ._host import any_requires_grad, named_params
 from ._lib import Operand, ptr
 from .encoder import DIMS
-from .train_ops import colsum_acc, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
+from .train_ops import colsum_acc, deliver, grads_out, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
 
 def _first_trainable_child(enc):
@@ -113,7 +113,7 @@ class _BlockFn(torch.autograd.Function):
         # depthwise conv: bias, filter and data gradients; residual add fused into the data-gradient launch
         colsum_acc(du, grads["block.0.bias"])
         _lib.check(L.ccx_dwconv7_wgrad(ptr(x_in), ptr(du), ptr(dw), B, H, W, C, st), "dwconv7_wgrad")
-        grads["block.0.weight"] = dw.t().reshape(C, 1, 7, 7).contiguous()     # tap-major -> (C,1,7,7)
+        deliver(grads, "block.0.weight", blk.block[0].weight, dw.t().reshape(C, 1, 7, 7))     # tap-major -> (C,1,7,7)
         dprev = None
         if ctx.needs_input_grad[4]:
             w_flip = ops["dw_w"].flip(0).contiguous()                                  # tiny (49 x C) re-layout
@@ -121,7 +121,7 @@ class _BlockFn(torch.autograd.Function):
             _lib.check(L.ccx_dwconv7_plain(ptr(du), ptr(w_flip), None, ptr(dout), ptr(dprev), B, H, W, C, st),
                        "dwconv7_dgrad")
             dprev = dprev.view(B, H, W, C)
-        return (None, None, None, None, dprev, None) + tuple(grads[n] for n, _ in named)
+        return (None, None, None, None, dprev, None) + grads_out(grads, named)
 
 
 class _DownFn(torch.autograd.Function):
@@ -159,11 +159,11 @@ class _DownFn(torch.autograd.Function):
         gw = torch.zeros((Cout, 4 * C), dtype=torch.float32, device=dout.device)
         w_perm = mod[1].weight.detach().permute(0, 2, 3, 1).reshape(Cout, 4 * C)       # (Cout, kh, kw, Cin)
         dmerged = linear_bwd(dout, y_op, weight_t(w_perm, cd), cd, gw, grads["1.bias"])
-        grads["1.weight"] = gw.view(Cout, 2, 2, C).permute(0, 3, 1, 2).contiguous()
+        deliver(grads, "1.weight", mod[1].weight, gw.view(Cout, 2, 2, C).permute(0, 3, 1, 2))
         dx = ln_bwd(dmerged, x_in.view(M, C), mod[0].weight.detach(), grads["0.weight"], grads["0.bias"], 1e-6,
                     merge_hw=(H, W))
         dx = dx.view(B, H, W, C) if ctx.needs_input_grad[2] else None
-        return (None, None, dx) + tuple(grads[n] for n, _ in named)
+        return (None, None, dx) + grads_out(grads, named)
 
 
 class _PoolFn(torch.autograd.Function):

@@ -25,16 +25,73 @@ def zeros_many(shapes, device):
     return [flat[o:o + torch.Size(sh).numel()].view(sh) for o, sh in zip(offs, shapes)]
 
 
+# ---- direct gradient accumulation --------------------------------------------------------------------------------------
+# By default a backward pass accumulates into fresh zero buffers and RETURNS them; autograd's AccumulateGrad then adds
+# each one into ``p.grad`` (one more kernel per parameter, ~50 per train step, plus the zero fills).  Inside
+# ``with direct_grads():`` the accumulators ARE the existing ``p.grad`` tensors (the weight-gradient GEMMs accumulate
+# in place through their residual epilogue) and the Function returns None for those parameters.  The caller owns the
+# zeroing of ``p.grad`` (``optimizer.zero_grad(set_to_none=False)`` / the flat buckets of CapturedTrainStep).
+_DIRECT = [False]
+
+
+class direct_grads:
+    def __enter__(self):
+        self._old = _DIRECT[0]
+        _DIRECT[0] = True
+
+    def __exit__(self, *exc):
+        _DIRECT[0] = self._old
+
+
+def _direct_target(p):
+    g = p.grad
+    if _DIRECT[0] and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape \
+            and g.device == p.device:
+        return g
+    return None
+
+
 def zero_grads_like(named_params, extra_shapes=None):
-    """{name: zero fp32 gradient buffer} for the parameters that require grad (one allocation, see zeros_many).
+    """{name: fp32 gradient accumulator} for the parameters that require grad: zero buffers carved from one allocation
+    (see zeros_many), or — under direct_grads() — the parameters' own ``.grad`` tensors.
     extra_shapes: further zero buffers carved from the same allocation -> returns (dict, [extras])."""
     items = [(n, p) for n, p in named_params if p.requires_grad]
     if not items:
         return {} if extra_shapes is None else ({}, zeros_many(list(extra_shapes), named_params[0][1].device))
-    shapes = [tuple(p.shape) for _, p in items] + list(extra_shapes or ())
-    bufs = zeros_many(shapes, items[0][1].device)
-    grads = {n: b for (n, _), b in zip(items, bufs)}
-    return grads if extra_shapes is None else (grads, bufs[len(items):])
+    grads = {}
+    fresh = []
+    for n, p in items:
+        t = _direct_target(p)
+        if t is None:
+            fresh.append((n, p))
+        else:
+            grads[n] = t
+    shapes = [tuple(p.shape) for _, p in fresh] + list(extra_shapes or ())
+    bufs = zeros_many(shapes, items[0][1].device) if shapes else []
+    for (n, _), b in zip(fresh, bufs):
+        grads[n] = b
+    return grads if extra_shapes is None else (grads, bufs[len(fresh):])
+
+
+def grads_out(grads, named_params):
+    """What a Function's backward returns for its parameter inputs: the accumulator, or None when it IS the
+    parameter's .grad (already accumulated in place)."""
+    out = []
+    for n, p in named_params:
+        g = grads.get(n)
+        out.append(None if (g is not None and p.grad is not None and g.data_ptr() == p.grad.data_ptr()
+                            and g.shape == p.grad.shape) else g)
+    return tuple(out)
+
+
+def deliver(grads, name, param, value):
+    """Hand a gradient that was computed in its own buffer (a slice of a combined GEMM result, a re-laid-out filter)
+    to parameter `name`: added into .grad under direct_grads(), else returned through autograd."""
+    t = grads.get(name)
+    if t is not None and param.grad is not None and t.data_ptr() == param.grad.data_ptr():
+        t.add_(value.view_as(t) if value.shape != t.shape else value)
+    else:
+        grads[name] = value.contiguous() if not value.is_contiguous() else value
 
 
 def _pad8(n):

@@ -11,6 +11,7 @@ from ._host import device_twin, named_params, stash_host_copy
 from .decoder import DecoderWithAttention
 from .losses import free_running_cross_entropy, packed_cross_entropy
 from .optim import ClampAdam
+from .train_ops import direct_grads
 
 
 def _unwrap(m):
@@ -111,11 +112,12 @@ class CapturedTrainStep:
             ps = [p for g in opt.param_groups for p in g["params"] if p.requires_grad]
             if not ps:
                 continue
-            flat = torch.zeros(sum(p.numel() for p in ps), dtype=torch.float32, device=ps[0].device)
+            pad = lambda n: (n + 63) // 64 * 64          # every slice starts on a 256-byte boundary
+            flat = torch.zeros(sum(pad(p.numel()) for p in ps), dtype=torch.float32, device=ps[0].device)
             off = 0
             for p in ps:                       # gradients are views of one flat bucket: one all-reduce, no copies
                 p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+                off += pad(p.numel())
             opt.make_capturable()
             self._buckets.append(flat)
             if opt is encoder_optimizer:
@@ -123,8 +125,8 @@ class CapturedTrainStep:
                 # inside the bucket because the bucket follows the module order
                 where, off = {}, 0
                 for p in ps:
-                    where[id(p)] = (off, off + p.numel())
-                    off += p.numel()
+                    where[id(p)] = (off, off + pad(p.numel()))
+                    off += pad(p.numel())
                 self._enc_units = {}
                 for child, mod in enumerate(encoder.convnext.children()):
                     units = [(None, mod)] if child % 2 == 0 else list(enumerate(mod))
@@ -169,6 +171,12 @@ class CapturedTrainStep:
             loss = loss + self.alpha_c * ((1.0 - alphas.sum(dim=1)) ** 2).mean()
         for flat in self._buckets:
             flat.zero_()
+        # the backward kernels accumulate straight into the buckets (no returned gradient tensors, no AccumulateGrad adds)
+        with direct_grads():
+            return self._backward_and_update(loss, feats, feats_in, enc_trains)
+
+    def _backward_and_update(self, loss, feats, feats_in, enc_trains):
+        import torch.distributed as dist
         loss.backward()                                   # decoder part: parameter gradients + d features
         dec_work, enc_works, reduced = None, [], set()
         multi = self.world > 1

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._host import host_copy, named_params, params_of, stash_device_twin
 from ._lib import Operand, ptr
-from .train_ops import linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
+from .train_ops import grads_out, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
 _SITES = ("sa_p", "d1", "ca_p", "d2", "ff", "d3")
 
@@ -265,7 +265,7 @@ class _TransformerTF(torch.autograd.Function):
         st = ctx.gstate
         if st is None:
             denc, grads = _backward_body(ctx.payload, dpred, ctx.enc_needs_grad)
-            return (None, denc, None, None, None) + tuple(grads.get(n) for n in ctx.names)
+            return (None, denc, None, None, None) + grads_out(grads, named_params(ctx.payload.dec))
         if st.owner is None or st.owner() is not ctx.token:
             raise RuntimeError("graphed TransformerDecoder backward ran twice, or after its static buffers were reused")
         if st.bwd is None:
@@ -277,7 +277,7 @@ class _TransformerTF(torch.autograd.Function):
         st.dpred_in.copy_(dpred)
         st.bwd.replay()
         st.owner = None
-        return (None, st.denc, None, None, None) + tuple(st.grads.get(n) for n in ctx.names)
+        return (None, st.denc, None, None, None) + grads_out(st.grads, named_params(ctx.payload.dec))
 
 
 def transformer_teacher_forcing_with_grad(dec, encoder_out, encoded_captions, caption_lengths, tgt_key_padding_mask):
