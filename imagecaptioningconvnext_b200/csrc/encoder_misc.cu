@@ -384,10 +384,26 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16_rn(x[i]);
 }
+// 8 elements per thread: two 16-byte loads, one 16-byte store
+__global__ void __launch_bounds__(256) cast_bf16x8_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long n8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = x[2 * i], b = x[2 * i + 1];
+  uint4 pk;
+  pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(a.z, a.w);
+  pk.z = pack_bf16x2(b.x, b.y); pk.w = pack_bf16x2(b.z, b.w);
+  y[i] = pk;
+}
 int cast_bf16(const float* x, void* y, long long n, cudaStream_t stream) {
   if (n <= 0) return n == 0 ? CCX_OK : CCX_ERR_SHAPE;
-  const unsigned grid = static_cast<unsigned>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)n * 6.0);
+  if ((n % 8) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const long long n8 = n / 8;
+    cast_bf16x8_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<uint4*>(y), n8);
+    return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  }
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
   cast_bf16_kernel<<<grid, 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }

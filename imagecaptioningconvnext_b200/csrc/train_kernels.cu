@@ -86,6 +86,81 @@ convert_transpose_kernel(OpSrc x, long long ldx, const float* __restrict__ mul, 
   }
 }
 
+// ---- bf16-destination fast paths (the train step's operand conversions: ~45 launches per step) ------------------
+// The generic kernels above move one element per thread (4-byte loads, 2-byte stores, an integer division per element)
+// and measured 0.9-1.0 TB/s (profiles/r02_lstm_step_metrics.txt).  Here every thread moves 8 elements of a row with
+// 16-byte accesses; the transpose goes through a 64x64 tile and writes 128 bytes per warp instruction.
+template <bool SRC_BF16>
+__device__ __forceinline__ void load8(const void* base, long long idx, float (&v)[8]) {
+  if (SRC_BF16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+__device__ __forceinline__ void apply_mul8(float (&v)[8], const float* mul, long long idx, int mode, float mul_scale) {
+  if (mode == 0) return;
+  const float4 a = *reinterpret_cast<const float4*>(mul + idx), b = *reinterpret_cast<const float4*>(mul + idx + 4);
+  const float m[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = mode == 1 ? v[i] * m[i] : (m[i] > 0.f ? v[i] * mul_scale : 0.f);
+}
+
+template <bool SRC_BF16>
+__global__ void __launch_bounds__(256)
+convert_rows_bf16_kernel(const void* __restrict__ x, long long ldx, const float* __restrict__ mul, long long ldm,
+                         int mul_mode, float mul_scale, __nv_bfloat16* __restrict__ o, long long ldo, int R, int C8) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(R) * C8) return;
+  const int r = static_cast<int>(i / C8), c = static_cast<int>(i % C8) * 8;
+  float v[8];
+  load8<SRC_BF16>(x, r * ldx + c, v);
+  apply_mul8(v, mul, r * ldm + c, mul_mode, mul_scale);
+  uint4 pk;
+  pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+  pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(o + r * ldo + c) = pk;
+}
+
+// out[c, r] = x[r, c] (bf16), zero for R <= r < Rpad; 64 x 64 tile per CTA
+template <bool SRC_BF16>
+__global__ void __launch_bounds__(256)
+convert_transpose_bf16_kernel(const void* __restrict__ x, long long ldx, const float* __restrict__ mul, long long ldm,
+                              int mul_mode, float mul_scale, __nv_bfloat16* __restrict__ o, long long ldo, int R, int C,
+                              int Rpad) {
+  __shared__ float tile[64][65];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  {
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;     // 8 column groups of 8 x 32 rows
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = r0 + ty + 32 * k, c = c0 + 8 * tx;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (r < R && c < C) {             // C % 8 == 0 on this path: a group is entirely inside or outside
+        load8<SRC_BF16>(x, r * ldx + c, v);
+        apply_mul8(v, mul, r * ldm + c, mul_mode, mul_scale);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[ty + 32 * k][8 * tx + i] = v[i];
+    }
+  }
+  __syncthreads();
+  const int ox = threadIdx.x & 31, oy = threadIdx.x >> 5;      // lane -> two consecutive r, warp -> c
+  const int r = r0 + 2 * ox;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + oy + 8 * k;
+    if (c < C && r < Rpad)            // Rpad is even (a multiple of 8)
+      *reinterpret_cast<uint32_t*>(o + c * ldo + r) = pack_bf16x2(tile[2 * ox][oy + 8 * k], tile[2 * ox + 1][oy + 8 * k]);
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long ldx, const float* mul,
                     long long ldm, int mul_mode, float mul_scale, void* o_hi, float* o_lo, int o_dtype, long long ldo,
                     int R, int C, int transpose, int Rpad, cudaStream_t stream) {
@@ -93,6 +168,33 @@ int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long 
   OpDst o{o_hi, o_lo, o_dtype};
   OpSrc x{x_hi, x_lo, x_dtype};
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 8.0);
+  // fast paths: bf16 destination, plain fp32 or bf16 source, 8-element groups, 16-byte aligned rows
+  const bool src_bf16 = x_dtype == CCX_BF16;
+  const int sx = src_bf16 ? 2 : 4;
+  const bool fast = o_dtype == CCX_BF16 && x_lo == nullptr && (C % 8) == 0 && aligned16(x_hi) &&
+                    ((ldx * sx) % 16) == 0 && (mul_mode == 0 || (aligned16(mul) && (ldm % 4) == 0));
+  if (fast && !transpose && aligned16(o_hi) && ((ldo * 2) % 16) == 0) {
+    const long long n = static_cast<long long>(R) * (C / 8);
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (src_bf16)
+      convert_rows_bf16_kernel<true><<<grid, 256, 0, stream>>>(x_hi, ldx, mul, ldm, mul_mode, mul_scale,
+                                                               static_cast<__nv_bfloat16*>(o_hi), ldo, R, C / 8);
+    else
+      convert_rows_bf16_kernel<false><<<grid, 256, 0, stream>>>(x_hi, ldx, mul, ldm, mul_mode, mul_scale,
+                                                                static_cast<__nv_bfloat16*>(o_hi), ldo, R, C / 8);
+    return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  }
+  if (fast && transpose && Rpad >= R && (Rpad % 2) == 0 && (reinterpret_cast<uintptr_t>(o_hi) & 3) == 0 &&
+      (ldo % 2) == 0) {
+    dim3 grid((Rpad + 63) / 64, (C + 63) / 64);
+    if (src_bf16)
+      convert_transpose_bf16_kernel<true><<<grid, 256, 0, stream>>>(x_hi, ldx, mul, ldm, mul_mode, mul_scale,
+                                                                    static_cast<__nv_bfloat16*>(o_hi), ldo, R, C, Rpad);
+    else
+      convert_transpose_bf16_kernel<false><<<grid, 256, 0, stream>>>(x_hi, ldx, mul, ldm, mul_mode, mul_scale,
+                                                                     static_cast<__nv_bfloat16*>(o_hi), ldo, R, C, Rpad);
+    return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  }
   if (!transpose) {
     const long long n = static_cast<long long>(R) * C;
     convert_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale,
@@ -129,9 +231,60 @@ colsum_acc_kernel(const float* __restrict__ x, long long ldx, const float* __res
   }
 }
 
+// 128 columns per CTA (one float4 per lane), 8 warps stride the rows, four independent loads in flight per thread
+__global__ void __launch_bounds__(256)
+colsum_acc4_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mul, long long ldm,
+                   int mul_mode, float mul_scale, float* __restrict__ out, int R, int C, int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + 4 * lane;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(R, r_begin + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (int r = r_begin + ty; r < r_end; r += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = r + 8 * k;
+        v[k] = rr < r_end ? *reinterpret_cast<const float4*>(x + rr * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mul_mode != 0 && rr < r_end) {
+          const float4 m = *reinterpret_cast<const float4*>(mul + rr * ldm + c);
+          if (mul_mode == 1) { v[k].x *= m.x; v[k].y *= m.y; v[k].z *= m.z; v[k].w *= m.w; }
+          else {
+            v[k].x = m.x > 0.f ? v[k].x * mul_scale : 0.f; v[k].y = m.y > 0.f ? v[k].y * mul_scale : 0.f;
+            v[k].z = m.z > 0.f ? v[k].z * mul_scale : 0.f; v[k].w = m.w > 0.f ? v[k].w * mul_scale : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+    }
+  }
+  red[ty][lane] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float4 s4 = red[0][lane];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { s4.x += red[j][lane].x; s4.y += red[j][lane].y; s4.z += red[j][lane].z; s4.w += red[j][lane].w; }
+    atomicAdd(out + c, s4.x); atomicAdd(out + c + 1, s4.y); atomicAdd(out + c + 2, s4.z); atomicAdd(out + c + 3, s4.w);
+  }
+}
+
 int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
                float* out, int R, int C, cudaStream_t stream) {
   if (R <= 0 || C <= 0) return CCX_OK;
+  if ((C % 4) == 0 && (ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (mul_mode == 0 || ((ldm % 4) == 0 && (reinterpret_cast<uintptr_t>(mul) & 15) == 0))) {
+    // rows per CTA chosen so that the grid has a few CTAs per SM even for narrow matrices
+    const int col_blocks = (C + 127) / 128;
+    int rpb = 512;
+    while (rpb > 64 && static_cast<long long>(col_blocks) * ((R + rpb - 1) / rpb) < 148 * 4) rpb /= 2;
+    dim3 grid(col_blocks, (R + rpb - 1) / rpb);
+    ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 4.0);
+    colsum_acc4_kernel<<<grid, 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, rpb);
+    return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  }
   const int rpb = 256;
   dim3 grid((C + 31) / 32, (R + rpb - 1) / rpb);
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 4.0);

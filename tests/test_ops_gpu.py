@@ -171,3 +171,46 @@ def test_skinny_gemm_matches_exact_bf16_product(M, N, K):
     _lib.linear(A, Wt, residual=wide_res[:, 8:8 + N], out=wide_out[:, 16:16 + N])
     assert rel_err(wide_out[:, 16:16 + N].double(), exact + wide_res[:, 8:8 + N].cpu().double()) < 2e-5
     assert bool((wide_out[:, :16] == 7.0).all()) and bool((wide_out[:, 16 + N:] == 7.0).all())
+
+
+@pytest.mark.parametrize("R,C", [(1632, 2048), (200, 512), (77, 40), (33, 9490), (64, 24)])
+@pytest.mark.parametrize("src_bf16", [False, True])
+def test_convert_operand_rows_and_transpose_bf16_paths(R, C, src_bf16):
+    """ccx_convert_operand: the vectorised bf16-destination paths (8 elements per thread, 64x64 transpose tiles) and
+    the generic fallbacks (C % 8 != 0) against torch: cast, element-wise multiplier, ReLU-mask mode, zero padding of
+    the transposed rows."""
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import Operand
+    from imagecaptioningconvnext_b200.train_ops import to_operand
+    g = torch.Generator().manual_seed(R * 131 + C)
+    x = torch.randn(R, C, generator=g).cuda()
+    src = Operand(x.to(torch.bfloat16), None, torch.bfloat16) if src_bf16 else x
+    xr = src.hi.float() if src_bf16 else x
+    mul = torch.randn(R, C, generator=g).cuda()
+    for mode, scale, ref in ((0, 1.0, xr), (1, 1.0, xr * mul), (2, 2.0, torch.where(mul > 0, xr * 2.0, torch.zeros_like(xr)))):
+        m = None if mode == 0 else mul
+        o = to_operand(src, torch.bfloat16, m, mode, scale)
+        assert torch.equal(o.hi.float(), ref.to(torch.bfloat16).float()), (mode, "rows")
+        t = to_operand(src, torch.bfloat16, m, mode, scale, transpose=True)
+        assert t.hi.shape[0] == C and t.hi.shape[1] >= R
+        assert torch.equal(t.hi[:, :R].float(), ref.t().to(torch.bfloat16).float()), (mode, "transpose")
+        assert float(t.hi[:, R:].float().abs().max() if t.hi.shape[1] > R else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("R,C", [(1632, 9490), (8192, 512), (100, 36), (5, 7)])
+def test_colsum_acc_matches_torch(R, C):
+    from imagecaptioningconvnext_b200.train_ops import colsum_acc
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C, generator=g).cuda()
+    mul = torch.randn(R, C, generator=g).cuda()
+    for mode, scale, ref in ((0, 1.0, x), (1, 1.0, x * mul), (2, 2.0, torch.where(mul > 0, x * 2.0, torch.zeros_like(x)))):
+        out = torch.ones(C, device="cuda")                       # accumulates
+        colsum_acc(x, out, None if mode == 0 else mul, mode, scale)
+        assert rel_err(out, 1.0 + ref.double().sum(0).float()) < 1e-5, mode
+
+
+def test_cast_bf16_vector_and_tail_paths():
+    from imagecaptioningconvnext_b200 import _lib
+    for n in (8 * 1000, 8 * 1000 + 3, 5):
+        x = torch.randn(n, generator=torch.Generator().manual_seed(n)).cuda()
+        assert torch.equal(_lib.cast_bf16(x), x.to(torch.bfloat16))
