@@ -36,7 +36,7 @@ def _models(kind, start):
     return enc, dec, d_opt, e_opt
 
 
-@pytest.mark.parametrize("kind,start,B", [("lstm", 7, 32), ("lstm", None, 8)])
+@pytest.mark.parametrize("kind,start,B", [("lstm", 7, 32), ("lstm", None, 8), ("transformer", None, 8)])
 def test_captured_step_equals_eager_steps(kind, start, B):
     from imagecaptioningconvnext_b200.train_step import CapturedTrainStep, caption_train_step
     from synthetic import synthetic_captions, synthetic_images
