@@ -578,6 +578,33 @@ def encoder_line(args, ctx, with_cpu):
     return line
 
 
+def comm_attribution(ctx, enc, dec, cap_step, devbuf, ms_step):
+    """N > 1: where does the step time beyond the single-GPU step go?  (a) the gradient all-reduces of one step timed
+    alone, back to back, on an idle GPU; (b) the same captured step with the all-reduces left out.  exposed = step -
+    step without all-reduce; hidden fraction = 1 - exposed / (a)."""
+    import torch.distributed as dist
+    from imagecaptioningconvnext_b200.train_step import CapturedTrainStep, make_optimizers
+    dev, world = ctx.dev, ctx.world
+    slices = [cap_step._buckets[0]]
+    if len(cap_step._buckets) > 1:
+        slices += [cap_step._buckets[1][a:b] for a, b in cap_step._enc_units.values()]
+
+    def all_reduces():
+        for sl in slices:
+            dist.all_reduce(sl, op=dist.ReduceOp.AVG)
+    ms_ar = _timed(all_reduces, 10, 3, dev, world)
+    d_opt2, e_opt2 = make_optimizers(enc, dec)
+    quiet = CapturedTrainStep(enc, dec, d_opt2, e_opt2, skip_allreduce=True)
+    ms_quiet = _timed(lambda: quiet(*devbuf[0]), 20, 8, dev, world)
+    exposed = max(ms_step - ms_quiet, 0.0)
+    return {"bytes_per_step": int(sum(sl.numel() for sl in slices) * 4), "messages_per_step": len(slices),
+            "ms_alone_back_to_back": ms_ar, "ms_step_without_allreduce": ms_quiet, "ms_step": ms_step,
+            "exposed_ms": exposed, "hidden_fraction": 1.0 - min(exposed / ms_ar, 1.0) if ms_ar > 0 else None,
+            "algorithm_bandwidth_gbs": sum(sl.numel() for sl in slices) * 4 / (ms_ar * 1e-3) / 1e9,
+            "how": "fp32 buckets, NCCL average all-reduce inside the step's CUDA graph: decoder bucket after the "
+                   "decoder backward, one slice per CNBlock of the fine-tuned stage as each block's backward ends"}
+
+
 def count_kernels(step_fn, n):
     """GPU kernels per call of step_fn(i), counted by CUPTI (torch.profiler) — library, ATen and NCCL kernels alike,
     whether launched eagerly or from a CUDA-graph replay."""
@@ -741,6 +768,9 @@ def train_line(args, ctx):
             for i, (k, ms_i, wk) in enumerate(spans[:per]):
                 f.write(f"{i:4d} {k:12s} {ms_i * 1e3:9.1f} us  work={wk:.4g}\n")
     barrier()
+    comm = None
+    if world > 1 and captured:
+        comm = comm_attribution(ctx, enc, dec, cap_step, devbuf, ms_total / args.steps)
     del enc_w, dec_w, d_opt, e_opt, enc, dec, devbuf, stages
     if captured:
         del cap_step
@@ -798,6 +828,7 @@ def train_line(args, ctx):
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
         "last_loss": last_loss,
         "host_enqueue_ms_per_step": host_ms,
+        "allreduce": comm,
     }
 
 

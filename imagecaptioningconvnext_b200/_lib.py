@@ -76,6 +76,7 @@ SIGNATURES = {
     "ccx_num_sms": (C.c_int, []),
     "ccx_linear": (C.c_int, [C.POINTER(LinearDesc), _vp]),
     "ccx_set_gemm_pair_mode": (C.c_int, [_i32]),
+    "ccx_set_sm_limit": (C.c_int, [_i32]),
     "ccx_split_tf32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "ccx_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ccx_stem_ln": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp]),

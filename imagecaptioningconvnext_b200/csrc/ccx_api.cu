@@ -44,6 +44,11 @@ int ccx_linear(const ccx_linear_desc* d, void* stream) {
   return gemm_tn(g, as_stream(stream));
 }
 
+int ccx_set_sm_limit(int32_t n) {
+  set_sm_limit(n);
+  return CCX_OK;
+}
+
 int ccx_set_gemm_pair_mode(int32_t mode) {
   set_gemm_pair_mode(mode);
   return CCX_OK;

@@ -41,5 +41,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_fn();
 int num_sms();
+void set_sm_limit(int n);   // 0 = no cap; see gemm_tcgen05.cu
 
 }  // namespace ccx

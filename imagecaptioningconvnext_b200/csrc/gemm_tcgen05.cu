@@ -222,6 +222,13 @@ static int make_map_2d(CUtensorMap* map, const void* ptr, int is_f32, long long 
   return r == CUDA_SUCCESS ? CCX_OK : CCX_ERR_TMA;
 }
 
+// Optional cap on the SMs the persistent GEMM grids occupy (0 = all).  A persistent kernel with one CTA per SM that
+// owns the whole register file and shared memory cannot share an SM with an NCCL kernel: while a gradient all-reduce
+// runs next to the backward pass, either NCCL waits for SMs or the last CTAs of every GEMM wait for NCCL.  Leaving a
+// few SMs to the collective for that stretch lets both proceed (CapturedTrainStep sets it around the encoder backward).
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+
 int num_sms() {
   static PerDevice<int> cache;
   int& n = cache.ref();
@@ -230,7 +237,7 @@ int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 template <int BN, bool IS_TF32>

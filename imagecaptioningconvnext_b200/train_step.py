@@ -5,8 +5,11 @@ modules in ``torch.nn.parallel.DistributedDataParallel`` (as the reference does,
 gradient all-reduce over NCCL overlaps with the explicit backward.
 """
 
+import os
+
 import torch
 
+from . import _lib
 from ._host import device_twin, named_params, stash_host_copy
 from .decoder import DecoderWithAttention
 from .losses import free_running_cross_entropy, packed_cross_entropy
@@ -90,7 +93,7 @@ class CapturedTrainStep:
     """
 
     def __init__(self, encoder, decoder, decoder_optimizer, encoder_optimizer=None, pad_token=0, alpha_c=1.0,
-                 warmup_steps=3, process_group=None):
+                 warmup_steps=3, process_group=None, skip_allreduce=False):
         import torch.distributed as dist
         self.encoder, self.decoder = encoder, decoder
         self.d_opt, self.e_opt = decoder_optimizer, encoder_optimizer
@@ -99,6 +102,11 @@ class CapturedTrainStep:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.lstm = isinstance(decoder, DecoderWithAttention)
+        # SMs the persistent GEMMs leave to NCCL while an all-reduce runs next to the encoder backward (0 = none).
+        # Measured on 2 x B200 (gpurun_out / profiles/r02_allreduce_attribution.txt): 0, 16 and 32 give the same step
+        # time — the all-reduce is not the one waiting for SMs — so the default stays 0.
+        self.comm_sms = int(os.environ.get("CCX_COMM_SMS", "0"))
+        self.skip_allreduce = skip_allreduce   # diagnostics only (bench.py: how much of the all-reduce is exposed)
         self.graph, self.static, self.loss = None, None, None
         self._shape_key = None
         if self.lstm:
@@ -179,7 +187,7 @@ class CapturedTrainStep:
         import torch.distributed as dist
         loss.backward()                                   # decoder part: parameter gradients + d features
         dec_work, enc_works, reduced = None, [], set()
-        multi = self.world > 1
+        multi = self.world > 1 and not self.skip_allreduce
 
         def reduce_slice(flat, a, b):
             return dist.all_reduce(flat[a:b], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
@@ -194,7 +202,14 @@ class CapturedTrainStep:
                         reduced.add((child, i))
                         enc_works.append(reduce_slice(self._buckets[1], *self._enc_units[(child, i)]))
                 self.encoder._unit_grads_ready = ready
-            feats.backward(feats_in.grad)                 # fine-tuned encoder stage; overlaps the decoder all-reduce
+            if multi and self.comm_sms > 0:
+                # the persistent GEMMs leave `comm_sms` SMs to the NCCL kernels that run next to this backward
+                _lib.lib().ccx_set_sm_limit(max(_lib.lib().ccx_num_sms() - self.comm_sms, 1))
+            try:
+                feats.backward(feats_in.grad)             # fine-tuned encoder stage; overlaps the decoder all-reduce
+            finally:
+                if multi and self.comm_sms > 0:
+                    _lib.lib().ccx_set_sm_limit(0)
             self.encoder._unit_grads_ready = None
             if multi and len(self._buckets) > 1:
                 for key, (a, b) in self._enc_units.items():       # the first trainable unit (its input has no gradient)

@@ -85,6 +85,9 @@ CCX_API int ccx_linear(const ccx_linear_desc* d, void* stream);
 /* mode != 0: GEMMs that fill the machine with 256x256 tiles use the CTA-pair kernel (tcgen05 cta_group::2, UMMA
  * M=256 across two SMs, each SM streaming half of the B tile).  Off by default: on the ConvNeXt shapes it measures
  * equal or slower than the single-CTA kernel (profiles/r01_spans_v5*.txt). */
+/* Cap the number of SMs the persistent GEMM grids use from now on (0 = all SMs): leaves room for a concurrent NCCL
+ * kernel while a gradient all-reduce overlaps the backward pass.  Process-wide; takes effect at the next launch. */
+CCX_API int ccx_set_sm_limit(int32_t n_sms);
 CCX_API int ccx_set_gemm_pair_mode(int32_t mode);
 
 /* fp32 -> (tf32 hi, fp32 lo) and fp32 -> bf16 operand preparation (weights once, activations in epilogues) */
