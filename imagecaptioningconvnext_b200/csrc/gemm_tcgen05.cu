@@ -31,21 +31,51 @@ namespace ccx {
 
 static constexpr int BM = 128;          // UMMA M (one TMEM lane per row)
 static constexpr int ROW_BYTES = 128;   // one swizzle row = 64 bf16 or 32 tf32 elements
-static constexpr int NUM_THREADS = 384; // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-11 epilogue (2 per TMEM lane quarter)
-static constexpr int EPI_WARPS = 8;
+// warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4.. epilogue: EPI_CG warps per TMEM lane quarter, each draining every
+// EPI_CG-th column unit.  Measured (tools/gemm_timeline.cu): 4 warps per quarter drain a tile no faster than 2 — a
+// 128x256 GELU tile costs ~6.6 k cycles either way, of which the MUFU work is 25 % and the rest follows the L2
+// traffic of the operand stream and the output (the tile's TMEM read floor is 2 k cycles) — and cost an operand stage.
+static constexpr int EPI_CG = 2;
+static constexpr int EPI_WARPS = 4 * EPI_CG;
+static constexpr int NUM_THREADS = 128 + 32 * EPI_WARPS;
 
-template <int BN>
+// Shared-memory plan.  BOXES = 4 KB staging boxes per epilogue warp (TMA epilogue; box 0 doubles as the transposition
+// scratch of the generic epilogue): 2 lets a residual box load while the previous unit is still being stored, at the
+// price of one operand stage on the 256-wide tile.  The dynamic shared-memory window starts 1024-byte aligned (the
+// kernel has no static shared memory; checked at run time), so there is no alignment slack.
+template <int BN, int BOXES>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * ROW_BYTES;
   static constexpr int B_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int BAR_BYTES = 1024;
-  static constexpr int EPI_BYTES = 8 * EPI_SCRATCH_FLOATS * 4;   // transposition scratch of the 8 epilogue warps
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int EPI_BYTES = EPI_WARPS * BOXES * EPI_UNIT_BYTES;
+  static constexpr int BAR_BYTES = 512;                            // pipeline + accumulator + residual mbarriers, TMEM slot
+  static constexpr int PARAM_BYTES = 2 * BN * 4;                   // bias, layer-scale of the current tile
+  static constexpr int BUDGET = 232448;                            // 227 KB
+  static constexpr int MAX_STAGES = (BUDGET - EPI_BYTES - BAR_BYTES - PARAM_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + PARAM_BYTES;
+  static_assert(STAGES >= 3, "operand ring too short");
+  static_assert(EPI_UNIT_BYTES == EPI_SCRATCH_FLOATS * 4, "box 0 doubles as the generic epilogue's scratch");
 };
 
 
+
+// Developer timeline (tools/gemm_timeline.cu builds this file with -DCCX_GEMM_TIMELINE): per-role cycle accounting of
+// two CTAs, and switches that remove parts of the epilogue.  Compiled out of libccx.
+#ifdef CCX_GEMM_TIMELINE
+__device__ unsigned long long g_gemm_tl[2][16];
+#define TL_DECL(name) long long name = 0
+#define TL_T0(t) const long long t = clock64()
+#define TL_ADD(acc, t) acc += clock64() - t
+#define TL_PUT(slot, v) do { const int c_ = blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 1 ? 1 : -1); \
+                             if (c_ >= 0) g_gemm_tl[c_][slot] = (unsigned long long)(v); } while (0)
+#else
+#define TL_DECL(name)
+#define TL_T0(t)
+#define TL_ADD(acc, t)
+#define TL_PUT(slot, v)
+#endif
 
 template <typename T>
 __device__ __forceinline__ float ld_as_float(const T* p);
@@ -57,28 +87,36 @@ __device__ __forceinline__ float ld_as_float<__nv_bfloat16>(const __nv_bfloat16*
 }
 
 // IS_TF32: fp32 words in smem, kind::tf32, UMMA_K = 8; else bf16, kind::f16, UMMA_K = 16
-template <int BN, bool IS_TF32>
+template <int BN, bool IS_TF32, int BOXES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmB_hi,
                const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                int M, int N, int K, int nseg, EpiArgs ep) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, BOXES>;
   constexpr int STAGES = S::STAGES;
   constexpr int BK = IS_TF32 ? 32 : 64;  // elements per 128-byte row
   constexpr uint32_t IDESC = umma_idesc(IS_TF32 ? 2u : 1u, BM, BN);
   constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+    printf("ccx: gemm shared-memory window not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * S::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint8_t* epi_boxes = smem + STAGES * S::STAGE_BYTES;                       // 1024-byte aligned: TMA swizzle atoms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_boxes + S::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;                                 // [EPI_WARPS][BOXES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS * BOXES);
+  static_assert((2 * 8 + 4 + EPI_WARPS * 2) * 8 + 4 <= S::BAR_BYTES, "barrier block");
+  static_assert(BN <= 128 * EPI_CG, "one epilogue thread per tile column loads the parameters");
+  float* epi_params = reinterpret_cast<float*>(epi_boxes + S::EPI_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,6 +126,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
   const int k_iters = num_kb * nseg;
+  // tiles of this CTA (the grid never exceeds the tile count), and whether its last tile's residual uses the ring
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  constexpr int RING_BPS = (S::B_BYTES / EPI_UNIT_BYTES) > 0 ? (S::B_BYTES / EPI_UNIT_BYTES) : 1;   // boxes per B stage
+  const bool ring_res = ep.tma && ep.residual != nullptr && BN >= 64 &&
+                        4 * (BN / ((ep.out_dtype == CCX_F32) ? 32 : 64)) <= STAGES * RING_BPS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi);
@@ -95,6 +138,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (nseg > 1) {
       tma_prefetch_desc(&tmA_lo);
       tma_prefetch_desc(&tmB_lo);
+    }
+    if (ep.tma) {
+      tma_prefetch_desc(&tmC);
+      if (ep.residual != nullptr) tma_prefetch_desc(&tmR);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -106,6 +153,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], EPI_WARPS);
     }
+    for (int i = 0; i < EPI_WARPS * BOXES; ++i) mbar_init(&res_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -122,6 +170,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+    TL_DECL(w_empty);
+    TL_T0(t_begin);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       for (int it = 0; it < k_iters; ++it) {
@@ -129,25 +179,57 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // segment order: (Alo,Bhi), (Ahi,Blo), (Ahi,Bhi); single-segment runs use (hi,hi)
         const CUtensorMap* ta = (nseg > 1 && seg == 0) ? &tmA_lo : &tmA_hi;
         const CUtensorMap* tb = (nseg > 1 && seg == 1) ? &tmB_lo : &tmB_hi;
+        TL_T0(t0);
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        TL_ADD(w_empty, t0);
         mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
         tma_load_2d(smem_a + stage * S::A_BYTES, ta, &full_bar[stage], kb * BK, m_blk * BM);
         tma_load_2d(smem_b + stage * S::B_BYTES, tb, &full_bar[stage], kb * BK, n_blk * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    if (ring_res) {
+      // the residual of this CTA's last tile, queued behind its last operand loads (see EpiRing)
+      const int last = blockIdx.x + (my_tiles - 1) * gridDim.x;
+      const int m_blk = last / n_tiles, n_blk = last % n_tiles;
+      const int ucols = (ep.out_dtype == CCX_F32) ? 32 : 64;
+      const int nboxes = 4 * (BN / ucols);
+      for (int b0 = 0; b0 < nboxes; b0 += RING_BPS) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], RING_BPS * EPI_UNIT_BYTES);
+        for (int i = 0; i < RING_BPS; ++i) {
+          const int b = b0 + i;
+          tma_load_2d(smem_b + stage * S::B_BYTES + i * EPI_UNIT_BYTES, &tmR, &full_bar[stage],
+                      n_blk * BN + (b >> 2) * ucols, m_blk * BM + (b & 3) * 32);
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    TL_PUT(0, w_empty);
+    TL_PUT(1, clock64() - t_begin);
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    TL_DECL(w_full);
+    TL_DECL(w_tempty);
+    TL_DECL(w_first);
+    TL_T0(t_begin);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      TL_T0(t1);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      TL_ADD(w_tempty, t1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int it = 0; it < k_iters; ++it) {
+        TL_T0(t0);
         mbar_wait(&full_bar[stage], phase);
+        TL_ADD(w_full, t0);
+#ifdef CCX_GEMM_TIMELINE
+        if (tile == (int)blockIdx.x && it == 0) w_first = clock64() - t_begin;
+#endif
         tc_fence_after();
         const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * S::A_BYTES));
         const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * S::B_BYTES));
@@ -164,20 +246,77 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tc_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    TL_PUT(2, w_full);
+    TL_PUT(3, w_tempty);
+    TL_PUT(4, clock64() - t_begin);
+    TL_PUT(5, w_first);
   } else if (warp >= 4) {
     // ===================== epilogue warps =====================
     const int ew = warp & 3;          // TMEM lane quarter this warp may access (warp id % 4)
-    const int half = (warp - 4) >> 2;  // two warps share a quarter and split the 32-column chunks by parity
+    const int half = (warp - 4) >> 2;  // column group: EPI_CG warps share a quarter and take every EPI_CG-th unit
     int acc = 0;
     uint32_t acc_phase = 0;
+    TL_DECL(w_tfull);
+    TL_T0(t_begin);
+    EpiTmaState tma_state;
+    EpiRing ring;
+    {
+      const long long iters = static_cast<long long>(my_tiles) * k_iters;
+      ring.base = smem_b;
+      ring.full_bar = full_bar;
+      ring.stage0 = static_cast<int>(iters % STAGES);
+      ring.phase0 = static_cast<uint32_t>((iters / STAGES) & 1);
+      ring.stages = STAGES;
+      ring.stage_bytes = S::B_BYTES;
+      ring.boxes_per_stage = RING_BPS;
+    }
+    if (ep.tma && static_cast<int>(blockIdx.x) < num_tiles)
+      epilogue_params_prefetch<BN>(ep, tma_state, blockIdx.x % n_tiles, (blockIdx.x / n_tiles) * BM + ew * 32 + lane,
+                                   threadIdx.x - 128, M, N);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half, m_blk * BM + ew * 32, lane,
-                        epi_scratch + (warp - 4) * EPI_SCRATCH_FLOATS, n_blk, M, N, &tfull_bar[acc], acc_phase);
+#ifdef CCX_GEMM_TIMELINE
+      {
+        TL_T0(t0);
+        mbar_wait(&tfull_bar[acc], acc_phase);     // the wait inside epilogue_tile then returns at once
+        TL_ADD(w_tfull, t0);
+      }
+#endif
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      uint8_t* my_boxes = epi_boxes + (warp - 4) * (BOXES * EPI_UNIT_BYTES);
+      if (ep.tma) {
+        const int next_tile = tile + gridDim.x;
+        const int next_n = next_tile < num_tiles ? next_tile % n_tiles : -1;
+        const int next_row0 = next_tile < num_tiles ? (next_tile / n_tiles) * BM + ew * 32 : 0;
+        const EpiRing* rp = (ring_res && next_tile >= num_tiles) ? &ring : nullptr;              // this is the last tile
+        const bool next_ring = ring_res && next_tile < num_tiles && next_tile + static_cast<int>(gridDim.x) >= num_tiles;
+        if (ep.out_dtype == CCX_F32)
+          epilogue_tile_tma<BN, BOXES, true, EPI_CG>(ep, &tmC, &tmR, taddr, half, m_blk * BM + ew * 32, lane,
+                                                     threadIdx.x - 128, my_boxes, epi_params,
+                                                     res_bar + (warp - 4) * BOXES, tma_state, n_blk, M, N,
+                                                     &tfull_bar[acc], acc_phase, next_n, next_row0, rp, next_ring);
+        else
+          epilogue_tile_tma<BN, BOXES, false, EPI_CG>(ep, &tmC, &tmR, taddr, half, m_blk * BM + ew * 32, lane,
+                                                      threadIdx.x - 128, my_boxes, epi_params,
+                                                      res_bar + (warp - 4) * BOXES, tma_state, n_blk, M, N,
+                                                      &tfull_bar[acc], acc_phase, next_n, next_row0, rp, next_ring);
+      } else {
+        epilogue_tile<BN, EPI_CG, EPI_CG == 2>(ep, taddr, half, m_blk * BM + ew * 32, lane, reinterpret_cast<float*>(my_boxes),
+                                         n_blk, M, N, &tfull_bar[acc], acc_phase);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (ep.tma && lane == 0) tma_store_wait_read<0>();     // the boxes must outlive the stores that read them
+#ifdef CCX_GEMM_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 128)
+      for (int i = 0; i < 5; ++i) g_epi_tl[i] += tma_state.tl[i];
+#endif
+    if (warp == 4 && lane == 0) {
+      TL_PUT(6, w_tfull);
+      TL_PUT(7, clock64() - t_begin);
     }
   }
 
@@ -192,6 +331,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // ----------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------
+#ifdef CCX_GEMM_TIMELINE
+void gemm_timeline_mode(int mode) { cudaMemcpyToSymbol(g_gemm_dbg_mode, &mode, sizeof(int)); }
+void gemm_timeline_read(unsigned long long* out32) { cudaMemcpyFromSymbol(out32, g_gemm_tl, sizeof(g_gemm_tl)); }
+void gemm_epi_timeline(unsigned long long* out8) {          // read and clear
+  cudaMemcpyFromSymbol(out8, g_epi_tl, sizeof(g_epi_tl));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_epi_tl, z, sizeof(z));
+}
+#endif
 PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
   if (fn == nullptr) {
@@ -240,14 +388,16 @@ int num_sms() {
   return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
-template <int BN, bool IS_TF32>
-static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo,
-                  const CUtensorMap& b_lo, int M, int N, int K, int nseg, const EpiArgs& ep,
-                  cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+struct GemmMaps {
+  CUtensorMap a_hi, b_hi, a_lo, b_lo, c, r;
+};
+
+template <int BN, bool IS_TF32, int BOXES>
+static int launch(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiArgs& ep, cudaStream_t stream) {
+  using S = GemmSmem<BN, BOXES>;
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.ref();
-  auto kfn = gemm_tn_kernel<BN, IS_TF32>;
+  auto kfn = gemm_tn_kernel<BN, IS_TF32, BOXES>;
   if (!configured) {
     if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL) != cudaSuccess)
       return CCX_ERR_CUDA;
@@ -256,16 +406,31 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtens
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid < 1) return CCX_OK;
-  return launch_pdl(kfn, dim3(grid), dim3(NUM_THREADS), S::TOTAL, stream, a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep) ==
-                 cudaSuccess
+  return launch_pdl(kfn, dim3(grid), dim3(NUM_THREADS), S::TOTAL, stream, tm.a_hi, tm.b_hi, tm.a_lo, tm.b_lo, tm.c, tm.r,
+                    M, N, K, nseg, ep) == cudaSuccess
              ? CCX_OK : CCX_ERR_CUDA;
 }
 
+template <int BN, bool IS_TF32>
+static int launch_boxes(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiArgs& ep, int boxes,
+                        cudaStream_t stream) {
+  // (two boxes per warp only fit next to a useful operand ring on the narrow tiles)
+  if constexpr (BN <= 128) {
+    if (boxes == 2) return launch<BN, IS_TF32, 2>(tm, M, N, K, nseg, ep, stream);
+  }
+  return launch<BN, IS_TF32, 1>(tm, M, N, K, nseg, ep, stream);
+}
+
 int gemm_tn_2cta(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
-                 int M, int N, int K, int nseg, const EpiArgs& ep, bool tf32, cudaStream_t stream);
+                 const CUtensorMap& c, const CUtensorMap& r, int M, int N, int K, int nseg, const EpiArgs& ep, bool tf32,
+                 cudaStream_t stream);
 
 static int g_pair_mode = -1;
 void set_gemm_pair_mode(int mode) { g_pair_mode = mode ? 1 : 0; }
+// developer overrides (tools/gemm_timeline.cu): epilogue 0 = generic only, -1 = auto; staging boxes 0 = auto, 1, 2
+static int g_epi_override = -1;
+static int g_boxes_override = 0;
+void set_gemm_epilogue_override(int epi, int boxes) { g_epi_override = epi; g_boxes_override = boxes; }
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return g.M == 0 ? CCX_OK : CCX_ERR_SHAPE;
@@ -296,7 +461,8 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   const bool use_pair = pair_mode && g.force_bn == 0 && (g.N % 256 == 0) && g.M >= 256 &&
                         pair_tiles >= num_sms() / 2;
   if (use_pair) bn = 128;   // B box = this CTA's half of the 256-row B tile
-  CUtensorMap a_hi, b_hi, a_lo, b_lo;
+  GemmMaps tm;
+  CUtensorMap &a_hi = tm.a_hi, &b_hi = tm.b_hi, &a_lo = tm.a_lo, &b_lo = tm.b_lo;
   int rc;
   if ((rc = make_map_2d(&a_hi, g.A, tf32, g.M, g.K, g.lda, BM))) return rc;
   if ((rc = make_map_2d(&b_hi, g.B, tf32, g.N, g.K, g.ldb, bn))) return rc;
@@ -309,6 +475,26 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
     a_lo = a_hi;
     b_lo = b_hi;
   }
+  // TMA epilogue: output (and residual) rows must start 16-byte aligned; the dropout-mask and hi/lo-split epilogues
+  // stay on the generic path
+  const bool out_f32 = (g.out_dtype == CCX_F32);
+  const long long oes = out_f32 ? 4 : 2;
+  auto tma_ok = [&](const void* p, long long ld) {
+    return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((ld * oes) & 15) == 0;
+  };
+  static const int epi_mode = getenv("CCX_GEMM_EPI") ? atoi(getenv("CCX_GEMM_EPI")) : -1;   // 0 = generic only
+  const bool use_tma = epi_mode != 0 && g_epi_override != 0 && g.emask == nullptr &&
+                       !(g.split && g.C_lo != nullptr) && tma_ok(g.C, g.ldc) &&
+                       (g.residual == nullptr || tma_ok(g.residual, g.ldr));
+  tm.c = a_hi;
+  tm.r = a_hi;
+  if (use_tma) {
+    if ((rc = make_map_2d(&tm.c, g.C, out_f32, g.M, g.N, g.ldc, 32))) return rc;
+    if (g.residual != nullptr && (rc = make_map_2d(&tm.r, g.residual, out_f32, g.M, g.N, g.ldr, 32))) return rc;
+  }
+  // staging boxes per epilogue warp
+  int boxes = 1;
+  if (g_boxes_override > 0) boxes = g_boxes_override;
   ProfScope prof(PROF_GEMM, stream, 2.0 * g.M * (double)g.N * g.K);
   EpiArgs ep;
   ep.out = g.C;
@@ -325,15 +511,16 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   ep.act = g.act;
   ep.out_dtype = g.out_dtype;
   ep.split = (g.split && g.C_lo != nullptr) ? 1 : 0;
-  if (use_pair) return gemm_tn_2cta(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, tf32, stream);
+  ep.tma = use_tma ? 1 : 0;
+  if (use_pair) return gemm_tn_2cta(a_hi, b_hi, a_lo, b_lo, tm.c, tm.r, g.M, g.N, g.K, nseg, ep, tf32, stream);
   if (tf32) {
-    if (bn == 256) return launch<256, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
-    if (bn == 128) return launch<128, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
-    return launch<64, true>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+    if (bn == 256) return launch_boxes<256, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
+    if (bn == 128) return launch_boxes<128, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
+    return launch_boxes<64, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
   } else {
-    if (bn == 256) return launch<256, false>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
-    if (bn == 128) return launch<128, false>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
-    return launch<64, false>(a_hi, b_hi, a_lo, b_lo, g.M, g.N, g.K, nseg, ep, stream);
+    if (bn == 256) return launch_boxes<256, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
+    if (bn == 128) return launch_boxes<128, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
+    return launch_boxes<64, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
   }
 }
 

@@ -25,9 +25,12 @@ struct Gemm2Smem {
   static constexpr int B_BYTES = (BN / 2) * ROW_BYTES2;     // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
-  static constexpr int BAR_BYTES = 1024;
-  static constexpr int EPI_BYTES = 8 * EPI_SCRATCH_FLOATS * 4;   // transposition scratch of the 8 epilogue warps
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
+  static constexpr int EPI_BYTES = EPI_WARPS2 * EPI_UNIT_BYTES;  // one 4 KB staging box per epilogue warp (TMA epilogue;
+                                                                 // doubles as the generic epilogue's transposition scratch)
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int PARAM_BYTES = 2 * BN * 4;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + PARAM_BYTES;   // window is 1024-aligned
+  static_assert(TOTAL <= 232448, "shared memory");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -101,7 +104,8 @@ __device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, u
 template <int BN, bool IS_TF32>
 __global__ void __launch_bounds__(NUM_THREADS2, 1)
 gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmB_hi,
-                    const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo, int M,
+                    const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, int M,
                     int N, int K, int nseg, EpiArgs ep) {
   using S = Gemm2Smem<BN>;
   constexpr int STAGES = S::STAGES;
@@ -109,17 +113,23 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   constexpr uint32_t IDESC = umma_idesc(IS_TF32 ? 2u : 1u, 2 * BM2, BN);   // UMMA M = 256 across the pair
   constexpr uint32_t TMEM_COLS = 2 * BN;                                    // two accumulator stages
 
-  extern __shared__ uint8_t smem_raw2[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+  extern __shared__ uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) {
+    printf("ccx: gemm shared-memory window not 1024-byte aligned\n");
+    __trap();
+  }
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * S::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint8_t* epi_boxes = smem + STAGES * S::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_boxes + S::EPI_BYTES);
   uint64_t* full_bar = bars;                    // used on the leader: both CTAs' TMA bytes land here
   uint64_t* empty_bar = bars + STAGES;          // per CTA: the pair-MMA commit frees this CTA's stage
   uint64_t* tfull_bar = bars + 2 * STAGES;      // per CTA: accumulator stage complete
   uint64_t* tempty_bar = bars + 2 * STAGES + 2; // leader: both CTAs' epilogues drained the stage
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  float* epi_scratch = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + S::BAR_BYTES);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;    // per epilogue warp: residual box landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS2);
+  static_assert((2 * 8 + 4 + EPI_WARPS2) * 8 + 4 <= S::BAR_BYTES, "barrier block");
+  float* epi_params = reinterpret_cast<float*>(epi_boxes + S::EPI_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,6 +151,10 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       tma_prefetch_desc(&tmA_lo);
       tma_prefetch_desc(&tmB_lo);
     }
+    if (ep.tma) {
+      tma_prefetch_desc(&tmC);
+      if (ep.residual != nullptr) tma_prefetch_desc(&tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -151,6 +165,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * EPI_WARPS2);
     }
+    for (int i = 0; i < EPI_WARPS2; ++i) mbar_init(&res_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -161,6 +176,7 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();      // barriers of BOTH CTAs are initialised before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_sync();          // PDL: everything above overlaps the previous kernel's tail
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -216,16 +232,37 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    EpiTmaState tma_state;
+    const int tid_e = threadIdx.x - 128;
+    auto tile_row0 = [&](int t) { return ((t / n_tiles) * 2 + static_cast<int>(rank)) * BM2 + ew * 32; };
+    if (ep.tma && pair < num_tiles)
+      epilogue_params_prefetch<BN>(ep, tma_state, pair % n_tiles, tile_row0(pair) + lane, tid_e, M, N);
+    uint8_t* my_box = epi_boxes + (warp - 4) * EPI_UNIT_BYTES;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int ms = tile / n_tiles, n_blk = tile % n_tiles;
-      epilogue_tile<BN>(ep, tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN, half,
-                        (ms * 2 + static_cast<int>(rank)) * BM2 + ew * 32, lane,
-                        epi_scratch + (warp - 4) * EPI_SCRATCH_FLOATS, n_blk, M, N, &tfull_bar[acc], acc_phase);
+      const int n_blk = tile % n_tiles;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      if (ep.tma) {
+        const int next_tile = tile + num_pairs;
+        const int next_n = next_tile < num_tiles ? next_tile % n_tiles : -1;
+        const int next_row0 = next_tile < num_tiles ? tile_row0(next_tile) : 0;
+        if (ep.out_dtype == CCX_F32)
+          epilogue_tile_tma<BN, 1, true, 2>(ep, &tmC, &tmR, taddr, half, tile_row0(tile), lane, tid_e, my_box, epi_params,
+                                            res_bar + (warp - 4), tma_state, n_blk, M, N, &tfull_bar[acc], acc_phase,
+                                            next_n, next_row0);
+        else
+          epilogue_tile_tma<BN, 1, false, 2>(ep, &tmC, &tmR, taddr, half, tile_row0(tile), lane, tid_e, my_box, epi_params,
+                                             res_bar + (warp - 4), tma_state, n_blk, M, N, &tfull_bar[acc], acc_phase,
+                                             next_n, next_row0);
+      } else {
+        epilogue_tile<BN>(ep, taddr, half, tile_row0(tile), lane, reinterpret_cast<float*>(my_box), n_blk, M, N,
+                          &tfull_bar[acc], acc_phase);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (ep.tma && lane == 0) tma_store_wait_read<0>();     // the boxes must outlive the stores that read them
   }
 
   tc_fence_before();
@@ -238,7 +275,8 @@ gemm_tn_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
 template <int BN, bool IS_TF32>
 static int launch2(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
-                   int M, int N, int K, int nseg, const EpiArgs& ep, cudaStream_t stream) {
+                   const CUtensorMap& c, const CUtensorMap& r, int M, int N, int K, int nseg, const EpiArgs& ep,
+                   cudaStream_t stream) {
   using S = Gemm2Smem<BN>;
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.ref();
@@ -257,22 +295,25 @@ static int launch2(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUten
   cfg.blockDim = dim3(NUM_THREADS2, 1, 1);
   cfg.dynamicSmemBytes = S::TOTAL;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // the kernel calls grid_dep_sync()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, kfn, a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep) != cudaSuccess) return CCX_ERR_CUDA;
+  cfg.numAttrs = 2;
+  if (cudaLaunchKernelEx(&cfg, kfn, a_hi, b_hi, a_lo, b_lo, c, r, M, N, K, nseg, ep) != cudaSuccess) return CCX_ERR_CUDA;
   return CCX_OK;
 }
 
 // Called by gemm_tn() for shapes that fill the machine with 256x256 pair tiles.  Maps: A box 128 rows, B box 128 rows.
 int gemm_tn_2cta(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
-                 int M, int N, int K, int nseg, const EpiArgs& ep, bool tf32, cudaStream_t stream) {
-  if (tf32) return launch2<256, true>(a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep, stream);
-  return launch2<256, false>(a_hi, b_hi, a_lo, b_lo, M, N, K, nseg, ep, stream);
+                 const CUtensorMap& c, const CUtensorMap& r, int M, int N, int K, int nseg, const EpiArgs& ep, bool tf32,
+                 cudaStream_t stream) {
+  if (tf32) return launch2<256, true>(a_hi, b_hi, a_lo, b_lo, c, r, M, N, K, nseg, ep, stream);
+  return launch2<256, false>(a_hi, b_hi, a_lo, b_lo, c, r, M, N, K, nseg, ep, stream);
 }
 
 }  // namespace ccx

