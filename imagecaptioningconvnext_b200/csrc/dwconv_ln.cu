@@ -383,6 +383,210 @@ dwconv7_ln_kernel_v2(const __grid_constant__ CUtensorMap tmX, DwArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v3: persistent.  The one-tile kernels above are a chain of latencies per CTA (launch, 49 tap loads, the halo TMA,
+// ~1.8 k cycles of FFMA2, the LayerNorm exchange with a cluster barrier, the stores) of which only the arithmetic is
+// throughput; with 4 co-resident CTAs that all start together the phases line up instead of overlapping (ncu r02:
+// 10.9 % warps active, 0.17 of the HBM rate).  Here a CTA owns 128 channels (4 warps, every lane two adjacent
+// channels as in v2), TWO CTAs share an SM (2 warps per scheduler: one warp alone cannot hide the LDS -> FFMA2
+// latency — a one-CTA-per-SM double-buffered version measured 30 % slower than v2) and a CLUSTER of C/128 CTAs walks
+// over the 8x8 pixel tiles: taps / affine parameters are loaded once, the halo of the next tile is requested as soon
+// as the last warp has read the current one (it streams in under the LayerNorm exchange, the stores and the other
+// CTA's arithmetic), and the per-pixel LayerNorm sums travel between the CTAs as st.async stores that complete on
+// the receiver's mbarrier (double-buffered by tile parity) — no cluster barrier after start-up.
+//   parity argument: a CTA sends its sums of tile i+1 only after it has read everybody's sums of tile i, so when a
+//   peer's tile i+2 sums arrive (same buffer as tile i) they cannot overtake a reader.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int DW3_CH = 128;
+static constexpr int DW3_THREADS = 128;
+static constexpr int DW3_TILE_BYTES = DW_HALO * DW_HALO * DW3_CH * 4;       // 100,352
+static constexpr int DW3_MAX_NC = 4;                                          // C <= 512
+static constexpr int DW3_SMEM = DW3_TILE_BYTES + 1024 /*part*/ + 2 * DW3_MAX_NC * 512 /*clpart*/ + 1024;   // x2 per SM
+
+__device__ __forceinline__ uint32_t dw_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dw_st_async(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(DW3_THREADS, 2)
+dwconv7_ln_kernel_v3(const __grid_constant__ CUtensorMap tmX, DwArgs a, int nc, int n_clusters, int num_tiles) {
+  extern __shared__ __align__(1024) float dw_smem[];
+  float* tile = dw_smem;                                             // [14][14][128]
+  float* part = dw_smem + DW3_TILE_BYTES / 4;                        // [2 stat][2 p][2 g][32 px]
+  float* clpart = part + 256;                                        // [2 buf][nc rank][2 stat][64 px]
+  __shared__ uint64_t full_bar, stat_bar[2];
+  __shared__ float s_mean[64], s_rstd[64];
+
+  const int crank = blockIdx.x % nc;
+  const int cluster_id = blockIdx.x / nc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = warp >> 1;   // pixel half: output rows p*4 .. p*4+3
+  const int g = warp & 1;    // 64-channel group
+  const int ch_local = g * 64 + lane * 2;
+  const int ch = crank * DW3_CH + ch_local;
+  const int tiles_per_img = a.tiles_w * a.tiles_h;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(&full_bar, 1);
+    mbar_init(&stat_bar[0], 1);
+    mbar_init(&stat_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (nc > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // peers may signal us after this
+  grid_dep_sync();          // PDL: everything above overlaps the previous kernel's tail
+
+  auto issue = [&](int t) {     // thread 0; every warp is done reading the tile buffer
+    const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+    const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
+    mbar_expect_tx(&full_bar, DW3_TILE_BYTES);
+    tma_load_4d(tile, &tmX, &full_bar, crank * DW3_CH, tw * DW_TILE - 3, th * DW_TILE - 3, b);
+  };
+  if (threadIdx.x == 0 && cluster_id < num_tiles) issue(cluster_id);
+
+  // taps / affine parameters: once per kernel
+  float2 wt[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wt[t] = __ldg(reinterpret_cast<const float2*>(a.w + t * a.C + ch));
+  const float2 bias = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + ch)) : make_float2(0.f, 0.f);
+  const float2 gam = __ldg(reinterpret_cast<const float2*>(a.gamma + ch));
+  const float2 bet = __ldg(reinterpret_cast<const float2*>(a.beta + ch));
+  if (nc > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  int it = 0;
+  for (int t = cluster_id; t < num_tiles; t += n_clusters, ++it) {
+    const int buf = it & 1;
+    const uint32_t par = (it >> 1) & 1;
+    if (threadIdx.x == 0 && nc > 1) mbar_expect_tx(&stat_bar[buf], nc * 512);
+    const int b = t / tiles_per_img, r = t - b * tiles_per_img;
+    const int th = r / a.tiles_w, tw = r - th * a.tiles_w;
+    const int h0 = th * DW_TILE, w0 = tw * DW_TILE;
+
+    float2 acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = bias;
+    mbar_wait(&full_bar, it & 1);
+    const float* tp = tile + (p * 4) * DW_HALO * DW3_CH + ch_local;
+#pragma unroll
+    for (int rr = 0; rr < 10; ++rr) {
+#pragma unroll
+      for (int c = 0; c < DW_HALO; ++c) {
+        const float2 v = *reinterpret_cast<const float2*>(tp + (rr * DW_HALO + c) * DW3_CH);
+#pragma unroll
+        for (int oh = 0; oh < 4; ++oh) {
+          const int kr = rr - oh;
+          if (kr < 0 || kr > 6) continue;
+#pragma unroll
+          for (int ow = 0; ow < 8; ++ow) {
+            const int kc = c - ow;
+            if (kc < 0 || kc > 6) continue;
+            acc[oh * 8 + ow] = ffma2(v, wt[kr * 7 + kc], acc[oh * 8 + ow]);
+          }
+        }
+      }
+    }
+    {
+      float s1[32], s2[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        s1[i] = acc[i].x + acc[i].y;
+        s2[i] = fmaf(acc[i].x, acc[i].x, acc[i].y * acc[i].y);
+      }
+      warp_transpose_reduce32(s1, lane);
+      warp_transpose_reduce32(s2, lane);
+      part[((0 * 2 + p) * 2 + g) * 32 + lane] = s1[0];
+      part[((1 * 2 + p) * 2 + g) * 32 + lane] = s2[0];
+    }
+    __syncthreads();                                   // (also: every warp is done reading the tile)
+    if (threadIdx.x == 0 && t + n_clusters < num_tiles) issue(t + n_clusters);
+    {
+      // thread -> (stat, pixel half, px): sum the two channel groups, publish to every CTA of the cluster
+      const int stat = threadIdx.x >> 6, pp = (threadIdx.x >> 5) & 1, px = threadIdx.x & 31;
+      const float* src = part + ((stat * 2 + pp) * 2) * 32 + px;
+      const float tot = src[0] + src[32];
+      float* dst = clpart + ((buf * nc + crank) * 2 + stat) * 64 + pp * 32 + px;
+      if (nc == 1) {
+        *dst = tot;
+      } else {
+        const uint32_t daddr = smem_u32(dst), baddr = smem_u32(&stat_bar[buf]);
+        for (int rk = 0; rk < nc; ++rk) dw_st_async(dw_mapa(daddr, rk), tot, dw_mapa(baddr, rk));
+      }
+    }
+    if (nc == 1) __syncthreads();
+    else mbar_wait(&stat_bar[buf], par);
+    if (threadIdx.x < 64) {
+      float sm = 0.f, q = 0.f;
+      for (int rk = 0; rk < nc; ++rk) {
+        sm += clpart[((buf * nc + rk) * 2 + 0) * 64 + threadIdx.x];
+        q += clpart[((buf * nc + rk) * 2 + 1) * 64 + threadIdx.x];
+      }
+      const float inv = 1.0f / static_cast<float>(a.C);
+      const float mean = sm * inv;
+      const float var = fmaxf(q * inv - mean * mean, 0.0f);
+      s_mean[threadIdx.x] = mean;
+      s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+    }
+    __syncthreads();
+    const long long base = ((static_cast<long long>(b) * a.H + h0 + p * 4) * a.W + w0) * a.C + ch;
+    const int row_stride = a.W * a.C;
+    const bool interior = (h0 + DW_TILE <= a.H) && (w0 + DW_TILE <= a.W);
+    if (interior && a.out_dtype == CCX_BF16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + base;
+#pragma unroll
+      for (int oh = 0; oh < 4; ++oh) {
+#pragma unroll
+        for (int ow = 0; ow < 8; ++ow) {
+          const int px = p * 32 + oh * 8 + ow;
+          const float m = s_mean[px], rs = s_rstd[px];
+          const float y0 = (acc[oh * 8 + ow].x - m) * rs * gam.x + bet.x;
+          const float y1 = (acc[oh * 8 + ow].y - m) * rs * gam.y + bet.y;
+          *reinterpret_cast<uint32_t*>(o + oh * row_stride + ow * a.C) = pack_bf16x2(y0, y1);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int oh = 0; oh < 4; ++oh) {
+        const int h = h0 + p * 4 + oh;
+#pragma unroll
+        for (int ow = 0; ow < 8; ++ow) {
+          const int w = w0 + ow;
+          const int px = p * 32 + oh * 8 + ow;
+          const float m = s_mean[px], rs = s_rstd[px];
+          const float y0 = (acc[oh * 8 + ow].x - m) * rs * gam.x + bet.x;
+          const float y1 = (acc[oh * 8 + ow].y - m) * rs * gam.y + bet.y;
+          if (h < a.H && w < a.W) {
+            const long long idx = base + oh * row_stride + ow * a.C;
+            if (a.out_dtype == CCX_BF16) {
+              *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(a.out) + idx) = pack_bf16x2(y0, y1);
+            } else if (a.out_lo != nullptr) {
+              const float h0v = tf32_hi(y0), h1v = tf32_hi(y1);
+              *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out) + idx) = make_float2(h0v, h1v);
+              *reinterpret_cast<float2*>(a.out_lo + idx) = make_float2(y0 - h0v, y1 - h1v);
+            } else {
+              *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.out) + idx) = make_float2(y0, y1);
+            }
+          }
+        }
+      }
+    }
+    // s_mean / part of this tile are overwritten only after the next tile's first __syncthreads
+  }
+  // nobody may leave while a peer can still store into this CTA's shared memory or wait for this CTA's sums:
+  // every CTA of the cluster runs the same number of tiles and has received all sums of its last tile, and its own
+  // st.async stores were consumed by peers that are still alive; one closing cluster barrier keeps the exit ordered
+  if (nc > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+}
+
 int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float* gamma, const float* beta,
                void* out, float* out_lo, int B, int H, int W, int C, float eps, int out_dtype,
                cudaStream_t stream, const float* addend) {
@@ -397,10 +601,19 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   if (reinterpret_cast<uintptr_t>(x) & 15) return CCX_ERR_SHAPE;
   if (static_cast<long long>(W) * C * 8 >= 0x7fffffffLL) return CCX_ERR_SHAPE;
 
+  // persistent double-buffered kernel: LayerNorm mode, C = 128 .. 512 (clusters of 1 .. 4 CTAs, one CTA per SM)
+  static const bool no_v3 = (getenv("CCX_DWCONV_V2") != nullptr);
+  // (measured at batch 32, tools/dwconv_bench.py: v3 48.0 / 26.7 / 17.3 us against v2 54.0 / 29.8 / 16.8 us for
+  //  C = 128 / 256 / 512 — all of them ~2x the FP32-pipe floor of 49 MACs per output, which is what bounds this op:
+  //  22.8 / 11.4 / 5.7 us, above the HBM floor of 15.5 / 7.7 / 3.9 us; v3 where it wins)
+  static const bool force_v3 = (getenv("CCX_DWCONV_V3") != nullptr);
+  const bool use_v3 = !use_v1 && !no_v3 && gamma != nullptr && beta != nullptr && addend == nullptr &&
+                      C % DW3_CH == 0 && C / DW3_CH <= (force_v3 ? DW3_MAX_NC : 2);
+  const int CHB = use_v3 ? DW3_CH : CH;
   CUtensorMap tm;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)CH, DW_HALO, DW_HALO, 1};
+  cuuint32_t box[4] = {(cuuint32_t)CHB, DW_HALO, DW_HALO, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -415,7 +628,8 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
         cudaFuncSetAttribute(dwconv7_ln_kernel_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM) !=
             cudaSuccess ||
         cudaFuncSetAttribute(dwconv7_ln_kernel_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM64) !=
-            cudaSuccess)
+            cudaSuccess ||
+        cudaFuncSetAttribute(dwconv7_ln_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, DW3_SMEM) != cudaSuccess)
       return CCX_ERR_CUDA;
     configured = true;
   }
@@ -428,6 +642,31 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   a.eps = eps;
   a.out_dtype = out_dtype;
 
+  const double bytes = (double)B * H * W * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0)));
+  if (use_v3) {
+    const int nc3 = C / DW3_CH;
+    const int num_tiles = a.tiles_w * a.tiles_h * B;
+    int n_clusters = 2 * num_sms() / nc3;       // two CTAs per SM
+    if (n_clusters > num_tiles) n_clusters = num_tiles;
+    cudaLaunchConfig_t cfg3{};
+    cfg3.gridDim = dim3(nc3 * n_clusters, 1, 1);
+    cfg3.blockDim = dim3(DW3_THREADS, 1, 1);
+    cfg3.dynamicSmemBytes = DW3_SMEM;
+    cfg3.stream = stream;
+    cudaLaunchAttribute attr3[2];
+    attr3[0].id = cudaLaunchAttributeClusterDimension;
+    attr3[0].val.clusterDim.x = nc3;
+    attr3[0].val.clusterDim.y = 1;
+    attr3[0].val.clusterDim.z = 1;
+    attr3[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr3[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg3.attrs = attr3;
+    cfg3.numAttrs = 2;
+    ProfScope prof(PROF_DWCONV_LN, stream, bytes);
+    if (cudaLaunchKernelEx(&cfg3, dwconv7_ln_kernel_v3, tm, a, nc3, n_clusters, num_tiles) != cudaSuccess)
+      return CCX_ERR_CUDA;
+    return CCX_OK;
+  }
   const int nc = C / CH;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nc, a.tiles_w * a.tiles_h, B);
@@ -443,7 +682,6 @@ int dwconv7_ln(const float* x, const float* w49c, const float* bias, const float
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_v1 ? 1 : 2;
-  const double bytes = (double)B * H * W * C * (4.0 + (out_dtype == CCX_BF16 ? 2.0 : (out_lo ? 8.0 : 4.0)));
   ProfScope prof(PROF_DWCONV_LN, stream, bytes);
   if (use_v1) {
     if (cudaLaunchKernelEx(&cfg, dwconv7_ln_kernel, tm, a) != cudaSuccess) return CCX_ERR_CUDA;

@@ -192,6 +192,9 @@ def encoder_features_with_grad(enc, images, noise, begin_child=0, image_hw=None)
                                   "startingLayer 1..7 are supported (reference defaults: 7 and 5)")
     with torch.no_grad():
         x = images if begin_child >= first else enc.run_children(images, begin_child, first, noise, image_hw=image_hw)
+    pre = getattr(enc, "_before_trainable", None)
+    if pre is not None:          # CapturedTrainStep: the refreshed weight copies come from its side stream
+        pre()
     enc.prepared()
     # optional callback hook(child, i): the gradients of block i of child `child` (i = None: a downsample child) are
     # complete — fired from a tensor hook on the unit's INPUT, i.e. when its backward node has run and (AccumulateGrad

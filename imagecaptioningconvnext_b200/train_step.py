@@ -113,6 +113,12 @@ class CapturedTrainStep:
             decoder.fixed_T = True
         self._trainable = [p for _, p in named_params(decoder) if p.requires_grad] + \
                           [p for _, p in named_params(encoder) if p.requires_grad]
+        # optional second stream (CCX_STEP_OVERLAP bit 0: the re-cast of the updated weights into their kernel-side copies
+        # runs next to the frozen encoder stages; bit 1: the decoder's gradient all-reduce + Adam run next to the encoder's
+        # backward).  Off by default: measured on one B200 (bench.py, 30 steps) 5.79 / 5.81 / 5.90 / 5.79 ms per step
+        # for modes 0 / 1 / 2 / 3 — the persistent GEMM / dwconv CTAs own every SM, so there is nothing to run next to.
+        self.overlap = int(os.environ.get("CCX_STEP_OVERLAP", "0"))
+        self._side = None
         self._buckets = []
         for opt in (decoder_optimizer, encoder_optimizer):
             if opt is None:
@@ -163,7 +169,24 @@ class CapturedTrainStep:
         # the only use of the lengths on the host is to size the step buffers; they always span every step here
         fake = self._fake_lens
         stash_host_copy(caplens, fake)
-        feats = self.encoder(imgs)                                                         # trainMultiGPU.py:361
+        main = torch.cuda.current_stream()
+        if self.overlap and self._side is None:
+            self._side = torch.cuda.Stream(device=imgs.device)
+        side = self._side if (self.overlap & 1) else None
+        if side is not None:
+            # the weights the last step moved are re-cast on the side stream while the frozen stages run; the first
+            # trainable encoder unit (and everything after it) waits for them
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.encoder.prepared()
+                self.decoder._cache.get()
+            self.encoder._before_trainable = lambda: main.wait_stream(side)
+        try:
+            feats = self.encoder(imgs)                                                     # trainMultiGPU.py:361
+        finally:
+            self.encoder._before_trainable = None
+        if side is not None:
+            main.wait_stream(side)         # (frozen encoder: no trainable unit fired the hook)
         enc_trains = feats.requires_grad
         feats_in = feats.detach().requires_grad_() if enc_trains else feats
         if self.lstm:
@@ -191,7 +214,17 @@ class CapturedTrainStep:
 
         def reduce_slice(flat, a, b):
             return dist.all_reduce(flat[a:b], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-        if multi:
+        main = torch.cuda.current_stream()
+        side = self._side if ((self.overlap & 2) and enc_trains) else None
+        if side is not None:
+            # the decoder's gradients are final: their all-reduce and the decoder's Adam run on the side stream,
+            # under the encoder's backward
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if multi:
+                    reduce_slice(self._buckets[0], 0, self._buckets[0].numel()).wait()
+                self.d_opt.step()
+        elif multi:
             dec_work = reduce_slice(self._buckets[0], 0, self._buckets[0].numel())
         if enc_trains:
             if multi and len(self._buckets) > 1:
@@ -215,13 +248,16 @@ class CapturedTrainStep:
                 for key, (a, b) in self._enc_units.items():       # the first trainable unit (its input has no gradient)
                     if key not in reduced:
                         enc_works.append(reduce_slice(self._buckets[1], a, b))
-        if dec_work is not None:
-            dec_work.wait()
-        self.d_opt.step()
+        if side is None:
+            if dec_work is not None:
+                dec_work.wait()
+            self.d_opt.step()
         if self.e_opt is not None:
             for w in enc_works:
                 w.wait()
             self.e_opt.step()
+        if side is not None:
+            main.wait_stream(side)
         return loss.detach()
 
     def __call__(self, imgs, caps, caplens):

@@ -13,7 +13,9 @@ def _g(seed=0):
 
 
 @pytest.mark.parametrize("C,H,W,B", [(128, 64, 64, 2), (256, 32, 32, 2), (512, 16, 16, 3), (1024, 8, 8, 3),
-                                     (128, 13, 21, 1), (384, 5, 9, 2)])
+                                     (128, 13, 21, 1), (384, 5, 9, 2),
+                                     # more tiles than resident clusters: the persistent kernel's multi-tile loop
+                                     (128, 64, 64, 5), (256, 32, 32, 11), (512, 16, 16, 41), (512, 24, 40, 7)])
 @pytest.mark.parametrize("mode", ["bf16", "split", "plain"])
 def test_dwconv7_ln(C, H, W, B, mode):
     from imagecaptioningconvnext_b200 import _lib
@@ -147,6 +149,44 @@ def _linear_epilogue_checks(M, N, K, dtype):
     else:
         y = _lib.linear(A, Wt, bias=bias.cuda(), out_dtype=torch.bfloat16)
         assert y.dtype == torch.bfloat16 and rel_err(y.float(), a @ w.t() + bias) < tol
+
+
+# The TMA epilogue of gemm_tn_kernel (csrc/ccx_gemm_epilogue.cuh): bf16 operands, output rows 16-byte aligned.
+#  (40000,256,128) / (40000,128,256): several tiles per CTA (box prefetch across tiles, the last one through the ring);
+#  (8192,512,2048): one tile per CTA (ring only); (300,200,192) / (1000,72,64): ragged M and N, clipped by the tensor map;
+#  (2100,1536,512): N tiles of different CTAs share rows.
+@pytest.mark.parametrize("M,N,K", [(40000, 256, 128), (40000, 128, 256), (8192, 512, 2048), (300, 200, 192),
+                                   (1000, 72, 64), (2100, 1536, 512)])
+def test_linear_tma_epilogue_paths(M, N, K):
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import Operand
+    g = _g(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    cs = torch.rand(N, generator=g) + 0.5
+    rpg = 49
+    rs = torch.rand((M + rpg - 1) // rpg, generator=g) + 0.5
+    res = torch.randn(M, N, generator=g)
+    A, Wt = Operand(a.cuda(), None, torch.bfloat16), Operand(w.cuda(), None, torch.bfloat16)
+    prod = a.float() @ w.float().t()
+    tol = 1e-2          # bf16 output rounding (2^-9) plus the tanh-form GELU; the products themselves are exact
+    # Linear + GELU -> bf16 (the CNBlock's first Linear)
+    y = _lib.linear(A, Wt, bias=bias.cuda(), act=_lib.ACT_GELU, out_dtype=torch.bfloat16)
+    assert rel_err(y.float(), F.gelu(prod + bias)) < tol
+    # bias + layer-scale x row-scale + fp32 residual, written IN PLACE over the residual (the CNBlock's second Linear)
+    x = res.clone().cuda()
+    y = _lib.linear(A, Wt, bias=bias.cuda(), colscale=cs.cuda(), rowscale=rs.cuda(), rows_per_group=rpg, residual=x, out=x)
+    ref = (prod + bias) * cs * rs.repeat_interleave(rpg)[:M, None] + res
+    assert y.data_ptr() == x.data_ptr() and rel_err(y, ref) < 1e-5
+    # bf16 output with a bf16 residual and ReLU
+    rb = res.to(torch.bfloat16).cuda()
+    y = _lib.linear(A, Wt, bias=bias.cuda(), act=_lib.ACT_RELU, residual=rb, out_dtype=torch.bfloat16)
+    assert rel_err(y.float(), F.relu(prod + bias) + rb.float().cpu()) < tol
+    # a strided output view (row pitch 2N): the tensor map carries the pitch
+    wide = torch.zeros(M, 2 * N, device="cuda")
+    _lib.linear(A, Wt, bias=bias.cuda(), out=wide[:, N:])
+    assert rel_err(wide[:, N:], prod + bias) < 1e-5 and float(wide[:, :N].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("M,N,K", [(32, 2048, 2048), (17, 2048, 2048), (1, 1536, 512), (32, 512, 1536), (9, 72, 64),
