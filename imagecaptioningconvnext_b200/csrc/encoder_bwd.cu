@@ -8,6 +8,7 @@
 //   avgpool_nhwc_bwd    AdaptiveAvgPool2d backward
 // The depthwise-conv data gradient re-uses dwconv7_ln_kernel in "plain" mode with flipped taps.
 #include "ccx_common.cuh"
+#include "ccx_gemm.h"
 #include "ccx_ops.h"
 #include "ccx_prof.h"
 
@@ -91,57 +92,83 @@ int cnblock_param_grads(const float* G, const float* W2, const float* b2, const 
 }
 
 // dw[tap][c] += sum_{b,h,w} du[b,h,w,c] * x[b,h+kh-3,w+kw-3,c]
-// one CTA = 64 channels x one 8x8 output patch of one image: the 14x14 halo of x (zero padded) and the 8x8 patch of
-// du are staged in shared memory once, then thread (c, q) accumulates the 49 taps over output rows 2q, 2q+1 from
-// shared memory (the first version re-read x through L1 49 times per pixel with bounds checks: 128 us per launch)
+// one CTA = 64 channels x one 8x8 output patch x a RANGE of images: per image the 14x14 halo of x (zero padded) and
+// the 8x8 patch of du are staged in shared memory, then thread (c, q) accumulates the 49 taps over output rows 2q, 2q+1
+// in registers — an x row segment of 14 values serves 8 pixels x 7 taps, so shared memory is read once per 3.7 FMAs —
+// and keeps accumulating over the CTA's images; the four row-pair partials are summed through shared memory and ONE
+// atomicAdd per (tap, channel) leaves the CTA.  (History: re-reading x through L1 49 times per pixel: 128 us per
+// launch at batch 32 / C=1024; one image per CTA, one LDS per FMA and 49 atomics per thread — 6.4 M atomics on 50 K
+// addresses: 50 us.)
 static constexpr int WG_C = 64;
 __global__ void __launch_bounds__(256)
-dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ dw, int H, int W,
-                     int C, int tiles_w) {
+dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ dw, int B, int H,
+                     int W, int C, int tiles_w, int imgs_per_cta) {
   extern __shared__ __align__(16) float wg_sm[];
-  float* xs = wg_sm;                     // [14][14][WG_C]
+  float* xs = wg_sm;                     // [14][14][WG_C]   (afterwards: [4 q][49][WG_C] partials, same size)
   float* ds = wg_sm + 14 * 14 * WG_C;    // [8][8][WG_C]
-  const int c0 = blockIdx.x * WG_C, b = blockIdx.y;
-  const int th0 = (blockIdx.z / tiles_w) * 8, tw0 = (blockIdx.z % tiles_w) * 8;
-  const float* xb = x + static_cast<long long>(b) * H * W * C;
-  const float* db = du + static_cast<long long>(b) * H * W * C;
-  for (int i = threadIdx.x; i < 14 * 14 * WG_C; i += 256) {
-    const int cc = i % WG_C, pix = i / WG_C;
-    const int ih = th0 + pix / 14 - 3, iw = tw0 + pix % 14 - 3;
-    xs[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W && c0 + cc < C)
-                ? __ldg(xb + (static_cast<long long>(ih) * W + iw) * C + c0 + cc) : 0.f;
-  }
-  for (int i = threadIdx.x; i < 8 * 8 * WG_C; i += 256) {
-    const int cc = i % WG_C, pix = i / WG_C;
-    const int h = th0 + pix / 8, w = tw0 + pix % 8;
-    ds[i] = (h < H && w < W && c0 + cc < C) ? __ldg(db + (static_cast<long long>(h) * W + w) * C + c0 + cc) : 0.f;
-  }
-  __syncthreads();
+  const int c0 = blockIdx.x * WG_C;
+  const int th0 = (blockIdx.y / tiles_w) * 8, tw0 = (blockIdx.y % tiles_w) * 8;
+  const int b_begin = blockIdx.z * imgs_per_cta;
+  const int b_end = min(B, b_begin + imgs_per_cta);
   const int c = threadIdx.x % WG_C, q = threadIdx.x / WG_C;
   float acc[49];
 #pragma unroll
   for (int t = 0; t < 49; ++t) acc[t] = 0.f;
-#pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const int h = q * 2 + hh;
-    for (int w = 0; w < 8; ++w) {
-      const float d = ds[(h * 8 + w) * WG_C + c];
-#pragma unroll
-      for (int kh = 0; kh < 7; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 7; ++kw)
-          acc[kh * 7 + kw] = fmaf(d, xs[((h + kh) * 14 + (w + kw)) * WG_C + c], acc[kh * 7 + kw]);
+  for (int b = b_begin; b < b_end; ++b) {
+    const float* xb = x + static_cast<long long>(b) * H * W * C;
+    const float* db = du + static_cast<long long>(b) * H * W * C;
+    for (int i = threadIdx.x; i < 14 * 14 * WG_C; i += 256) {
+      const int cc = i % WG_C, pix = i / WG_C;
+      const int ih = th0 + pix / 14 - 3, iw = tw0 + pix % 14 - 3;
+      xs[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W && c0 + cc < C)
+                  ? __ldg(xb + (static_cast<long long>(ih) * W + iw) * C + c0 + cc) : 0.f;
     }
-  }
-  if (c0 + c < C) {
+    for (int i = threadIdx.x; i < 8 * 8 * WG_C; i += 256) {
+      const int cc = i % WG_C, pix = i / WG_C;
+      const int h = th0 + pix / 8, w = tw0 + pix % 8;
+      ds[i] = (h < H && w < W && c0 + cc < C) ? __ldg(db + (static_cast<long long>(h) * W + w) * C + c0 + cc) : 0.f;
+    }
+    __syncthreads();
 #pragma unroll
-    for (int t = 0; t < 49; ++t) atomicAdd(dw + static_cast<long long>(t) * C + c0 + c, acc[t]);
+    for (int hh = 0; hh < 2; ++hh) {
+      const int h = q * 2 + hh;
+      float d[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) d[w] = ds[(h * 8 + w) * WG_C + c];
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+        float xr[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) xr[j] = xs[((h + kh) * 14 + j) * WG_C + c];
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) {
+          float a = acc[kh * 7 + kw];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) a = fmaf(d[w], xr[w + kw], a);
+          acc[kh * 7 + kw] = a;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // sum the four row-pair partials, one atomic per (tap, channel)
+#pragma unroll
+  for (int t = 0; t < 49; ++t) xs[(q * 49 + t) * WG_C + c] = acc[t];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 49 * WG_C; i += 256) {
+    const int cc = i % WG_C, t = i / WG_C;
+    if (c0 + cc < C) {
+      const float v = xs[(0 * 49 + t) * WG_C + cc] + xs[(1 * 49 + t) * WG_C + cc] + xs[(2 * 49 + t) * WG_C + cc] +
+                      xs[(3 * 49 + t) * WG_C + cc];
+      atomicAdd(dw + static_cast<long long>(t) * C + c0 + cc, v);
+    }
   }
 }
 int dwconv7_wgrad(const float* x, const float* du, float* dw49c, int B, int H, int W, int C, cudaStream_t stream) {
   if (B <= 0) return CCX_OK;
   const int tiles_h = (H + 7) / 8, tiles_w = (W + 7) / 8;
-  if (B > 65535 || tiles_h * tiles_w > 65535) return CCX_ERR_SHAPE;
+  const int groups = (C + WG_C - 1) / WG_C;
+  if (tiles_h * tiles_w > 65535) return CCX_ERR_SHAPE;
   constexpr int smem = (14 * 14 + 8 * 8) * WG_C * static_cast<int>(sizeof(float));
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.ref();
@@ -150,9 +177,15 @@ int dwconv7_wgrad(const float* x, const float* du, float* dw49c, int B, int H, i
       return CCX_ERR_CUDA;
     configured = true;
   }
+  // about two CTAs per SM in flight; each keeps its taps in registers across its images
+  int splits = (2 * num_sms()) / (groups * tiles_h * tiles_w);
+  splits = splits < 1 ? 1 : (splits > B ? B : splits);
+  const int imgs_per_cta = (B + splits - 1) / splits;
+  splits = (B + imgs_per_cta - 1) / imgs_per_cta;
+  if (splits > 65535) return CCX_ERR_SHAPE;
   ProfScope prof(PROF_DWCONV_LN, stream, (double)B * H * W * C * 8.0);
-  dwconv7_wgrad_kernel<<<dim3((C + WG_C - 1) / WG_C, B, tiles_h * tiles_w), 256, smem, stream>>>(x, du, dw49c, H, W,
-                                                                                                C, tiles_w);
+  dwconv7_wgrad_kernel<<<dim3(groups, tiles_h * tiles_w, splits), 256, smem, stream>>>(x, du, dw49c, B, H, W, C, tiles_w,
+                                                                                       imgs_per_cta);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -49,6 +49,24 @@ def test_dwconv7_ln(C, H, W, B, mode):
         assert int((out.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
+@pytest.mark.parametrize("C,H,W,B", [(1024, 8, 8, 32), (512, 16, 16, 5), (128, 13, 21, 3), (96, 5, 9, 1), (1024, 8, 8, 1)])
+def test_dwconv7_wgrad_accumulates_the_filter_gradient(C, H, W, B):
+    """ccx_dwconv7_wgrad: dw[tap][c] += sum du * shifted x (torchvision convnext.py:52, the depthwise Conv2d's weight
+    gradient) against torch autograd; the buffer is accumulated into, not overwritten."""
+    from imagecaptioningconvnext_b200 import _lib
+    g = _g(C + H + B)
+    x = torch.randn(B, C, H, W, generator=g)
+    du = torch.randn(B, C, H, W, generator=g)
+    w = torch.zeros(C, 1, 7, 7, requires_grad=True)
+    F.conv2d(x, w, None, padding=3, groups=C).backward(du)
+    ref = w.grad.reshape(C, 49).t()                                    # tap-major [49][C]
+    xd, dd = x.permute(0, 2, 3, 1).contiguous().cuda(), du.permute(0, 2, 3, 1).contiguous().cuda()
+    base = torch.randn(49, C, generator=g)
+    dw = base.clone().cuda()
+    _lib.check(_lib.lib().ccx_dwconv7_wgrad(xd.data_ptr(), dd.data_ptr(), dw.data_ptr(), B, H, W, C, _lib.stream_ptr()))
+    assert rel_err(dw.cpu() - base, ref) < 2e-5
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 256, 256), (1, 64, 96), (3, 32, 32)])
 def test_stem_ln(B, H, W):
     from imagecaptioningconvnext_b200 import _lib

@@ -142,15 +142,21 @@ def test_transformer_graph_replayed_steps_equal_eager_steps(dtype):
     assert max(abs(a - b) / abs(a) for a, b in zip(l0, l1)) < (1e-4 if dtype == torch.float32 else 2e-3), (l0, l1)
     for step, (a, b) in enumerate(zip(g0, g1)):
         # bf16: step 0 runs on identical weights; afterwards the two trajectories drift apart through weight-rounding
-        # flips (measured 0.05 .. 0.12 Frobenius by step 4), so only the first step is held to the gradient tolerance
+        # flips (0.122 Frobenius observed on a later step), so only the first step is held to the gradient tolerance
         # and the later ones to twice that; fp32 is the strict check
         tol = 2e-3 if dtype == torch.float32 else GRAD_TOL[dtype] * (1 if step == 0 else 2)
         assert _grad_err(a, b, dtype) < tol, (step, _grad_err(a, b, dtype))
+    lr, n_steps = 1e-3, len(batches)
     for (n, p), (_, q) in zip(m0.named_parameters(), m1.named_parameters()):
-        # an Adam step moves every element by ~lr whatever the gradient's size, so a noise-level gradient may flip
-        moved = ((p - q).abs() > 2e-4).float().mean().item()
-        # (bf16, 5 steps: up to ~0.10 of a bias vector's elements measured, so 0.15 marks "same trajectory")
-        assert moved < (5e-3 if dtype == torch.float32 else 0.15), (n, moved)
+        # an Adam step moves every element by ~lr whatever the gradient's size, so an element whose gradient is at
+        # noise level (float-atomic ordering, bf16 rounding flips) may walk the other way: per element the two runs can
+        # differ by at most ~2 lr per step; what "same trajectory" means is that this stays rare
+        diff = (p - q).abs()
+        if dtype == torch.float32:
+            assert (diff > 2e-4).float().mean().item() < 5e-3, n
+        else:
+            assert float(diff.max()) <= 3 * lr * n_steps and float(diff.mean()) <= 0.15 * lr * n_steps, \
+                (n, float(diff.max()), float(diff.mean()))
     # two forwards in flight: the second must not reuse the static buffers
     enc, caps, lens, kpm = batches[0]
     pa, _, dla = m1(teacherForcing=True, encoder_out=enc, encoded_captions=caps, caption_lengths=lens,
