@@ -47,8 +47,9 @@ def measured_peaks():
     if os.path.exists(p):
         d = json.load(open(p))
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
-                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "sm_ghz": d.get("sm_max_mhz", 1965.0) / 1e3, "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_ghz": 1.965, "source": "fallback"}
 
 
 class ClockSampler:
@@ -636,6 +637,15 @@ def kernel_row(kind, v, n_steps, tot_ms, peaks):
     else:
         row["gbs"] = rate / 1e9
         row["frac_of_hbm_peak"] = rate / 1e9 / peaks["hbm_gbs"]
+    if kind == "dwconv_ln":
+        # 49 MACs per output element: the FP32 FMA pipe, not HBM, is this kernel's roofline (per element the pipe needs
+        # 49 / (148 SMs x 128 lanes) cycles = 1.36 ps at 1.9 GHz against 6 bytes / 6.5 TB/s = 0.92 ps of HBM time);
+        # work column = bytes at 6 per element (fp32 in, bf16 out), so MACs = bytes / 6 x 49 (a lower bound for the
+        # fp32-output backward calls)
+        fp32_peak = 148 * 128 * 2 * peaks.get("sm_ghz", 1.9) * 1e9
+        row["fp32_tflops"] = rate / 6.0 * 49 * 2 / 1e12
+        row["frac_of_fp32_pipe_peak"] = rate / 6.0 * 49 * 2 / fp32_peak
+        row["note"] = "bound by the FP32 FMA pipe (49 MACs per output), see frac_of_fp32_pipe_peak; frac_of_hbm_peak kept for reference"
     if kind in _LATENCY_KINDS:
         row["note"] = _LATENCY_KINDS[kind]
     return row

@@ -23,7 +23,8 @@ class LinearDesc(C.Structure):
                 ("bias", _vp), ("colscale", _vp), ("rowscale", _vp), ("residual", _vp), ("emask", _vp),
                 ("lda", _i64), ("ldw", _i64), ("ldc", _i64), ("ldr", _i64), ("ldm", _i64),
                 ("M", _i32), ("N", _i32), ("K", _i32), ("rows_per_group", _i32),
-                ("act", _i32), ("in_dtype", _i32), ("out_dtype", _i32), ("split", _i32)]
+                ("act", _i32), ("in_dtype", _i32), ("out_dtype", _i32), ("split", _i32),
+                ("a_mn", _i32), ("w_mn", _i32)]
 
 
 class CNBlockWeights(C.Structure):
@@ -285,11 +286,12 @@ class Operand:
 
 
 def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per_group=1, residual=None,
-           out=None, out_dtype=torch.float32, split=False, emask=None, k=None, n=None):
+           out=None, out_dtype=torch.float32, split=False, emask=None, k=None, n=None, a_mn=False, w_mn=False):
     """C = epilogue(A . W^T).  a, w: Operand (2-D, row-major, unit inner stride).  Returns a tensor, or an
-    Operand when split=True (fp32 compute only)."""
-    M, K = a.hi.shape
-    N, K2 = w.hi.shape
+    Operand when split=True (fp32 compute only).  a_mn / w_mn (bf16 only): the operand is handed over TRANSPOSED,
+    as a [K, M] / [K, N] row-major array, and read in place (see ccx_linear_desc)."""
+    M, K = a.hi.shape[::-1] if a_mn else a.hi.shape
+    N, K2 = w.hi.shape[::-1] if w_mn else w.hi.shape
     if k is not None:      # logical contraction length when the operands carry zero-padded columns
         K = K2 = k
     if n is not None:
@@ -319,5 +321,6 @@ def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per
     d.act = act
     d.in_dtype, d.out_dtype = dt_code(a.dtype), dt_code(out_dtype)
     d.split = 1 if split else 0
+    d.a_mn, d.w_mn = (1 if a_mn else 0), (1 if w_mn else 0)
     check(lib().ccx_linear(C.byref(d), stream_ptr()), f"linear M={M} N={N} K={K}")
     return res

@@ -41,6 +41,7 @@ int ccx_linear(const ccx_linear_desc* d, void* stream) {
   g.M = d->M; g.N = d->N; g.K = d->K;
   g.rows_per_group = d->rows_per_group;
   g.act = d->act; g.in_dtype = d->in_dtype; g.out_dtype = d->out_dtype; g.split = d->split;
+  g.a_mn = d->a_mn != 0; g.b_mn = d->w_mn != 0;
   return gemm_tn(g, as_stream(stream));
 }
 

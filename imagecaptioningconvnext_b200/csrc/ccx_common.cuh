@@ -209,7 +209,21 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulator, both operands K-major.
+// Same for an MN-major operand tile (the operand's transpose is what sits in memory: rows = k, 64 MN elements = 128
+// bytes per row): a TMA box of {64 MN, 64 k} with 128-byte swizzle is 8 swizzle atoms of 8 k-rows, 1024 B apart (SBO);
+// the next 64 MN elements are the next box, lbo_bytes further (LBO).  One UMMA K step (16 k) = 2 atoms = 2048 B.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulator, both operands K-major
+// (bit 15 / bit 16 set = A / B MN-major, kind::f16 only).
 // fmt: 0 = f16, 1 = bf16, 2 = tf32
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);

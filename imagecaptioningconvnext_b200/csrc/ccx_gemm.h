@@ -26,6 +26,8 @@ struct GemmDesc {
   int out_dtype = 1;  // CCX_F32 / CCX_BF16
   int split = 0;
   int force_bn = 0;   // 0 = auto, else 64/128/256
+  bool a_mn = false;  // bf16: A given as [K, M] row-major (lda = row pitch), read MN-major by the tensor core
+  bool b_mn = false;  // bf16: B given as [K, N] row-major (ldb = row pitch)
 };
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream);

@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmB_hi,
                const __grid_constant__ CUtensorMap tmA_lo, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-               int M, int N, int K, int nseg, EpiArgs ep) {
+               int M, int N, int K, int nseg, EpiArgs ep, int mn_flags) {
+  // mn_flags bit 0 / 1: A / B is given transposed ([K, M] / [K, N] row-major) and read MN-major (bf16 only)
   using S = GemmSmem<BN, BOXES>;
   constexpr int STAGES = S::STAGES;
   constexpr int BK = IS_TF32 ? 32 : 64;  // elements per 128-byte row
@@ -183,8 +184,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1);
         TL_ADD(w_empty, t0);
         mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
-        tma_load_2d(smem_a + stage * S::A_BYTES, ta, &full_bar[stage], kb * BK, m_blk * BM);
-        tma_load_2d(smem_b + stage * S::B_BYTES, tb, &full_bar[stage], kb * BK, n_blk * BN);
+        if (mn_flags & 1) {                      // {64 MN, 64 k} boxes, 8 KB each
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(smem_a + stage * S::A_BYTES + j * 8192, ta, &full_bar[stage], m_blk * BM + 64 * j, kb * BK);
+        } else {
+          tma_load_2d(smem_a + stage * S::A_BYTES, ta, &full_bar[stage], kb * BK, m_blk * BM);
+        }
+        if (mn_flags & 2) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(smem_b + stage * S::B_BYTES + j * 8192, tb, &full_bar[stage], n_blk * BN + 64 * j, kb * BK);
+        } else {
+          tma_load_2d(smem_b + stage * S::B_BYTES, tb, &full_bar[stage], kb * BK, n_blk * BN);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -231,14 +244,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (tile == (int)blockIdx.x && it == 0) w_first = clock64() - t_begin;
 #endif
         tc_fence_after();
-        const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * S::A_BYTES));
-        const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * S::B_BYTES));
+        const uint32_t a_addr = smem_u32(smem_a + stage * S::A_BYTES), b_addr = smem_u32(smem_b + stage * S::B_BYTES);
+        // K-major: one UMMA K step = 32 bytes along the 128-byte row; MN-major: 16 k-rows = 2048 bytes
+        const uint64_t adesc = (mn_flags & 1) ? umma_desc_mn_sw128(a_addr, 8192) : umma_desc_k_sw128(a_addr);
+        const uint64_t bdesc = (mn_flags & 2) ? umma_desc_mn_sw128(b_addr, 8192) : umma_desc_k_sw128(b_addr);
+        const uint32_t a_step = (mn_flags & 1) ? 128u : 2u, b_step = (mn_flags & 2) ? 128u : 2u;
+        const uint32_t idesc = IDESC | ((mn_flags & 1) ? (1u << 15) : 0u) | ((mn_flags & 2) ? (1u << 16) : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x 32-byte K slices per 128-byte row
+        for (int k = 0; k < 4; ++k) {
           if constexpr (IS_TF32)
             mma_tf32_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) ? 1u : 0u);
           else
-            mma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (it | k) ? 1u : 0u);
+            mma_f16_ss(d_tmem, adesc + a_step * k, bdesc + b_step * k, idesc, (it | k) ? 1u : 0u);
         }
         tc_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -352,6 +369,21 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// MN-major operand: the array is [k_rows, mn_cols] bf16 row-major; box = {64 mn, 64 k}, 128-byte swizzle
+static int make_map_mn(CUtensorMap* map, const void* ptr, long long k_rows, long long mn_cols, long long ld_elems) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return CCX_ERR_TMA;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld_elems * 2) & 15)) return CCX_ERR_SHAPE;
+  cuuint64_t gdim[2] = {(cuuint64_t)mn_cols, (cuuint64_t)k_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)(ld_elems * 2)};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CCX_OK : CCX_ERR_TMA;
+}
+
 // 2-D row-major [rows, cols] tensor, box = [box_rows, 128 bytes], 128-byte swizzle
 static int make_map_2d(CUtensorMap* map, const void* ptr, int is_f32, long long rows, long long cols,
                        long long ld_elems, int box_rows) {
@@ -393,7 +425,8 @@ struct GemmMaps {
 };
 
 template <int BN, bool IS_TF32, int BOXES>
-static int launch(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiArgs& ep, cudaStream_t stream) {
+static int launch(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiArgs& ep, int mn_flags,
+                  cudaStream_t stream) {
   using S = GemmSmem<BN, BOXES>;
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.ref();
@@ -407,18 +440,18 @@ static int launch(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiAr
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid < 1) return CCX_OK;
   return launch_pdl(kfn, dim3(grid), dim3(NUM_THREADS), S::TOTAL, stream, tm.a_hi, tm.b_hi, tm.a_lo, tm.b_lo, tm.c, tm.r,
-                    M, N, K, nseg, ep) == cudaSuccess
+                    M, N, K, nseg, ep, mn_flags) == cudaSuccess
              ? CCX_OK : CCX_ERR_CUDA;
 }
 
 template <int BN, bool IS_TF32>
-static int launch_boxes(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiArgs& ep, int boxes,
+static int launch_boxes(const GemmMaps& tm, int M, int N, int K, int nseg, const EpiArgs& ep, int boxes, int mn_flags,
                         cudaStream_t stream) {
   // (two boxes per warp only fit next to a useful operand ring on the narrow tiles)
   if constexpr (BN <= 128) {
-    if (boxes == 2) return launch<BN, IS_TF32, 2>(tm, M, N, K, nseg, ep, stream);
+    if (boxes == 2) return launch<BN, IS_TF32, 2>(tm, M, N, K, nseg, ep, mn_flags, stream);
   }
-  return launch<BN, IS_TF32, 1>(tm, M, N, K, nseg, ep, stream);
+  return launch<BN, IS_TF32, 1>(tm, M, N, K, nseg, ep, mn_flags, stream);
 }
 
 int gemm_tn_2cta(const CUtensorMap& a_hi, const CUtensorMap& b_hi, const CUtensorMap& a_lo, const CUtensorMap& b_lo,
@@ -439,6 +472,8 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (!tf32 && g.out_dtype == CCX_F32 && g.split) return CCX_ERR_DTYPE;
   if (tf32 && g.out_dtype != CCX_F32) return CCX_ERR_DTYPE;
   (void)BK;
+  const int mn_flags = (g.a_mn ? 1 : 0) | (g.b_mn ? 2 : 0);
+  if (mn_flags && (tf32 || g.A_lo != nullptr || g.B_lo != nullptr)) return CCX_ERR_DTYPE;
   if (gemm_skinny_eligible(g)) return gemm_skinny(g, stream);
   // tile-N choice: widest tile that still gives every SM work
   int bn = g.force_bn;
@@ -458,14 +493,16 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   if (g_pair_mode < 0) g_pair_mode = getenv("CCX_GEMM_2CTA") ? atoi(getenv("CCX_GEMM_2CTA")) : 0;
   const int pair_mode = g_pair_mode;
   const long long pair_tiles = ((g.M + 255LL) / 256) * (g.N / 256);
-  const bool use_pair = pair_mode && g.force_bn == 0 && (g.N % 256 == 0) && g.M >= 256 &&
+  const bool use_pair = pair_mode && !mn_flags && g.force_bn == 0 && (g.N % 256 == 0) && g.M >= 256 &&
                         pair_tiles >= num_sms() / 2;
   if (use_pair) bn = 128;   // B box = this CTA's half of the 256-row B tile
   GemmMaps tm;
   CUtensorMap &a_hi = tm.a_hi, &b_hi = tm.b_hi, &a_lo = tm.a_lo, &b_lo = tm.b_lo;
   int rc;
-  if ((rc = make_map_2d(&a_hi, g.A, tf32, g.M, g.K, g.lda, BM))) return rc;
-  if ((rc = make_map_2d(&b_hi, g.B, tf32, g.N, g.K, g.ldb, bn))) return rc;
+  if ((rc = g.a_mn ? make_map_mn(&a_hi, g.A, g.K, g.M, g.lda) : make_map_2d(&a_hi, g.A, tf32, g.M, g.K, g.lda, BM)))
+    return rc;
+  if ((rc = g.b_mn ? make_map_mn(&b_hi, g.B, g.K, g.N, g.ldb) : make_map_2d(&b_hi, g.B, tf32, g.N, g.K, g.ldb, bn)))
+    return rc;
   int nseg = 1;
   if (tf32 && g.A_lo != nullptr && g.B_lo != nullptr) {
     nseg = 3;
@@ -514,13 +551,13 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   ep.tma = use_tma ? 1 : 0;
   if (use_pair) return gemm_tn_2cta(a_hi, b_hi, a_lo, b_lo, tm.c, tm.r, g.M, g.N, g.K, nseg, ep, tf32, stream);
   if (tf32) {
-    if (bn == 256) return launch_boxes<256, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
-    if (bn == 128) return launch_boxes<128, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
-    return launch_boxes<64, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
+    if (bn == 256) return launch_boxes<256, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);
+    if (bn == 128) return launch_boxes<128, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);
+    return launch_boxes<64, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);
   } else {
-    if (bn == 256) return launch_boxes<256, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
-    if (bn == 128) return launch_boxes<128, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
-    return launch_boxes<64, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, stream);
+    if (bn == 256) return launch_boxes<256, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);
+    if (bn == 128) return launch_boxes<128, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);
+    return launch_boxes<64, false>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);
   }
 }
 

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._host import named_params, params_of
 from ._lib import Operand, ptr
-from .train_ops import deliver, grads_out, linear_bwd, weight_t, zero_grads_like, zeros_many
+from .train_ops import deliver, grads_out, linear_bwd, to_operand, weight_t, zero_grads_like, zeros_many
 
 
 def _bptt_launch_loop(dec, S, dH_all, dalphas, need_enc, cd, dev):
@@ -25,8 +25,11 @@ def _bptt_launch_loop(dec, S, dH_all, dalphas, need_enc, cd, dev):
     B, Pn, E = enc.shape
     D, A, Emb = dec.decoder_dim, dec.attention_dim, dec.embed_dim
     K = Emb + E + D
-    w_lstm_t = weight_t(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd)
-    w_h_t = weight_t(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd)
+    # (the C runner takes W^T [K, pad8(N)] operands: explicit transposed copies, whatever weight_t would pick)
+    w_lstm_t = to_operand(torch.cat([dec.decode_step.weight_ih.detach(), dec.decode_step.weight_hh.detach()], 1), cd,
+                          transpose=True)
+    w_h_t = to_operand(torch.cat([dec.attention.decoder_att.weight.detach(), dec.f_beta.weight.detach()], 0), cd,
+                       transpose=True)
     (dG_all, dHG_all, dXH_all, d_att1, d_enc, d_wf, dc, dh, dawe_all, dalpha_all) = zeros_many(
         [(T, B, 4 * D), (T, B, A + E), (T, B, K), (B * Pn, A), (B, Pn, E), (A,), (B, D), (B, D), (T, B, E),
          (2, T, B, Pn)], dev)
@@ -81,7 +84,7 @@ class _LstmTF(torch.autograd.Function):
 
         # hoisted fc: dH_all[b,t,:] = dpred[b,t,:] . W_fc   (rows past a caption's length carry zero gradient)
         dpred = dpred.contiguous().view(B * T, V)
-        dH_all = linear_bwd(dpred, H_all.map(lambda x: x.view(B * T, D)), weight_t(dec.fc.weight, cd), cd,
+        dH_all = linear_bwd(dpred, H_all.map(lambda x: x.view(B * T, D)), weight_t(dec.fc.weight, cd, Pw.get("w_fc")), cd,
                             g("fc.weight"), g("fc.bias"))
         persist = S.get("awe_all") is not None
         if persist:
@@ -148,13 +151,13 @@ class _LstmTF(torch.autograd.Function):
             _lib.check(L.ccx_embedding_bwd(ptr(caps), caps.stride(0), 0, ptr(dx), sb, stt, None, ptr(ge), V,
                                            Emb, B, T, st), "embedding_bwd")
         # ---- initial state and hoisted encoder_att -------------------------------------------------------------
-        dmean = linear_bwd(dh, S["m_op"], weight_t(dec.init_h.weight, cd), cd, g("init_h.weight"), g("init_h.bias"),
+        dmean = linear_bwd(dh, S["m_op"], weight_t(dec.init_h.weight, cd, Pw.get("w_init_h")), cd, g("init_h.weight"), g("init_h.bias"),
                            need_dx=need_enc)
-        dmean = linear_bwd(dc, S["m_op"], weight_t(dec.init_c.weight, cd), cd, g("init_c.weight"), g("init_c.bias"),
+        dmean = linear_bwd(dc, S["m_op"], weight_t(dec.init_c.weight, cd, Pw.get("w_init_c")), cd, g("init_c.weight"), g("init_c.bias"),
                            need_dx=need_enc, dx_residual=dmean)
         if need_enc:
             _lib.check(L.ccx_bcast_add_rows(ptr(d_enc), ptr(dmean), 1.0 / Pn, B, Pn, E, st), "bcast_add_rows")
-        d_enc_flat = linear_bwd(d_att1, S["enc_op"], weight_t(dec.attention.encoder_att.weight, cd), cd,
+        d_enc_flat = linear_bwd(d_att1, S["enc_op"], weight_t(dec.attention.encoder_att.weight, cd, Pw.get("w_enc_att")), cd,
                                 g("attention.encoder_att.weight"), g("attention.encoder_att.bias"), need_dx=need_enc,
                                 dx_residual=None if d_enc is None else d_enc.view(B * Pn, E))
         d_encoder_out = None

@@ -17,7 +17,8 @@ from . import _lib
 from ._host import any_requires_grad, named_params
 from ._lib import Operand, ptr
 from .encoder import DIMS
-from .train_ops import colsum_acc, deliver, grads_out, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
+from .train_ops import (colsum_acc, deliver, grads_out, linear_bwd, linear_dgrad, ln_bwd, mn_operands, to_operand,
+                        weight_t, zero_grads_like)
 
 
 def _first_trainable_child(enc):
@@ -94,8 +95,12 @@ class _BlockFn(torch.autograd.Function):
         else:
             doutp = dout
         # second Linear: dgrad, un-scaled wgrad G, and the layer_scale / W2 / b2 gradients from it
-        dh = _lib.linear(to_operand(dz, cd), weight_t(W2, cd), k=C)                       # [M, 4C]
-        G = _lib.linear(to_operand(doutp, cd, transpose=True), to_operand(h_op, cd, transpose=True))  # [C, 4C]
+        dh = linear_dgrad(to_operand(dz, cd), weight_t(W2, cd, ops["w2"]), n=C)             # [M, 4C]
+        if mn_operands(cd, h_op):
+            # G = doutp^T . h on the row-major operands themselves (tensor core reads both transposed in place)
+            G = _lib.linear(to_operand(doutp, cd), h_op, a_mn=True, w_mn=True)                       # [C, 4C]
+        else:
+            G = _lib.linear(to_operand(doutp, cd, transpose=True), to_operand(h_op, cd, transpose=True))
         colsum_acc(doutp, s)
         _lib.check(L.ccx_cnblock_param_grads(ptr(G), ptr(W2), ptr(blk.block[5].bias.detach()), ptr(gamma), ptr(s),
                                              ptr(grads["block.5.weight"]), ptr(grads["layer_scale"]),
@@ -103,7 +108,7 @@ class _BlockFn(torch.autograd.Function):
         # GELU' on the recomputed pre-activation, first Linear
         pre = _lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach())
         _lib.check(L.ccx_gelu_bwd(ptr(pre), ptr(dh), M * K4, st), "gelu_bwd")
-        dy = linear_bwd(dh, y_op, weight_t(W1, cd), cd, grads["block.3.weight"], grads["block.3.bias"])
+        dy = linear_bwd(dh, y_op, weight_t(W1, cd, ops["w1"]), cd, grads["block.3.weight"], grads["block.3.bias"])
         del pre, dh
         # LayerNorm backward on the recomputed conv output
         u = torch.empty((M, C), **f32)

@@ -4,9 +4,12 @@ Linear backward re-uses the forward tcgen05 GEMM (``ccx_linear``):
     dX[M,K] = dY[M,N] . W[N,K]        -> A = dY (row-major, contraction over N), B = W^T [K, N]
     dW[N,K] = dY^T[N,M] . X[M,K]      -> A = dY^T [N, M], B = X^T [K, M]   (+= through the `residual` epilogue)
     db[N]   = column sums of dY
-with the transposed / converted operands produced by ``ccx_convert_operand`` (optionally fused with a dropout
-multiplier or the ReLU mask).
+bf16: the tensor core reads an operand's transpose in place (``a_mn`` / ``w_mn`` of ccx_linear: MN-major UMMA
+descriptors), so B = W as the forward has it and A = dY, B = X as they are — one bf16 cast of dY is the only copy.
+fp32 (3xTF32, K-major only): transposed / converted operands from ``ccx_convert_operand`` (optionally fused with a
+dropout multiplier or the ReLU mask).
 """
+import os
 import torch
 
 from . import _lib
@@ -129,6 +132,33 @@ def to_operand(x, cd, mul=None, mul_mode=0, mul_scale=1.0, transpose=False):
     return view
 
 
+_MN = os.environ.get("CCX_GEMM_MN", "1") != "0"        # A/B switch: 0 = transposed copies as in the fp32 path
+
+
+class MnWeight:
+    """A Linear weight for the dgrad GEMM in bf16: the plain [N, K] operand, read MN-major (no W^T copy)."""
+
+    def __init__(self, op):
+        self.op = op
+
+
+def _mn_ready(op):
+    return (isinstance(op, Operand) and op.dtype == torch.bfloat16 and op.lo is None and op.hi.stride(1) == 1 and
+            op.hi.stride(0) % 8 == 0 and op.hi.data_ptr() % 16 == 0)
+
+
+def mn_operands(cd, *ops):
+    """True when the bf16 operands `ops` can be read transposed in place (pitch / alignment) and the switch is on."""
+    return _MN and cd == torch.bfloat16 and all(_mn_ready(o) for o in ops)
+
+
+def linear_dgrad(dy_op, wt, residual=None, n=None):
+    """dX = dY . W for wt = weight_t(W): MnWeight (bf16, W read in place) or the transposed Operand W^T [K, pad8(N)]."""
+    if isinstance(wt, MnWeight):
+        return _lib.linear(dy_op, wt.op, residual=residual, w_mn=True)
+    return _lib.linear(dy_op, wt, residual=residual, k=n)
+
+
 def colsum_acc(dy, out, mul=None, mul_mode=0, mul_scale=1.0):
     R, C = dy.shape
     _lib.check(_lib.lib().ccx_colsum_acc(ptr(dy), dy.stride(0), ptr(mul), mul.stride(0) if mul is not None else 0,
@@ -143,13 +173,23 @@ def linear_bwd(dy, x, wt, cd, w_grad=None, b_grad=None, need_dx=True, dx_residua
     w_grad [N, K] / b_grad [N]: fp32 accumulators (+=).  Returns dX [M, K] fp32 (+ dx_residual) or None."""
     M, N = dy.shape
     dx = None
+    dy_op = None
     if need_dx:
         dy_op = to_operand(dy, cd, mul, mul_mode, mul_scale)
-        dx = _lib.linear(dy_op, wt, residual=dx_residual, k=N)
+        dx = linear_dgrad(dy_op, wt, residual=dx_residual, n=N)
     if w_grad is not None:
-        dy_t = to_operand(dy, cd, mul, mul_mode, mul_scale, transpose=True)      # [N, Mp]
-        x_t = to_operand(x, cd, transpose=True)                                   # [K, Mp]
-        _lib.linear(dy_t, x_t, residual=w_grad, out=w_grad)
+        x_op = x if _mn_ready(x) else None
+        if _MN and cd == torch.bfloat16 and (x_op is not None or not isinstance(x, Operand)):
+            # dW += dY^T . X on the row-major bf16 dY and X themselves (both read MN-major, contraction over rows)
+            if dy_op is None:
+                dy_op = to_operand(dy, cd, mul, mul_mode, mul_scale)
+            if x_op is None:
+                x_op = to_operand(x, cd)
+            _lib.linear(dy_op, x_op, residual=w_grad, out=w_grad, a_mn=True, w_mn=True)
+        else:
+            dy_t = to_operand(dy, cd, mul, mul_mode, mul_scale, transpose=True)      # [N, Mp]
+            x_t = to_operand(x, cd, transpose=True)                                   # [K, Mp]
+            _lib.linear(dy_t, x_t, residual=w_grad, out=w_grad)
     if b_grad is not None:
         colsum_acc(dy, b_grad, mul, mul_mode, mul_scale)
     return dx
@@ -165,6 +205,13 @@ def ln_bwd(dy, x_in, gamma, dgamma, dbeta, eps, merge_hw=None):
     return dx
 
 
-def weight_t(w, cd):
-    """W [N, K] fp32 parameter -> Operand W^T [K, pad8(N)] for dgrad GEMMs."""
+def weight_t(w, cd, op=None):
+    """W [N, K] fp32 parameter -> what the dgrad GEMM dX = dY . W takes as its B operand: in bf16 the plain [N, K]
+    operand read MN-major (`op`: the forward's own bf16 copy of W if the caller has it — then nothing is launched),
+    otherwise the transposed Operand W^T [K, pad8(N)]."""
+    if _MN and cd == torch.bfloat16:
+        if op is not None and _mn_ready(op) and tuple(op.hi.shape) == tuple(w.shape):
+            return MnWeight(op)
+        if w.shape[1] % 8 == 0:
+            return MnWeight(to_operand(w.detach(), cd))
     return to_operand(w.detach(), cd, transpose=True)

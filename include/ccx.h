@@ -80,6 +80,11 @@ typedef struct ccx_linear_desc {
   int32_t in_dtype;
   int32_t out_dtype;
   int32_t split;
+  /* bf16 operands only.  a_mn != 0: A is given as its transpose, a row-major [K, M] array (lda = its row pitch) — the
+   * tensor core reads it "MN-major", no transposed copy is made; w_mn != 0: W likewise as [K, N] (ldw = row pitch).
+   * Row pitches must be multiples of 8 elements.  This is what lets a Linear layer's backward run on the buffers the
+   * forward already has: dX = dY . W uses W [N,K] as it is (w_mn), dW = dY^T . X uses dY [M,N] (a_mn) and X [M,K] (w_mn). */
+  int32_t a_mn, w_mn;
 } ccx_linear_desc;
 CCX_API int ccx_linear(const ccx_linear_desc* d, void* stream);
 /* mode != 0: GEMMs that fill the machine with 256x256 tiles use the CTA-pair kernel (tcgen05 cta_group::2, UMMA

@@ -169,6 +169,32 @@ def _linear_epilogue_checks(M, N, K, dtype):
         assert y.dtype == torch.bfloat16 and rel_err(y.float(), a @ w.t() + bias) < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(512, 256, 320), (1024, 4096, 2048), (304, 200, 136), (4096, 1024, 1664), (128, 64, 64)])
+@pytest.mark.parametrize("a_mn,w_mn", [(True, False), (False, True), (True, True)])
+def test_linear_reads_transposed_operands_in_place(M, N, K, a_mn, w_mn):
+    """ccx_linear with a_mn / w_mn: the operand is handed over as its transpose ([K, M] / [K, N] row-major, pitch a
+    multiple of 8) and read MN-major by the tensor core — what lets dX = dY . W and dW = dY^T . X run on the forward's
+    own buffers.  bf16 products are exact in fp32, so the result matches the plain call up to summation order."""
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import Operand
+    g = _g(M + N + K)
+    a = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+
+    def op(x, transposed):
+        if not transposed:
+            return Operand(x.cuda(), None, torch.bfloat16)
+        rows, cols = x.shape[1], x.shape[0]                      # [K, M] storage with the pitch padded to 8
+        buf = torch.zeros(rows, (cols + 7) // 8 * 8, dtype=torch.bfloat16, device="cuda")
+        buf[:, :cols] = x.t().cuda()
+        return Operand(buf[:, :cols], None, torch.bfloat16)
+    y = _lib.linear(op(a, a_mn), op(w, w_mn), bias=bias.cuda(), residual=res.cuda(), a_mn=a_mn, w_mn=w_mn)
+    ref = a.float() @ w.float().t() + bias + res
+    assert rel_err(y, ref) < 1e-5
+
+
 # The TMA epilogue of gemm_tn_kernel (csrc/ccx_gemm_epilogue.cuh): bf16 operands, output rows 16-byte aligned.
 #  (40000,256,128) / (40000,128,256): several tiles per CTA (box prefetch across tiles, the last one through the ring);
 #  (8192,512,2048): one tile per CTA (ring only); (300,200,192) / (1000,72,64): ragged M and N, clipped by the tensor map;
