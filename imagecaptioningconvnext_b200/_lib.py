@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libccx.so")
 
 CCX_F32, CCX_BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_GRAD = 0, 1, 2, 3
 MAX_BLOCKS = 64
 
 _vp, _i32, _i64, _f32, _sz = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -24,7 +24,7 @@ class LinearDesc(C.Structure):
                 ("lda", _i64), ("ldw", _i64), ("ldc", _i64), ("ldr", _i64), ("ldm", _i64),
                 ("M", _i32), ("N", _i32), ("K", _i32), ("rows_per_group", _i32),
                 ("act", _i32), ("in_dtype", _i32), ("out_dtype", _i32), ("split", _i32),
-                ("a_mn", _i32), ("w_mn", _i32)]
+                ("a_mn", _i32), ("w_mn", _i32), ("res_mul", _i32)]
 
 
 class CNBlockWeights(C.Structure):
@@ -286,7 +286,8 @@ class Operand:
 
 
 def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per_group=1, residual=None,
-           out=None, out_dtype=torch.float32, split=False, emask=None, k=None, n=None, a_mn=False, w_mn=False):
+           out=None, out_dtype=torch.float32, split=False, emask=None, k=None, n=None, a_mn=False, w_mn=False,
+           res_mul=False):
     """C = epilogue(A . W^T).  a, w: Operand (2-D, row-major, unit inner stride).  Returns a tensor, or an
     Operand when split=True (fp32 compute only).  a_mn / w_mn (bf16 only): the operand is handed over TRANSPOSED,
     as a [K, M] / [K, N] row-major array, and read in place (see ccx_linear_desc)."""
@@ -322,5 +323,6 @@ def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per
     d.in_dtype, d.out_dtype = dt_code(a.dtype), dt_code(out_dtype)
     d.split = 1 if split else 0
     d.a_mn, d.w_mn = (1 if a_mn else 0), (1 if w_mn else 0)
+    d.res_mul = 1 if res_mul else 0
     check(lib().ccx_linear(C.byref(d), stream_ptr()), f"linear M={M} N={N} K={K}")
     return res

@@ -42,6 +42,8 @@ int ccx_linear(const ccx_linear_desc* d, void* stream) {
   g.rows_per_group = d->rows_per_group;
   g.act = d->act; g.in_dtype = d->in_dtype; g.out_dtype = d->out_dtype; g.split = d->split;
   g.a_mn = d->a_mn != 0; g.b_mn = d->w_mn != 0;
+  g.res_mul = d->res_mul != 0;
+  if (g.res_mul && (g.residual == nullptr || g.colscale != nullptr || g.rowscale != nullptr || g.split)) return CCX_ERR_SHAPE;
   return gemm_tn(g, as_stream(stream));
 }
 

@@ -252,6 +252,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
+// d GELU(x) / dx for the exact (erf) form: Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return fmaf(x, pdf, cdf);
+}
+
 // GELU for bf16 OUTPUTS: 0.5x(1 + tanh(sqrt(2/pi)(x + 0.044715 x^3))) with MUFU.TANH — 5 FMA-pipe instructions and
 // one MUFU per element instead of the 12 + 2 of the erf form, which makes the Linear(C->4C)+GELU epilogue MUFU/issue
 // bound above the MMA time.  |tanh form - erf form| <= 4.7e-4 absolute; after rounding to bf16 the RMS error against
@@ -266,6 +273,18 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float u = x * fmaf(0.035677408136f, x * x, 0.7978845608f);
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx(u), hx);
+}
+
+// ... and of the tanh form the bf16 forward evaluates (gelu_tanh_fast): the exact derivative of THAT function,
+// 10 FMA-pipe instructions + one MUFU instead of erff + expf (~50): in a GEMM epilogue only 8 warps per SM do this math
+__device__ __forceinline__ float gelu_grad_tanh_fast(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(0.035677408136f, x2, 0.7978845608f);
+  const float t = tanh_approx(u);
+  const float dudx = fmaf(0.107032224408f, x2, 0.7978845608f);
+  const float a = fmaf(0.5f, t, 0.5f);
+  const float b = 0.5f * x * fmaf(-t, t, 1.0f);
+  return fmaf(b, dudx, a);
 }
 
 // Two GELUs per instruction stream for the bf16 epilogue: the tanh form evaluated in packed fp16 (HMUL2/HFMA2 +

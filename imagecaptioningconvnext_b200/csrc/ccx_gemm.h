@@ -21,13 +21,14 @@ struct GemmDesc {
   long long lda = 0, ldb = 0, ldc = 0, ldr = 0, ldm = 0;
   int M = 0, N = 0, K = 0;
   int rows_per_group = 1;
-  int act = 0;        // 0 none, 1 gelu(erf), 2 relu
+  int act = 0;        // 0 none, 1 gelu(erf), 2 relu, 3 gelu'(x)
   int in_dtype = 1;   // CCX_F32 (tf32 path) / CCX_BF16
   int out_dtype = 1;  // CCX_F32 / CCX_BF16
   int split = 0;
   int force_bn = 0;   // 0 = auto, else 64/128/256
   bool a_mn = false;  // bf16: A given as [K, M] row-major (lda = row pitch), read MN-major by the tensor core
   bool b_mn = false;  // bf16: B given as [K, N] row-major (ldb = row pitch)
+  bool res_mul = false;  // residual multiplies the activated result instead of being added
 };
 
 int gemm_tn(const GemmDesc& g, cudaStream_t stream);

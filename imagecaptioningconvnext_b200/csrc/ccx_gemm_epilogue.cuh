@@ -21,10 +21,12 @@ struct EpiArgs {
   const float* emask;     // [M, ldm] element-wise multiplier applied after the activation (dropout), or nullptr
   long long ldc, ldr, ldm;
   int rows_per_group;
-  int act;              // 0 none, 1 gelu(erf), 2 relu
+  int act;              // 0 none, 1 gelu(erf), 2 relu, 3 gelu'(x) (erf form)
   int out_dtype;        // CCX_F32 / CCX_BF16
   int split;            // 1: write tf32 hi to out, residual lo to out_lo
   int tma;              // 1: output (and residual) move through TMA boxes (epilogue_tile_tma); set by the launcher
+  int res_mul;          // 1: the residual multiplies the activated result instead of being added
+  int fast;             // 1: bf16 operands — act 3 differentiates the tanh-form GELU the bf16 forward evaluates
 };
 
 static constexpr int EPI_SCRATCH_FLOATS = 32 * 32;   // per epilogue warp
@@ -72,6 +74,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
     } else if (ep.act == 2) {
 #pragma unroll
       for (int r = 0; r < 32; ++r) y[r] = fmaxf(y[r], 0.0f);
+    } else if (ep.act == 3) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) y[r] = ep.fast ? gelu_grad_tanh_fast(y[r]) : gelu_grad_erf(y[r]);
     }
     if (ep.emask != nullptr) {
       const float* mp = ep.emask + (long long)row0 * ep.ldm + col;
@@ -92,7 +97,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
       if (ep.residual != nullptr) {
         const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + (long long)row0 * ep.ldr + col;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) y[r] += __bfloat162float(rp[r * ep.ldr]);
+        for (int r = 0; r < 32; ++r) {
+          const float rv = __bfloat162float(rp[r * ep.ldr]);
+          y[r] = ep.res_mul ? y[r] * rv : y[r] + rv;
+        }
       }
 #pragma unroll
       for (int r = 0; r < 32; ++r) op[r * ep.ldc] = __float2bfloat16_rn(y[r]);
@@ -104,7 +112,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
 #pragma unroll
         for (int r = 0; r < 32; ++r) rv[r] = __ldg(rp + r * ep.ldr);
 #pragma unroll
-        for (int r = 0; r < 32; ++r) y[r] += rv[r];
+        for (int r = 0; r < 32; ++r) y[r] = ep.res_mul ? y[r] * rv[r] : y[r] + rv[r];
       }
       if (ep.split) {
         float* lp = ep.out_lo + (long long)row0 * ep.ldc + col;
@@ -126,14 +134,20 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& ep, const float (&
       float y = scratch[r * 32 + ((cq ^ (r & 7)) << 2) + cr] + b;
       if (ep.act == 1) y = (ep.out_dtype == CCX_BF16) ? gelu_tanh_fast(y) : gelu_erf(y);
       else if (ep.act == 2) y = fmaxf(y, 0.0f);
+      else if (ep.act == 3) y = ep.fast ? gelu_grad_tanh_fast(y) : gelu_grad_erf(y);
       if (ep.emask != nullptr) y *= __ldg(ep.emask + (long long)row * ep.ldm + col);
       if (scale) y *= cs * (ep.rowscale ? __ldg(ep.rowscale + row / ep.rows_per_group) : 1.0f);
       if (ep.out_dtype == CCX_BF16) {
-        if (ep.residual != nullptr)
-          y += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ep.residual)[(long long)row * ep.ldr + col]);
+        if (ep.residual != nullptr) {
+          const float rv = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ep.residual)[(long long)row * ep.ldr + col]);
+          y = ep.res_mul ? y * rv : y + rv;
+        }
         reinterpret_cast<__nv_bfloat16*>(ep.out)[(long long)row * ep.ldc + col] = __float2bfloat16_rn(y);
       } else {
-        if (ep.residual != nullptr) y += __ldg(reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col);
+        if (ep.residual != nullptr) {
+          const float rv = __ldg(reinterpret_cast<const float*>(ep.residual) + (long long)row * ep.ldr + col);
+          y = ep.res_mul ? y * rv : y + rv;
+        }
         if (ep.split) {
           const float h = tf32_hi(y);
           reinterpret_cast<float*>(ep.out)[(long long)row * ep.ldc + col] = h;
@@ -182,6 +196,9 @@ __device__ __forceinline__ void epilogue_unit_bf16(const EpiArgs& ep, float (&f)
     } else if (ep.act == 2) {
 #pragma unroll
       for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
+    } else if (ep.act == 3) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[j] = ep.fast ? gelu_grad_tanh_fast(f[j]) : gelu_grad_erf(f[j]);
     }
     if (ep.colscale != nullptr) {
 #pragma unroll
@@ -345,6 +362,9 @@ __device__ __forceinline__ void epilogue_chunk_tma(const EpiArgs& ep, float (&f)
   } else if (ep.act == 2) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (ep.act == 3) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = ep.fast ? gelu_grad_tanh_fast(f[j]) : gelu_grad_erf(f[j]);
   }
   if (ep.colscale != nullptr) {
 #pragma unroll
@@ -363,7 +383,8 @@ __device__ __forceinline__ void epilogue_chunk_tma(const EpiArgs& ep, float (&f)
       float4 y = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
       if (has_res) {
         const float4 r = *reinterpret_cast<const float4*>(resrow + ((q ^ sw) << 4));
-        y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+        if (ep.res_mul) { y.x *= r.x; y.y *= r.y; y.z *= r.z; y.w *= r.w; }
+        else { y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w; }
       }
       *cp = y;
     }
@@ -374,10 +395,17 @@ __device__ __forceinline__ void epilogue_chunk_tma(const EpiArgs& ep, float (&f)
       if (has_res) {
         const uint4 r = *reinterpret_cast<const uint4*>(resrow + (((q0 + q) ^ sw) << 4));
         float2 t;
-        t = unpack_bf16x2(r.x); f[8 * q] += t.x;     f[8 * q + 1] += t.y;
-        t = unpack_bf16x2(r.y); f[8 * q + 2] += t.x; f[8 * q + 3] += t.y;
-        t = unpack_bf16x2(r.z); f[8 * q + 4] += t.x; f[8 * q + 5] += t.y;
-        t = unpack_bf16x2(r.w); f[8 * q + 6] += t.x; f[8 * q + 7] += t.y;
+        if (ep.res_mul) {
+          t = unpack_bf16x2(r.x); f[8 * q] *= t.x;     f[8 * q + 1] *= t.y;
+          t = unpack_bf16x2(r.y); f[8 * q + 2] *= t.x; f[8 * q + 3] *= t.y;
+          t = unpack_bf16x2(r.z); f[8 * q + 4] *= t.x; f[8 * q + 5] *= t.y;
+          t = unpack_bf16x2(r.w); f[8 * q + 6] *= t.x; f[8 * q + 7] *= t.y;
+        } else {
+          t = unpack_bf16x2(r.x); f[8 * q] += t.x;     f[8 * q + 1] += t.y;
+          t = unpack_bf16x2(r.y); f[8 * q + 2] += t.x; f[8 * q + 3] += t.y;
+          t = unpack_bf16x2(r.z); f[8 * q + 4] += t.x; f[8 * q + 5] += t.y;
+          t = unpack_bf16x2(r.w); f[8 * q + 6] += t.x; f[8 * q + 7] += t.y;
+        }
       }
       uint4 pk;
       pk.x = pack_bf16x2(f[8 * q], f[8 * q + 1]);

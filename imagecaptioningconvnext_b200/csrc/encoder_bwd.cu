@@ -63,19 +63,33 @@ int gelu_bwd(const float* pre, float* dh, long long n, cudaStream_t stream) {
 // G[c, :] = sum_m dout'[m,c] h[m,:]  (dout' = dout * rowscale).  With z = h W2^T + b2 and out = x + gamma*rs*z:
 //   dW2[c,:] += gamma[c] * G[c,:] ;  d gamma[c] += W2[c,:] . G[c,:] + b2[c] * s[c] ;  d b2[c] += gamma[c] * s[c]
 // where s[c] = sum_m dout'[m,c].  One warp per output channel c.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 cnblock_param_grads_kernel(const float* __restrict__ G, const float* __restrict__ W2, const float* __restrict__ b2,
                            const float* __restrict__ gamma, const float* __restrict__ s, float* __restrict__ dW2,
                            float* __restrict__ dgamma, float* __restrict__ db2, int C, int K) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 8 + warp;
+  const int c = blockIdx.x * 4 + warp;
   if (c >= C) return;
   const float g = gamma[c];
   float dot = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float gv = G[static_cast<long long>(c) * K + k];
-    dot = fmaf(W2[static_cast<long long>(c) * K + k], gv, dot);
-    dW2[static_cast<long long>(c) * K + k] += g * gv;
+  const long long row = static_cast<long long>(c) * K;
+  if ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(dW2)) & 15) == 0) {
+    const float4* G4 = reinterpret_cast<const float4*>(G + row);
+    const float4* W4 = reinterpret_cast<const float4*>(W2 + row);
+    float4* D4 = reinterpret_cast<float4*>(dW2 + row);
+    for (int k = lane; k < (K >> 2); k += 32) {
+      const float4 gv = __ldg(G4 + k), wv = __ldg(W4 + k);
+      float4 d = D4[k];
+      dot = fmaf(wv.x, gv.x, fmaf(wv.y, gv.y, fmaf(wv.z, gv.z, fmaf(wv.w, gv.w, dot))));
+      d.x = fmaf(g, gv.x, d.x); d.y = fmaf(g, gv.y, d.y); d.z = fmaf(g, gv.z, d.z); d.w = fmaf(g, gv.w, d.w);
+      D4[k] = d;
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float gv = G[row + k];
+      dot = fmaf(W2[row + k], gv, dot);
+      dW2[row + k] += g * gv;
+    }
   }
   dot = warp_sum(dot);
   if (lane == 0) {
@@ -87,7 +101,7 @@ int cnblock_param_grads(const float* G, const float* W2, const float* b2, const 
                         float* dW2, float* dgamma, float* db2, int C, int K, cudaStream_t stream) {
   if (C <= 0) return CCX_OK;
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)C * K * 16.0);
-  cnblock_param_grads_kernel<<<(C + 7) / 8, 256, 0, stream>>>(G, W2, b2, gamma, s, dW2, dgamma, db2, C, K);
+  cnblock_param_grads_kernel<<<(C + 3) / 4, 128, 0, stream>>>(G, W2, b2, gamma, s, dW2, dgamma, db2, C, K);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -102,7 +102,7 @@ static int g_skinny = -1;
 
 bool gemm_skinny_eligible(const GemmDesc& g) {
   if (g_skinny < 0) g_skinny = getenv("CCX_GEMM_SKINNY") ? atoi(getenv("CCX_GEMM_SKINNY")) : 1;
-  return g_skinny && !g.a_mn && !g.b_mn && g.in_dtype == CCX_BF16 && g.out_dtype == CCX_F32 && g.M >= 1 && g.M <= 32 && g.act == 0 &&
+  return g_skinny && !g.a_mn && !g.b_mn && !g.res_mul && g.in_dtype == CCX_BF16 && g.out_dtype == CCX_F32 && g.M >= 1 && g.M <= 32 && g.act == 0 &&
          g.colscale == nullptr && g.rowscale == nullptr && g.emask == nullptr && !g.split && g.force_bn == 0 &&
          g.A_lo == nullptr && g.B_lo == nullptr && (g.K % 32) == 0 && (g.lda % 8) == 0 && (g.ldb % 8) == 0 &&
          g.N >= 64 && (reinterpret_cast<uintptr_t>(g.A) % 16) == 0 && (reinterpret_cast<uintptr_t>(g.B) % 16) == 0;

@@ -549,6 +549,8 @@ int gemm_tn(const GemmDesc& g, cudaStream_t stream) {
   ep.out_dtype = g.out_dtype;
   ep.split = (g.split && g.C_lo != nullptr) ? 1 : 0;
   ep.tma = use_tma ? 1 : 0;
+  ep.res_mul = g.res_mul ? 1 : 0;
+  ep.fast = tf32 ? 0 : 1;
   if (use_pair) return gemm_tn_2cta(a_hi, b_hi, a_lo, b_lo, tm.c, tm.r, g.M, g.N, g.K, nseg, ep, tf32, stream);
   if (tf32) {
     if (bn == 256) return launch_boxes<256, true>(tm, g.M, g.N, g.K, nseg, ep, boxes, mn_flags, stream);

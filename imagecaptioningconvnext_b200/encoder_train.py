@@ -11,6 +11,8 @@ only):
              depthwise-conv data gradient (the same TMA/cluster kernel with flipped taps) and filter gradient;
   downsample: patch-merge GEMM dgrad/wgrad -> LayerNorm2d backward reading dy in the merged layout.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -35,6 +37,9 @@ def _block_index0(enc, child):
 
 def _named(mod):
     return named_params(mod)
+
+
+_FUSED_GELU_BWD = os.environ.get("CCX_FUSED_GELU_BWD", "0") != "0"     # 1: GELU backward inside the re-computing GEMM (measured: no gain)
 
 
 class _BlockFn(torch.autograd.Function):
@@ -106,10 +111,16 @@ class _BlockFn(torch.autograd.Function):
                                              ptr(grads["block.5.weight"]), ptr(grads["layer_scale"]),
                                              ptr(grads["block.5.bias"]), C, K4, st), "cnblock_param_grads")
         # GELU' on the recomputed pre-activation, first Linear
-        pre = _lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach())
-        _lib.check(L.ccx_gelu_bwd(ptr(pre), ptr(dh), M * K4, st), "gelu_bwd")
+        if _FUSED_GELU_BWD:
+            # dh *= GELU'(y . W1^T + b1): the pre-activation is recomputed and consumed inside the GEMM's epilogue
+            _lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach(), act=_lib.ACT_GELU_GRAD, residual=dh, out=dh,
+                        res_mul=True)
+        else:
+            pre = _lib.linear(y_op, ops["w1"], bias=blk.block[3].bias.detach())
+            _lib.check(L.ccx_gelu_bwd(ptr(pre), ptr(dh), M * K4, st), "gelu_bwd")
+            del pre
         dy = linear_bwd(dh, y_op, weight_t(W1, cd, ops["w1"]), cd, grads["block.3.weight"], grads["block.3.bias"])
-        del pre, dh
+        del dh
         # LayerNorm backward on the recomputed conv output
         u = torch.empty((M, C), **f32)
         _lib.check(L.ccx_dwconv7_plain(ptr(x_in), ptr(ops["dw_w"]), ptr(blk.block[0].bias.detach()), None, ptr(u),

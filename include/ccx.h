@@ -45,6 +45,7 @@ extern "C" {
 #define CCX_ACT_NONE 0
 #define CCX_ACT_GELU 1 /* exact erf GELU (nn.GELU default) */
 #define CCX_ACT_RELU 2
+#define CCX_ACT_GELU_GRAD 3 /* d GELU(x) / dx = Phi(x) + x phi(x): with res_mul the backward of Linear+GELU in one GEMM */
 
 CCX_API int ccx_version(void);
 CCX_API const char* ccx_status_string(int status);
@@ -85,6 +86,10 @@ typedef struct ccx_linear_desc {
    * Row pitches must be multiples of 8 elements.  This is what lets a Linear layer's backward run on the buffers the
    * forward already has: dX = dY . W uses W [N,K] as it is (w_mn), dW = dY^T . X uses dY [M,N] (a_mn) and X [M,K] (w_mn). */
   int32_t a_mn, w_mn;
+  /* res_mul != 0: `residual` MULTIPLIES the activated result instead of being added (no layer-/row-scale then):
+   * C = act(A.W^T + bias) * residual.  With CCX_ACT_GELU_GRAD and residual = C = d(hidden): the GELU backward of a
+   * CNBlock fused into the re-computation of its pre-activation (torchvision convnext.py:55-56). */
+  int32_t res_mul;
 } ccx_linear_desc;
 CCX_API int ccx_linear(const ccx_linear_desc* d, void* stream);
 /* mode != 0: GEMMs that fill the machine with 256x256 tiles use the CTA-pair kernel (tcgen05 cta_group::2, UMMA

@@ -227,6 +227,18 @@ def test_linear_tma_epilogue_paths(M, N, K):
     rb = res.to(torch.bfloat16).cuda()
     y = _lib.linear(A, Wt, bias=bias.cuda(), act=_lib.ACT_RELU, residual=rb, out_dtype=torch.bfloat16)
     assert rel_err(y.float(), F.relu(prod + bias) + rb.float().cpu()) < tol
+    # GELU' of the recomputed pre-activation times an upstream gradient, in place (CNBlock backward)
+    dh = res.clone().cuda()
+    _lib.linear(A, Wt, bias=bias.cuda(), act=_lib.ACT_GELU_GRAD, residual=dh, out=dh, res_mul=True)
+    # (bf16 operands: the derivative of the tanh-form GELU the bf16 forward evaluates, with tanh.approx ~5e-4 abs;
+    #  the erf form of the fp32 path is covered by the fp32 encoder-backward parity tests)
+    xr = (prod + bias).double()
+    u = xr * (0.7978845608 + 0.035677408136 * xr * xr)
+    t = torch.tanh(u)
+    gp = 0.5 * (1 + t) + 0.5 * xr * (1 - t * t) * (0.7978845608 + 3 * 0.035677408136 * xr * xr)
+    assert rel_err(dh, (gp * res.double()).float()) < 2e-3
+    exact = 0.5 * (1 + torch.erf(xr / 2 ** 0.5)) + xr * torch.exp(-0.5 * xr * xr) / (2 * torch.pi) ** 0.5
+    assert float((gp - exact).abs().max()) < 2e-3          # the two forms of GELU' agree to 1e-3
     # a strided output view (row pitch 2N): the tensor map carries the pitch
     wide = torch.zeros(M, 2 * N, device="cuda")
     _lib.linear(A, Wt, bias=bias.cuda(), out=wide[:, N:])
