@@ -113,6 +113,9 @@ SIGNATURES = {
     "ccx_mha_bwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
                               _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
                               _f32, _vp]),
+    "ccx_mha_bwd_tc": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
+                              _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
+                              _f32, _vp]),
     "ccx_softmax_ce": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i64, _vp, _i32, _vp]),
     "ccx_softmax_ce_dev": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _vp]),
     "ccx_free_running_targets": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _vp]),

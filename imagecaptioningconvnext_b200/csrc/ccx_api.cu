@@ -202,6 +202,16 @@ int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float* k, int6
   return mha_bwd(q, q_sb, q_st, k, k_sb, k_st, v, v_sb, v_st, dctx, d_sb, d_st, probs, prob_mask, dq, dq_sb, dq_st,
                  dk, dk_sb, dk_st, dv, dv_sb, dv_st, B, H, Tq, Tk, hd, scale, as_stream(stream));
 }
+
+int ccx_mha_bwd_tc(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
+                const float* v, int64_t v_sb, int64_t v_st, const float* dctx, int64_t d_sb, int64_t d_st,
+                const float* probs, const float* prob_mask, float* dq, int64_t dq_sb, int64_t dq_st, float* dk,
+                int64_t dk_sb, int64_t dk_st, float* dv, int64_t dv_sb, int64_t dv_st, int32_t B, int32_t H,
+                int32_t Tq, int32_t Tk, int32_t hd, float scale, void* stream) {
+  if (!mha_tc_eligible(Tq, Tk, hd)) return CCX_ERR_SHAPE;
+  return mha_tc_bwd(q, q_sb, q_st, k, k_sb, k_st, v, v_sb, v_st, dctx, d_sb, d_st, probs, prob_mask, dq, dq_sb, dq_st,
+                    dk, dk_sb, dk_st, dv, dv_sb, dv_st, B, H, Tq, Tk, scale, as_stream(stream));
+}
 int ccx_softmax_ce(const float* logits, int64_t ld, const int64_t* targets, int64_t R, int32_t V, float inv_n,
                    float* loss_sum, float* dlogits, int64_t ldd, float* stats, int32_t topk, void* stream) {
   return softmax_ce(logits, ld, reinterpret_cast<const long long*>(targets), R, V, inv_n, loss_sum, dlogits, ldd,

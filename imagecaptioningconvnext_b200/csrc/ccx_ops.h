@@ -67,6 +67,17 @@ int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, i
                float* out, int R, int C, cudaStream_t stream);
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
            long long M, int C, float eps, cudaStream_t stream, int merge = 0, int H = 1, int W = 1);
+// tensor-core (mma.sync, bf16) versions for T <= 64 and head dim 64: mha_tc.cu
+bool mha_tc_eligible(int Tq, int Tk, int hd);
+int mha_tc_fwd(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
+               const float* v, long long v_sb, long long v_st, void* ctx_bf16, long long c_sb, long long c_st,
+               const unsigned char* key_pad, const float* prob_mask, float* probs_out, int B, int H, int Tq, int Tk,
+               int causal, int q_pos0, float scale, int kv_group, cudaStream_t stream);
+int mha_tc_bwd(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
+               const float* v, long long v_sb, long long v_st, const float* dctx, long long d_sb, long long d_st,
+               const float* probs, const float* prob_mask, float* dq, long long dq_sb, long long dq_st, float* dk,
+               long long dk_sb, long long dk_st, float* dv, long long dv_sb, long long dv_st, int B, int H, int Tq,
+               int Tk, float scale, cudaStream_t stream);
 int mha_bwd(const float* q, long long q_sb, long long q_st, const float* k, long long k_sb, long long k_st,
             const float* v, long long v_sb, long long v_st, const float* dctx, long long d_sb, long long d_st,
             const float* probs, const float* prob_mask, float* dq, long long dq_sb, long long dq_st, float* dk,

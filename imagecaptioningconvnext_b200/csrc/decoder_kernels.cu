@@ -11,6 +11,8 @@
 // "Operand" outputs feed the next tcgen05 GEMM: bf16, or an fp32 (tf32-hi, lo) pair for the 3xTF32 path.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "ccx_common.cuh"
 #include "ccx_ops.h"
 #include "ccx_prof.h"
@@ -569,6 +571,11 @@ int mha_small(const float* q, long long q_sb, long long q_st, const float* k, lo
               float* probs_out, int B, int H, int Tq, int Tk, int hd, int causal, int q_pos0, float scale,
               int kv_group, cudaStream_t stream) {
   if (B <= 0 || Tq <= 0) return CCX_OK;
+  // bf16 compute mode, short sequences: the tensor-core kernel (mha_tc.cu)
+  static const bool no_tc = getenv("CCX_MHA_TC") != nullptr && atoi(getenv("CCX_MHA_TC")) == 0;
+  if (!no_tc && ctx_dtype == CCX_BF16 && ctx_lo == nullptr && H > 0 && mha_tc_eligible(Tq, Tk, hd))
+    return mha_tc_fwd(q, q_sb, q_st, k, k_sb, k_st, v, v_sb, v_st, ctx_hi, c_sb, c_st, key_pad, prob_mask, probs_out, B,
+                      H, Tq, Tk, causal, q_pos0, scale, kv_group, stream);
   if (Tk <= 0 || hd <= 0 || H <= 0 || (hd & 3) || (k_sb & 3) || (k_st & 3) || (v_sb & 3) || (v_st & 3) ||
       (reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15) || (q_sb & 3) || (q_st & 3) ||
       (reinterpret_cast<uintptr_t>(q) & 15))

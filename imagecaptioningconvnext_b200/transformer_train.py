@@ -6,6 +6,7 @@ the FFN hidden dropout — torch/nn/modules/transformer.py:1158-1199) uses multi
 torch.bernoulli (or injected by tests) and applied inside the GEMM epilogues / attention kernel.
 """
 import math
+import os
 import weakref
 
 import torch
@@ -120,6 +121,10 @@ def _backward_body(ctx, dpred, enc_needs_grad):
         mode = 0 if masks is None else 1
         keep_scale = 1.0 if masks is None else 1.0 / (1.0 - dec.dropout_p)
         scale = 1.0 / math.sqrt(D // H)
+        # bf16 compute mode at the decoder's shapes (<= 64 tokens / pixels, heads of 64): attention backward on the
+        # tensor cores (csrc/mha_tc.cu); otherwise the fp32 SIMT kernel
+        mha_bwd_fn = (L.ccx_mha_bwd_tc if (cd == torch.bfloat16 and T <= 64 and Pn <= 64 and D // H == 64 and
+                                           os.environ.get("CCX_MHA_TC", "1") != "0") else L.ccx_mha_bwd)
         names = [n for n, _ in named_params(dec)]
         params = dict(named_params(dec))
         grads = zero_grads_like(params.items())
@@ -148,7 +153,7 @@ def _backward_body(ctx, dpred, enc_needs_grad):
             dq2 = torch.empty((M, D), dtype=torch.float32, device=dev)
             dkv = torch.empty((B * Pn, 2 * D), dtype=torch.float32, device=dev)
             q2, kv = S["q2"], S["kv"]
-            _lib.check(L.ccx_mha_bwd(ptr(q2), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, Pn * 2 * D,
+            _lib.check(mha_bwd_fn(ptr(q2), T * D, D, ptr(kv), Pn * 2 * D, 2 * D, kv.data_ptr() + 4 * D, Pn * 2 * D,
                                      2 * D, ptr(dctx2), T * D, D, ptr(S["probs2"]), ptr(mk((li, "ca_p"))),
                                      ptr(dq2), T * D, D, ptr(dkv), Pn * 2 * D, 2 * D, dkv.data_ptr() + 4 * D,
                                      Pn * 2 * D, 2 * D, B, H, T, Pn, D // H, scale, st), "mha_bwd")
@@ -165,7 +170,7 @@ def _backward_body(ctx, dpred, enc_needs_grad):
                                g(pre + "self_attn.out_proj.bias"), mul=mk((li, "d1")), mul_mode=mode)
             qkv = S["qkv"]
             dqkv = torch.empty((M, 3 * D), dtype=torch.float32, device=dev)
-            _lib.check(L.ccx_mha_bwd(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
+            _lib.check(mha_bwd_fn(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
                                      qkv.data_ptr() + 8 * D, T * 3 * D, 3 * D, ptr(dctx1), T * D, D,
                                      ptr(S["probs1"]), ptr(mk((li, "sa_p"))), ptr(dqkv), T * 3 * D, 3 * D,
                                      dqkv.data_ptr() + 4 * D, T * 3 * D, 3 * D, dqkv.data_ptr() + 8 * D, T * 3 * D,

@@ -322,6 +322,14 @@ CCX_API int ccx_mha_bwd(const float* q, int64_t q_sb, int64_t q_st, const float*
                         const float* probs, const float* prob_mask, float* dq, int64_t dq_sb, int64_t dq_st,
                         float* dk, int64_t dk_sb, int64_t dk_st, float* dv, int64_t dv_sb, int64_t dv_st, int32_t B,
                         int32_t H, int32_t Tq, int32_t Tk, int32_t hd, float scale, void* stream);
+/* The same on the tensor cores (mma.sync, bf16 operands, fp32 accumulation) for Tq, Tk <= 64 and hd == 64 — the
+ * Transformer decoder's shapes (52 tokens, 49 pixels, 8 heads of 64); CCX_ERR_SHAPE otherwise.  ccx_mha_small takes
+ * the matching forward kernel by itself when its context output is bf16. */
+CCX_API int ccx_mha_bwd_tc(const float* q, int64_t q_sb, int64_t q_st, const float* k, int64_t k_sb, int64_t k_st,
+                           const float* v, int64_t v_sb, int64_t v_st, const float* dctx, int64_t d_sb, int64_t d_st,
+                           const float* probs, const float* prob_mask, float* dq, int64_t dq_sb, int64_t dq_st,
+                           float* dk, int64_t dk_sb, int64_t dk_st, float* dv, int64_t dv_sb, int64_t dv_st, int32_t B,
+                           int32_t H, int32_t Tq, int32_t Tk, int32_t hd, float scale, void* stream);
 /* CrossEntropyLoss(mean) over the rows with targets[r] >= 0 (= pack_padded_sequence's selection,
  * trainMultiGPU.py:365-367): *loss_sum += sum_r (lse_r - logit_r[target]) * inv_n;
  * dlogits[r] = (softmax_r - onehot) * inv_n, zero rows for targets < 0 (loss_sum / dlogits may be NULL).

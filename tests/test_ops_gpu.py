@@ -310,3 +310,49 @@ def test_cast_bf16_vector_and_tail_paths():
     for n in (8 * 1000, 8 * 1000 + 3, 5):
         x = torch.randn(n, generator=torch.Generator().manual_seed(n)).cuda()
         assert torch.equal(_lib.cast_bf16(x), x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("Tq,Tk,causal,pad,drop", [(52, 52, 1, True, True), (52, 49, 0, False, True), (64, 64, 1, False, False),
+                                                   (7, 49, 0, False, False), (33, 17, 0, True, True)])
+def test_tensor_core_attention_matches_the_simt_kernels(Tq, Tk, causal, pad, drop):
+    """csrc/mha_tc.cu (mma.sync, bf16 operands) against mha_small_kernel / mha_bwd_kernel (fp32 SIMT) on the same inputs:
+    context, the softmax probabilities handed to the backward, and dQ / dK / dV.  nn.MultiheadAttention inside
+    nn.TransformerDecoderLayer (models/transformerDecoder.py:102-106), B x 8 heads of 64."""
+    import math
+    from imagecaptioningconvnext_b200 import _lib
+    L, st = _lib.lib(), _lib.stream_ptr()
+    B, H, hd = 3, 8, 64
+    D = H * hd
+    g = _g(Tq * 100 + Tk)
+    q = torch.randn(B, Tq, D, generator=g).cuda()
+    k = torch.randn(B, Tk, D, generator=g).cuda()
+    v = torch.randn(B, Tk, D, generator=g).cuda()
+    key_pad = None
+    if pad:
+        key_pad = torch.zeros(B, Tk, dtype=torch.uint8)
+        key_pad[0, Tk - 3:] = 1
+        key_pad[2, Tk // 2:] = 1
+        key_pad = key_pad.cuda()
+    pm = ((torch.rand(B, H, Tq, Tk, generator=g) > 0.1).float() / 0.9).cuda() if drop else None
+    scale = 1.0 / math.sqrt(hd)
+    outs = {}
+    for name, dt, tdt in (("simt", _lib.CCX_F32, torch.float32), ("tc", _lib.CCX_BF16, torch.bfloat16)):
+        ctx = torch.zeros(B, Tq, D, dtype=tdt, device="cuda")
+        probs = torch.zeros(B, H, Tq, Tk, device="cuda")
+        _lib.check(L.ccx_mha_small(q.data_ptr(), Tq * D, D, k.data_ptr(), Tk * D, D, v.data_ptr(), Tk * D, D,
+                                   ctx.data_ptr(), None, dt, Tq * D, D, _lib.ptr(key_pad), _lib.ptr(pm),
+                                   probs.data_ptr(), B, H, Tq, Tk, hd, causal, 0, scale, 1, st))
+        outs[name] = (ctx.float(), probs)
+    assert rel_err(outs["tc"][0], outs["simt"][0]) < 2e-2
+    assert rel_err(outs["tc"][1], outs["simt"][1]) < 2e-2
+    dctx = torch.randn(B, Tq, D, generator=g).cuda()
+    probs = outs["simt"][1]
+    grads = {}
+    for name, fn in (("simt", L.ccx_mha_bwd), ("tc", L.ccx_mha_bwd_tc)):
+        dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        _lib.check(fn(q.data_ptr(), Tq * D, D, k.data_ptr(), Tk * D, D, v.data_ptr(), Tk * D, D, dctx.data_ptr(), Tq * D, D,
+                      probs.data_ptr(), _lib.ptr(pm), dq.data_ptr(), Tq * D, D, dk.data_ptr(), Tk * D, D,
+                      dv.data_ptr(), Tk * D, D, B, H, Tq, Tk, hd, scale, st))
+        grads[name] = (dq, dk, dv)
+    for a, b in zip(grads["tc"], grads["simt"]):
+        assert rel_err(a, b) < 2e-2
