@@ -1,5 +1,6 @@
 """Host-side helpers shared by the decoder modules: parameter holders whose ``forward`` runs on libccx, and the
 prepared-weight cache (bf16 / tf32-split copies of the fp32 master weights, rebuilt when a parameter changes)."""
+import os
 import weakref
 
 import torch
@@ -46,6 +47,9 @@ class CcxEmbedding(nn.Embedding):
         return out.view(*tokens.shape, D)
 
 
+PLAN_REFRESH = [os.environ.get("CCX_PLAN_REFRESH", "1") != "0"]    # A/B switch: 0 = re-run _prepare() on every refresh
+
+
 def _refresh_into(old, new):
     """Copy freshly prepared values into the buffers of a previous preparation (same structure), so that device
     pointers stay stable across optimizer steps (weight tables, captured CUDA graphs)."""
@@ -56,9 +60,10 @@ def _refresh_into(old, new):
         for a, b in zip(old, new):
             _refresh_into(a, b)
     elif isinstance(old, Operand):
-        old.hi.copy_(new.hi)
-        if old.lo is not None:
-            old.lo.copy_(new.lo)
+        if old.hi.data_ptr() != new.hi.data_ptr():      # (refreshed in place by Operand.prepare: nothing to copy)
+            old.hi.copy_(new.hi)
+            if old.lo is not None:
+                old.lo.copy_(new.lo)
     elif torch.is_tensor(old):
         if old.data_ptr() != new.data_ptr():      # views of the parameter storage need no copy
             old.copy_(new)
@@ -78,13 +83,73 @@ def _same_structure(a, b):
     return True
 
 
+class RefreshPlan:
+    """The weight refresh of a module as ONE ``ccx_cast_segments`` launch: a table of rectangular pieces
+    ``dst <- src`` (optionally row-permuted, transposed, or the sum of two sources) built once against the buffers of
+    a preparation, replayed after every optimizer step.  ``add`` takes 2-D views (unit inner stride) — slices of the
+    prepared buffers on the left, slices of the fp32 parameters on the right — so concatenations are just several
+    pieces with different destination views."""
+
+    def __init__(self):
+        self.segs, self.keep, self.tiles, self.bytes = [], [], 0, 0.0
+        self._table = None
+
+    @staticmethod
+    def _2d(t):
+        return t.unsqueeze(0) if t.dim() == 1 else t
+
+    def add(self, dst, src, src2=None, row_map=None, transpose=False):
+        dst, src = self._2d(dst), self._2d(src.detach())
+        rows = src.shape[0] if row_map is None else int(row_map.numel())
+        cols = src.shape[1]
+        want = (cols, rows) if transpose else (rows, cols)
+        if tuple(dst.shape) != want or dst.stride(1) != 1 or (src.stride(1) != 1 and cols > 1) or \
+                src.dtype != torch.float32 or dst.dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError(f"RefreshPlan.add: dst {tuple(dst.shape)} {dst.dtype} vs src block {want}")
+        seg = _lib.CastSeg()
+        seg.src, seg.dst = src.data_ptr(), dst.data_ptr()
+        seg.src_ld, seg.dst_ld = src.stride(0), dst.stride(0)
+        if src2 is not None:
+            src2 = self._2d(src2.detach())
+            if tuple(src2.shape) != tuple(src.shape) or src2.stride(0) != src.stride(0) or src2.dtype != torch.float32:
+                raise ValueError("RefreshPlan.add: src2 must mirror src")
+            seg.src2 = src2.data_ptr()
+        if row_map is not None:
+            row_map = row_map.to(device=src.device, dtype=torch.int32).contiguous()
+            seg.row_map = row_map.data_ptr()
+        seg.rows, seg.cols = rows, cols
+        seg.flags = (1 if transpose else 0) | (2 if dst.dtype == torch.float32 else 0)
+        seg.tile0 = self.tiles
+        self.tiles += ((rows + 63) // 64) * ((cols + 63) // 64)
+        self.bytes += rows * cols * (4.0 * (2 if src2 is not None else 1) + dst.element_size())
+        self.segs.append(seg)
+        self.keep.append((dst, src, src2, row_map))
+        self._table = None
+        return self
+
+    def sources(self):
+        return [(k[1].data_ptr(), k[0].data_ptr()) for k in self.keep]
+
+    def run(self):
+        if not self.segs:
+            return
+        if self._table is None:
+            arr = (_lib.CastSeg * len(self.segs))(*self.segs)
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._table = host.to(self.keep[0][0].device)
+        _lib.check(_lib.lib().ccx_cast_segments(self._table.data_ptr(), len(self.segs), self.tiles, self.bytes,
+                                                _lib.stream_ptr()), "cast_segments")
+
+
 class PreparedCache:
-    """Caches ``owner._prepare()`` (dict of kernel-side weight tensors).  When a parameter changes the new values are
-    copied INTO the existing buffers (pointer-stable), unless storage / dtype / shapes changed."""
+    """Caches ``owner._prepare()`` (dict of kernel-side weight tensors).  When a parameter changes, the existing
+    buffers are refreshed in place (pointer-stable: weight tables and captured CUDA graphs hold their addresses),
+    unless storage / dtype / shapes changed: by the owner's one-launch ``_refresh_plan`` (bf16), else by re-running
+    ``_prepare()`` with every ``Operand.prepare`` converting straight into the operand it made last time."""
 
     def __init__(self, owner):
         self._owner = [owner]   # list: keep the module out of nn.Module's attribute registration
-        self._key, self._val = None, None
+        self._key, self._val, self._made, self._plan, self._plan_src = None, None, None, None, None
 
     def get(self):
         owner = self._owner[0]
@@ -95,14 +160,42 @@ class PreparedCache:
             for p in params:
                 if not p.is_cuda or p.dtype != torch.float32:
                     raise ValueError("parameters must be float32 CUDA tensors (call .cuda()); there is no CPU path")
-            fresh = owner._prepare()
-            if self._val is not None and self._key is not None and self._key[:3] == key[:3] and \
-                    _same_structure(self._val, fresh):
+            refresh = self._val is not None and self._key is not None and self._key[:3] == key[:3]
+            if refresh and self._run_plan(owner):
+                self._key = key
+                return self._val
+            # a refresh converts the changed masters straight into the operands of the previous preparation (same
+            # call sequence), so the bf16 / tf32 copies are written once and their device pointers never move
+            with _lib.prepare_log(reuse=self._made if refresh else None) as log:
+                fresh = owner._prepare()
+            if refresh and _same_structure(self._val, fresh):
                 _refresh_into(self._val, fresh)
             else:
                 self._val = fresh
+                self._made = log["made"]
+                self._plan = None
             self._key = key
         return self._val
+
+    def _run_plan(self, owner):
+        """One-launch refresh (``owner._refresh_plan(prepared dict) -> RefreshPlan``) of the current buffers; False
+        when the module has no plan for this compute dtype or a parameter's storage moved since the plan was built."""
+        make = getattr(owner, "_refresh_plan", None)
+        if make is None or not PLAN_REFRESH[0]:
+            return False
+        if self._plan is None:
+            self._plan = make(self._val)
+            if self._plan is None:
+                self._plan = False
+            else:
+                self._plan_src = [(p, p.data_ptr()) for p in params_of(owner)]
+        if self._plan is False:
+            return False
+        if any(p.data_ptr() != a for p, a in self._plan_src):
+            self._plan = None
+            return False
+        self._plan.run()
+        return True
 
     def storage_key(self):
         return None if self._key is None else self._key[:3]

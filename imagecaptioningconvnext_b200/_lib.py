@@ -70,6 +70,12 @@ class LstmPersistBwd(C.Structure):
                 ("att1_bf", _vp), ("enc_bf", _vp), ("decode_len", _vp), ("counters", _vp), ("dbg", _vp)]
 
 
+class CastSeg(C.Structure):
+    """ccx_cast_seg (include/ccx.h): one rectangular piece of a weight refresh."""
+    _fields_ = [("src", _vp), ("src2", _vp), ("dst", _vp), ("row_map", _vp), ("src_ld", _i64), ("dst_ld", _i64),
+                ("rows", _i32), ("cols", _i32), ("flags", _i32), ("tile0", _i32)]
+
+
 # name -> (restype, argtypes); must list every symbol include/ccx.h declares (tests/test_abi.py checks it)
 SIGNATURES = {
     "ccx_version": (C.c_int, []),
@@ -109,6 +115,7 @@ SIGNATURES = {
     "ccx_convert_operand": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _i32, _f32, _vp, _vp, _i32, _i64, _i32, _i32,
                                       _i32, _i32, _vp]),
     "ccx_colsum_acc": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i32, _i32, _vp]),
+    "ccx_cast_segments": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp]),
     "ccx_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "ccx_mha_bwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
                               _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,
@@ -238,6 +245,25 @@ def cast_bf16(x):
     return y
 
 
+_PREPARE_LOG = [None]     # {"made": [Operand, ...], "reuse": [Operand, ...] or None} while a PreparedCache prepares
+
+
+class prepare_log:
+    """Context around ``owner._prepare()``: records the Operands ``Operand.prepare`` hands out, in call order, and —
+    given the record of the previous preparation — makes it refresh those in place instead of allocating."""
+
+    def __init__(self, reuse=None):
+        self.state = {"made": [], "reuse": list(reuse) if reuse else None}
+
+    def __enter__(self):
+        self._old = _PREPARE_LOG[0]
+        _PREPARE_LOG[0] = self.state
+        return self.state
+
+    def __exit__(self, *exc):
+        _PREPARE_LOG[0] = self._old
+
+
 class Operand:
     """A GEMM operand prepared for the chosen compute dtype: bf16 tensor, or (hi, lo) fp32 pair."""
     __slots__ = ("hi", "lo", "dtype")
@@ -275,10 +301,25 @@ class Operand:
 
     @staticmethod
     def prepare(x_fp32, compute_dtype):
+        if _PREPARE_LOG[0] is not None:
+            # PreparedCache (see _host.py): a weight refresh converts straight INTO the operand the previous preparation
+            # created at this position of the call sequence (no second buffer, no device-to-device copy) ...
+            reuse = _PREPARE_LOG[0].get("reuse")
+            if reuse:
+                old = reuse.pop(0)
+                if old.dtype == (torch.bfloat16 if compute_dtype == torch.bfloat16 else torch.float32) and \
+                        tuple(old.hi.shape) == tuple(x_fp32.shape) and old.hi.is_contiguous():
+                    _PREPARE_LOG[0]["made"].append(old)
+                    return old.refresh(x_fp32)
+                reuse.clear()                      # the sequence changed: allocate from here on
         if compute_dtype == torch.bfloat16:
-            return Operand(cast_bf16(x_fp32), None, torch.bfloat16)
-        hi, lo = split_tf32(x_fp32)
-        return Operand(hi, lo, torch.float32)
+            op = Operand(cast_bf16(x_fp32), None, torch.bfloat16)
+        else:
+            hi, lo = split_tf32(x_fp32)
+            op = Operand(hi, lo, torch.float32)
+        if _PREPARE_LOG[0] is not None:           # ... and a first preparation records that sequence
+            _PREPARE_LOG[0]["made"].append(op)
+        return op
 
     @staticmethod
     def empty(shape, compute_dtype, device):

@@ -189,6 +189,9 @@ int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, i
                    float* out, int32_t R, int32_t C, void* stream) {
   return colsum_acc(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, as_stream(stream));
 }
+int ccx_cast_segments(const ccx_cast_seg* segs_dev, int32_t nseg, int32_t total_tiles, double bytes, void* stream) {
+  return cast_segments(segs_dev, nseg, total_tiles, bytes, as_stream(stream));
+}
 int ccx_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
                int64_t M, int32_t C, float eps, int32_t merge, int32_t H, int32_t W, void* stream) {
   if (merge && ((H & 1) || (W & 1) || H <= 0 || W <= 0)) return CCX_ERR_SHAPE;

@@ -214,10 +214,14 @@ avgpool_nhwc_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dx, 
     const int h = static_cast<int>((i / (static_cast<long long>(C / 4) * W)) % H);
     const int b = static_cast<int>(i / (static_cast<long long>(C / 4) * W * H));
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int oh = 0; oh < S; ++oh) {
+    // output windows that can contain (h, w): [floor(h S / H) - 1, floor((h + 1) S / H) + 1]; the exact membership test
+    // stays below (scanning all S x S windows per element cost 33 us at B = 32, ncu r02)
+    const int oh_lo = max((h * S) / H - 1, 0), oh_hi = min(((h + 1) * S) / H + 1, S - 1);
+    const int ow_lo = max((w * S) / W - 1, 0), ow_hi = min(((w + 1) * S) / W + 1, S - 1);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
       const int hs = (oh * H) / S, he = ((oh + 1) * H + S - 1) / S;
       if (h < hs || h >= he) continue;
-      for (int ow = 0; ow < S; ++ow) {
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
         const int ws = (ow * W) / S, we = ((ow + 1) * W + S - 1) / S;
         if (w < ws || w >= we) continue;
         const float inv = 1.0f / static_cast<float>((he - hs) * (we - ws));

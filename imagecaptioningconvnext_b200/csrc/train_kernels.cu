@@ -1056,4 +1056,110 @@ int adam_clamp(const void* table, const int* block_entry, const long long* block
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight refresh: every kernel-side copy of the decoder's fp32 master weights in ONE launch.
+// After an optimizer step the bf16 operands (plain, concatenated, row-permuted or transposed images of the
+// parameters — DecoderWithAttention._prepare / TransformerDecoder._prepare) have to follow their masters.  Per operand
+// that was a cat / index / transpose in ATen, a cast kernel and a device-to-device copy: ~45 (LSTM decoder) to ~110
+// (Transformer) launches of a few microseconds each per train step.  Here a table of rectangular segments
+//   dst[i, j] (or dst[j, i] when transposed) = src[row_map ? row_map[i] : i, j] (+ src2[...])
+// is walked by one grid: 64 x 64 tiles, fp32 -> bf16 (or fp32 for the small bias vectors), both sides coalesced.
+// ---------------------------------------------------------------------------------------------
+struct CastSeg {
+  const float* src;
+  const float* src2;
+  void* dst;
+  const int* row_map;
+  long long src_ld, dst_ld;
+  int rows, cols;        // of the (row-mapped) source block
+  int flags;             // bit 0: transpose, bit 1: fp32 destination
+  int tile0;             // first tile of this segment in the grid
+};
+static_assert(sizeof(CastSeg) == 64, "CastSeg is mirrored by ctypes (imagecaptioningconvnext_b200/_lib.py)");
+
+__global__ void __launch_bounds__(256)
+cast_segments_kernel(const CastSeg* __restrict__ segs, int nseg) {
+  __shared__ float tile[64][65];
+  const int t = blockIdx.x;
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {                      // last segment with tile0 <= t
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].tile0 <= t) lo = mid; else hi = mid - 1;
+  }
+  const CastSeg s = segs[lo];
+  const int tiles_c = (s.cols + 63) >> 6;
+  const int lt = t - s.tile0;
+  const int r0 = (lt / tiles_c) << 6, c0 = (lt % tiles_c) << 6;
+  const bool f32 = (s.flags & 2) != 0;
+  const bool vec_in = ((reinterpret_cast<uintptr_t>(s.src) & 15) == 0) && ((s.src_ld & 3) == 0) && ((s.cols & 3) == 0) &&
+                      (s.src2 == nullptr || (reinterpret_cast<uintptr_t>(s.src2) & 15) == 0);
+  if (vec_in) {
+    const int q = threadIdx.x & 15, ty = threadIdx.x >> 4;          // 16 float4 per tile row, 16 rows per pass
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = ty + 16 * k, r = r0 + i, c = c0 + 4 * q;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < s.rows && c < s.cols) {
+        const long long sr = s.row_map ? s.row_map[r] : r;
+        v = *reinterpret_cast<const float4*>(s.src + sr * s.src_ld + c);
+        if (s.src2) {
+          const float4 w = *reinterpret_cast<const float4*>(s.src2 + sr * s.src_ld + c);
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+      }
+      tile[i][4 * q] = v.x; tile[i][4 * q + 1] = v.y; tile[i][4 * q + 2] = v.z; tile[i][4 * q + 3] = v.w;
+    }
+  } else {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const int i = ty + 4 * k, r = r0 + i, c = c0 + tx;
+      float v = 0.f;
+      if (r < s.rows && c < s.cols) {
+        const long long sr = s.row_map ? s.row_map[r] : r;
+        v = s.src[sr * s.src_ld + c];
+        if (s.src2) v += s.src2[sr * s.src_ld + c];
+      }
+      tile[i][tx] = v;
+    }
+  }
+  __syncthreads();
+  // destination rows / columns of this tile: plain -> (r, c); transposed -> (c, r)
+  const bool tr = (s.flags & 1) != 0;
+  const int d_rows = tr ? s.cols : s.rows, d_cols = tr ? s.rows : s.cols;
+  const int dr0 = tr ? c0 : r0, dc0 = tr ? r0 : c0;
+  const bool pair_out = !f32 && ((reinterpret_cast<uintptr_t>(s.dst) & 3) == 0) && ((s.dst_ld & 1) == 0) && ((d_cols & 1) == 0);
+  if (pair_out) {
+    const int px = threadIdx.x & 31, ty = threadIdx.x >> 5;         // lane -> two consecutive destination columns
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = ty + 8 * k, dr = dr0 + i, dc = dc0 + 2 * px;
+      if (dr < d_rows && dc < d_cols) {
+        const float a = tr ? tile[2 * px][i] : tile[i][2 * px];
+        const float b = tr ? tile[2 * px + 1][i] : tile[i][2 * px + 1];
+        *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(s.dst) + dr * s.dst_ld + dc) = pack_bf16x2(a, b);
+      }
+    }
+  } else {
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const int i = ty + 4 * k, dr = dr0 + i, dc = dc0 + tx;
+      if (dr < d_rows && dc < d_cols) {
+        const float v = tr ? tile[tx][i] : tile[i][tx];
+        if (f32) static_cast<float*>(s.dst)[dr * s.dst_ld + dc] = v;
+        else static_cast<__nv_bfloat16*>(s.dst)[dr * s.dst_ld + dc] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
+
+int cast_segments(const void* segs_dev, int nseg, int total_tiles, double bytes, cudaStream_t stream) {
+  if (nseg <= 0 || total_tiles <= 0) return CCX_OK;
+  ProfScope prof(PROF_ELEMENTWISE, stream, bytes);
+  cast_segments_kernel<<<total_tiles, 256, 0, stream>>>(reinterpret_cast<const CastSeg*>(segs_dev), nseg);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+
 }  // namespace ccx

@@ -22,7 +22,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy, stash_device_twin
+from ._host import (CcxEmbedding, CcxLinear, PreparedCache, RefreshPlan, any_requires_grad, host_copy,
+                    stash_device_twin)
 from ._lib import Operand, ptr
 
 
@@ -161,6 +162,34 @@ class DecoderWithAttention(nn.Module):
             P["w_emb_t"] = Operand.prepare(d(ds.weight_ih)[:, :Emb].t().contiguous(), cd)      # [Emb, 4D]
         return P
 
+    def _refresh_plan(self, P):
+        """The refresh of every entry of ``_prepare()`` that is not a view of its parameter, as one launch (see
+        _host.RefreshPlan); bf16 compute only (the tf32 hi/lo split keeps the per-operand path)."""
+        if self.compute_dtype != torch.bfloat16:
+            return None
+        att, ds = self.attention, self.decode_step
+        A, Emb, D = self.attention_dim, self.embed_dim, self.decoder_dim
+        w_ih, w_hh = ds.weight_ih, ds.weight_hh
+        plan = RefreshPlan()
+        plan.add(P["w_enc_att"].hi, att.encoder_att.weight)
+        plan.add(P["w_h"].hi[:A], att.decoder_att.weight).add(P["w_h"].hi[A:], self.f_beta.weight)
+        plan.add(P["b_h"][:A], att.decoder_att.bias).add(P["b_h"][A:], self.f_beta.bias)
+        plan.add(P["w_init_h"].hi, self.init_h.weight).add(P["w_init_c"].hi, self.init_c.weight)
+        K1 = w_ih.shape[1]
+        plan.add(P["w_lstm"].hi[:, :K1], w_ih).add(P["w_lstm"].hi[:, K1:], w_hh)
+        plan.add(P["b_lstm"], ds.bias_ih, src2=ds.bias_hh)
+        plan.add(P["w_fc"].hi, self.fc.weight)
+        if "w2p" in P:
+            perm = torch.arange(4 * D, device=w_ih.device).view(4, D // 8, 8).permute(1, 0, 2).reshape(-1)
+            plan.add(P["w2p"].hi[:, :D], w_hh, row_map=perm).add(P["w2p"].hi[:, D:], w_ih[:, Emb:], row_map=perm)
+            plan.add(P["w2p_emb"].hi, w_ih[:, :Emb], row_map=perm)
+            plan.add(P["b_perm"].view(-1, 1), ds.bias_ih.view(-1, 1), src2=ds.bias_hh.view(-1, 1), row_map=perm)
+            plan.add(P["wx"].hi[:K1 - Emb], w_ih[:, Emb:], transpose=True).add(P["wx"].hi[K1 - Emb:], w_hh, transpose=True)
+            plan.add(P["wht"].hi[:, :A], att.decoder_att.weight, transpose=True)
+            plan.add(P["wht"].hi[:, A:], self.f_beta.weight, transpose=True)
+            plan.add(P["w_emb_t"].hi, w_ih[:, :Emb], transpose=True)
+        return plan
+
     def _persist_dims_ok(self):
         return (self.compute_dtype == torch.bfloat16 and self.decoder_dim == 512 and self.attention_dim == 512 and
                 self.embed_dim == 512 and self.encoder_dim == 1024)
@@ -253,7 +282,7 @@ class DecoderWithAttention(nn.Module):
         if self.inject_dropmask is not None:
             return self.inject_dropmask.to(device=dev, dtype=torch.float32).contiguous()
         keep = 1.0 - self.dropout_p
-        return (torch.bernoulli(torch.full((B, T, self.decoder_dim), keep, device=dev)) / keep).contiguous()
+        return torch.empty((B, T, self.decoder_dim), dtype=torch.float32, device=dev).bernoulli_(keep).div_(keep)
 
     # ---- reference API -----------------------------------------------------------------------------------------
     def forwardWithTeacherForcing(self, encoder_out, encoded_captions, caption_lengths):

@@ -87,7 +87,8 @@ class _BlockFn(torch.autograd.Function):
         named = _named(blk)
         grads, (s, dw) = zero_grads_like(named, extra_shapes=[(C,), (49, C)])
         for n, p in named:                     # frozen parameters inside the tail (not a reference use case)
-            grads.setdefault(n, torch.zeros_like(p, dtype=torch.float32))
+            if n not in grads:                 # (never `setdefault(n, zeros_like(p))`: that fills a buffer per parameter)
+                grads[n] = torch.zeros_like(p, dtype=torch.float32)
         dout = dout.contiguous().view(M, C)
         gamma = blk.layer_scale.detach().view(C)
         W1, W2 = blk.block[3].weight.detach(), blk.block[5].weight.detach()
@@ -169,7 +170,8 @@ class _DownFn(torch.autograd.Function):
         named = _named(mod)
         grads = zero_grads_like(named)
         for n, p in named:
-            grads.setdefault(n, torch.zeros_like(p, dtype=torch.float32))
+            if n not in grads:
+                grads[n] = torch.zeros_like(p, dtype=torch.float32)
         Cout = mod[1].weight.shape[0]
         dout = dout.contiguous().view(M // 4, Cout)
         gw = torch.zeros((Cout, 4 * C), dtype=torch.float32, device=dout.device)

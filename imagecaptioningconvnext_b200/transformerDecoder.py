@@ -21,7 +21,8 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import CcxEmbedding, CcxLinear, PreparedCache, any_requires_grad, host_copy, stash_device_twin
+from ._host import (CcxEmbedding, CcxLinear, PreparedCache, RefreshPlan, any_requires_grad, host_copy,
+                    stash_device_twin)
 from ._lib import Operand, ptr
 
 
@@ -161,6 +162,27 @@ class TransformerDecoder(nn.Module):
             P["proj_b"] = d(self.encoder_proj.bias).contiguous()
         P["pe"] = d(self.pos_encoding.pe)[0].contiguous().float()
         return P
+
+    def _refresh_plan(self, P):
+        """One-launch refresh of the bf16 copies ``_prepare()`` made (see _host.RefreshPlan).  Everything else in P is
+        a view of its parameter, except the two halves of the cross-attention in-proj bias (copied as fp32)."""
+        if self.compute_dtype != torch.bfloat16:
+            return None
+        D = self.embed_dim
+        plan = RefreshPlan()
+        for lyr, L in zip(self.transformer_decoder.layers, P["layers"]):
+            sa, ca = lyr.self_attn, lyr.multihead_attn
+            plan.add(L["sa_in"].hi, sa.in_proj_weight).add(L["sa_out"].hi, sa.out_proj.weight)
+            plan.add(L["ca_q"].hi, ca.in_proj_weight[:D]).add(L["ca_kv"].hi, ca.in_proj_weight[D:])
+            for key, src in (("ca_q_b", ca.in_proj_bias[:D]), ("ca_kv_b", ca.in_proj_bias[D:])):
+                if L[key].data_ptr() != src.data_ptr():
+                    plan.add(L[key], src)
+            plan.add(L["ca_out"].hi, ca.out_proj.weight)
+            plan.add(L["l1"].hi, lyr.linear1.weight).add(L["l2"].hi, lyr.linear2.weight)
+        plan.add(P["fc"].hi, self.fc_out.weight)
+        if P["proj"] is not None:
+            plan.add(P["proj"].hi, self.encoder_proj.weight)
+        return plan
 
     # ---- building blocks ----------------------------------------------------------------------------------------
     def _memory(self, Pw, encoder_out):

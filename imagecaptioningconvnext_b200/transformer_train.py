@@ -27,19 +27,18 @@ def _masks(dec, B, T, Pn, dev):
     if dec.inject_dropout is not None:
         return {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in dec.inject_dropout.items()}
     keep = 1.0 - dec.dropout_p
-
-    def draw(*shape):
-        return (torch.bernoulli(torch.full(shape, keep, device=dev)) / keep).contiguous()
-
-    m = {"emb": draw(B * T, D)}
+    # all 6 L + 1 masks of a forward are views of ONE buffer drawn by one bernoulli_ / one div_ (a draw per site was
+    # 3 launches x 37 sites per train step); every view starts on a 256-byte boundary (the kernels read them as float4)
+    shapes = [("emb", (B * T, D))]
     for l in range(L):
-        m[(l, "sa_p")] = draw(B, H, T, T)
-        m[(l, "d1")] = draw(B * T, D)
-        m[(l, "ca_p")] = draw(B, H, T, Pn)
-        m[(l, "d2")] = draw(B * T, D)
-        m[(l, "ff")] = draw(B * T, Dff)
-        m[(l, "d3")] = draw(B * T, D)
-    return m
+        shapes += [((l, "sa_p"), (B, H, T, T)), ((l, "d1"), (B * T, D)), ((l, "ca_p"), (B, H, T, Pn)),
+                   ((l, "d2"), (B * T, D)), ((l, "ff"), (B * T, Dff)), ((l, "d3"), (B * T, D))]
+    offs, total = [], 0
+    for _, sh in shapes:
+        offs.append(total)
+        total += (torch.Size(sh).numel() + 63) // 64 * 64
+    flat = torch.empty(total, dtype=torch.float32, device=dev).bernoulli_(keep).div_(keep)
+    return {k: flat[o:o + torch.Size(sh).numel()].view(sh) for (k, sh), o in zip(shapes, offs)}
 
 
 class _Payload:

@@ -312,6 +312,25 @@ CCX_API int ccx_convert_operand(const void* x_hi, const float* x_lo, int32_t x_d
 /* out[c] += sum_r x[r,c] (* multiplier as above): bias gradients. */
 CCX_API int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode,
                            float mul_scale, float* out, int32_t R, int32_t C, void* stream);
+/* Weight refresh after an optimizer step (trainMultiGPU.py:387-394 moves the fp32 masters; the kernels read bf16 /
+ * re-laid-out copies): ONE launch over a device-resident table of rectangular segments,
+ *   dst[i, j]  (dst[j, i] if flags & 1)  =  src[row_map ? row_map[i] : i, j]  (+ src2[same index] if src2)
+ * for i < rows, j < cols; dst is bf16 (round to nearest even) or, if flags & 2, fp32.  tile0 = index of the segment's
+ * first 64 x 64 tile in the grid (segments sorted by it), total_tiles = sum over segments of
+ * ceil(rows/64) * ceil(cols/64); `bytes` is only used by the profiling hooks.  Replaces the per-operand
+ * cat / index / transpose + cast + copy chains of the decoders' weight preparation. */
+typedef struct ccx_cast_seg {
+  const float* src;
+  const float* src2;
+  void* dst;
+  const int32_t* row_map;
+  int64_t src_ld, dst_ld;
+  int32_t rows, cols;
+  int32_t flags;
+  int32_t tile0;
+} ccx_cast_seg;
+CCX_API int ccx_cast_segments(const ccx_cast_seg* segs_dev, int32_t nseg, int32_t total_tiles, double bytes,
+                              void* stream);
 /* LayerNorm backward over rows of x[M,C]; dgamma/dbeta are accumulated (+=).  merge != 0: dy is read in the 2x2
  * patch-merged [M/4, 4C] layout that ccx_ln_rows(merge=1) wrote (downsample LayerNorm2d, convnext.py:146-151). */
 CCX_API int ccx_ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
