@@ -358,7 +358,12 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            opts = None
+            if os.environ.get("CCX_NCCL_HIGH_PRIO", "0") != "0":
+                # the gradient all-reduce runs next to the rest of the backward (CapturedTrainStep): on a high-priority
+                # stream its CTAs are placed ahead of the already queued CTAs of the compute kernels
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=self.dev, pg_options=opts)
 
     def barrier(self):
         if self.world > 1:
