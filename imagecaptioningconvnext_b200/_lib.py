@@ -116,6 +116,7 @@ SIGNATURES = {
                                       _i32, _i32, _vp]),
     "ccx_colsum_acc": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i32, _i32, _vp]),
     "ccx_cast_segments": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp]),
+    "ccx_convert_colsum": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i64, _vp, _i32, _i32, _vp]),
     "ccx_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "ccx_mha_bwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
                               _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32,

@@ -189,6 +189,10 @@ int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, i
                    float* out, int32_t R, int32_t C, void* stream) {
   return colsum_acc(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, as_stream(stream));
 }
+int ccx_convert_colsum(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode, float mul_scale,
+                       void* o_bf16, int64_t ldo, float* sums, int32_t R, int32_t C, void* stream) {
+  return convert_colsum(x, ldx, mul, ldm, mul_mode, mul_scale, o_bf16, ldo, sums, R, C, as_stream(stream));
+}
 int ccx_cast_segments(const ccx_cast_seg* segs_dev, int32_t nseg, int32_t total_tiles, double bytes, void* stream) {
   return cast_segments(segs_dev, nseg, total_tiles, bytes, as_stream(stream));
 }

@@ -66,6 +66,8 @@ int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long 
 int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
                float* out, int R, int C, cudaStream_t stream);
 int cast_segments(const void* segs_dev, int nseg, int total_tiles, double bytes, cudaStream_t stream);
+int convert_colsum(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
+                   void* o_bf16, long long ldo, float* sums, int R, int C, cudaStream_t stream);
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, float* dgamma, float* dbeta,
            long long M, int C, float eps, cudaStream_t stream, int merge = 0, int H = 1, int W = 1);
 // tensor-core (mma.sync, bf16) versions for T <= 64 and head dim 64: mha_tc.cu

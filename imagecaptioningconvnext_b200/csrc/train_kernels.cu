@@ -159,6 +159,23 @@ convert_transpose_bf16_kernel(const void* __restrict__ x, long long ldx, const f
   }
 }
 
+// rows whose length is even but not a multiple of 8 (the vocabulary: d logits [B*T, 9490] -> bf16 once per step, 62 MB
+// that the one-element-per-thread kernel moved at 1.1 TB/s): one row per blockIdx.y, a float2 -> bf16x2 per thread
+__global__ void __launch_bounds__(256)
+convert_rows_bf16x2_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mul, long long ldm,
+                           int mul_mode, float mul_scale, __nv_bfloat16* __restrict__ o, long long ldo, int C2) {
+  const int r = blockIdx.y;
+  for (int c2 = blockIdx.x * 256 + threadIdx.x; c2 < C2; c2 += gridDim.x * 256) {
+    float2 v = *reinterpret_cast<const float2*>(x + r * ldx + 2 * c2);
+    if (mul_mode != 0) {
+      const float2 m = *reinterpret_cast<const float2*>(mul + r * ldm + 2 * c2);
+      v.x = mul_mode == 1 ? v.x * m.x : (m.x > 0.f ? v.x * mul_scale : 0.f);
+      v.y = mul_mode == 1 ? v.y * m.y : (m.y > 0.f ? v.y * mul_scale : 0.f);
+    }
+    *reinterpret_cast<uint32_t*>(o + r * ldo + 2 * c2) = pack_bf16x2(v.x, v.y);
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long ldx, const float* mul,
@@ -193,6 +210,17 @@ int convert_operand(const void* x_hi, const float* x_lo, int x_dtype, long long 
     else
       convert_transpose_bf16_kernel<false><<<grid, 256, 0, stream>>>(x_hi, ldx, mul, ldm, mul_mode, mul_scale,
                                                                      static_cast<__nv_bfloat16*>(o_hi), ldo, R, C, Rpad);
+    return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+  }
+  if (!transpose && o_dtype == CCX_BF16 && !src_bf16 && x_lo == nullptr && (C % 2) == 0 && (ldx % 2) == 0 &&
+      (ldo % 2) == 0 && R <= 65535 && (reinterpret_cast<uintptr_t>(x_hi) & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(o_hi) & 3) == 0 &&
+      (mul_mode == 0 || ((ldm % 2) == 0 && (reinterpret_cast<uintptr_t>(mul) & 7) == 0))) {
+    const int C2 = C / 2;
+    int gx = (C2 + 255) / 256;
+    if (gx > 8) gx = 8;                       // a few pairs per thread on long rows
+    convert_rows_bf16x2_kernel<<<dim3(gx, R), 256, 0, stream>>>(static_cast<const float*>(x_hi), ldx, mul, ldm, mul_mode,
+                                                                mul_scale, static_cast<__nv_bfloat16*>(o_hi), ldo, C2);
     return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
   }
   if (!transpose) {
@@ -289,6 +317,78 @@ int colsum_acc(const float* x, long long ldx, const float* mul, long long ldm, i
   dim3 grid((C + 31) / 32, (R + rpb - 1) / rpb);
   ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 4.0);
   colsum_acc_kernel<<<grid, 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, rpb);
+  return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Linear backward, first pass over dY: the bf16 GEMM operand AND the bias gradient (column sums) from ONE read.
+// Every Linear of the backward pass used to run convert_rows (read dY, write bf16) and then colsum_acc (read dY
+// again): 14 such pairs per LSTM train step, 43 per Transformer step.  Same tiling as colsum_acc4_kernel — 128 columns
+// per CTA (one float4 per lane), 8 warps stride the rows — plus an 8-byte bf16 store per element group.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+convert_colsum_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ mul, long long ldm,
+                      int mul_mode, float mul_scale, __nv_bfloat16* __restrict__ o, long long ldo,
+                      float* __restrict__ sums, int R, int C, int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + 4 * lane;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(R, r_begin + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+    for (int r = r_begin + ty; r < r_end; r += 32) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = r + 8 * k;
+        v[k] = rr < r_end ? *reinterpret_cast<const float4*>(x + rr * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mul_mode != 0 && rr < r_end) {
+          const float4 m = *reinterpret_cast<const float4*>(mul + rr * ldm + c);
+          if (mul_mode == 1) { v[k].x *= m.x; v[k].y *= m.y; v[k].z *= m.z; v[k].w *= m.w; }
+          else {
+            v[k].x = m.x > 0.f ? v[k].x * mul_scale : 0.f; v[k].y = m.y > 0.f ? v[k].y * mul_scale : 0.f;
+            v[k].z = m.z > 0.f ? v[k].z * mul_scale : 0.f; v[k].w = m.w > 0.f ? v[k].w * mul_scale : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = r + 8 * k;
+        if (rr < r_end) {
+          uint2 pk;
+          pk.x = pack_bf16x2(v[k].x, v[k].y);
+          pk.y = pack_bf16x2(v[k].z, v[k].w);
+          *reinterpret_cast<uint2*>(o + rr * ldo + c) = pk;
+        }
+        acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
+      }
+    }
+  }
+  red[ty][lane] = acc;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float4 s4 = red[0][lane];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { s4.x += red[j][lane].x; s4.y += red[j][lane].y; s4.z += red[j][lane].z; s4.w += red[j][lane].w; }
+    atomicAdd(sums + c, s4.x); atomicAdd(sums + c + 1, s4.y); atomicAdd(sums + c + 2, s4.z); atomicAdd(sums + c + 3, s4.w);
+  }
+}
+
+int convert_colsum(const float* x, long long ldx, const float* mul, long long ldm, int mul_mode, float mul_scale,
+                   void* o_bf16, long long ldo, float* sums, int R, int C, cudaStream_t stream) {
+  if (R <= 0 || C <= 0) return CCX_OK;
+  if ((C % 4) != 0 || (ldx % 4) != 0 || (ldo % 4) != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(o_bf16) & 7) != 0 ||
+      (mul_mode != 0 && ((ldm % 4) != 0 || (reinterpret_cast<uintptr_t>(mul) & 15) != 0)))
+    return CCX_ERR_SHAPE;
+  const int col_blocks = (C + 127) / 128;
+  int rpb = 512;
+  while (rpb > 64 && static_cast<long long>(col_blocks) * ((R + rpb - 1) / rpb) < 148 * 4) rpb /= 2;
+  dim3 grid(col_blocks, (R + rpb - 1) / rpb);
+  ProfScope prof(PROF_ELEMENTWISE, stream, (double)R * C * 6.0);
+  convert_colsum_kernel<<<grid, 256, 0, stream>>>(x, ldx, mul, ldm, mul_mode, mul_scale,
+                                                  static_cast<__nv_bfloat16*>(o_bf16), ldo, sums, R, C, rpb);
   return cudaGetLastError() == cudaSuccess ? CCX_OK : CCX_ERR_CUDA;
 }
 

@@ -165,6 +165,16 @@ def colsum_acc(dy, out, mul=None, mul_mode=0, mul_scale=1.0):
                                          mul_mode, mul_scale, ptr(out), R, C, _lib.stream_ptr()), "colsum_acc")
 
 
+_FUSE_CAST_COLSUM = os.environ.get("CCX_FUSE_CAST_COLSUM", "1") != "0"      # A/B switch
+
+
+def _fusable_cast_colsum(dy, cd, mul):
+    return (_FUSE_CAST_COLSUM and cd == torch.bfloat16 and torch.is_tensor(dy) and dy.dtype == torch.float32 and
+            dy.dim() == 2 and dy.stride(1) == 1 and dy.shape[1] % 8 == 0 and dy.stride(0) % 4 == 0 and
+            dy.data_ptr() % 16 == 0 and
+            (mul is None or (mul.stride(1) == 1 and mul.stride(0) % 4 == 0 and mul.data_ptr() % 16 == 0)))
+
+
 def linear_bwd(dy, x, wt, cd, w_grad=None, b_grad=None, need_dx=True, dx_residual=None, mul=None, mul_mode=0,
                mul_scale=1.0):
     """Backward of y = x . W^T + b.
@@ -174,8 +184,17 @@ def linear_bwd(dy, x, wt, cd, w_grad=None, b_grad=None, need_dx=True, dx_residua
     M, N = dy.shape
     dx = None
     dy_op = None
+    mn_wgrad = w_grad is not None and _MN and cd == torch.bfloat16 and (_mn_ready(x) or not isinstance(x, Operand))
+    if (need_dx or mn_wgrad) and b_grad is not None and _fusable_cast_colsum(dy, cd, mul):
+        # one pass over dY: its bf16 GEMM operand and the bias gradient (ccx_convert_colsum)
+        dy_op = Operand.empty((M, N), cd, dy.device)
+        _lib.check(_lib.lib().ccx_convert_colsum(ptr(dy), dy.stride(0), ptr(mul), mul.stride(0) if mul is not None else 0,
+                                                 mul_mode, mul_scale, ptr(dy_op.hi), N, ptr(b_grad), M, N,
+                                                 _lib.stream_ptr()), "convert_colsum")
+        b_grad = None
     if need_dx:
-        dy_op = to_operand(dy, cd, mul, mul_mode, mul_scale)
+        if dy_op is None:
+            dy_op = to_operand(dy, cd, mul, mul_mode, mul_scale)
         dx = linear_dgrad(dy_op, wt, residual=dx_residual, n=N)
     if w_grad is not None:
         x_op = x if _mn_ready(x) else None

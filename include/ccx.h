@@ -312,6 +312,12 @@ CCX_API int ccx_convert_operand(const void* x_hi, const float* x_lo, int32_t x_d
 /* out[c] += sum_r x[r,c] (* multiplier as above): bias gradients. */
 CCX_API int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode,
                            float mul_scale, float* out, int32_t R, int32_t C, void* stream);
+/* Both of the above in one pass over x (fp32, plain): o_bf16[r,c] = bf16(x[r,c] * multiplier) and sums[c] += the same
+ * products — the first step of every Linear backward (GEMM operand dY + bias gradient).  Needs C % 4 == 0, ldx % 4 == 0,
+ * ldo % 4 == 0 and 16-byte aligned x (CCX_ERR_SHAPE otherwise: call the two entry points above). */
+CCX_API int ccx_convert_colsum(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode,
+                               float mul_scale, void* o_bf16, int64_t ldo, float* sums, int32_t R, int32_t C,
+                               void* stream);
 /* Weight refresh after an optimizer step (trainMultiGPU.py:387-394 moves the fp32 masters; the kernels read bf16 /
  * re-laid-out copies): ONE launch over a device-resident table of rectangular segments,
  *   dst[i, j]  (dst[j, i] if flags & 1)  =  src[row_map ? row_map[i] : i, j]  (+ src2[same index] if src2)

@@ -305,6 +305,30 @@ def test_colsum_acc_matches_torch(R, C):
         assert rel_err(out, 1.0 + ref.double().sum(0).float()) < 1e-5, mode
 
 
+@pytest.mark.parametrize("R,C", [(1632, 512), (2048, 4096), (37, 24), (5, 8)])
+def test_convert_colsum_equals_the_two_separate_passes(R, C):
+    """ccx_convert_colsum (one read of dY -> bf16 operand + bias gradient) against ccx_convert_operand and torch sums,
+    for the three multiplier modes; the sums accumulate (+=)."""
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._lib import ptr
+    from imagecaptioningconvnext_b200.train_ops import to_operand
+    g = torch.Generator().manual_seed(R * 7 + C)
+    wide = torch.randn(R, C + 8, generator=g).cuda()
+    x = wide[:, 4:4 + C]                                            # leading dimension != C, still 16-byte aligned
+    mul = torch.randn(R, C, generator=g).cuda()
+    for mode, scale, ref in ((0, 1.0, x), (1, 1.0, x * mul), (2, 2.0, torch.where(mul > 0, x * 2.0, torch.zeros_like(x)))):
+        m = None if mode == 0 else mul
+        out = torch.full((R, C), 9.0, dtype=torch.bfloat16, device="cuda")
+        sums = torch.ones(C, device="cuda")
+        _lib.check(_lib.lib().ccx_convert_colsum(ptr(x), x.stride(0), ptr(m), C if m is not None else 0, mode, scale,
+                                                 ptr(out), C, ptr(sums), R, C, _lib.stream_ptr()), "convert_colsum")
+        assert torch.equal(out, to_operand(x.contiguous(), torch.bfloat16, m, mode, scale).hi), mode
+        assert rel_err(sums, 1.0 + ref.double().sum(0).float()) < 1e-5, mode
+    bad = torch.randn(8, 6).cuda()                                   # C % 4 != 0: refused, never a silent fallback
+    assert _lib.lib().ccx_convert_colsum(ptr(bad), 6, None, 0, 0, 1.0, ptr(out), 6, ptr(sums), 8, 6,
+                                         _lib.stream_ptr()) != 0
+
+
 def test_cast_bf16_vector_and_tail_paths():
     from imagecaptioningconvnext_b200 import _lib
     for n in (8 * 1000, 8 * 1000 + 3, 5):
