@@ -47,6 +47,27 @@ class CcxEmbedding(nn.Embedding):
         return out.view(*tokens.shape, D)
 
 
+class no_gc:
+    """No cyclic garbage collection while a stream captures (``with no_gc(), torch.cuda.graph(g): ...``).  The modules
+    here sit in reference cycles (``_owner`` back-references), so a decoder that went out of scope — with the CUDA graphs
+    and private memory pools it captured — is only freed by the cyclic collector; if that runs in the middle of a later
+    capture, the graph's destructor (cudaGraphExecDestroy, cudaFree of its pool) invalidates the capture
+    ("operation failed due to a previous error during capture"; torch.cuda.graph no longer collects by itself).
+    Collect once before the capture begins, then keep the collector off until it ends."""
+
+    def __enter__(self):
+        import gc
+        self._was = gc.isenabled()
+        gc.collect()
+        gc.disable()
+        return self
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+
+
 PLAN_REFRESH = [os.environ.get("CCX_PLAN_REFRESH", "1") != "0"]    # A/B switch: 0 = re-run _prepare() on every refresh
 
 

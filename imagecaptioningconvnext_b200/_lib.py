@@ -116,6 +116,7 @@ SIGNATURES = {
                                       _i32, _i32, _vp]),
     "ccx_colsum_acc": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i32, _i32, _vp]),
     "ccx_cast_segments": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp]),
+    "ccx_stream_capture_status": (C.c_int, [_vp]),
     "ccx_convert_colsum": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i64, _vp, _i32, _i32, _vp]),
     "ccx_ln_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _i32, _i32, _i32, _vp]),
     "ccx_mha_bwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
@@ -175,7 +176,25 @@ def lib():
     return _lib
 
 
+_DEBUG_CAPTURE = os.environ.get("CCX_DEBUG_CAPTURE", "0") != "0"
+_capture_seen = [0]
+
+
+def capture_probe(label):
+    """CCX_DEBUG_CAPTURE=1: report (stderr) the first point at which the current stream's capture is found invalidated —
+    the call just before `label` broke it (an API that is illegal while a stream captures)."""
+    if not _DEBUG_CAPTURE:
+        return
+    import sys
+    st = lib().ccx_stream_capture_status(stream_ptr())
+    if st != _capture_seen[0]:
+        print(f"[ccx capture] status {_capture_seen[0]} -> {st} at: {label}", file=sys.stderr, flush=True)
+        _capture_seen[0] = st
+
+
 def check(rc, what=""):
+    if _DEBUG_CAPTURE:
+        capture_probe("after " + what)
     if rc != 0:
         msg = lib().ccx_status_string(rc).decode()
         raise RuntimeError(f"libccx {what} failed: {msg} (status {rc})")
@@ -369,5 +388,7 @@ def linear(a, w, bias=None, act=ACT_NONE, colscale=None, rowscale=None, rows_per
     d.split = 1 if split else 0
     d.a_mn, d.w_mn = (1 if a_mn else 0), (1 if w_mn else 0)
     d.res_mul = 1 if res_mul else 0
+    if _DEBUG_CAPTURE:
+        capture_probe(f"before linear M={M} N={N} K={K} (host-side preparation / torch allocations since the last call)")
     check(lib().ccx_linear(C.byref(d), stream_ptr()), f"linear M={M} N={N} K={K}")
     return res

@@ -13,6 +13,7 @@ completed (the reference raises ValueError there).
 import torch
 
 from . import _lib
+from ._host import no_gc
 from ._lib import Operand, ptr
 
 
@@ -266,7 +267,7 @@ class CapturedBeamSearch:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with no_gc(), torch.cuda.graph(self.graph):
                 self.state = self._run(self.static_in)
         self.static_in.copy_(encoder_out)
         self.graph.replay()

@@ -189,6 +189,11 @@ int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, i
                    float* out, int32_t R, int32_t C, void* stream) {
   return colsum_acc(x, ldx, mul, ldm, mul_mode, mul_scale, out, R, C, as_stream(stream));
 }
+int ccx_stream_capture_status(void* stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(as_stream(stream), &st) != cudaSuccess) return CCX_ERR_CUDA;
+  return static_cast<int>(st);
+}
 int ccx_convert_colsum(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode, float mul_scale,
                        void* o_bf16, int64_t ldo, float* sums, int32_t R, int32_t C, void* stream) {
   return convert_colsum(x, ldx, mul, ldm, mul_mode, mul_scale, o_bf16, ldo, sums, R, C, as_stream(stream));

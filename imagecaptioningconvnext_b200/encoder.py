@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._host import any_requires_grad, params_of
+from ._host import any_requires_grad, no_gc, params_of
 from ._lib import Operand
 
 DEPTHS = (3, 3, 27, 3)
@@ -165,7 +165,7 @@ class Encoder(nn.Module):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with no_gc(), torch.cuda.graph(g):
                 static_out = self._forward_eager_nograd(static_in)
             entry = (g, static_in, static_out, self._prep_key[:3])
             self._graphs[key] = entry

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib
-from ._host import device_twin, named_params, stash_host_copy
+from ._host import device_twin, named_params, no_gc, stash_host_copy
 from .decoder import DecoderWithAttention
 from .losses import free_running_cross_entropy, packed_cross_entropy
 from .optim import ClampAdam
@@ -275,7 +275,7 @@ class CapturedTrainStep:
             self.static = (imgs.clone(), caps.clone(), caplens.clone())
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):          # records the step; nothing runs yet
+            with no_gc(), torch.cuda.graph(self.graph):          # records the step; nothing runs yet
                 self.loss = self._body(*self.static)
         for dst, src in zip(self.static, (imgs, caps, caplens)):
             dst.copy_(src, non_blocking=True)

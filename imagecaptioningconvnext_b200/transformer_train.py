@@ -12,7 +12,7 @@ import weakref
 import torch
 
 from . import _lib
-from ._host import host_copy, named_params, params_of, stash_device_twin
+from ._host import host_copy, named_params, no_gc, params_of, stash_device_twin
 from ._lib import Operand, ptr
 from .train_ops import grads_out, linear_bwd, ln_bwd, to_operand, weight_t, zero_grads_like
 
@@ -27,6 +27,14 @@ def _masks(dec, B, T, Pn, dev):
     if dec.inject_dropout is not None:
         return {k: v.to(device=dev, dtype=torch.float32).contiguous() for k, v in dec.inject_dropout.items()}
     keep = 1.0 - dec.dropout_p
+    if os.environ.get("CCX_DROPOUT_FLAT", "1") == "0":          # A/B switch: one draw per site (3 launches each)
+        def draw(*shape):
+            return (torch.bernoulli(torch.full(shape, keep, device=dev)) / keep).contiguous()
+        m = {"emb": draw(B * T, D)}
+        for l in range(L):
+            m[(l, "sa_p")], m[(l, "d1")], m[(l, "ca_p")] = draw(B, H, T, T), draw(B * T, D), draw(B, H, T, Pn)
+            m[(l, "d2")], m[(l, "ff")], m[(l, "d3")] = draw(B * T, D), draw(B * T, Dff), draw(B * T, D)
+        return m
     # all 6 L + 1 masks of a forward are views of ONE buffer drawn by one bernoulli_ / one div_ (a draw per site was
     # 3 launches x 37 sites per train step); every view starts on a 256-byte boundary (the kernels read them as float4)
     shapes = [("emb", (B * T, D))]
@@ -61,7 +69,9 @@ def _forward_body(dec, encoder_out, caps, kpm):
         Pn = enc.size(1)
         enc_op = Operand.prepare(enc.view(B * Pn, E), cd)
         mem = dec._linear_op(enc_op, Pw["proj"], Pw["proj_b"]) if Pw["proj"] is not None else enc_op
+        _lib.capture_probe("before the dropout draw")
         masks = _masks(dec, B, T, Pn, dev)
+        _lib.capture_probe("after the dropout draw")
         mk = (lambda k: None) if masks is None else (lambda k: masks.get(k))
         scale = 1.0 / math.sqrt(D // H)
 
@@ -76,6 +86,7 @@ def _forward_body(dec, encoder_out, caps, kpm):
             S = {"x0_op": x_op}
             qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
             probs1 = torch.empty((B, H, T, T), dtype=torch.float32, device=dev)
+            _lib.capture_probe("after torch.empty(probs1)")
             ctx1 = dec._mha(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
                             qkv.data_ptr() + 8 * D, B, T, T, 1, 0, kpm, mk((li, "sa_p")), 1, dev, probs_out=probs1)
             y1 = _lib.linear(ctx1, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain, emask=mk((li, "d1")))
@@ -250,7 +261,7 @@ class _TransformerTF(torch.autograd.Function):
             st.kpm_in = None if kpm is None else kpm.clone()
             torch.cuda.synchronize()
             st.fwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(st.fwd):
+            with no_gc(), torch.cuda.graph(st.fwd):
                 st.predictions, st.payload = _forward_body(dec, st.enc_in, st.caps_in, st.kpm_in)
             st.pool = st.fwd.pool()
         st.enc_in.copy_(encoder_out.detach())
@@ -276,7 +287,7 @@ class _TransformerTF(torch.autograd.Function):
             st.dpred_in = dpred.detach().contiguous().clone()
             torch.cuda.synchronize()
             st.bwd = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(st.bwd, pool=st.pool):
+            with no_gc(), torch.cuda.graph(st.bwd, pool=st.pool):
                 st.denc, st.grads = _backward_body(st.payload, st.dpred_in, ctx.enc_needs_grad)
         st.dpred_in.copy_(dpred)
         st.bwd.replay()

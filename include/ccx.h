@@ -312,6 +312,9 @@ CCX_API int ccx_convert_operand(const void* x_hi, const float* x_lo, int32_t x_d
 /* out[c] += sum_r x[r,c] (* multiplier as above): bias gradients. */
 CCX_API int ccx_colsum_acc(const float* x, int64_t ldx, const float* mul, int64_t ldm, int32_t mul_mode,
                            float mul_scale, float* out, int32_t R, int32_t C, void* stream);
+/* Capture state of `stream` (0 none, 1 capturing, 2 capture invalidated; < 0 = CCX_ERR_*): lets a caller that records
+ * the step into a CUDA graph find the call that broke a capture (CCX_DEBUG_CAPTURE=1 in the Python binding). */
+CCX_API int ccx_stream_capture_status(void* stream);
 /* Both of the above in one pass over x (fp32, plain): o_bf16[r,c] = bf16(x[r,c] * multiplier) and sums[c] += the same
  * products — the first step of every Linear backward (GEMM operand dY + bias gradient).  Needs C % 4 == 0, ldx % 4 == 0,
  * ldo % 4 == 0 and 16-byte aligned x (CCX_ERR_SHAPE otherwise: call the two entry points above). */
