@@ -213,7 +213,6 @@ class TransformerDecoder(nn.Module):
              probs_out=None):
         D, H, cd = self.embed_dim, self.num_heads, self.compute_dtype
         ctx = Operand.empty((B * Tq, D), cd, dev)
-        _lib.capture_probe("after Operand.empty(ctx) in _mha")
         _lib.check(_lib.lib().ccx_mha_small(q, q_sb, q_st, k, k_sb, k_st, v, k_sb, k_st, ptr(ctx.hi), ctx.lo_ptr,
                                             _lib.dt_code(cd), Tq * D, D, ptr(key_pad), ptr(prob_mask),
                                             ptr(probs_out), B, H, Tq, Tk, D // H, causal, q_pos0,

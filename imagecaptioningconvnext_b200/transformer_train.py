@@ -69,9 +69,7 @@ def _forward_body(dec, encoder_out, caps, kpm):
         Pn = enc.size(1)
         enc_op = Operand.prepare(enc.view(B * Pn, E), cd)
         mem = dec._linear_op(enc_op, Pw["proj"], Pw["proj_b"]) if Pw["proj"] is not None else enc_op
-        _lib.capture_probe("before the dropout draw")
         masks = _masks(dec, B, T, Pn, dev)
-        _lib.capture_probe("after the dropout draw")
         mk = (lambda k: None) if masks is None else (lambda k: masks.get(k))
         scale = 1.0 / math.sqrt(D // H)
 
@@ -86,7 +84,6 @@ def _forward_body(dec, encoder_out, caps, kpm):
             S = {"x0_op": x_op}
             qkv = _lib.linear(x_op, lw["sa_in"], bias=lw["sa_in_b"])
             probs1 = torch.empty((B, H, T, T), dtype=torch.float32, device=dev)
-            _lib.capture_probe("after torch.empty(probs1)")
             ctx1 = dec._mha(ptr(qkv), T * 3 * D, 3 * D, qkv.data_ptr() + 4 * D, T * 3 * D, 3 * D,
                             qkv.data_ptr() + 8 * D, B, T, T, 1, 0, kpm, mk((li, "sa_p")), 1, dev, probs_out=probs1)
             y1 = _lib.linear(ctx1, lw["sa_out"], bias=lw["sa_out_b"], residual=x_plain, emask=mk((li, "d1")))

@@ -124,3 +124,72 @@ def test_clamp_adam_loads_a_reference_adam_state_dict_and_survives_pickling():
     bad["param_groups"][0]["amsgrad"] = True
     with pytest.raises(ValueError):
         ClampAdam(w, lr=1e-4).load_state_dict(bad)
+
+
+def test_refresh_plan_table_layout_and_shape_checks():
+    """_host.RefreshPlan (the table behind ccx_cast_segments): tile offsets accumulate per piece, flags encode
+    transpose / fp32 destination, 1-D tensors become one-row pieces, and a mismatched destination is refused when the
+    plan is built (not discovered on the device)."""
+    import ctypes
+
+    import pytest
+
+    from imagecaptioningconvnext_b200 import _lib
+    from imagecaptioningconvnext_b200._host import RefreshPlan
+    assert ctypes.sizeof(_lib.CastSeg) == 64                       # mirrors `ccx_cast_seg` (include/ccx.h)
+    w = torch.zeros(130, 70)
+    b = torch.zeros(70)
+    plan = RefreshPlan()
+    plan.add(torch.zeros(130, 70, dtype=torch.bfloat16), w)                                   # 3 x 2 tiles
+    plan.add(torch.zeros(70, 200, dtype=torch.bfloat16)[:, 10:140], w, transpose=True)        # 3 x 2 tiles
+    plan.add(torch.zeros(5, 70, dtype=torch.bfloat16), w, row_map=torch.tensor([4, 3, 2, 1, 0]))   # 1 x 2 tiles
+    plan.add(torch.zeros(70), b, src2=b)                                                      # 1 x 2 tiles, fp32
+    assert [s.tile0 for s in plan.segs] == [0, 6, 12, 14] and plan.tiles == 16
+    assert [s.flags for s in plan.segs] == [0, 1, 0, 2]
+    assert [(s.rows, s.cols) for s in plan.segs] == [(130, 70), (130, 70), (5, 70), (1, 70)]
+    assert plan.segs[1].dst_ld == 200 and plan.segs[1].src_ld == 70
+    assert plan.segs[3].src2 == b.data_ptr() and plan.segs[0].src2 is None
+    for bad_dst, kw in ((torch.zeros(70, 130, dtype=torch.bfloat16), {}),                     # not transposed: wrong shape
+                        (torch.zeros(130, 70, dtype=torch.bfloat16), {"transpose": True}),
+                        (torch.zeros(130, 70, dtype=torch.float16), {}),                      # unsupported destination type
+                        (torch.zeros(130, 140, dtype=torch.bfloat16)[:, ::2], {})):           # inner stride != 1
+        with pytest.raises(ValueError):
+            RefreshPlan().add(bad_dst, w, **kw)
+    with pytest.raises(ValueError):
+        RefreshPlan().add(torch.zeros(130, 70, dtype=torch.bfloat16), w, src2=torch.zeros(130, 71)[:, :70])
+
+
+def test_no_gc_collects_first_and_restores_the_collector():
+    """_host.no_gc (wrapped around every CUDA-graph capture): cycles that died earlier are collected BEFORE the block,
+    nothing is collected inside it, and the collector's state is restored afterwards."""
+    import gc
+    import weakref
+
+    from imagecaptioningconvnext_b200._host import no_gc
+
+    class Node:
+        pass
+
+    def dead_cycle():
+        a, b = Node(), Node()
+        a.other, b.other = b, a
+        return weakref.ref(a)
+
+    assert gc.isenabled()
+    early = dead_cycle()
+    with no_gc():
+        assert early() is None and not gc.isenabled()
+        inside = dead_cycle()
+        junk = [[] for _ in range(5000)]                  # enough allocations to trip an automatic collection
+        del junk
+        assert inside() is not None
+    assert gc.isenabled()
+    gc.collect()
+    assert inside() is None
+    gc.disable()
+    try:
+        with no_gc():
+            pass
+        assert not gc.isenabled()                         # was off before: stays off
+    finally:
+        gc.enable()
