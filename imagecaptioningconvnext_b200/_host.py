@@ -204,6 +204,9 @@ class PreparedCache:
         make = getattr(owner, "_refresh_plan", None)
         if make is None or not PLAN_REFRESH[0]:
             return False
+        if (self._plan is None or (self._plan is not False and self._plan._table is None)) and \
+                torch.cuda.is_current_stream_capturing():
+            return False        # building the plan uploads its table (a host-to-device copy): never inside a capture
         if self._plan is None:
             self._plan = make(self._val)
             if self._plan is None:
