@@ -52,7 +52,8 @@ class no_gc:
     here sit in reference cycles (``_owner`` back-references), so a decoder that went out of scope — with the CUDA graphs
     and private memory pools it captured — is only freed by the cyclic collector; if that runs in the middle of a later
     capture, the graph's destructor (cudaGraphExecDestroy, cudaFree of its pool) invalidates the capture
-    ("operation failed due to a previous error during capture"; torch.cuda.graph no longer collects by itself).
+    ("operation failed due to a previous error during capture"; torch.cuda.graph only collects by itself when
+    torch.compiler.config.force_cudagraph_gc is set).
     Collect once before the capture begins, then keep the collector off until it ends."""
 
     def __enter__(self):
