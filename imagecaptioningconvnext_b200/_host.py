@@ -201,13 +201,13 @@ class PreparedCache:
 
     def _run_plan(self, owner):
         """One-launch refresh (``owner._refresh_plan(prepared dict) -> RefreshPlan``) of the current buffers; False
-        when the module has no plan for this compute dtype or a parameter's storage moved since the plan was built."""
+        when the module has no plan for this compute dtype or a parameter's storage moved since the plan was built.
+        The plan (and its device table: one host-to-device copy) is built at the FIRST refresh, which must not happen
+        inside a stream capture — every capturing caller (CapturedTrainStep, enable_cuda_graph) runs at least two eager
+        steps first, so the first refresh is the second eager step's."""
         make = getattr(owner, "_refresh_plan", None)
         if make is None or not PLAN_REFRESH[0]:
             return False
-        if (self._plan is None or (self._plan is not False and self._plan._table is None)) and \
-                torch.cuda.is_current_stream_capturing():
-            return False        # building the plan uploads its table (a host-to-device copy): never inside a capture
         if self._plan is None:
             self._plan = make(self._val)
             if self._plan is None:
